@@ -1,0 +1,824 @@
+// art_api.cu — C ABI of include/art.h: handle, device memory, pipeline driver, NCCL reduce.
+//
+// The pipeline driver is the body of main_runner_tree's event loop (reference
+// MainRunner.jl:450-747), restructured from "one event at a time on the host" into
+// generations of batched device work over a chunk of events:
+//   sample → weights → back-trace (axions) → back-finish → { trace photons, trace axions,
+//   tree-update } × generations → (patch rows) → histogram.
+// The host only reads two queue counters per generation.  There is no CPU compute path: every
+// entry point that computes needs a CUDA device and fails with ART_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/art.h"
+#include "art_host.hpp"
+#include "art_kernels.cuh"
+
+using namespace art;
+
+namespace {
+
+std::string g_create_error;
+
+struct DBuf {  // grow-only device buffer
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() { return (T*)p; }
+};
+
+// ---- NCCL through dlopen: no build-time dependency; a Julia host picks up the system
+// libnccl.so.2, a torchrun-launched bench the copy torch already loaded. -------------------
+struct Id128 {  // ncclUniqueId is passed BY VALUE to ncclCommInitRank
+  char b[128];
+};
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+
+bool nccl_load(std::string& err) {
+  if (g_nccl.lib) return true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.lib) break;
+  }
+  if (!g_nccl.lib) {
+    err = std::string("cannot dlopen libnccl.so.2: ") + dlerror();
+    return false;
+  }
+  g_nccl.GetUniqueId = (int (*)(void*))dlsym(g_nccl.lib, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(g_nccl.lib, "ncclCommInitRank");
+  g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
+  g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.lib, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
+    err = "libnccl lacks a required symbol";
+    return false;
+  }
+  return true;
+}
+
+}  // namespace
+
+struct art_handle {
+  art_params params;
+  DevParams dp;
+  int device = 0, n_sm = 0;
+  int blocks_trace_ph = 0, blocks_trace_ax = 0, blocks_sample = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  // pipeline buffers (per chunk)
+  DBuf samples, events, tstate, stacks, q[4], rout[2], rec[2], counters, stats, fin_count, fin_info;
+  DBuf rows, keys, hist, scratch[12];
+  long long rows_cap = 0;   // rows held on device
+  long long n_rows_dev = 0;
+  int ncols = 13;
+  int n_ct = 16, n_ph = 16;
+  double host_counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  void* comm = nullptr;
+  int nranks = 1, rank = 0;
+  long long launches = 0;  // kernels launched since the current pipeline call began
+};
+
+namespace {
+
+int fail(art_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  else g_create_error = msg;
+  return code;
+}
+
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(h, ART_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));      \
+  } while (0)
+
+inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
+
+int upload(art_handle* h, DBuf& b, const void* src, size_t bytes) {
+  CU(b.ensure(bytes ? bytes : 8));
+  if (bytes) CU(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, h->stream));
+  return ART_OK;
+}
+
+// launches the tracer for one species over a device queue; zeroes the queue head first
+template <bool AXION>
+int launch_trace(art_handle* h, const QueuedRay* q, long long n, RayOut* out, double* rec, int rec_cap,
+                 unsigned long long* head, DevStats* stats) {
+  if (n <= 0) return ART_OK;
+  CU(cudaMemsetAsync(head, 0, sizeof(unsigned long long), h->stream));
+  const int maxb = AXION ? h->blocks_trace_ax : h->blocks_trace_ph;
+  const int blocks = (int)std::min<long long>(maxb, (n + TRACE_THREADS - 1) / TRACE_THREADS);
+  k_trace<AXION><<<blocks, TRACE_THREADS, 0, h->stream>>>(h->dp, q, n, out, rec, rec_cap, head, stats);
+  h->launches++;
+  CU(cudaGetLastError());
+  return ART_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* art_version(void) { return "adiabatic_raytracer_b200 0.1 (sm_100a, DP5 integrator spec v1)"; }
+
+int art_params_default(art_params* p) {
+  if (!p) return ART_ERR_ARG;
+  memset(p, 0, sizeof(*p));
+  p->Mass_a = 1e-5; p->Ax_g = 1e-12; p->theta_m = 0.0; p->omega_pul = 1.0; p->B0 = 1e14; p->rNS = 10.0; p->Mass_NS = 1.0;
+  p->bndry_lyr = -1.0; p->ode_err = 1e-6; p->reltol = 1e-7; p->fix_time = 0.0; p->rho_DM = 0.45; p->vmean_ax = 220.0;
+  p->prob_cutoff = 1e-10; p->ln_t_start = -30.0; p->t0_sample = 0.0; p->metric_interior_radius = 10.0;
+  p->sampler_dt = 0.5; p->dtmin = 1e-13;
+  p->flat = 0; p->isotropic = 0; p->melrose = 1; p->thick_surface = 1; p->n_maxSample = 6; p->num_cutoff = 5;
+  p->MC_nodes = 5; p->max_nodes = 50; p->ntimes = 3; p->save_mode = 0; p->interp_points_ray = 50;
+  p->interp_points_sampler = 20; p->maxiters = 100000; p->cross_cap = 16;
+  return ART_OK;
+}
+
+int art_max_radius(const art_params* p, double* maxR) {
+  if (!p || !maxR) return ART_ERR_ARG;
+  DevParams d;
+  std::string e;
+  int rc = make_dev_params(*p, d, e);
+  if (rc == ART_OK || rc == ART_ERR_NO_SURFACE) *maxR = d.maxR;
+  if (rc != ART_OK) g_create_error = e;
+  return rc;
+}
+
+const char* art_last_error(const art_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int art_create(const art_params* p, int device_id, art_handle** out) {
+  art_handle* h = nullptr;
+  if (!p || !out) return fail(nullptr, ART_ERR_ARG, "null argument");
+  *out = nullptr;
+  DevParams d;
+  std::string e;
+  int rc = make_dev_params(*p, d, e);
+  if (rc != ART_OK) return fail(nullptr, rc, e);
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    return fail(nullptr, ART_ERR_CUDA,
+                std::string("no CUDA device (this library has no CPU fallback): ") + cudaGetErrorString(ce));
+  if (device_id < 0 || device_id >= ndev) return fail(nullptr, ART_ERR_ARG, "device_id out of range");
+  ce = cudaSetDevice(device_id);
+  if (ce != cudaSuccess) return fail(nullptr, ART_ERR_CUDA, cudaGetErrorString(ce));
+  h = new art_handle();
+  h->params = *p;
+  h->dp = d;
+  h->device = device_id;
+  h->ncols = p->save_mode > 0 ? ART_ROW_COLS_LONG : ART_ROW_COLS_SHORT;
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device_id);
+  h->n_sm = prop.multiProcessorCount;
+  int occ = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<false>, TRACE_THREADS, 0);
+  h->blocks_trace_ph = h->n_sm * std::max(occ, 1);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<true>, TRACE_THREADS, 0);
+  h->blocks_trace_ax = h->n_sm * std::max(occ, 1);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sample_events, SAMPLE_THREADS, 0);
+  h->blocks_sample = h->n_sm * std::max(occ, 1);
+  ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (ce != cudaSuccess) {
+    std::string m = cudaGetErrorString(ce);
+    delete h;
+    return fail(nullptr, ART_ERR_CUDA, m);
+  }
+  *out = h;
+  return ART_OK;
+}
+
+void art_destroy(art_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  DBuf* all[] = {&h->samples, &h->events, &h->tstate, &h->stacks, &h->q[0], &h->q[1], &h->q[2], &h->q[3],
+                 &h->rout[0], &h->rout[1], &h->rec[0], &h->rec[1], &h->counters, &h->stats, &h->fin_count,
+                 &h->fin_info, &h->rows, &h->keys, &h->hist};
+  for (DBuf* b : all) b->release();
+  for (DBuf& b : h->scratch) b.release();
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+// ---- fine-grained entry points -------------------------------------------------------------
+
+int art_sample_from_uniforms(art_handle* h, int64_t n, const double* u, double* x, double* v_loc, double* v_inf,
+                             int32_t* accepted, int32_t* n_cross) {
+  if (!h || n < 0) return ART_ERR_ARG;
+  CU(cudaSetDevice(h->device));
+  if (n == 0) return ART_OK;
+  DBuf* s = h->scratch;
+  if (upload(h, s[0], u, n * 10 * sizeof(double))) return ART_ERR_CUDA;
+  for (int k = 1; k <= 3; ++k) CU(s[k].ensure(3 * n * sizeof(double)));
+  CU(s[4].ensure(n * sizeof(int)));
+  CU(s[5].ensure(n * sizeof(int)));
+  k_sample_uniforms<<<nblk(n, 128), 128, 0, h->stream>>>(h->dp, n, s[0].as<double>(), s[1].as<double>(), s[2].as<double>(),
+                                                         s[3].as<double>(), s[4].as<int>(), s[5].as<int>());
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(x, s[1].p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(v_loc, s[2].p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(v_inf, s[3].p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(accepted, s[4].p, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(n_cross, s[5].p, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return ART_OK;
+}
+
+int art_sample(art_handle* h, uint64_t seed, int64_t first_event, int64_t n, double* x, double* v_loc, double* v_inf,
+               int32_t* n_cross, int32_t* n_failed) {
+  if (!h || n < 0) return ART_ERR_ARG;
+  CU(cudaSetDevice(h->device));
+  if (n == 0) return ART_OK;
+  CU(h->samples.ensure(n * sizeof(EventSample)));
+  CU(h->counters.ensure(64));
+  CU(cudaMemsetAsync(h->counters.p, 0, 64, h->stream));
+  const int blocks = (int)std::min<long long>(h->blocks_sample, (n + SAMPLE_THREADS - 1) / SAMPLE_THREADS);
+  k_sample_events<<<blocks, SAMPLE_THREADS, 0, h->stream>>>(h->dp, seed, first_event, n, h->samples.as<EventSample>(),
+                                                            h->counters.as<unsigned long long>(), nullptr);
+  CU(cudaGetLastError());
+  std::vector<EventSample> host((size_t)n);
+  CU(cudaMemcpyAsync(host.data(), h->samples.p, n * sizeof(EventSample), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  for (int64_t i = 0; i < n; ++i) {
+    for (int c = 0; c < 3; ++c) {
+      x[c * n + i] = host[i].x[c];
+      v_loc[c * n + i] = host[i].vloc[c];
+      v_inf[c * n + i] = host[i].vinf[c];
+    }
+    n_cross[i] = host[i].n_cross;
+    n_failed[i] = host[i].n_failed;
+  }
+  return ART_OK;
+}
+
+int art_weights(art_handle* h, int64_t n, const double* x, const double* v_loc, const double* v_inf, double* k_init,
+                double* cos_w, double* jac_gr, double* sln_prob, double* erg_inf, double* vel_eng) {
+  if (!h || n < 0) return ART_ERR_ARG;
+  CU(cudaSetDevice(h->device));
+  if (n == 0) return ART_OK;
+  DBuf* s = h->scratch;
+  if (upload(h, s[0], x, 3 * n * 8) || upload(h, s[1], v_loc, 3 * n * 8) || upload(h, s[2], v_inf, 3 * n * 8)) return ART_ERR_CUDA;
+  CU(s[3].ensure(3 * n * 8));
+  for (int k = 4; k <= 8; ++k) CU(s[k].ensure(n * 8));
+  k_weights_api<<<nblk(n, 128), 128, 0, h->stream>>>(h->dp, n, s[0].as<double>(), s[1].as<double>(), s[2].as<double>(),
+                                                     s[3].as<double>(), s[4].as<double>(), s[5].as<double>(),
+                                                     s[6].as<double>(), s[7].as<double>(), s[8].as<double>());
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(k_init, s[3].p, 3 * n * 8, cudaMemcpyDeviceToHost, h->stream));
+  double* outs[5] = {cos_w, jac_gr, sln_prob, erg_inf, vel_eng};
+  for (int k = 0; k < 5; ++k) CU(cudaMemcpyAsync(outs[k], s[4 + k].p, n * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return ART_OK;
+}
+
+int art_conv_prob(art_handle* h, int64_t n, const double* x, const double* k, const double* erg_scaled, int32_t b_sign,
+                  double* P_nonAD) {
+  if (!h || n < 0) return ART_ERR_ARG;
+  CU(cudaSetDevice(h->device));
+  if (n == 0) return ART_OK;
+  DBuf* s = h->scratch;
+  if (upload(h, s[0], x, 3 * n * 8) || upload(h, s[1], k, 3 * n * 8) || upload(h, s[2], erg_scaled, n * 8)) return ART_ERR_CUDA;
+  CU(s[3].ensure(n * 8));
+  k_conv_prob_api<<<nblk(n, 128), 128, 0, h->stream>>>(h->dp, n, s[0].as<double>(), s[1].as<double>(), s[2].as<double>(),
+                                                       b_sign < 0 ? -1.0 : 1.0, s[3].as<double>());
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(P_nonAD, s[3].p, n * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return ART_OK;
+}
+
+int art_rhs(art_handle* h, int64_t n, const int32_t* species, const double* u, const double* erg, const double* lnt,
+            double* du) {
+  if (!h || n < 0) return ART_ERR_ARG;
+  CU(cudaSetDevice(h->device));
+  if (n == 0) return ART_OK;
+  DBuf* s = h->scratch;
+  if (upload(h, s[0], species, n * 4) || upload(h, s[1], u, 7 * n * 8) || upload(h, s[2], erg, n * 8) ||
+      upload(h, s[3], lnt, n * 8))
+    return ART_ERR_CUDA;
+  CU(s[4].ensure(7 * n * 8));
+  k_rhs_api<<<nblk(n, 128), 128, 0, h->stream>>>(h->dp, n, s[0].as<int>(), s[1].as<double>(), s[2].as<double>(),
+                                                 s[3].as<double>(), s[4].as<double>());
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(du, s[4].p, 7 * n * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return ART_OK;
+}
+
+int art_propagate(art_handle* h, int64_t n, const int32_t* species, const double* x0, const double* k0,
+                  const double* erg, const double* t_start, const double* dOmega, int32_t b_sign,
+                  int32_t max_crossings, double* x_f, double* k_f, double* u7_f, int32_t* status, int32_t* n_cross,
+                  double* cross_rec, int32_t cross_cap, int32_t* counters) {
+  (void)b_sign;  // the sign of B0 drops out of the ray equations and of the crossing condition
+  if (!h || n < 0 || cross_cap < 1) return ART_ERR_ARG;
+  CU(cudaSetDevice(h->device));
+  if (n == 0) return ART_OK;
+  // split by species on the host (two kernels: the photon and axion right-hand sides differ)
+  std::vector<QueuedRay> qs[2];
+  for (int64_t i = 0; i < n; ++i) {
+    QueuedRay r;
+    for (int c = 0; c < 3; ++c) { r.in.x0[c] = x0[c * n + i]; r.in.k0[c] = k0[c * n + i]; }
+    r.in.erg = erg[i]; r.in.t_start = t_start[i]; r.in.dOmega = dOmega[i]; r.in.max_cross = max_crossings;
+    r.owner = (int)i; r.pad_ = 0;
+    qs[species[i] == ART_SPECIES_PHOTON ? 0 : 1].push_back(r);
+  }
+  CU(h->counters.ensure(64));
+  for (int sp = 0; sp < 2; ++sp) {
+    const long long m = (long long)qs[sp].size();
+    if (!m) continue;
+    if (upload(h, h->q[sp], qs[sp].data(), m * sizeof(QueuedRay))) return ART_ERR_CUDA;
+    CU(h->rout[sp].ensure(m * sizeof(RayOut)));
+    CU(h->rec[sp].ensure((size_t)m * cross_cap * 8 * sizeof(double)));
+    CU(cudaMemsetAsync(h->rec[sp].p, 0, (size_t)m * cross_cap * 8 * sizeof(double), h->stream));
+    int rc = sp == 0 ? launch_trace<false>(h, h->q[sp].as<QueuedRay>(), m, h->rout[sp].as<RayOut>(), h->rec[sp].as<double>(),
+                                           cross_cap, h->counters.as<unsigned long long>() + sp, nullptr)
+                     : launch_trace<true>(h, h->q[sp].as<QueuedRay>(), m, h->rout[sp].as<RayOut>(), h->rec[sp].as<double>(),
+                                          cross_cap, h->counters.as<unsigned long long>() + sp, nullptr);
+    if (rc) return rc;
+  }
+  for (int sp = 0; sp < 2; ++sp) {
+    const long long m = (long long)qs[sp].size();
+    if (!m) continue;
+    std::vector<RayOut> ro((size_t)m);
+    std::vector<double> rc_((size_t)m * cross_cap * 8);
+    CU(cudaMemcpyAsync(ro.data(), h->rout[sp].p, m * sizeof(RayOut), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(rc_.data(), h->rec[sp].p, rc_.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (long long j = 0; j < m; ++j) {
+      const int64_t i = qs[sp][j].owner;
+      for (int c = 0; c < 3; ++c) { x_f[c * n + i] = ro[j].xf[c]; k_f[c * n + i] = ro[j].kf[c]; }
+      u7_f[i] = ro[j].u7f; status[i] = ro[j].status; n_cross[i] = ro[j].n_cross;
+      memcpy(cross_rec + (size_t)i * cross_cap * 8, rc_.data() + (size_t)j * cross_cap * 8, (size_t)cross_cap * 8 * sizeof(double));
+      if (counters) {
+        counters[4 * i] = ro[j].n_acc; counters[4 * i + 1] = ro[j].n_rej; counters[4 * i + 2] = ro[j].n_rhs;
+        counters[4 * i + 3] = ro[j].n_cond;
+      }
+    }
+  }
+  return ART_OK;
+}
+
+// ---- fused pipeline ----------------------------------------------------------------------------
+
+int art_hist_config(art_handle* h, int32_t n_costheta, int32_t n_phi) {
+  if (!h || n_costheta < 1 || n_phi < 1 || (long long)n_costheta * n_phi > (1 << 20)) return ART_ERR_ARG;
+  h->n_ct = n_costheta;
+  h->n_ph = n_phi;
+  return art_hist_reset(h);
+}
+
+int64_t art_hist_len(const art_handle* h) { return h ? (int64_t)2 * h->n_ct * h->n_ph * 4 + 8 : 0; }
+
+int art_hist_reset(art_handle* h) {
+  if (!h) return ART_ERR_ARG;
+  CU(cudaSetDevice(h->device));
+  const size_t bytes = (size_t)art_hist_len(h) * sizeof(double);
+  CU(h->hist.ensure(bytes));
+  CU(cudaMemsetAsync(h->hist.p, 0, bytes, h->stream));
+  for (double& c : h->host_counters) c = 0.0;
+  CU(cudaStreamSynchronize(h->stream));
+  return ART_OK;
+}
+
+static int hist_push_counters(art_handle* h) {
+  const size_t off = (size_t)(art_hist_len(h) - 8) * sizeof(double);
+  CU(cudaMemcpyAsync((char*)h->hist.p + off, h->host_counters, 8 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  return ART_OK;
+}
+
+int art_hist_get(art_handle* h, double* out, int64_t cap) {
+  if (!h || !out || cap < art_hist_len(h)) return ART_ERR_ARG;
+  CU(cudaSetDevice(h->device));
+  if (!h->hist.p) {
+    int rc = art_hist_reset(h);
+    if (rc) return rc;
+  }
+  if (!h->comm || h->nranks == 1) {
+    int rc = hist_push_counters(h);
+    if (rc) return rc;
+  }
+  CU(cudaMemcpyAsync(out, h->hist.p, (size_t)art_hist_len(h) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return ART_OK;
+}
+
+int art_run_device(art_handle* h, uint64_t seed, int64_t first_event, int64_t n_events, int64_t* n_rows_out,
+                   int64_t* f_inx_out, int64_t* tot_count_out, art_stats* st_out) {
+  if (!h || n_events < 0) return ART_ERR_ARG;
+  CU(cudaSetDevice(h->device));
+  const DevParams& P = h->dp;
+  const int ncols = h->ncols;
+  const int cap = h->params.cross_cap;
+  const int stack_stride = h->params.max_nodes + 4;
+  const long long CH = std::min<long long>(std::max<long long>(n_events, 1), 1LL << 20);
+  if (!h->hist.p) {
+    int rc = art_hist_reset(h);
+    if (rc) return rc;
+  }
+  // buffers
+  CU(h->samples.ensure(CH * sizeof(EventSample)));
+  CU(h->events.ensure(CH * sizeof(EventData)));
+  CU(h->tstate.ensure(CH * sizeof(TreeState)));
+  CU(h->stacks.ensure((size_t)CH * stack_stride * sizeof(TreeNode)));
+  for (int k = 0; k < 4; ++k) CU(h->q[k].ensure(CH * sizeof(QueuedRay)));
+  for (int k = 0; k < 2; ++k) {
+    CU(h->rout[k].ensure(CH * sizeof(RayOut)));
+    CU(h->rec[k].ensure((size_t)CH * cap * 8 * sizeof(double)));
+  }
+  CU(h->fin_count.ensure(CH * sizeof(int)));
+  CU(h->fin_info.ensure(CH * sizeof(int)));
+  CU(h->counters.ensure(16 * sizeof(unsigned long long)));
+  CU(h->stats.ensure(sizeof(DevStats)));
+  // rows: the reference appends without bound; start with 3 rows/event and report overflow
+  const long long want_rows = n_events * 3 + 1024;
+  if (want_rows > h->rows_cap) {
+    CU(h->rows.ensure((size_t)want_rows * ncols * sizeof(double)));
+    CU(h->keys.ensure((size_t)want_rows * sizeof(long long)));
+    h->rows_cap = want_rows;
+  }
+  h->n_rows_dev = 0;
+  h->launches = 0;
+  unsigned long long* ctr = h->counters.as<unsigned long long>();
+  // ctr layout: [0] sampler head, [1] trace head ph, [2] trace head ax, [3] tot_count,
+  //             [4,5] next-queue counts (ph, ax), [6] n_rows, [7,8] n_final (ph, ax)
+  CU(cudaMemsetAsync(ctr, 0, 16 * sizeof(unsigned long long), h->stream));
+  CU(cudaMemsetAsync(h->stats.p, 0, sizeof(DevStats), h->stream));
+  DevStats* dstats = h->stats.as<DevStats>();
+  RowSink sink{h->rows.as<double>(), h->keys.as<long long>(), ctr + 6, (unsigned long long)h->rows_cap, ncols, ctr + 7};
+
+  cudaEvent_t ev[8];
+  for (auto& e : ev) CU(cudaEventCreate(&e));
+  float ms_s = 0, ms_w = 0, ms_t = 0, ms_tree = 0, ms_tot = 0;
+  long long failed_total = 0;
+  CU(cudaEventRecord(ev[6], h->stream));
+
+  for (long long base = 0; base < n_events; base += CH) {
+    const long long n = std::min(CH, n_events - base);
+    unsigned long long rows_before = 0;
+    CU(cudaMemcpyAsync(&rows_before, ctr + 6, 8, cudaMemcpyDeviceToHost, h->stream));
+    // K1 sampler
+    CU(cudaEventRecord(ev[0], h->stream));
+    CU(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), h->stream));
+    {
+      const int blocks = (int)std::min<long long>(h->blocks_sample, (n + SAMPLE_THREADS - 1) / SAMPLE_THREADS);
+      k_sample_events<<<blocks, SAMPLE_THREADS, 0, h->stream>>>(P, seed, first_event + base, n, h->samples.as<EventSample>(),
+                                                                ctr, dstats);
+      h->launches++;
+      CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(ev[1], h->stream));
+    // K2 weights (+ back-trace queue)
+    k_weights_events<<<nblk(n, 128), 128, 0, h->stream>>>(P, n, h->samples.as<EventSample>(), h->events.as<EventData>(),
+                                                          h->q[1].as<QueuedRay>());
+    h->launches++;
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ev[2], h->stream));
+    // K3 back-trace (axions), K4 back-finish
+    if (int rc = launch_trace<true>(h, h->q[1].as<QueuedRay>(), n, h->rout[1].as<RayOut>(), h->rec[1].as<double>(), cap,
+                                    ctr + 2, dstats))
+      return rc;
+    CU(cudaEventRecord(ev[3], h->stream));
+    k_back_finish<<<nblk(n, 128), 128, 0, h->stream>>>(P, n, h->events.as<EventData>(), h->rout[1].as<RayOut>(),
+                                                       h->rec[1].as<double>(), cap, h->tstate.as<TreeState>(),
+                                                       h->q[0].as<QueuedRay>());
+    h->launches++;
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ev[4], h->stream));
+    float t01, t12, t23, t34;
+    // forward generations: queues q[0]/q[1] = current photon/axion, q[2]/q[3] = next
+    long long n_ph = n, n_ax = 0;
+    int cur = 0;
+    float ms_gen_trace = 0, ms_gen_tree = 0;
+    while (n_ph + n_ax > 0) {
+      QueuedRay* qph = h->q[cur * 2 + 0].as<QueuedRay>();
+      QueuedRay* qax = h->q[cur * 2 + 1].as<QueuedRay>();
+      QueuedRay* nph = h->q[(1 - cur) * 2 + 0].as<QueuedRay>();
+      QueuedRay* nax = h->q[(1 - cur) * 2 + 1].as<QueuedRay>();
+      CU(cudaMemsetAsync(ctr + 4, 0, 2 * sizeof(unsigned long long), h->stream));
+      cudaEvent_t a, b, c;
+      CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b)); CU(cudaEventCreate(&c));
+      CU(cudaEventRecord(a, h->stream));
+      if (int rc = launch_trace<false>(h, qph, n_ph, h->rout[0].as<RayOut>(), h->rec[0].as<double>(), cap, ctr + 1, dstats)) return rc;
+      if (int rc = launch_trace<true>(h, qax, n_ax, h->rout[1].as<RayOut>(), h->rec[1].as<double>(), cap, ctr + 2, dstats)) return rc;
+      CU(cudaEventRecord(b, h->stream));
+      if (n_ph > 0) {
+        k_tree_update<<<nblk(n_ph, 128), 128, 0, h->stream>>>(
+            P, n_ph, qph, h->rout[0].as<RayOut>(), h->rec[0].as<double>(), cap, h->events.as<EventData>(),
+            h->tstate.as<TreeState>(), h->stacks.as<TreeNode>(), stack_stride, seed, first_event, base, sink, nph, nax,
+            ctr + 4, ctr + 3, h->fin_count.as<int>(), h->fin_info.as<int>());
+        h->launches++;
+        CU(cudaGetLastError());
+      }
+      if (n_ax > 0) {
+        k_tree_update<<<nblk(n_ax, 128), 128, 0, h->stream>>>(
+            P, n_ax, qax, h->rout[1].as<RayOut>(), h->rec[1].as<double>(), cap, h->events.as<EventData>(),
+            h->tstate.as<TreeState>(), h->stacks.as<TreeNode>(), stack_stride, seed, first_event, base, sink, nph, nax,
+            ctr + 4, ctr + 3, h->fin_count.as<int>(), h->fin_info.as<int>());
+        h->launches++;
+        CU(cudaGetLastError());
+      }
+      CU(cudaEventRecord(c, h->stream));
+      unsigned long long nxt[2];
+      CU(cudaMemcpyAsync(nxt, ctr + 4, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+      float x1 = 0, x2 = 0;
+      cudaEventElapsedTime(&x1, a, b);
+      cudaEventElapsedTime(&x2, b, c);
+      ms_gen_trace += x1;
+      ms_gen_tree += x2;
+      cudaEventDestroy(a); cudaEventDestroy(b); cudaEventDestroy(c);
+      n_ph = (long long)nxt[0];
+      n_ax = (long long)nxt[1];
+      cur = 1 - cur;
+    }
+    // failed sampler attempts of this chunk (→ f_inx)
+    {
+      std::vector<EventSample> hs;  // only n_failed is needed: reduce on host from the small struct
+      hs.resize((size_t)n);
+      CU(cudaMemcpyAsync(hs.data(), h->samples.p, n * sizeof(EventSample), cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+      for (auto& s : hs) failed_total += s.n_failed;
+    }
+    unsigned long long rows_after = 0;
+    CU(cudaMemcpy(&rows_after, ctr + 6, 8, cudaMemcpyDeviceToHost));
+    if ((long long)rows_after > h->rows_cap) {
+      for (auto& e : ev) cudaEventDestroy(e);
+      return fail(h, ART_ERR_CAPACITY, "device row buffer overflow (more than 3 rows per event on average)");
+    }
+    const long long nr = (long long)rows_after - (long long)rows_before;
+    if (nr > 0) {
+      if (ncols > 13) {
+        k_patch_rows<<<nblk(nr, 256), 256, 0, h->stream>>>((long long)rows_after, h->rows.as<double>(), h->keys.as<long long>(),
+                                                           ncols, base, h->fin_count.as<int>(), h->fin_info.as<int>(),
+                                                           (long long)rows_before);
+        h->launches++;
+        CU(cudaGetLastError());
+      }
+      const int nb = 2 * h->n_ct * h->n_ph * 4;
+      const int use_smem = nb * (int)sizeof(double) <= 48 * 1024;
+      const int blocks = (int)std::min<long long>(h->n_sm * 4, (nr + 255) / 256);
+      k_hist<<<blocks, 256, use_smem ? nb * sizeof(double) : 0, h->stream>>>((long long)rows_before, (long long)rows_after,
+                                                                             h->rows.as<double>(), ncols, h->n_ct, h->n_ph,
+                                                                             h->hist.as<double>(), use_smem);
+      h->launches++;
+      CU(cudaGetLastError());
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    cudaEventElapsedTime(&t01, ev[0], ev[1]);
+    cudaEventElapsedTime(&t12, ev[1], ev[2]);
+    cudaEventElapsedTime(&t23, ev[2], ev[3]);
+    cudaEventElapsedTime(&t34, ev[3], ev[4]);
+    ms_s += t01; ms_w += t12; ms_t += t23 + ms_gen_trace; ms_tree += t34 + ms_gen_tree;
+  }
+  CU(cudaEventRecord(ev[7], h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  cudaEventElapsedTime(&ms_tot, ev[6], ev[7]);
+  for (auto& e : ev) cudaEventDestroy(e);
+
+  unsigned long long hc[16];
+  DevStats ds;
+  CU(cudaMemcpy(hc, ctr, sizeof(hc), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(&ds, dstats, sizeof(ds), cudaMemcpyDeviceToHost));
+  h->n_rows_dev = (long long)hc[6];
+  const long long f_inx = failed_total + (long long)hc[7];
+  if (n_rows_out) *n_rows_out = h->n_rows_dev;
+  if (f_inx_out) *f_inx_out = f_inx;
+  if (tot_count_out) *tot_count_out = (long long)hc[3];
+  art_stats S;
+  memset(&S, 0, sizeof(S));
+  S.n_events = n_events; S.n_attempts = (long long)ds.n_attempts; S.n_sampler_cond = (long long)ds.n_sampler_cond;
+  S.n_rays = (long long)ds.n_rays; S.n_rays_photon = (long long)ds.n_rays_photon; S.n_acc = (long long)ds.n_acc;
+  S.n_rej = (long long)ds.n_rej; S.n_rhs = (long long)ds.n_rhs; S.n_cond = (long long)ds.n_cond;
+  S.n_final_photon = (long long)hc[7]; S.n_final_axion = (long long)hc[8];
+  for (int k = 0; k < 5; ++k) S.n_status[k] = (long long)ds.n_status[k];
+  S.ms_sampler = ms_s; S.ms_weights = ms_w; S.ms_tracer = ms_t; S.ms_tree = ms_tree; S.ms_total = ms_tot;
+  S.n_launches = h->launches;
+  if (st_out) *st_out = S;
+  // trailing histogram counters: [f_inx, n_rows, n_events, n_acc, n_rej, n_rhs, n_cond, n_rays]
+  h->host_counters[0] += (double)f_inx; h->host_counters[1] += (double)h->n_rows_dev; h->host_counters[2] += (double)n_events;
+  h->host_counters[3] += (double)S.n_acc; h->host_counters[4] += (double)S.n_rej; h->host_counters[5] += (double)S.n_rhs;
+  h->host_counters[6] += (double)S.n_cond; h->host_counters[7] += (double)S.n_rays;
+  return ART_OK;
+}
+
+int art_fetch_rows(art_handle* h, double* rows, int64_t rows_cap, int64_t* n_rows) {
+  if (!h || !rows) return ART_ERR_ARG;
+  CU(cudaSetDevice(h->device));
+  const long long n = h->n_rows_dev;
+  if (n_rows) *n_rows = n;
+  if (n > rows_cap) return fail(h, ART_ERR_CAPACITY, "rows_cap too small");
+  if (n == 0) return ART_OK;
+  const int ncols = h->ncols;
+  std::vector<double> tmp((size_t)n * ncols);
+  std::vector<long long> keys((size_t)n);
+  CU(cudaMemcpy(tmp.data(), h->rows.p, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(keys.data(), h->keys.p, keys.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+  // order rows as the reference writes them: by event, then by position in the tree
+  std::vector<long long> order((size_t)n);
+  for (long long i = 0; i < n; ++i) order[(size_t)i] = i;
+  std::sort(order.begin(), order.end(), [&](long long a, long long b) { return keys[(size_t)a] < keys[(size_t)b]; });
+  for (long long i = 0; i < n; ++i)
+    memcpy(rows + (size_t)i * ncols, tmp.data() + (size_t)order[(size_t)i] * ncols, (size_t)ncols * sizeof(double));
+  return ART_OK;
+}
+
+int art_run(art_handle* h, uint64_t seed, int64_t first_event, int64_t n_events, double* rows, int64_t rows_cap,
+            int64_t* n_rows, int64_t* f_inx, int64_t* tot_count, art_stats* stats) {
+  int rc = art_run_device(h, seed, first_event, n_events, n_rows, f_inx, tot_count, stats);
+  if (rc) return rc;
+  return art_fetch_rows(h, rows, rows_cap, n_rows);
+}
+
+int art_normalize_rows(double* rows, int64_t n_rows, int32_t ncols, int64_t f_inx_total) {
+  if (!rows || ncols < 8 || f_inx_total <= 0) return ART_ERR_ARG;
+  const double f = (double)f_inx_total;
+  for (int64_t i = 0; i < n_rows; ++i) rows[i * ncols + 7] /= f;  // MainRunner.jl:749 (saveAll[:, 8])
+  return ART_OK;
+}
+
+// Julia's string(::Float64) (Ryu shortest round-trip; fixed notation iff -4 < point <= 6,
+// otherwise d.ddde±x) for the file name, MainRunner.jl:750-760.
+static std::string julia_float(double v) {
+  if (v == 0.0) return "0.0";
+  char buf[64];
+  for (int prec = 1; prec <= 17; ++prec) {
+    snprintf(buf, sizeof buf, "%.*e", prec - 1, v);
+    if (strtod(buf, nullptr) == v) break;
+  }
+  std::string s(buf);
+  const size_t epos = s.find('e');
+  std::string mant = s.substr(0, epos);
+  const int ex = atoi(s.c_str() + epos + 1);
+  bool neg = false;
+  if (mant[0] == '-') {
+    neg = true;
+    mant = mant.substr(1);
+  }
+  std::string digits;
+  for (char c : mant)
+    if (c != '.') digits.push_back(c);
+  while (digits.size() > 1 && digits.back() == '0') digits.pop_back();
+  const int nd = (int)digits.size();
+  const int pt = ex + 1;  // position of the decimal point relative to the digit string
+  std::string out;
+  if (pt > -4 && pt <= 6) {
+    if (pt <= 0) out = "0." + std::string((size_t)(-pt), '0') + digits;
+    else if (pt >= nd) out = digits + std::string((size_t)(pt - nd), '0') + ".0";
+    else out = digits.substr(0, (size_t)pt) + "." + digits.substr((size_t)pt);
+  } else {
+    out = digits.substr(0, 1) + "." + (nd > 1 ? digits.substr(1) : std::string("0")) + "e" + std::to_string(ex);
+  }
+  return (neg ? "-" : "") + out;
+}
+
+int art_npy_name(const art_params* p, int64_t Ntajs, const char* dir_tag, const char* file_tag, char* out, int64_t out_cap) {
+  if (!p || !out) return ART_ERR_ARG;
+  std::string s = std::string(dir_tag ? dir_tag : "results") + "/npy/tree_";
+  s += "MassAx_" + julia_float(p->Mass_a) + "_AxionG_" + julia_float(p->Ax_g);
+  s += "_ThetaM_" + julia_float(p->theta_m) + "_rotPulsar_" + julia_float(p->omega_pul) + "_B0_" + julia_float(p->B0);
+  s += "_Ax_trajs_" + std::to_string((long long)Ntajs);
+  s += "_N_Times_" + std::to_string(p->ntimes);
+  s += "_num_cutoff_" + std::to_string(p->num_cutoff);
+  s += "_MC_nodes_" + std::to_string(p->MC_nodes);
+  s += "_max_nodes_" + std::to_string(p->max_nodes);
+  s += std::string("_") + (file_tag ? file_tag : "") + ".npy";
+  if ((int64_t)s.size() + 1 > out_cap) return ART_ERR_CAPACITY;
+  memcpy(out, s.c_str(), s.size() + 1);
+  return ART_OK;
+}
+
+int art_write_npy(const char* path, const double* rows, int64_t n_rows, int32_t ncols) {
+  if (!path || (!rows && n_rows > 0)) return ART_ERR_ARG;
+  FILE* f = fopen(path, "wb");
+  if (!f) return ART_ERR_IO;
+  char dict[256];
+  int len = snprintf(dict, sizeof dict, "{'descr': '<f8', 'fortran_order': True, 'shape': (%lld, %d), }", (long long)n_rows, ncols);
+  int total = 10 + len + 1;
+  int pad = (64 - total % 64) % 64;
+  unsigned short hlen = (unsigned short)(len + pad + 1);
+  fwrite("\x93NUMPY\x01\x00", 1, 8, f);
+  fwrite(&hlen, 2, 1, f);
+  fwrite(dict, 1, (size_t)len, f);
+  for (int i = 0; i < pad; ++i) fputc(' ', f);
+  fputc('\n', f);
+  // NPZ.jl writes the Julia (column-major) array as is: column by column
+  std::vector<double> col((size_t)n_rows);
+  for (int c = 0; c < ncols; ++c) {
+    for (int64_t i = 0; i < n_rows; ++i) col[(size_t)i] = rows[i * ncols + c];
+    fwrite(col.data(), sizeof(double), (size_t)n_rows, f);
+  }
+  fclose(f);
+  return ART_OK;
+}
+
+// ---- multi-GPU -------------------------------------------------------------------------------
+
+int art_comm_unique_id(char* id128) {
+  std::string e;
+  if (!id128) return ART_ERR_ARG;
+  if (!nccl_load(e)) return fail(nullptr, ART_ERR_NCCL, e);
+  int rc = g_nccl.GetUniqueId(id128);
+  return rc == 0 ? ART_OK : fail(nullptr, ART_ERR_NCCL, "ncclGetUniqueId failed");
+}
+
+int art_comm_init(art_handle* h, int32_t nranks, int32_t rank, const char* id128) {
+  if (!h || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return ART_ERR_ARG;
+  std::string e;
+  if (!nccl_load(e)) return fail(h, ART_ERR_NCCL, e);
+  CU(cudaSetDevice(h->device));
+  Id128 id;
+  memcpy(id.b, id128, 128);
+  int rc = g_nccl.CommInitRank(&h->comm, nranks, id, rank);
+  if (rc != 0) return fail(h, ART_ERR_NCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+  h->nranks = nranks;
+  h->rank = rank;
+  return ART_OK;
+}
+
+int art_comm_allreduce_hist(art_handle* h) {
+  if (!h) return ART_ERR_ARG;
+  CU(cudaSetDevice(h->device));
+  if (!h->hist.p) {
+    int rc = art_hist_reset(h);
+    if (rc) return rc;
+  }
+  int rc = hist_push_counters(h);
+  if (rc) return rc;
+  if (h->comm && h->nranks > 1) {
+    // ncclAllReduce(sum, f64) over [bins | counters] in place — the only collective of the path
+    rc = g_nccl.AllReduce(h->hist.p, h->hist.p, (size_t)art_hist_len(h), /*ncclFloat64*/ 8, /*ncclSum*/ 0, h->comm, h->stream);
+    if (rc != 0) return fail(h, ART_ERR_NCCL, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+  }
+  CU(cudaStreamSynchronize(h->stream));
+  // after the reduce the device copy holds global counters; keep the host mirror in sync
+  const size_t off = (size_t)(art_hist_len(h) - 8) * sizeof(double);
+  CU(cudaMemcpy(h->host_counters, (char*)h->hist.p + off, 8 * sizeof(double), cudaMemcpyDeviceToHost));
+  return ART_OK;
+}
+
+int art_comm_destroy(art_handle* h) {
+  if (!h) return ART_ERR_ARG;
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  h->comm = nullptr;
+  h->nranks = 1;
+  h->rank = 0;
+  return ART_OK;
+}
+
+int art_fp64_peak(art_handle* h, double* tflops, double* ms_out) {
+  if (!h || !tflops) return ART_ERR_ARG;
+  CU(cudaSetDevice(h->device));
+  const int blocks = h->n_sm * 8, threads = 256, iters = 4096;
+  CU(h->scratch[0].ensure((size_t)blocks * threads * sizeof(double)));
+  cudaEvent_t a, b;
+  CU(cudaEventCreate(&a));
+  CU(cudaEventCreate(&b));
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    CU(cudaEventRecord(a, h->stream));
+    k_fp64_peak<<<blocks, threads, 0, h->stream>>>(h->scratch[0].as<double>(), iters, 0.999999, 1e-9);
+    CU(cudaEventRecord(b, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    float ms;
+    cudaEventElapsedTime(&ms, a, b);
+    if (rep > 0) best = std::min(best, ms);
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  const double flops = 2.0 * 64.0 * iters * (double)blocks * threads;  // 8×8 FMAs per iteration
+  *tflops = flops / (best * 1e-3) / 1e12;
+  if (ms_out) *ms_out = best;
+  return ART_OK;
+}
+
+}  // extern "C"

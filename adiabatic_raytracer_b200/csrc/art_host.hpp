@@ -1,0 +1,88 @@
+// art_host.hpp — host-side derivation of the run constants from art_params.
+#pragma once
+#include <math.h>
+#include <string>
+
+#include "../../include/art.h"
+#include "art_physics.cuh"
+#include "art_sampler.cuh"
+
+namespace art {
+
+// Validates the switches this build supports (unsupported ones fail loudly, never silently
+// fall back) and fills DevParams.  Returns ART_OK / ART_ERR_ARG / ART_ERR_NO_SURFACE.
+inline int make_dev_params(const art_params& p, DevParams& d, std::string& err) {
+  if (!(p.Mass_a > 0) || !(p.rNS > 0) || !(p.omega_pul > 0) || !(p.Mass_NS >= 0)) {
+    err = "Mass_a, rNS, omega_pul must be positive";
+    return ART_ERR_ARG;
+  }
+  if (p.bndry_lyr > 0) {
+    err = "bndry_lyr > 0 (boundary-layer plasma term, RayTracer.jl:1156-1162) is not supported by this build";
+    return ART_ERR_ARG;
+  }
+  if (!p.melrose && !p.isotropic) {
+    err = "melrose=false (Ctheta_B_sphere branch, RayTracer.jl:546-548) is not supported by this build";
+    return ART_ERR_ARG;
+  }
+  if (!p.thick_surface) {
+    err = "thick_surface=false is not supported by this build";
+    return ART_ERR_ARG;
+  }
+  if (p.n_maxSample < 1 || p.n_maxSample > SAMP_KEEP) {
+    err = "n_maxSample must be in 1..8";
+    return ART_ERR_ARG;
+  }
+  if (p.max_nodes < 1 || p.max_nodes > 250 || p.interp_points_ray < 2 || p.interp_points_sampler < 2 ||
+      p.cross_cap < 1 || p.cross_cap > 64 || !(p.reltol > 0) || !(p.ode_err > 0) || !(p.sampler_dt > 0)) {
+    err = "numerics parameter out of range";
+    return ART_ERR_ARG;
+  }
+  d.cm = cos(p.theta_m);
+  d.sm = sin(p.theta_m);
+  d.Omega = p.omega_pul;
+  // ωp² = 4π n_e/137/5e5, n_e = |2Ω B_z|/√(4π/137)·1.95e-2·ħ, B_z = B0 (rNS/r)³/2 · b_z   (RT.jl:1143-1154)
+  const double K2 = 4.0 * PI / 137.0 / 5.0e5 * (1.95e-2 * HBAR / sqrt(4.0 * PI / 137.0));
+  d.Q = K2 * fabs(p.omega_pul) * fabs(p.B0) * p.rNS * p.rNS * p.rNS;
+  d.Bn0 = fabs(p.B0) * p.rNS * p.rNS * p.rNS * 0.5;
+  d.rNS = p.rNS;
+  d.rNS101 = p.rNS * 1.01;
+  d.rs_real = 2.0 * p.Mass_NS * GNEW / (C_KM * C_KM);
+  d.rs_ray = p.flat ? 0.0 : d.rs_real;
+  d.r_int = p.metric_interior_radius;
+  d.ma = p.Mass_a;
+  d.ma2 = p.Mass_a * p.Mass_a;
+  d.Ax_g = p.Ax_g;
+  d.t0 = p.t0_sample;
+  d.rtol = p.reltol;
+  d.atol = p.ode_err;
+  d.dtmin = p.dtmin;
+  d.ln_t0 = p.ln_t_start;
+  d.ln_tend = log(1.0 / p.omega_pul);  // MainRunner.jl:412
+  d.t_floor = exp(p.ln_t_start);
+  d.samp_dt = p.sampler_dt;
+  d.rho_DM = p.rho_DM;
+  d.maxiters = p.maxiters;
+  d.M_ray = p.interp_points_ray;
+  d.M_samp = p.interp_points_sampler;
+  d.n_max = p.n_maxSample;
+  d.isotropic = p.isotropic ? 1 : 0;
+  d.flat = p.flat ? 1 : 0;
+  d.num_cutoff = p.num_cutoff;
+  d.MC_nodes = p.MC_nodes;
+  d.max_nodes = p.max_nodes;
+  d.prob_cutoff = p.prob_cutoff;
+  // Find_Conversion_Surface, RT.jl:1250-1263: ωp at r = rNS, θ* = θm/2 (or (θm+π)/2), φ = 0, t = fix_time
+  const double thE = (p.theta_m < PI / 2.0) ? p.theta_m / 2.0 : (p.theta_m + PI) / 2.0;
+  const Fld f = field<false>(d, thE, 0.0 - p.omega_pul * p.fix_time);
+  const double om_test = sqrt(d.Q / (p.rNS * p.rNS * p.rNS) * fabs(f.bz));
+  d.maxR = 1.01 * p.rNS * pow(om_test / p.Mass_a, 2.0 / 3.0);
+  // radius beyond which ωp < m_a for every direction: max |b_z| = (3 + |cos θm|)/2
+  d.Rcut = cbrt(d.Q * 0.5 * (3.0 + fabs(d.cm)) / d.ma2);
+  if (d.maxR < p.rNS) {
+    err = "Too small Max R (no conversion surface outside the star), MainRunner.jl:389-396";
+    return ART_ERR_NO_SURFACE;
+  }
+  return ART_OK;
+}
+
+}  // namespace art

@@ -1,0 +1,376 @@
+// art_kernels.cuh — sm_100a kernels of the hot path.
+//
+//   K1 k_sample_events    surface sampler, persistent threads, one attempt per lane, events
+//                         pulled from a device queue by warp-aggregated atomics (FP64 ALU)
+//   K2 k_weights          per-sample flux weights (FP64, pointwise)
+//   K3 k_trace<AXION>     adaptive ray integrator, one ray per lane, RK stages in registers,
+//                         finished lanes are retired and refilled in place by ballot/popc
+//                         (the "compaction" is the refill: survivors never move) (FP64 ALU)
+//   K4 k_tree_update      get_tree loop body per event + next-generation queue build
+//                         (warp-aggregated append = stream compaction; HBM bound)
+//   K5 k_hist             binned flux with shared-memory privatised bins (atomics)
+//
+// None of this has a dense contraction: tensor cores / TMA are deliberately not used
+// (BASELINE.json north_star); the rules that matter are register residency, grid = SM count ×
+// resident CTAs, coalesced SoA/record I/O once per ray.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "art_sampler.cuh"
+#include "art_tracer.cuh"
+#include "art_tree.cuh"
+
+namespace art {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int TRACE_THREADS = 128;
+constexpr int SAMPLE_THREADS = 128;
+
+struct DevStats {  // accumulated with atomics; mirrors the counters of art_stats
+  unsigned long long n_attempts, n_sampler_cond, n_rays, n_rays_photon, n_acc, n_rej, n_rhs, n_cond;
+  unsigned long long n_status[5];
+};
+
+struct QueuedRay {  // one node to propagate
+  RayIn in;
+  int owner;  // local event index (fused pipeline) or caller's ray index (art_propagate)
+  int pad_;
+};
+
+// Pops one work item per requesting lane with a single atomic per warp.
+__device__ __forceinline__ long long warp_pop(unsigned long long* head, bool want) {
+  const unsigned m = __ballot_sync(FULL, want);
+  if (m == 0) return -1;
+  const unsigned lane = threadIdx.x & 31;
+  const int leader = __ffs(m) - 1;
+  unsigned long long base = 0;
+  if ((int)lane == leader) base = atomicAdd(head, (unsigned long long)__popc(m));
+  base = __shfl_sync(FULL, base, leader);
+  return want ? (long long)(base + __popc(m & ((1u << lane) - 1u))) : -1;
+}
+
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: ray tracer
+// ------------------------------------------------------------------------------------------
+template <bool AXION>
+__global__ void __launch_bounds__(TRACE_THREADS)
+k_trace(const __grid_constant__ DevParams P, const QueuedRay* __restrict__ q, long long n,
+        RayOut* __restrict__ out, double* __restrict__ rec, int rec_cap, unsigned long long* head,
+        DevStats* stats) {
+  Ray<AXION> R;
+  bool have = false, exhausted = false;
+  long long idx = -1;
+  unsigned long long c_acc = 0, c_rej = 0, c_rhs = 0, c_cond = 0, c_rays = 0;
+  unsigned long long c_st[5] = {0, 0, 0, 0, 0};
+  for (;;) {
+    const long long got = warp_pop(head, !have && !exhausted);
+    if (!have && !exhausted) {
+      if (got >= 0 && got < n) {
+        idx = got;
+        R.init(P, q[idx].in, rec + (size_t)idx * rec_cap * 8, rec_cap);
+        have = true;
+      } else {
+        exhausted = true;
+      }
+    }
+    if (__ballot_sync(FULL, have) == 0) break;
+    if (have) {
+      if (!R.done) R.step(P);
+      if (R.done) {
+        RayOut o;
+        R.finish(P, o);
+        out[idx] = o;
+        c_acc += o.n_acc; c_rej += o.n_rej; c_rhs += o.n_rhs; c_cond += o.n_cond; c_rays++;
+        c_st[o.status]++;
+        have = false;
+      }
+    }
+  }
+  c_acc = warp_sum(c_acc); c_rej = warp_sum(c_rej); c_rhs = warp_sum(c_rhs); c_cond = warp_sum(c_cond);
+  c_rays = warp_sum(c_rays);
+#pragma unroll
+  for (int k = 0; k < 5; ++k) c_st[k] = warp_sum(c_st[k]);
+  if ((threadIdx.x & 31) == 0 && stats) {
+    atomicAdd(&stats->n_acc, c_acc); atomicAdd(&stats->n_rej, c_rej); atomicAdd(&stats->n_rhs, c_rhs);
+    atomicAdd(&stats->n_cond, c_cond); atomicAdd(&stats->n_rays, c_rays);
+    if (!AXION) atomicAdd(&stats->n_rays_photon, c_rays);
+    for (int k = 0; k < 5; ++k)
+      if (c_st[k]) atomicAdd(&stats->n_status[k], c_st[k]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: surface sampler (fused pipeline): event e draws attempts j = 0,1,… until accepted.
+// ------------------------------------------------------------------------------------------
+struct EventSample {
+  double x[3], vloc[3], vinf[3];
+  int n_cross, n_failed;
+};
+
+__global__ void __launch_bounds__(SAMPLE_THREADS)
+k_sample_events(const __grid_constant__ DevParams P, unsigned long long seed, long long first_event, long long n,
+                EventSample* __restrict__ out, unsigned long long* head, DevStats* stats) {
+  Sampler S;
+  bool have = false, exhausted = false;
+  long long idx = -1;
+  unsigned attempt = 0;
+  double u_idx = 0.0;
+  unsigned long long c_att = 0, c_cond = 0;
+  for (;;) {
+    const long long got = warp_pop(head, !have && !exhausted);
+    if (!have && !exhausted) {
+      if (got >= 0 && got < n) {
+        idx = got;
+        attempt = 0;
+        double U[10];
+        sampler_uniforms(seed, (unsigned long long)(first_event + idx), attempt, U);
+        u_idx = U[9];
+        S.begin(P, U);
+        have = true;
+      } else {
+        exhausted = true;
+      }
+    }
+    if (__ballot_sync(FULL, have) == 0) break;
+    if (have) {
+      if (!S.done) S.advance(P);
+      if (S.done) {
+        SampleResult R;
+        S.finish(P, u_idx, R);
+        c_att++;
+        c_cond += R.n_cond;
+        if (R.accepted) {
+          EventSample e;
+          for (int c = 0; c < 3; ++c) { e.x[c] = R.x[c]; e.vloc[c] = R.vloc[c]; e.vinf[c] = R.vinf[c]; }
+          e.n_cross = R.n_cross;
+          e.n_failed = (int)attempt;
+          out[idx] = e;
+          have = false;
+        } else {  // MainRunner.jl:463-494: try again (f_inx counts the failure)
+          attempt++;
+          double U[10];
+          sampler_uniforms(seed, (unsigned long long)(first_event + idx), attempt, U);
+          u_idx = U[9];
+          S.begin(P, U);
+        }
+      }
+    }
+  }
+  c_att = warp_sum(c_att);
+  c_cond = warp_sum(c_cond);
+  if ((threadIdx.x & 31) == 0 && stats) {
+    atomicAdd(&stats->n_attempts, c_att);
+    atomicAdd(&stats->n_sampler_cond, c_cond);
+  }
+}
+
+// fine-grained API: one attempt per thread from caller uniforms
+__global__ void k_sample_uniforms(const __grid_constant__ DevParams P, long long n, const double* __restrict__ U,
+                                  double* x, double* vloc, double* vinf, int* accepted, int* n_cross) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double u[10];
+  for (int k = 0; k < 10; ++k) u[k] = U[i * 10 + k];
+  SampleResult R;
+  sample_attempt(P, u, R);
+  accepted[i] = R.accepted;
+  n_cross[i] = R.n_cross;
+  for (int c = 0; c < 3; ++c) {
+    x[c * n + i] = R.x[c];
+    vloc[c * n + i] = R.vloc[c];
+    vinf[c * n + i] = R.vinf[c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: weights (fused: EventSample → EventData + back-trace ray) and fine-grained variants
+// ------------------------------------------------------------------------------------------
+__global__ void k_weights_events(const __grid_constant__ DevParams P, long long n, const EventSample* __restrict__ s,
+                                 EventData* __restrict__ ev, QueuedRay* __restrict__ back_q) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const EventSample e = s[i];
+  const SampleWeights W = sample_weights(P, e.x, e.vloc, e.vinf);
+  EventData E;
+  for (int c = 0; c < 3; ++c) { E.x[c] = e.x[c]; E.k_init[c] = W.k_init[c]; }
+  E.erg_inf = W.erg_inf; E.vel_eng = W.vel_eng; E.sln_prob = W.sln_prob; E.cos_w = W.cos_w;
+  E.back_weight = 0.0; E.prob0 = 0.0; E.c_bck = 0; E.n_failed = e.n_failed;
+  ev[i] = E;
+  // back-trace parent: axion, −k, t = 0, Δω = −1, collect all crossings (MR.jl:581-589)
+  QueuedRay r;
+  for (int c = 0; c < 3; ++c) { r.in.x0[c] = e.x[c]; r.in.k0[c] = -W.k_init[c]; }
+  r.in.erg = W.erg_inf; r.in.t_start = 0.0; r.in.dOmega = -1.0; r.in.max_cross = 100000;
+  r.owner = (int)i; r.pad_ = 0;
+  back_q[i] = r;
+}
+
+__global__ void k_weights_api(const __grid_constant__ DevParams P, long long n, const double* x, const double* vloc,
+                              const double* vinf, double* k_init, double* cos_w, double* jac, double* sln,
+                              double* erg, double* vel) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double xx[3] = {x[i], x[n + i], x[2 * n + i]}, vl[3] = {vloc[i], vloc[n + i], vloc[2 * n + i]},
+               vi[3] = {vinf[i], vinf[n + i], vinf[2 * n + i]};
+  const SampleWeights W = sample_weights(P, xx, vl, vi);
+  for (int c = 0; c < 3; ++c) k_init[c * n + i] = W.k_init[c];
+  cos_w[i] = W.cos_w; jac[i] = W.jac_gr; sln[i] = W.sln_prob; erg[i] = W.erg_inf; vel[i] = W.vel_eng;
+}
+
+__global__ void k_conv_prob_api(const __grid_constant__ DevParams P, long long n, const double* x, const double* k,
+                                const double* erg, double bsign, double* out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double xx[3] = {x[i], x[n + i], x[2 * n + i]}, kk[3] = {k[i], k[n + i], k[2 * n + i]};
+  out[i] = conv_prob_nonAD(P, xx, kk, erg[i], bsign);
+}
+
+__global__ void k_rhs_api(const __grid_constant__ DevParams P, long long n, const int* species, const double* u,
+                          const double* erg, const double* lnt, double* du) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* v = u + 7 * i;
+  double o[6];
+  const double t = exp(lnt[i]);
+  if (species[i] == SPECIES_PHOTON) {
+    rhs_photon(P, v[0], v[1], v[2], v[3] * erg[i], v[4] * erg[i], v[5] * erg[i], -v[6], t, erg[i], o);
+    du[7 * i + 6] = P.Omega * erg[i] / C_KM * o[5];
+  } else {
+    rhs_axion(P, v[0], v[1], v[3] * erg[i], v[4] * erg[i], v[5] * erg[i], t, erg[i], o);
+    du[7 * i + 6] = 0.0;
+  }
+  for (int c = 0; c < 6; ++c) du[7 * i + c] = o[c];
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: tree
+// ------------------------------------------------------------------------------------------
+// after the back-trace: samp_back_weight, then the first forward node (a photon) → photon queue
+__global__ void k_back_finish(const __grid_constant__ DevParams P, long long n, EventData* __restrict__ ev,
+                              const RayOut* __restrict__ bout, const double* __restrict__ rec, int rec_cap,
+                              TreeState* __restrict__ ts, QueuedRay* __restrict__ ph_q) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  EventData E = ev[i];
+  const RayOut R = bout[i];
+  tree_backward(P, E, R, rec + (size_t)i * rec_cap * 8, rec_cap);
+  ev[i] = E;
+  TreeState T;
+  tree_forward_start(P, E, T);
+  T.back_status = R.status;
+  ts[i] = T;
+  QueuedRay r;
+  r.in.x0[0] = T.cur.x; r.in.x0[1] = T.cur.y; r.in.x0[2] = T.cur.z;
+  r.in.k0[0] = T.cur.kx; r.in.k0[1] = T.cur.ky; r.in.k0[2] = T.cur.kz;
+  r.in.erg = E.erg_inf; r.in.t_start = T.cur.t; r.in.dOmega = T.cur.dw; r.in.max_cross = -1;
+  r.owner = (int)i; r.pad_ = 0;
+  ph_q[i] = r;
+}
+
+// one thread per just-propagated node: get_tree loop body, rows, next-generation queues
+__global__ void k_tree_update(const __grid_constant__ DevParams P, long long n_rays, const QueuedRay* __restrict__ q,
+                              const RayOut* __restrict__ out, const double* __restrict__ rec, int rec_cap,
+                              const EventData* __restrict__ ev, TreeState* __restrict__ ts,
+                              TreeNode* __restrict__ stacks, int stack_stride, unsigned long long seed,
+                              long long first_event, long long chunk_base, RowSink sink,
+                              QueuedRay* __restrict__ next_ph, QueuedRay* __restrict__ next_ax,
+                              unsigned long long* next_counts /*[0] photon, [1] axion*/,
+                              unsigned long long* tot_count, int* fin_count, int* fin_info) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  bool push = false;
+  int species = 0;
+  QueuedRay r;
+  if (i < n_rays) {
+    const int e = q[i].owner;
+    const EventData E = ev[e];
+    TreeState T = ts[e];
+    tree_forward_update(P, E, T, stacks + (size_t)e * stack_stride, out[i], rec + (size_t)i * rec_cap * 8, seed,
+                        (unsigned long long)(first_event + chunk_base + e), chunk_base + e, sink);
+    if (T.active) {
+      push = true;
+      species = T.cur.species;
+      r.in.x0[0] = T.cur.x; r.in.x0[1] = T.cur.y; r.in.x0[2] = T.cur.z;
+      r.in.k0[0] = T.cur.kx; r.in.k0[1] = T.cur.ky; r.in.k0[2] = T.cur.kz;
+      r.in.erg = E.erg_inf; r.in.t_start = T.cur.t; r.in.dOmega = T.cur.dw; r.in.max_cross = -1;
+      r.owner = e; r.pad_ = 0;
+    } else {
+      atomicAdd(tot_count, (unsigned long long)T.tree_len);
+      fin_count[e] = T.count;
+      fin_info[e] = T.info;
+    }
+    ts[e] = T;
+  }
+  // warp-aggregated append to the two species queues
+  for (int sp = 0; sp < 2; ++sp) {
+    const bool mine = push && species == sp;
+    const long long slot = warp_pop(next_counts + (sp == SPECIES_PHOTON ? 0 : 1), mine);
+    if (mine) (sp == SPECIES_PHOTON ? next_ph : next_ax)[slot] = r;
+  }
+}
+
+// save_mode ≥ 1: columns c (20) and info (21) are known only when the tree is complete
+__global__ void k_patch_rows(long long n_rows, double* rows, const long long* keys, int ncols, long long chunk_base,
+                             const int* fin_count, const int* fin_info, long long row_begin) {
+  const long long i = row_begin + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n_rows) return;
+  const long long e = (keys[i] >> 8) - chunk_base;
+  rows[i * ncols + 20] = (double)fin_count[e];
+  rows[i * ncols + 21] = (double)fin_info[e];
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: binned flux.  bins: [species(2)][n_ct][n_ph][4] = Σ w·sln, Σ (w·sln)², Σ w, count
+// ------------------------------------------------------------------------------------------
+__global__ void k_hist(long long row_begin, long long n_rows, const double* __restrict__ rows, int ncols, int n_ct,
+                       int n_ph, double* __restrict__ hist, int use_smem) {
+  extern __shared__ double sh[];
+  const int nb = 2 * n_ct * n_ph * 4;
+  if (use_smem) {
+    for (int k = threadIdx.x; k < nb; k += blockDim.x) sh[k] = 0.0;
+    __syncthreads();
+  }
+  double* H = use_smem ? sh : hist;
+  for (long long i = row_begin + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_rows;
+       i += (long long)gridDim.x * blockDim.x) {
+    const double* r = rows + i * ncols;
+    const int id = (int)r[1];
+    const double ct = cos(r[2]);
+    int ic = (int)floor((ct + 1.0) * 0.5 * n_ct);
+    ic = ic < 0 ? 0 : (ic >= n_ct ? n_ct - 1 : ic);
+    int ip = (int)floor((r[3] + PI) / (2.0 * PI) * n_ph);
+    ip = ip < 0 ? 0 : (ip >= n_ph ? n_ph - 1 : ip);
+    const double w = r[8] * r[7];
+    double* b = H + ((size_t)(id * n_ct + ic) * n_ph + ip) * 4;
+    atomicAdd(b + 0, w);
+    atomicAdd(b + 1, w * w);
+    atomicAdd(b + 2, r[8]);
+    atomicAdd(b + 3, 1.0);
+  }
+  if (use_smem) {
+    __syncthreads();
+    for (int k = threadIdx.x; k < nb; k += blockDim.x)
+      if (sh[k] != 0.0) atomicAdd(hist + k, sh[k]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// FP64 DFMA peak probe (roofline denominator; MEASURED_PEAKS.json carries no FP64 figure)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+}  // namespace art

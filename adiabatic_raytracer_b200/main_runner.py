@@ -1,0 +1,81 @@
+"""Host-side mirror of the reference's entry point ``main_runner_tree`` (MainRunner.jl:355-765).
+
+Same positional arguments, keyword arguments, units, return value (``tot_count``) and output
+file (``<dir_tag>/npy/tree_MassAx_..._<file_tag>.npy``, Float64, 13 or 29 columns, consumed by
+Combine_Files.py).  The reference's toolchain (Julia) is not installed in this image, so this
+mirror is Python; ``julia/MainRunnerGPU.jl`` is the same thing written with ``ccall`` for a Julia
+host.  All arithmetic happens in libart_b200.so on the GPU.
+
+Differences a user can observe:
+  * random numbers come from per-event Philox streams, not Julia's global RNG;
+  * ``iseed < 0`` draws a seed from os.urandom like the reference draws rand(0:1e8);
+  * saveMode ≥ 2 clear-text dumps (MainRunner.jl:435-444, 565-611, 689-701) are not written.
+"""
+import math
+import os
+
+import numpy as np
+
+from . import lib as _lib
+from .params import ArtParams, ART_ERR_NO_SURFACE
+
+
+def params_from_call(Mass_a, Ax_g, theta_m, omega_pul, B0, rNS, Mass_NS, *, flat=True, isotropic=False,
+                     melrose=False, thick_surface=True, bndry_lyr=-1, ode_err=1e-6, fix_time=0.0, ntimes=1000,
+                     rho_DM=0.45, vmean_ax=220.0, saveMode=0, n_maxSample=6, num_cutoff=5, MC_nodes=5,
+                     max_nodes=50, prob_cutoff=1e-10, **extra) -> ArtParams:
+    """Keyword defaults are those of main_runner_tree's own signature (MainRunner.jl:356-363) —
+    NOT Gen_Samples.jl's (which passes flat=false, melrose=true explicitly)."""
+    if saveMode < 3:
+        ntimes = 3  # MainRunner.jl:379-381
+    return ArtParams.default(
+        Mass_a=Mass_a, Ax_g=Ax_g, theta_m=theta_m, omega_pul=omega_pul, B0=B0, rNS=rNS, Mass_NS=Mass_NS,
+        flat=int(bool(flat)), isotropic=int(bool(isotropic)), melrose=int(bool(melrose)),
+        thick_surface=int(bool(thick_surface)), bndry_lyr=float(bndry_lyr), ode_err=ode_err, fix_time=fix_time,
+        ntimes=int(ntimes), rho_DM=rho_DM, vmean_ax=vmean_ax, save_mode=int(saveMode), n_maxSample=int(n_maxSample),
+        num_cutoff=int(num_cutoff), MC_nodes=int(MC_nodes), max_nodes=int(max_nodes), prob_cutoff=prob_cutoff, **extra)
+
+
+def main_runner_tree(Mass_a, Ax_g, theta_m, omega_pul, B0, rNS, Mass_NS, omega_prop, Ntajs, gammaF, *,
+                     flat=True, isotropic=False, melrose=False, thick_surface=True, bndry_lyr=-1, ode_err=1e-6,
+                     cutT=100000, fix_time=0.0, CLen_Scale=True, file_tag="", ntimes=1000, v_NS=(0, 0, 0),
+                     rho_DM=0.45, vmean_ax=220.0, saveMode=0, ntimes_ax=1000, dir_tag="results", n_maxSample=6,
+                     iseed=-1, num_cutoff=5, MC_nodes=5, max_nodes=50, prob_cutoff=1e-10, device=0,
+                     return_rows=False):
+    """Drop-in for ``main_runner_tree`` (MainRunner.jl:355).  Returns tot_count (or None when
+    there is no conversion surface, MainRunner.jl:389-396)."""
+    if iseed < 0:  # MainRunner.jl:365-372
+        iseed = int.from_bytes(os.urandom(4), "little") % 100000001
+    elif iseed == 0:
+        iseed = int.from_bytes(os.urandom(8), "little")
+    print(f"Using seed {iseed}")
+    p = params_from_call(Mass_a, Ax_g, theta_m, omega_pul, B0, rNS, Mass_NS, flat=flat, isotropic=isotropic,
+                         melrose=melrose, thick_surface=thick_surface, bndry_lyr=bndry_lyr, ode_err=ode_err,
+                         fix_time=fix_time, ntimes=ntimes, rho_DM=rho_DM, vmean_ax=vmean_ax, saveMode=saveMode,
+                         n_maxSample=n_maxSample, num_cutoff=num_cutoff, MC_nodes=MC_nodes, max_nodes=max_nodes,
+                         prob_cutoff=prob_cutoff)
+    rc, maxR = _lib.max_radius(p)
+    if rc == ART_ERR_NO_SURFACE:
+        print("Too small Max R.... quitting.... ")
+        print(f"Max radius found...\t{maxR}")
+        return None
+    h = _lib.Handle(p, device)
+    try:
+        # `while photon_trajs < desired_trajs` with photon_trajs starting at 1 ⇒ Ntajs−1 events,
+        # numbered 1 … Ntajs−1 (MainRunner.jl:399,450)
+        n_events = max(int(Ntajs) - 1, 0)
+        out = h.run(iseed, 1, n_events)
+    finally:
+        pass
+    rows = np.ascontiguousarray(out["rows"])
+    if rows.shape[0] == 0:
+        h.close()
+        raise RuntimeError("no final particles: the reference fails here too (saveAll is nothing, MainRunner.jl:749)")
+    _lib.normalize_rows(rows, out["f_inx"])  # MainRunner.jl:749
+    fname = _lib.npy_name(p, int(Ntajs), dir_tag, file_tag)
+    os.makedirs(os.path.dirname(fname), exist_ok=True)
+    _lib.write_npy(fname, rows)
+    h.close()
+    if return_rows:
+        return out["tot_count"], rows, fname, out
+    return out["tot_count"]

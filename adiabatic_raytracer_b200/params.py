@@ -93,6 +93,7 @@ class ArtStats(C.Structure):
         ("ms_tracer", C.c_double),
         ("ms_tree", C.c_double),
         ("ms_total", C.c_double),
+        ("n_launches", C.c_int64),
     ]
 
     def as_dict(self):

@@ -118,6 +118,7 @@ typedef struct art_stats {
   double ms_tracer;
   double ms_tree;
   double ms_total;
+  int64_t n_launches;     /* kernels launched by the pipeline call                          */
 } art_stats;
 
 typedef struct art_handle art_handle;

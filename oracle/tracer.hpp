@@ -399,8 +399,6 @@ inline RayResult propagate(const double x0[3], const double k0_in[3], const RayP
         if (!terminated) {
           rhs(P, u, s, k1);
           R.n_rhs++;
-          g_prev = ray_condition(P, u, s);
-          R.n_cond++;
         }
         event_last = true;
       }

@@ -1,0 +1,228 @@
+// tests/hostcheck/hostcheck.cpp — TEST INFRASTRUCTURE: compiles the product's device headers
+// (adiabatic_raytracer_b200/csrc/*.cuh, all `__host__ __device__`) for the CPU so that the
+// `-m "not gpu"` suite can compare the kernel arithmetic with the oracle without a GPU.
+// It is NOT part of the shipped library and is never loaded by the package.
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../adiabatic_raytracer_b200/csrc/art_host.hpp"
+#include "../../adiabatic_raytracer_b200/csrc/art_sampler.cuh"
+#include "../../adiabatic_raytracer_b200/csrc/art_tracer.cuh"
+#include "../../adiabatic_raytracer_b200/csrc/art_tree.cuh"
+
+using namespace art;
+
+static int dev(const art_params* p, DevParams& d) {
+  std::string e;
+  return make_dev_params(*p, d, e);
+}
+
+template <bool AX>
+static void trace_one(const DevParams& P, const RayIn& in, double* rec, int cap, RayOut& o) {
+  Ray<AX> R;
+  R.init(P, in, rec, cap);
+  while (!R.done) R.step(P);
+  R.finish(P, o);
+}
+
+extern "C" {
+
+int hc_max_radius(const art_params* p, double* maxR, double* Rcut) {
+  DevParams d;
+  int rc = dev(p, d);
+  *maxR = d.maxR;
+  *Rcut = d.Rcut;
+  return rc;
+}
+
+int hc_rhs(const art_params* p, int64_t n, const int32_t* species, const double* u, const double* erg,
+           const double* lnt, double* du) {
+  DevParams P;
+  int rc = dev(p, P);
+  if (rc) return rc;
+  for (int64_t i = 0; i < n; ++i) {
+    const double* v = u + 7 * i;
+    double* o = du + 7 * i;
+    double t = exp(lnt[i]);
+    if (species[i] == SPECIES_PHOTON) {
+      rhs_photon(P, v[0], v[1], v[2], v[3] * erg[i], v[4] * erg[i], v[5] * erg[i], -v[6], t, erg[i], o);
+      o[6] = P.Omega * erg[i] / C_KM * o[5];
+    } else {
+      rhs_axion(P, v[0], v[1], v[3] * erg[i], v[4] * erg[i], v[5] * erg[i], t, erg[i], o);
+      o[6] = 0.0;
+    }
+  }
+  return 0;
+}
+
+// thick condition in ray form: in = u[7], lnt
+int hc_condition(const art_params* p, int64_t n, const double* in, double* out) {
+  DevParams P;
+  int rc = dev(p, P);
+  if (rc) return rc;
+  for (int64_t i = 0; i < n; ++i) {
+    const double* a = in + 8 * i;
+    out[i] = thick_condition(P, a[0], a[1], a[2] - P.Omega * exp(a[7]), a[3], a[4], a[5], a[6], P.rs_ray, true);
+  }
+  return 0;
+}
+
+int hc_sample_from_uniforms(const art_params* p, int64_t n, const double* u, double* x, double* v_loc,
+                            double* v_inf, int32_t* accepted, int32_t* n_cross, int32_t* n_cond) {
+  DevParams P;
+  int rc = dev(p, P);
+  if (rc) return rc;
+#pragma omp parallel for schedule(dynamic, 16)
+  for (int64_t i = 0; i < n; ++i) {
+    SampleResult R;
+    sample_attempt(P, u + 10 * i, R);
+    accepted[i] = R.accepted;
+    n_cross[i] = R.n_cross;
+    if (n_cond) n_cond[i] = R.n_cond;
+    for (int c = 0; c < 3; ++c) {
+      x[c * n + i] = R.x[c];
+      v_loc[c * n + i] = R.vloc[c];
+      v_inf[c * n + i] = R.vinf[c];
+    }
+  }
+  return 0;
+}
+
+int hc_weights(const art_params* p, int64_t n, const double* x, const double* v_loc, const double* v_inf,
+               double* k_init, double* cos_w, double* jac_gr, double* sln_prob, double* erg_inf, double* vel_eng) {
+  DevParams P;
+  int rc = dev(p, P);
+  if (rc) return rc;
+  for (int64_t i = 0; i < n; ++i) {
+    double xx[3] = {x[i], x[n + i], x[2 * n + i]}, vl[3] = {v_loc[i], v_loc[n + i], v_loc[2 * n + i]},
+           vi[3] = {v_inf[i], v_inf[n + i], v_inf[2 * n + i]};
+    SampleWeights W = sample_weights(P, xx, vl, vi);
+    for (int c = 0; c < 3; ++c) k_init[c * n + i] = W.k_init[c];
+    cos_w[i] = W.cos_w; jac_gr[i] = W.jac_gr; sln_prob[i] = W.sln_prob; erg_inf[i] = W.erg_inf; vel_eng[i] = W.vel_eng;
+  }
+  return 0;
+}
+
+int hc_conv_prob(const art_params* p, int64_t n, const double* x, const double* k, const double* erg_scaled,
+                 int32_t b_sign, double* out) {
+  DevParams P;
+  int rc = dev(p, P);
+  if (rc) return rc;
+  for (int64_t i = 0; i < n; ++i) {
+    double xx[3] = {x[i], x[n + i], x[2 * n + i]}, kk[3] = {k[i], k[n + i], k[2 * n + i]};
+    out[i] = conv_prob_nonAD(P, xx, kk, erg_scaled[i], b_sign < 0 ? -1.0 : 1.0);
+  }
+  return 0;
+}
+
+int hc_propagate(const art_params* p, int64_t n, const int32_t* species, const double* x0, const double* k0,
+                 const double* erg, const double* t_start, const double* dOmega, int32_t b_sign,
+                 int32_t max_crossings, double* x_f, double* k_f, double* u7_f, int32_t* status, int32_t* n_cross,
+                 double* cross_rec, int32_t cross_cap, int32_t* counters) {
+  DevParams P;
+  int rc = dev(p, P);
+  if (rc) return rc;
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int64_t i = 0; i < n; ++i) {
+    RayIn in;
+    for (int c = 0; c < 3; ++c) { in.x0[c] = x0[c * n + i]; in.k0[c] = k0[c * n + i]; }
+    in.erg = erg[i]; in.t_start = t_start[i]; in.dOmega = dOmega[i]; in.max_cross = max_crossings;
+    RayOut o;
+    double* rec = cross_rec + (size_t)i * cross_cap * 8;
+    if (species[i] == SPECIES_PHOTON) trace_one<false>(P, in, rec, cross_cap, o);
+    else trace_one<true>(P, in, rec, cross_cap, o);
+    for (int c = 0; c < 3; ++c) { x_f[c * n + i] = o.xf[c]; k_f[c * n + i] = o.kf[c]; }
+    u7_f[i] = o.u7f; status[i] = o.status; n_cross[i] = o.n_cross;
+    if (counters) { counters[4 * i] = o.n_acc; counters[4 * i + 1] = o.n_rej; counters[4 * i + 2] = o.n_rhs; counters[4 * i + 3] = o.n_cond; }
+  }
+  return 0;
+}
+
+// the whole event pipeline with the product's per-event functions, sequential generations
+int hc_run(const art_params* p, uint64_t seed, int64_t first_event, int64_t n_events, double* rows, int64_t rows_cap,
+           int64_t* n_rows, int64_t* f_inx, int64_t* tot_count) {
+  DevParams P;
+  int rc = dev(p, P);
+  if (rc) return rc;
+  const int ncols = p->save_mode > 0 ? ART_ROW_COLS_LONG : ART_ROW_COLS_SHORT;
+  std::vector<long long> keys((size_t)rows_cap);
+  unsigned long long nr = 0, nfin[2] = {0, 0};
+  RowSink S{rows, keys.data(), &nr, (unsigned long long)rows_cap, ncols, nfin};
+  int64_t failed = 0, tc = 0;
+  std::vector<double> rec((size_t)p->cross_cap * 8);
+  std::vector<TreeNode> stack((size_t)p->max_nodes + 4);
+  for (int64_t e = 0; e < n_events; ++e) {
+    const uint64_t ev = (uint64_t)(first_event + e);
+    SampleResult R;
+    for (uint32_t j = 0;; ++j) {
+      double U[10];
+      sampler_uniforms(seed, ev, j, U);
+      sample_attempt(P, U, R);
+      if (R.accepted) break;
+      failed++;
+    }
+    SampleWeights W = sample_weights(P, R.x, R.vloc, R.vinf);
+    EventData E;
+    for (int c = 0; c < 3; ++c) { E.x[c] = R.x[c]; E.k_init[c] = W.k_init[c]; }
+    E.erg_inf = W.erg_inf; E.vel_eng = W.vel_eng; E.sln_prob = W.sln_prob; E.cos_w = W.cos_w;
+    RayIn in;
+    for (int c = 0; c < 3; ++c) { in.x0[c] = E.x[c]; in.k0[c] = -E.k_init[c]; }
+    in.erg = E.erg_inf; in.t_start = 0.0; in.dOmega = -1.0; in.max_cross = 100000;
+    RayOut o;
+    trace_one<true>(P, in, rec.data(), p->cross_cap, o);
+    tree_backward(P, E, o, rec.data(), p->cross_cap);
+    TreeState T;
+    tree_forward_start(P, E, T);
+    unsigned long long row0 = nr;
+    while (T.active) {
+      for (int c = 0; c < 3; ++c) {
+        in.x0[c] = (&T.cur.x)[c];
+        in.k0[c] = (&T.cur.kx)[c];
+      }
+      in.t_start = T.cur.t; in.dOmega = T.cur.dw; in.max_cross = -1;
+      if (T.cur.species == SPECIES_PHOTON) trace_one<false>(P, in, rec.data(), p->cross_cap, o);
+      else trace_one<true>(P, in, rec.data(), p->cross_cap, o);
+      tree_forward_update(P, E, T, stack.data(), o, rec.data(), seed, ev, e, S);
+    }
+    tc += T.tree_len;
+    if (ncols > 13)
+      for (unsigned long long r = row0; r < nr && r < (unsigned long long)rows_cap; ++r) {
+        rows[r * ncols + 20] = T.count;
+        rows[r * ncols + 21] = T.info;
+      }
+  }
+  if (nr > (unsigned long long)rows_cap) return ART_ERR_CAPACITY;
+  *n_rows = (int64_t)nr;
+  *f_inx = failed + (int64_t)nfin[0];
+  *tot_count = tc;
+  return 0;
+}
+
+}  // extern "C"
+
+// step log of one ray (diagnostics): out[k*4 + (s_before, dt_before, accepted, n_cross_after)]
+extern "C" int hc_trace_ray(const art_params* p, int32_t species, const double* x0, const double* k0, double erg,
+                            double t_start, double dOmega, int32_t max_crossings, double* out, int cap) {
+  DevParams P;
+  int rc = dev(p, P);
+  if (rc) return rc;
+  RayIn in;
+  for (int c = 0; c < 3; ++c) { in.x0[c] = x0[c]; in.k0[c] = k0[c]; }
+  in.erg = erg; in.t_start = t_start; in.dOmega = dOmega; in.max_cross = max_crossings;
+  std::vector<double> rec((size_t)p->cross_cap * 8);
+  int n = 0;
+  auto run = [&](auto& R) {
+    R.init(P, in, rec.data(), p->cross_cap);
+    while (!R.done) {
+      double s = R.s, dt = R.dt;
+      int acc = R.n_acc;
+      R.step(P);
+      if (n < cap) { out[4 * n] = s; out[4 * n + 1] = dt; out[4 * n + 2] = R.n_acc - acc; out[4 * n + 3] = R.n_cross; }
+      n++;
+    }
+  };
+  if (species == SPECIES_PHOTON) { Ray<false> R; run(R); } else { Ray<true> R; run(R); }
+  return n;
+}

@@ -1,0 +1,331 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Every call goes through the C ABI
+(include/art.h → libart_b200.so) and is compared with the CPU oracle on the same seeded inputs,
+and with the committed golden fixtures (tests/golden).
+
+Tolerances (FP64 everywhere):
+  * pointwise kernels (RHS, weights, conversion probability): 1e-11 relative — closed-form
+    gradients vs dual numbers, different operation order;
+  * sampler: identical accept flags / crossing counts, positions 1e-10 relative;
+  * rays: same scheme on both sides ⇒ round-off-level agreement for rays whose accept/reject
+    sequence is identical (required for ≥ 97 % of rays, 1e-7 relative on final position), and
+    truncation-level agreement (the integrator's own reltol 1e-7 / abstol 1e-6 error, measured
+    2e-4 against the converged solution) for the few whose step sequence flips at the |B_z|
+    kink of the GJ model.
+"""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from adiabatic_raytracer_b200.params import ArtParams
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from adiabatic_raytracer_b200 import build, lib as L
+    build.build()
+    L.load()
+    return L
+
+
+def handle(lib, **kw):
+    return lib.Handle(ArtParams.default(**kw), 0)
+
+
+def rel(a, b):
+    return np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+
+
+def test_rhs_matches_oracle(lib, oracle):
+    rng = np.random.default_rng(3)
+    for kw in (dict(theta_m=0.2), dict(theta_m=0.9, omega_pul=2 * math.pi, flat=1), dict(theta_m=0.3, isotropic=1)):
+        p = ArtParams.default(**kw)
+        h = lib.Handle(p, 0)
+        n = 4096
+        u = np.zeros((n, 7))
+        u[:, 0] = 10.2 + 60 * rng.random(n)
+        u[:, 1] = 0.05 + 3.0 * rng.random(n)
+        u[:, 2] = -3 + 6 * rng.random(n)
+        u[:, 3] = rng.normal(size=n) * 0.5
+        u[:, 4] = rng.normal(size=n) * 0.5 * u[:, 0]
+        u[:, 5] = rng.normal(size=n) * 0.5 * u[:, 0] * np.sin(u[:, 1])
+        erg = np.full(n, 1.0000003e-5)
+        u[:, 6] = -erg * (1 + 1e-6 * rng.normal(size=n))
+        lnt = rng.uniform(-25, -4, n)
+        for sp in (1, 0):
+            if sp == 0:
+                u[: n // 4, 0] = 1.0 + 8.9 * rng.random(n // 4)  # axions inside the star (interior metric)
+            species = np.full(n, sp, np.int32)
+            d_gpu = h.rhs(species, u, erg, lnt)
+            d_ref = oracle.rhs(p, species, u, erg, lnt)
+            scale = np.abs(d_ref).max(axis=1, keepdims=True) + 1e-300
+            assert (np.abs(d_gpu - d_ref) / scale).max() < 1e-11
+        h.close()
+
+
+def test_sampler_from_uniforms_matches_oracle(lib, oracle):
+    rng = np.random.default_rng(11)
+    for kw in (dict(theta_m=0.2), dict(theta_m=1.1, Mass_a=2e-5, B0=2e14, omega_pul=3.0)):
+        p = ArtParams.default(**kw)
+        h = lib.Handle(p, 0)
+        U = rng.random((6000, 10))
+        a = h.sample_from_uniforms(U)
+        b = oracle.sample_from_uniforms(p, U)
+        assert np.array_equal(a["accepted"], b["accepted"])
+        assert np.array_equal(a["n_cross"], b["n_cross"])
+        m = b["accepted"] == 1
+        assert 0.1 < m.mean() < 0.5
+        assert rel(a["x"][:, m], b["x"][:, m]).max() < 1e-10
+        assert rel(a["v_loc"][:, m], b["v_loc"][:, m]).max() < 1e-12
+        assert rel(a["v_inf"][:, m], b["v_inf"][:, m]).max() < 1e-14
+        h.close()
+
+
+def test_sampler_edge_cases(lib):
+    """Lines that miss the surface, lines through the star, degenerate uniforms."""
+    p = ArtParams.default(theta_m=0.2)
+    h = lib.Handle(p, 0)
+    U = np.full((4, 10), 0.5)
+    U[0, 5] = 1.0 - 1e-16   # impact parameter = maxR: outside every crossing
+    U[1, 5] = 0.0           # straight through the centre of the star
+    U[2, 9] = 0.999999      # randInx = n_max
+    U[3, 0] = 0.0           # θi = 0 (line along the rotation axis)
+    out = h.sample_from_uniforms(U)
+    assert out["accepted"][0] == 0 and out["n_cross"][0] == 0
+    assert np.all(np.isfinite(out["x"]))
+    h.close()
+
+
+def test_philox_event_sampler_matches_oracle(lib, oracle):
+    p = ArtParams.default(theta_m=0.2)
+    h = lib.Handle(p, 0)
+    a = h.sample(1769, 1, 3000)
+    b = oracle.sample(p, 1769, 1, 3000)
+    assert np.array_equal(a["n_failed"], b["n_failed"])
+    assert np.array_equal(a["n_cross"], b["n_cross"])
+    assert rel(a["x"], b["x"]).max() < 1e-10
+    # per-event streams: a later window reproduces the same events
+    c = h.sample(1769, 1001, 500)
+    assert np.array_equal(c["x"], a["x"][:, 1000:1500])
+    h.close()
+
+
+def test_weights_and_conversion_probability(lib, oracle):
+    for kw in (dict(theta_m=0.2), dict(theta_m=0.2, flat=1), dict(theta_m=0.7, omega_pul=2 * math.pi, Mass_NS=1.4, rNS=12.0)):
+        p = ArtParams.default(**kw)
+        h = lib.Handle(p, 0)
+        s = oracle.sample(p, 7, 1, 2000)
+        a = h.weights(s["x"], s["v_loc"], s["v_inf"])
+        b = oracle.weights(p, s["x"], s["v_loc"], s["v_inf"])
+        for k in b:
+            assert rel(a[k], b[k]).max() < 1e-11, k
+        for bs, kk in ((1, b["k_init"]), (-1, -b["k_init"])):
+            Pa = h.conv_prob(s["x"], kk, b["erg_inf"], bs)
+            Pb = oracle.conv_prob(p, s["x"], kk, b["erg_inf"], bs)
+            assert rel(Pa, Pb).max() < 1e-9
+        h.close()
+
+
+def test_golden_conversion_probability(lib):
+    for c in json.load(open(os.path.join(G, "conv_prob.json"))):
+        par = c["par"]
+        p = ArtParams.default(theta_m=par["thm"], omega_pul=par["w"], B0=abs(par["B0"]), rNS=par["rNS"],
+                              Mass_NS=par["MNS"], Mass_a=par["ma"], Ax_g=par["Ax_g"], rho_DM=par["rho_DM"],
+                              n_maxSample=par["n_max"])
+        h = lib.Handle(p, 0)
+        x = np.array(c["x"]).reshape(3, 1)
+        W = h.weights(x, np.array(c["v_loc"]).reshape(3, 1), np.array(c["v_inf"]).reshape(3, 1))
+        rc, maxR = lib.max_radius(p)
+        assert rel(W["k_init"][:, 0], np.array(c["k_init"])).max() < 1e-12
+        assert rel(W["cos_w"][0], c["cos_w"]) < 1e-10
+        assert rel(W["jac_gr"][0], c["jac_gr"]) < 1e-12
+        assert rel(W["sln_prob"][0], c["sln_prob_over_maxR2"] * maxR**2) < 1e-10
+        P = h.conv_prob(x, np.array(c["k_init"]).reshape(3, 1), [c["erg_inf"]], 1 if par["B0"] > 0 else -1)[0]
+        assert rel(P, c["P_nonAD"]) < 1e-9
+        h.close()
+
+
+def _ray_inputs(oracle, p, n, seed=5):
+    s = oracle.sample(p, seed, 1, n)
+    w = oracle.weights(p, s["x"], s["v_loc"], s["v_inf"])
+    return s["x"], w["k_init"], w["erg_inf"]
+
+
+@pytest.mark.parametrize("kw", [dict(theta_m=0.2), dict(theta_m=0.2, flat=1), dict(theta_m=0.6, omega_pul=2 * math.pi)])
+def test_propagate_matches_oracle(lib, oracle, kw):
+    p = ArtParams.default(**kw)
+    h = lib.Handle(p, 0)
+    n = 1500
+    x, k, erg = _ray_inputs(oracle, p, n)
+    for sp, mc, bs in ((1, -1, 1), (0, 100000, -1)):
+        k0 = k if bs == 1 else -k
+        a = h.propagate(np.full(n, sp, np.int32), x, k0, erg, np.zeros(n), -np.ones(n), bs, mc)
+        b = oracle.propagate(p, np.full(n, sp, np.int32), x, k0, erg, np.zeros(n), -np.ones(n), bs, mc)
+        same = (a["status"] == b["status"]) & (a["n_cross"] == b["n_cross"])
+        assert same.mean() > 0.99
+        steps = same & (a["counters"][:, 0] == b["counters"][:, 0]) & (a["counters"][:, 1] == b["counters"][:, 1])
+        assert steps.mean() > 0.97
+        dx = np.linalg.norm(a["x_f"] - b["x_f"], axis=0) / np.linalg.norm(b["x_f"], axis=0)
+        dk = np.linalg.norm(a["k_f"] - b["k_f"], axis=0) / np.linalg.norm(b["k_f"], axis=0)
+        if sp == 1:
+            assert dx[steps].max() < 1e-5 and dk[steps].max() < 1e-5
+            assert np.median(dx[steps]) < 1e-10
+            assert (dx[steps] < 1e-7).mean() > 0.9
+            esc = steps & (b["status"] == 0)
+            assert rel(a["u7_f"][esc], b["u7_f"][esc]).max() < 1e-7
+        else:
+            # back-traced axions: what matters are the crossings near the star
+            assert np.median(dx[steps]) < 1e-9
+            nc = b["n_cross"]
+            for i in np.where(steps & (nc > 0) & (nc <= 16))[0][:200]:
+                ra, rb = a["cross_rec"][i, : nc[i]], b["cross_rec"][i, : nc[i]]
+                assert np.abs(ra[:, :3] - rb[:, :3]).max() < 1e-4
+    h.close()
+
+
+def test_rays_against_dop853_golden(lib):
+    """GPU integrator at tight tolerance vs scipy DOP853(rtol 1e-12) fixtures."""
+    worst = 0.0
+    for ray in json.load(open(os.path.join(G, "rays.json"))):
+        par = ray["par"]
+        p = ArtParams.default(theta_m=par["thm"], omega_pul=par["w"], B0=par["B0"], rNS=par["rNS"], Mass_NS=par["MNS"],
+                              Mass_a=par["ma"], reltol=1e-12, ode_err=1e-14)
+        h = lib.Handle(p, 0)
+        R = h.propagate([ray["species"]], np.array(ray["x0"]).reshape(3, 1), np.array(ray["khat"]).reshape(3, 1),
+                        [ray["erg"]], [0.0], [ray["dOmega"]], 1, 100000, 16)
+        uf = np.array(ray["uf"])
+        xg = uf[0] * np.array([math.sin(uf[1]) * math.cos(uf[2]), math.sin(uf[1]) * math.sin(uf[2]), math.cos(uf[1])])
+        worst = max(worst, np.linalg.norm(R["x_f"][:, 0] - xg) / np.linalg.norm(xg))
+        assert abs(R["u7_f"][0] - uf[6]) <= 1e-9 * abs(uf[6])
+        gold = [c for c in ray["crossings"] if c["u"][0] >= 1.01 * par["rNS"] and c["lnt"] > -25.0]
+        assert R["n_cross"][0] == len(gold)
+        for gc, c in zip(R["cross_rec"][0], gold):
+            assert abs(math.log(gc[6]) - c["lnt"]) < 1e-7
+        h.close()
+    assert worst < 1e-8
+
+
+@pytest.mark.parametrize("kw", [dict(theta_m=0.2, save_mode=1), dict(theta_m=0.2, save_mode=0, Ax_g=1e-10, MC_nodes=2, max_nodes=12),
+                                dict(theta_m=0.5, save_mode=1, omega_pul=2 * math.pi, Mass_a=2e-5)])
+def test_fused_pipeline_matches_oracle(lib, oracle, kw):
+    p = ArtParams.default(**kw)
+    h = lib.Handle(p, 0)
+    n = 1500
+    a = h.run(1769, 1, n)
+    b = oracle.run(p, 1769, 1, n)
+    ra, rb = a["rows"], b["rows"]
+    # events whose trees have the same shape on both sides
+    ca = np.bincount(ra[:, 0].astype(int), minlength=n + 1)
+    cb = np.bincount(rb[:, 0].astype(int), minlength=n + 1)
+    good = ca == cb
+    assert good[1:].mean() > 0.99
+    assert abs(a["f_inx"] - b["f_inx"]) <= 0.01 * b["f_inx"] + 2
+    assert abs(a["tot_count"] - b["tot_count"]) <= 0.01 * b["tot_count"] + 2
+    A = ra[good[ra[:, 0].astype(int)]]
+    B = rb[good[rb[:, 0].astype(int)]]
+    assert A.shape == B.shape
+    assert np.array_equal(A[:, :2], B[:, :2])  # event id, species, in the reference's order
+    ph = B[:, 1] == 1
+    for col, tol in ((7, 1e-9), (9, 1e-10), (10, 1e-10), (11, 1e-10)):  # sln_prob, x0
+        assert rel(A[:, col], B[:, col]).max() < tol
+    dth = np.abs(A[ph, 2] - B[ph, 2])
+    dph = np.abs((A[ph, 3] - B[ph, 3] + math.pi) % (2 * math.pi) - math.pi)
+    assert np.median(dth) < 1e-9 and np.median(dph) < 1e-9
+    assert (dth < 1e-6).mean() > 0.95 and dth.max() < 5e-3
+    w_ok = rel(A[:, 8], B[:, 8]) < 1e-6
+    assert w_ok.mean() > 0.97
+    if p.save_mode > 0:
+        assert (A[:, 20] == B[:, 20]).mean() > 0.99 and (A[:, 21] == B[:, 21]).mean() > 0.99
+    h.close()
+
+
+def test_pipeline_is_deterministic_and_chunk_invariant(lib):
+    p = ArtParams.default(theta_m=0.2)
+    h = lib.Handle(p, 0)
+    a = h.run(42, 1, 4000)
+    b = h.run(42, 1, 4000)
+    assert np.array_equal(a["rows"], b["rows"]) and a["f_inx"] == b["f_inx"]
+    c1 = h.run(42, 1, 1500)
+    c2 = h.run(42, 1501, 2500)
+    assert np.array_equal(np.vstack([c1["rows"], c2["rows"]]), a["rows"])
+    assert c1["f_inx"] + c2["f_inx"] == a["f_inx"] and c1["tot_count"] + c2["tot_count"] == a["tot_count"]
+    h.close()
+
+
+def test_histogram_matches_numpy(lib):
+    p = ArtParams.default(theta_m=0.2)
+    h = lib.Handle(p, 0)
+    h.hist_config(8, 12)
+    out = h.run(3, 1, 5000)
+    r = out["rows"]
+    H = h.hist_get()
+    bins = H[:-8].reshape(2, 8, 12, 4)
+    w = r[:, 8] * r[:, 7]
+    for sp in (0, 1):
+        m = r[:, 1] == sp
+        ic = np.clip(np.floor((np.cos(r[m, 2]) + 1) * 0.5 * 8).astype(int), 0, 7)
+        ip = np.clip(np.floor((r[m, 3] + math.pi) / (2 * math.pi) * 12).astype(int), 0, 11)
+        ref = np.zeros((8, 12))
+        np.add.at(ref, (ic, ip), w[m])
+        cnt = np.zeros((8, 12))
+        np.add.at(cnt, (ic, ip), 1.0)
+        assert np.allclose(bins[sp, :, :, 0], ref, rtol=1e-9, atol=0)
+        assert np.array_equal(bins[sp, :, :, 3], cnt)
+    assert H[-8] == out["f_inx"] and H[-7] == len(r) and H[-6] == 5000
+    h.close()
+
+
+def test_full_size_properties(lib):
+    """BASELINE config 2 (1e6 GR events): size-independent properties."""
+    p = ArtParams.default(theta_m=0.2)
+    h = lib.Handle(p, 0)
+    n = 1_000_000
+    out = h.run_device(1769, 1, n)
+    st = out["stats"]
+    assert st["n_events"] == n and st["n_rays"] >= 2 * n
+    assert out["f_inx"] == (st["n_attempts"] - n) + st["n_final_photon"]
+    assert sum(st["n_status"]) == st["n_rays"] and st["n_status"][3] == 0  # no maxiters
+    rows = h.fetch_rows(out["n_rows"])
+    assert rows.shape[0] == st["n_final_photon"] + st["n_final_axion"]
+    assert np.all(np.diff(rows[:, 0]) >= 0) and rows[0, 0] >= 1 and rows[-1, 0] <= n
+    assert np.all(np.isfinite(rows))
+    ph = rows[:, 1] == 1
+    assert np.all(rows[ph, 6] > 2.9e5)              # photons reach r ≈ c/ωPul: the observer sphere
+    assert np.all((rows[:, 8] > 0) & (rows[:, 8] <= 1.0))
+    # per event the final weights cannot exceed the back-traced weight (≤ P0 ≤ 1)
+    wsum = np.bincount(rows[:, 0].astype(np.int64), weights=rows[:, 8])
+    assert wsum.max() <= 1.0 + 1e-12
+    assert np.all((rows[ph, 12] > -1.5) & (rows[ph, 12] < -0.5))  # Δω stays O(−1) (MainRunner.jl:168)
+    # acceptance of the sampler ≈ 0.23-0.24
+    assert 0.2 < n / st["n_attempts"] < 0.28
+    h.close()
+
+
+def test_empty_and_error_paths(lib):
+    p = ArtParams.default(theta_m=0.2)
+    h = lib.Handle(p, 0)
+    out = h.run(1, 1, 0)
+    assert out["rows"].shape[0] == 0 and out["f_inx"] == 0
+    h.close()
+    with pytest.raises(lib.ArtError) as e:
+        lib.Handle(ArtParams.default(theta_m=0.2, Mass_a=1e-4), 0)
+    assert e.value.code == -3
+
+
+def test_main_runner_tree_drop_in(lib, tmp_path):
+    from adiabatic_raytracer_b200 import main_runner_tree
+    tot, rows, fname, out = main_runner_tree(1e-5, 1e-12, 0.2, 1.0, 1e14, 10.0, 1.0, "Simple", 501, [1.0, 1.0],
+                                             flat=False, isotropic=False, melrose=True, ode_err=1e-6, file_tag="t0",
+                                             ntimes=3, saveMode=0, dir_tag=str(tmp_path / "results"), iseed=1769,
+                                             return_rows=True)
+    assert os.path.basename(fname) == ("tree_MassAx_1.0e-5_AxionG_1.0e-12_ThetaM_0.2_rotPulsar_1.0_B0_1.0e14_Ax_trajs_501"
+                                       "_N_Times_3_num_cutoff_5_MC_nodes_5_max_nodes_50_t0.npy")
+    back = np.load(fname)
+    assert back.shape == rows.shape and back.shape[1] == 13 and np.array_equal(back, rows)
+    assert back[:, 0].max() <= 500 and tot >= 500            # Ntajs − 1 events (MainRunner.jl:399,450)
+    assert np.allclose(back[:, 7] * out["f_inx"], out["rows"][:, 7] * out["f_inx"])
