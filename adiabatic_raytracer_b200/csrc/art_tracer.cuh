@@ -75,6 +75,13 @@ struct Ray {
 
   // `condition` of propagate, RT.jl:254-298
   ART_HD double cond(const DevParams& P, const double v[6], double lnt) const {
+#ifdef ART_COUNT_FAR
+    
+    g_cond_total++;
+    if (v[0] > P.Rcut) g_cond_far++;
+    if (v[0] <= P.rNS) g_cond_in++;
+    if (lnt < -14.0) g_cond_early++;
+#endif
     const double t = exp(lnt);
     return thick_condition(P, v[0], v[1], v[2] - P.Omega * t, v[3], v[4], v[5], u7_of(v[5]), P.rs_ray, true);
   }
