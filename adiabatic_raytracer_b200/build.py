@@ -6,6 +6,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libart_b200.so")
+# tuning experiments: ART_DEFINES="-DART_TRACE_MINBLOCKS=3" ART_SO=/path/variant.so python -m ...build --force
+EXTRA = os.environ.get("ART_DEFINES", "").split()
+SO = os.environ.get("ART_SO", SO)
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -31,7 +34,7 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return SO
-    cmd = [NVCC] + FLAGS + ["-o", SO, os.path.join(CSRC, "art_api.cu"), "-ldl"]
+    cmd = [NVCC] + FLAGS + EXTRA + ["-o", SO, os.path.join(CSRC, "art_api.cu"), "-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -92,11 +92,11 @@ struct art_handle {
   art_params params;
   DevParams dp;
   int device = 0, n_sm = 0;
-  int blocks_trace_ph = 0, blocks_trace_ax = 0, blocks_sample = 0;
+  int blocks_trace = 0, blocks_sample = 0;
   cudaStream_t stream = nullptr;
   std::string err;
   // pipeline buffers (per chunk)
-  DBuf samples, events, tstate, stacks, q[4], rout[2], rec[2], counters, stats, fin_count, fin_info;
+  DBuf samples, events, tstate, stacks, q[2], rout, rec, counters, stats, fin_count, fin_info;
   DBuf rows, keys, hist, scratch[12];
   long long rows_cap = 0;   // rows held on device
   long long n_rows_dev = 0;
@@ -131,15 +131,13 @@ int upload(art_handle* h, DBuf& b, const void* src, size_t bytes) {
   return ART_OK;
 }
 
-// launches the tracer for one species over a device queue; zeroes the queue head first
-template <bool AXION>
+// launches the tracer over a device queue; zeroes the queue head first
 int launch_trace(art_handle* h, const QueuedRay* q, long long n, RayOut* out, double* rec, int rec_cap,
                  unsigned long long* head, DevStats* stats) {
   if (n <= 0) return ART_OK;
   CU(cudaMemsetAsync(head, 0, sizeof(unsigned long long), h->stream));
-  const int maxb = AXION ? h->blocks_trace_ax : h->blocks_trace_ph;
-  const int blocks = (int)std::min<long long>(maxb, (n + TRACE_THREADS - 1) / TRACE_THREADS);
-  k_trace<AXION><<<blocks, TRACE_THREADS, 0, h->stream>>>(h->dp, q, n, out, rec, rec_cap, head, stats);
+  const int blocks = (int)std::min<long long>(h->blocks_trace, (n + TRACE_THREADS - 1) / TRACE_THREADS);
+  k_trace<<<blocks, TRACE_THREADS, TRACE_SMEM, h->stream>>>(h->dp, q, n, out, rec, rec_cap, head, stats);
   h->launches++;
   CU(cudaGetLastError());
   return ART_OK;
@@ -201,10 +199,10 @@ int art_create(const art_params* p, int device_id, art_handle** out) {
   cudaGetDeviceProperties(&prop, device_id);
   h->n_sm = prop.multiProcessorCount;
   int occ = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<false>, TRACE_THREADS, 0);
-  h->blocks_trace_ph = h->n_sm * std::max(occ, 1);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<true>, TRACE_THREADS, 0);
-  h->blocks_trace_ax = h->n_sm * std::max(occ, 1);
+  cudaFuncSetAttribute(k_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRACE_SMEM);
+  cudaFuncSetAttribute(k_trace, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace, TRACE_THREADS, TRACE_SMEM);
+  h->blocks_trace = h->n_sm * std::max(occ, 1);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sample_events, SAMPLE_THREADS, 0);
   h->blocks_sample = h->n_sm * std::max(occ, 1);
   ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
@@ -221,9 +219,8 @@ void art_destroy(art_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-  DBuf* all[] = {&h->samples, &h->events, &h->tstate, &h->stacks, &h->q[0], &h->q[1], &h->q[2], &h->q[3],
-                 &h->rout[0], &h->rout[1], &h->rec[0], &h->rec[1], &h->counters, &h->stats, &h->fin_count,
-                 &h->fin_info, &h->rows, &h->keys, &h->hist};
+  DBuf* all[] = {&h->samples, &h->events, &h->tstate, &h->stacks, &h->q[0], &h->q[1], &h->rout, &h->rec,
+                 &h->counters, &h->stats, &h->fin_count, &h->fin_info, &h->rows, &h->keys, &h->hist};
   for (DBuf* b : all) b->release();
   for (DBuf& b : h->scratch) b.release();
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -343,46 +340,32 @@ int art_propagate(art_handle* h, int64_t n, const int32_t* species, const double
   if (!h || n < 0 || cross_cap < 1) return ART_ERR_ARG;
   CU(cudaSetDevice(h->device));
   if (n == 0) return ART_OK;
-  // split by species on the host (two kernels: the photon and axion right-hand sides differ)
-  std::vector<QueuedRay> qs[2];
+  std::vector<QueuedRay> qs((size_t)n);
   for (int64_t i = 0; i < n; ++i) {
-    QueuedRay r;
+    QueuedRay& r = qs[(size_t)i];
     for (int c = 0; c < 3; ++c) { r.in.x0[c] = x0[c * n + i]; r.in.k0[c] = k0[c * n + i]; }
     r.in.erg = erg[i]; r.in.t_start = t_start[i]; r.in.dOmega = dOmega[i]; r.in.max_cross = max_crossings;
+    r.in.species = species[i] == ART_SPECIES_PHOTON ? SPECIES_PHOTON : SPECIES_AXION;
     r.owner = (int)i; r.pad_ = 0;
-    qs[species[i] == ART_SPECIES_PHOTON ? 0 : 1].push_back(r);
   }
   CU(h->counters.ensure(64));
-  for (int sp = 0; sp < 2; ++sp) {
-    const long long m = (long long)qs[sp].size();
-    if (!m) continue;
-    if (upload(h, h->q[sp], qs[sp].data(), m * sizeof(QueuedRay))) return ART_ERR_CUDA;
-    CU(h->rout[sp].ensure(m * sizeof(RayOut)));
-    CU(h->rec[sp].ensure((size_t)m * cross_cap * 8 * sizeof(double)));
-    CU(cudaMemsetAsync(h->rec[sp].p, 0, (size_t)m * cross_cap * 8 * sizeof(double), h->stream));
-    int rc = sp == 0 ? launch_trace<false>(h, h->q[sp].as<QueuedRay>(), m, h->rout[sp].as<RayOut>(), h->rec[sp].as<double>(),
-                                           cross_cap, h->counters.as<unsigned long long>() + sp, nullptr)
-                     : launch_trace<true>(h, h->q[sp].as<QueuedRay>(), m, h->rout[sp].as<RayOut>(), h->rec[sp].as<double>(),
-                                          cross_cap, h->counters.as<unsigned long long>() + sp, nullptr);
-    if (rc) return rc;
-  }
-  for (int sp = 0; sp < 2; ++sp) {
-    const long long m = (long long)qs[sp].size();
-    if (!m) continue;
-    std::vector<RayOut> ro((size_t)m);
-    std::vector<double> rc_((size_t)m * cross_cap * 8);
-    CU(cudaMemcpyAsync(ro.data(), h->rout[sp].p, m * sizeof(RayOut), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaMemcpyAsync(rc_.data(), h->rec[sp].p, rc_.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    for (long long j = 0; j < m; ++j) {
-      const int64_t i = qs[sp][j].owner;
-      for (int c = 0; c < 3; ++c) { x_f[c * n + i] = ro[j].xf[c]; k_f[c * n + i] = ro[j].kf[c]; }
-      u7_f[i] = ro[j].u7f; status[i] = ro[j].status; n_cross[i] = ro[j].n_cross;
-      memcpy(cross_rec + (size_t)i * cross_cap * 8, rc_.data() + (size_t)j * cross_cap * 8, (size_t)cross_cap * 8 * sizeof(double));
-      if (counters) {
-        counters[4 * i] = ro[j].n_acc; counters[4 * i + 1] = ro[j].n_rej; counters[4 * i + 2] = ro[j].n_rhs;
-        counters[4 * i + 3] = ro[j].n_cond;
-      }
+  if (upload(h, h->q[0], qs.data(), n * sizeof(QueuedRay))) return ART_ERR_CUDA;
+  CU(h->rout.ensure(n * sizeof(RayOut)));
+  CU(h->rec.ensure((size_t)n * cross_cap * 8 * sizeof(double)));
+  CU(cudaMemsetAsync(h->rec.p, 0, (size_t)n * cross_cap * 8 * sizeof(double), h->stream));
+  if (int rc = launch_trace(h, h->q[0].as<QueuedRay>(), n, h->rout.as<RayOut>(), h->rec.as<double>(), cross_cap,
+                            h->counters.as<unsigned long long>(), nullptr))
+    return rc;
+  std::vector<RayOut> ro((size_t)n);
+  CU(cudaMemcpyAsync(ro.data(), h->rout.p, n * sizeof(RayOut), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(cross_rec, h->rec.p, (size_t)n * cross_cap * 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  for (int64_t i = 0; i < n; ++i) {
+    const RayOut& o = ro[(size_t)i];
+    for (int c = 0; c < 3; ++c) { x_f[c * n + i] = o.xf[c]; k_f[c * n + i] = o.kf[c]; }
+    u7_f[i] = o.u7f; status[i] = o.status; n_cross[i] = o.n_cross;
+    if (counters) {
+      counters[4 * i] = o.n_acc; counters[4 * i + 1] = o.n_rej; counters[4 * i + 2] = o.n_rhs; counters[4 * i + 3] = o.n_cond;
     }
   }
   return ART_OK;
@@ -445,16 +428,15 @@ int art_run_device(art_handle* h, uint64_t seed, int64_t first_event, int64_t n_
     int rc = art_hist_reset(h);
     if (rc) return rc;
   }
-  // buffers
+  // buffers (per chunk of CH events; the first launch propagates 2 rays per event)
   CU(h->samples.ensure(CH * sizeof(EventSample)));
   CU(h->events.ensure(CH * sizeof(EventData)));
   CU(h->tstate.ensure(CH * sizeof(TreeState)));
   CU(h->stacks.ensure((size_t)CH * stack_stride * sizeof(TreeNode)));
-  for (int k = 0; k < 4; ++k) CU(h->q[k].ensure(CH * sizeof(QueuedRay)));
-  for (int k = 0; k < 2; ++k) {
-    CU(h->rout[k].ensure(CH * sizeof(RayOut)));
-    CU(h->rec[k].ensure((size_t)CH * cap * 8 * sizeof(double)));
-  }
+  CU(h->q[0].ensure(2 * CH * sizeof(QueuedRay)));
+  CU(h->q[1].ensure(CH * sizeof(QueuedRay)));
+  CU(h->rout.ensure(2 * CH * sizeof(RayOut)));
+  CU(h->rec.ensure((size_t)2 * CH * cap * 8 * sizeof(double)));
   CU(h->fin_count.ensure(CH * sizeof(int)));
   CU(h->fin_info.ensure(CH * sizeof(int)));
   CU(h->counters.ensure(16 * sizeof(unsigned long long)));
@@ -469,18 +451,21 @@ int art_run_device(art_handle* h, uint64_t seed, int64_t first_event, int64_t n_
   h->n_rows_dev = 0;
   h->launches = 0;
   unsigned long long* ctr = h->counters.as<unsigned long long>();
-  // ctr layout: [0] sampler head, [1] trace head ph, [2] trace head ax, [3] tot_count,
-  //             [4,5] next-queue counts (ph, ax), [6] n_rows, [7,8] n_final (ph, ax)
+  // ctr layout: [0] sampler head, [1] trace head, [3] tot_count, [4] next-queue count,
+  //             [6] n_rows, [7,8] n_final (photon, axion)
   CU(cudaMemsetAsync(ctr, 0, 16 * sizeof(unsigned long long), h->stream));
   CU(cudaMemsetAsync(h->stats.p, 0, sizeof(DevStats), h->stream));
   DevStats* dstats = h->stats.as<DevStats>();
   RowSink sink{h->rows.as<double>(), h->keys.as<long long>(), ctr + 6, (unsigned long long)h->rows_cap, ncols, ctr + 7};
+  RayOut* rout = h->rout.as<RayOut>();
+  double* rec = h->rec.as<double>();
 
-  cudaEvent_t ev[8];
+  cudaEvent_t ev[6];
   for (auto& e : ev) CU(cudaEventCreate(&e));
+  std::vector<cudaEvent_t> gen_ev;  // (start, after trace, after tree) per generation
   float ms_s = 0, ms_w = 0, ms_t = 0, ms_tree = 0, ms_tot = 0;
   long long failed_total = 0;
-  CU(cudaEventRecord(ev[6], h->stream));
+  CU(cudaEventRecord(ev[4], h->stream));
 
   for (long long base = 0; base < n_events; base += CH) {
     const long long n = std::min(CH, n_events - base);
@@ -497,74 +482,52 @@ int art_run_device(art_handle* h, uint64_t seed, int64_t first_event, int64_t n_
       CU(cudaGetLastError());
     }
     CU(cudaEventRecord(ev[1], h->stream));
-    // K2 weights (+ back-trace queue)
+    // K2 weights: EventData, first tree node, and the 2n rays of the first launch
     k_weights_events<<<nblk(n, 128), 128, 0, h->stream>>>(P, n, h->samples.as<EventSample>(), h->events.as<EventData>(),
-                                                          h->q[1].as<QueuedRay>());
+                                                          h->tstate.as<TreeState>(), h->q[0].as<QueuedRay>());
     h->launches++;
     CU(cudaGetLastError());
     CU(cudaEventRecord(ev[2], h->stream));
-    // K3 back-trace (axions), K4 back-finish
-    if (int rc = launch_trace<true>(h, h->q[1].as<QueuedRay>(), n, h->rout[1].as<RayOut>(), h->rec[1].as<double>(), cap,
-                                    ctr + 2, dstats))
-      return rc;
+    // K3 first launch: n back-traced axions (slots 0..n) + n first forward photons (slots n..2n)
+    if (int rc = launch_trace(h, h->q[0].as<QueuedRay>(), 2 * n, rout, rec, cap, ctr + 1, dstats)) return rc;
     CU(cudaEventRecord(ev[3], h->stream));
-    k_back_finish<<<nblk(n, 128), 128, 0, h->stream>>>(P, n, h->events.as<EventData>(), h->rout[1].as<RayOut>(),
-                                                       h->rec[1].as<double>(), cap, h->tstate.as<TreeState>(),
-                                                       h->q[0].as<QueuedRay>());
+    // K4 back-finish (samp_back_weight), then the tree update of the first forward photons
+    k_back_finish<<<nblk(n, 128), 128, 0, h->stream>>>(P, n, h->events.as<EventData>(), rout, rec, cap,
+                                                       h->tstate.as<TreeState>());
     h->launches++;
     CU(cudaGetLastError());
-    CU(cudaEventRecord(ev[4], h->stream));
-    float t01, t12, t23, t34;
-    // forward generations: queues q[0]/q[1] = current photon/axion, q[2]/q[3] = next
-    long long n_ph = n, n_ax = 0;
-    int cur = 0;
-    float ms_gen_trace = 0, ms_gen_tree = 0;
-    while (n_ph + n_ax > 0) {
-      QueuedRay* qph = h->q[cur * 2 + 0].as<QueuedRay>();
-      QueuedRay* qax = h->q[cur * 2 + 1].as<QueuedRay>();
-      QueuedRay* nph = h->q[(1 - cur) * 2 + 0].as<QueuedRay>();
-      QueuedRay* nax = h->q[(1 - cur) * 2 + 1].as<QueuedRay>();
-      CU(cudaMemsetAsync(ctr + 4, 0, 2 * sizeof(unsigned long long), h->stream));
-      cudaEvent_t a, b, c;
-      CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b)); CU(cudaEventCreate(&c));
-      CU(cudaEventRecord(a, h->stream));
-      if (int rc = launch_trace<false>(h, qph, n_ph, h->rout[0].as<RayOut>(), h->rec[0].as<double>(), cap, ctr + 1, dstats)) return rc;
-      if (int rc = launch_trace<true>(h, qax, n_ax, h->rout[1].as<RayOut>(), h->rec[1].as<double>(), cap, ctr + 2, dstats)) return rc;
-      CU(cudaEventRecord(b, h->stream));
-      if (n_ph > 0) {
-        k_tree_update<<<nblk(n_ph, 128), 128, 0, h->stream>>>(
-            P, n_ph, qph, h->rout[0].as<RayOut>(), h->rec[0].as<double>(), cap, h->events.as<EventData>(),
-            h->tstate.as<TreeState>(), h->stacks.as<TreeNode>(), stack_stride, seed, first_event, base, sink, nph, nax,
-            ctr + 4, ctr + 3, h->fin_count.as<int>(), h->fin_info.as<int>());
-        h->launches++;
-        CU(cudaGetLastError());
-      }
-      if (n_ax > 0) {
-        k_tree_update<<<nblk(n_ax, 128), 128, 0, h->stream>>>(
-            P, n_ax, qax, h->rout[1].as<RayOut>(), h->rec[1].as<double>(), cap, h->events.as<EventData>(),
-            h->tstate.as<TreeState>(), h->stacks.as<TreeNode>(), stack_stride, seed, first_event, base, sink, nph, nax,
-            ctr + 4, ctr + 3, h->fin_count.as<int>(), h->fin_info.as<int>());
-        h->launches++;
-        CU(cudaGetLastError());
-      }
-      CU(cudaEventRecord(c, h->stream));
-      unsigned long long nxt[2];
-      CU(cudaMemcpyAsync(nxt, ctr + 4, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    int cur = 0;  // queue holding the rays that were just propagated
+    long long q_off = n, n_rays = n;  // forward rays of the first launch start at slot n
+    for (;;) {
+      QueuedRay* qc = h->q[cur].as<QueuedRay>() + q_off;
+      QueuedRay* qn = h->q[1 - cur].as<QueuedRay>();
+      CU(cudaMemsetAsync(ctr + 4, 0, sizeof(unsigned long long), h->stream));
+      k_tree_update<<<nblk(n_rays, 128), 128, 0, h->stream>>>(
+          P, n_rays, qc, rout + q_off, rec + (size_t)q_off * cap * 8, cap, h->events.as<EventData>(),
+          h->tstate.as<TreeState>(), h->stacks.as<TreeNode>(), stack_stride, seed, first_event, base, sink, qn,
+          ctr + 4, ctr + 3, h->fin_count.as<int>(), h->fin_info.as<int>());
+      h->launches++;
+      CU(cudaGetLastError());
+      cudaEvent_t e_tree;
+      CU(cudaEventCreate(&e_tree));
+      CU(cudaEventRecord(e_tree, h->stream));
+      gen_ev.push_back(e_tree);
+      unsigned long long nxt = 0;
+      CU(cudaMemcpyAsync(&nxt, ctr + 4, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
       CU(cudaStreamSynchronize(h->stream));
-      float x1 = 0, x2 = 0;
-      cudaEventElapsedTime(&x1, a, b);
-      cudaEventElapsedTime(&x2, b, c);
-      ms_gen_trace += x1;
-      ms_gen_tree += x2;
-      cudaEventDestroy(a); cudaEventDestroy(b); cudaEventDestroy(c);
-      n_ph = (long long)nxt[0];
-      n_ax = (long long)nxt[1];
+      n_rays = (long long)nxt;
+      if (n_rays == 0) break;
       cur = 1 - cur;
+      q_off = 0;
+      if (int rc = launch_trace(h, h->q[cur].as<QueuedRay>(), n_rays, rout, rec, cap, ctr + 1, dstats)) return rc;
+      cudaEvent_t e_tr;
+      CU(cudaEventCreate(&e_tr));
+      CU(cudaEventRecord(e_tr, h->stream));
+      gen_ev.push_back(e_tr);
     }
     // failed sampler attempts of this chunk (→ f_inx)
     {
-      std::vector<EventSample> hs;  // only n_failed is needed: reduce on host from the small struct
-      hs.resize((size_t)n);
+      std::vector<EventSample> hs((size_t)n);
       CU(cudaMemcpyAsync(hs.data(), h->samples.p, n * sizeof(EventSample), cudaMemcpyDeviceToHost, h->stream));
       CU(cudaStreamSynchronize(h->stream));
       for (auto& s : hs) failed_total += s.n_failed;
@@ -573,6 +536,7 @@ int art_run_device(art_handle* h, uint64_t seed, int64_t first_event, int64_t n_
     CU(cudaMemcpy(&rows_after, ctr + 6, 8, cudaMemcpyDeviceToHost));
     if ((long long)rows_after > h->rows_cap) {
       for (auto& e : ev) cudaEventDestroy(e);
+      for (auto& e : gen_ev) cudaEventDestroy(e);
       return fail(h, ART_ERR_CAPACITY, "device row buffer overflow (more than 3 rows per event on average)");
     }
     const long long nr = (long long)rows_after - (long long)rows_before;
@@ -594,15 +558,25 @@ int art_run_device(art_handle* h, uint64_t seed, int64_t first_event, int64_t n_
       CU(cudaGetLastError());
     }
     CU(cudaStreamSynchronize(h->stream));
+    float t01, t12, t23;
     cudaEventElapsedTime(&t01, ev[0], ev[1]);
     cudaEventElapsedTime(&t12, ev[1], ev[2]);
     cudaEventElapsedTime(&t23, ev[2], ev[3]);
-    cudaEventElapsedTime(&t34, ev[3], ev[4]);
-    ms_s += t01; ms_w += t12; ms_t += t23 + ms_gen_trace; ms_tree += t34 + ms_gen_tree;
+    ms_s += t01; ms_w += t12; ms_t += t23;
+    // generation events alternate: tree, trace, tree, trace, …, tree  (first "tree" follows ev[3])
+    cudaEvent_t prev = ev[3];
+    for (size_t k = 0; k < gen_ev.size(); ++k) {
+      float x = 0;
+      cudaEventElapsedTime(&x, prev, gen_ev[k]);
+      if (k % 2 == 0) ms_tree += x; else ms_t += x;
+      prev = gen_ev[k];
+    }
+    for (auto& e : gen_ev) cudaEventDestroy(e);
+    gen_ev.clear();
   }
-  CU(cudaEventRecord(ev[7], h->stream));
+  CU(cudaEventRecord(ev[5], h->stream));
   CU(cudaStreamSynchronize(h->stream));
-  cudaEventElapsedTime(&ms_tot, ev[6], ev[7]);
+  cudaEventElapsedTime(&ms_tot, ev[4], ev[5]);
   for (auto& e : ev) cudaEventDestroy(e);
 
   unsigned long long hc[16];

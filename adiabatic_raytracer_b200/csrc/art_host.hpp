@@ -77,7 +77,7 @@ inline int make_dev_params(const art_params& p, DevParams& d, std::string& err) 
   const double om_test = sqrt(d.Q / (p.rNS * p.rNS * p.rNS) * fabs(f.bz));
   d.maxR = 1.01 * p.rNS * pow(om_test / p.Mass_a, 2.0 / 3.0);
   // radius beyond which ωp < m_a for every direction: max |b_z| = (3 + |cos θm|)/2
-  d.Rcut = cbrt(d.Q * 0.5 * (3.0 + fabs(d.cm)) / d.ma2);
+  d.Rcut = cbrt(d.Q * 0.5 * (3.0 + fabs(d.cm)) / d.ma2) * (1.0 + 1e-9);
   if (d.maxR < p.rNS) {
     err = "Too small Max R (no conversion surface outside the star), MainRunner.jl:389-396";
     return ART_ERR_NO_SURFACE;

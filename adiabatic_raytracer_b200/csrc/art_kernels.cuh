@@ -56,17 +56,26 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 }
 
 // ------------------------------------------------------------------------------------------
-// K3: ray tracer
+// K3: ray tracer.  Persistent threads; every lane owns one ray at a time and pulls the next
+// one from the device queue when its ray retires (ballot + popc + one atomic per warp), so
+// survivors never move and no separate compaction pass exists.  Stage derivatives live in
+// shared memory: 7 × 6 doubles per thread, column-major over threads (conflict-free).
 // ------------------------------------------------------------------------------------------
-template <bool AXION>
-__global__ void __launch_bounds__(TRACE_THREADS)
+constexpr size_t TRACE_SMEM = (size_t)42 * TRACE_THREADS * sizeof(double);
+#ifndef ART_TRACE_MINBLOCKS
+#define ART_TRACE_MINBLOCKS 2  // resident CTAs per SM the register allocation is tuned for
+#endif
+
+__global__ void __launch_bounds__(TRACE_THREADS, ART_TRACE_MINBLOCKS)
 k_trace(const __grid_constant__ DevParams P, const QueuedRay* __restrict__ q, long long n,
         RayOut* __restrict__ out, double* __restrict__ rec, int rec_cap, unsigned long long* head,
         DevStats* stats) {
-  Ray<AXION> R;
+  extern __shared__ double ksm[];
+  const KStore K{ksm + threadIdx.x, (int)blockDim.x};
+  Ray R;
   bool have = false, exhausted = false;
   long long idx = -1;
-  unsigned long long c_acc = 0, c_rej = 0, c_rhs = 0, c_cond = 0, c_rays = 0;
+  unsigned long long c_acc = 0, c_rej = 0, c_rhs = 0, c_cond = 0, c_rays = 0, c_ph = 0;
   unsigned long long c_st[5] = {0, 0, 0, 0, 0};
   for (;;) {
     const long long got = warp_pop(head, !have && !exhausted);
@@ -81,25 +90,26 @@ k_trace(const __grid_constant__ DevParams P, const QueuedRay* __restrict__ q, lo
     }
     if (__ballot_sync(FULL, have) == 0) break;
     if (have) {
-      if (!R.done) R.step(P);
+      if (!R.done) R.step(P, K);
       if (R.done) {
         RayOut o;
         R.finish(P, o);
         out[idx] = o;
         c_acc += o.n_acc; c_rej += o.n_rej; c_rhs += o.n_rhs; c_cond += o.n_cond; c_rays++;
+        c_ph += R.axion ? 0 : 1;
         c_st[o.status]++;
         have = false;
       }
     }
   }
   c_acc = warp_sum(c_acc); c_rej = warp_sum(c_rej); c_rhs = warp_sum(c_rhs); c_cond = warp_sum(c_cond);
-  c_rays = warp_sum(c_rays);
+  c_rays = warp_sum(c_rays); c_ph = warp_sum(c_ph);
 #pragma unroll
   for (int k = 0; k < 5; ++k) c_st[k] = warp_sum(c_st[k]);
   if ((threadIdx.x & 31) == 0 && stats) {
     atomicAdd(&stats->n_acc, c_acc); atomicAdd(&stats->n_rej, c_rej); atomicAdd(&stats->n_rhs, c_rhs);
     atomicAdd(&stats->n_cond, c_cond); atomicAdd(&stats->n_rays, c_rays);
-    if (!AXION) atomicAdd(&stats->n_rays_photon, c_rays);
+    atomicAdd(&stats->n_rays_photon, c_ph);
     for (int k = 0; k < 5; ++k)
       if (c_st[k]) atomicAdd(&stats->n_status[k], c_st[k]);
   }
@@ -192,7 +202,7 @@ __global__ void k_sample_uniforms(const __grid_constant__ DevParams P, long long
 // K2: weights (fused: EventSample → EventData + back-trace ray) and fine-grained variants
 // ------------------------------------------------------------------------------------------
 __global__ void k_weights_events(const __grid_constant__ DevParams P, long long n, const EventSample* __restrict__ s,
-                                 EventData* __restrict__ ev, QueuedRay* __restrict__ back_q) {
+                                 EventData* __restrict__ ev, TreeState* __restrict__ ts, QueuedRay* __restrict__ q0) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const EventSample e = s[i];
@@ -202,12 +212,23 @@ __global__ void k_weights_events(const __grid_constant__ DevParams P, long long 
   E.erg_inf = W.erg_inf; E.vel_eng = W.vel_eng; E.sln_prob = W.sln_prob; E.cos_w = W.cos_w;
   E.back_weight = 0.0; E.prob0 = 0.0; E.c_bck = 0; E.n_failed = e.n_failed;
   ev[i] = E;
-  // back-trace parent: axion, −k, t = 0, Δω = −1, collect all crossings (MR.jl:581-589)
+  // slot i: back-trace parent — axion, −k, t = 0, Δω = −1, collect all crossings (MR.jl:581-589)
   QueuedRay r;
   for (int c = 0; c < 3; ++c) { r.in.x0[c] = e.x[c]; r.in.k0[c] = -W.k_init[c]; }
   r.in.erg = W.erg_inf; r.in.t_start = 0.0; r.in.dOmega = -1.0; r.in.max_cross = 100000;
+  r.in.species = SPECIES_AXION;
   r.owner = (int)i; r.pad_ = 0;
-  back_q[i] = r;
+  q0[i] = r;
+  // slot n+i: first node of the forward tree — photon, +k (MR.jl:653-657); independent of the
+  // back-trace, so both are propagated by the same launch
+  TreeState T;
+  tree_forward_start(P, E, T);
+  T.back_status = 0;
+  ts[i] = T;
+  for (int c = 0; c < 3; ++c) r.in.k0[c] = W.k_init[c];
+  r.in.max_cross = -1;
+  r.in.species = SPECIES_PHOTON;
+  q0[n + i] = r;
 }
 
 __global__ void k_weights_api(const __grid_constant__ DevParams P, long long n, const double* x, const double* vloc,
@@ -250,26 +271,17 @@ __global__ void k_rhs_api(const __grid_constant__ DevParams P, long long n, cons
 // ------------------------------------------------------------------------------------------
 // K4: tree
 // ------------------------------------------------------------------------------------------
-// after the back-trace: samp_back_weight, then the first forward node (a photon) → photon queue
+// after the first launch: samp_back_weight from the back-traced axion (slot i)
 __global__ void k_back_finish(const __grid_constant__ DevParams P, long long n, EventData* __restrict__ ev,
                               const RayOut* __restrict__ bout, const double* __restrict__ rec, int rec_cap,
-                              TreeState* __restrict__ ts, QueuedRay* __restrict__ ph_q) {
+                              TreeState* __restrict__ ts) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
   EventData E = ev[i];
   const RayOut R = bout[i];
   tree_backward(P, E, R, rec + (size_t)i * rec_cap * 8, rec_cap);
   ev[i] = E;
-  TreeState T;
-  tree_forward_start(P, E, T);
-  T.back_status = R.status;
-  ts[i] = T;
-  QueuedRay r;
-  r.in.x0[0] = T.cur.x; r.in.x0[1] = T.cur.y; r.in.x0[2] = T.cur.z;
-  r.in.k0[0] = T.cur.kx; r.in.k0[1] = T.cur.ky; r.in.k0[2] = T.cur.kz;
-  r.in.erg = E.erg_inf; r.in.t_start = T.cur.t; r.in.dOmega = T.cur.dw; r.in.max_cross = -1;
-  r.owner = (int)i; r.pad_ = 0;
-  ph_q[i] = r;
+  ts[i].back_status = R.status;
 }
 
 // one thread per just-propagated node: get_tree loop body, rows, next-generation queues
@@ -278,12 +290,10 @@ __global__ void k_tree_update(const __grid_constant__ DevParams P, long long n_r
                               const EventData* __restrict__ ev, TreeState* __restrict__ ts,
                               TreeNode* __restrict__ stacks, int stack_stride, unsigned long long seed,
                               long long first_event, long long chunk_base, RowSink sink,
-                              QueuedRay* __restrict__ next_ph, QueuedRay* __restrict__ next_ax,
-                              unsigned long long* next_counts /*[0] photon, [1] axion*/,
+                              QueuedRay* __restrict__ next_q, unsigned long long* next_count,
                               unsigned long long* tot_count, int* fin_count, int* fin_info) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   bool push = false;
-  int species = 0;
   QueuedRay r;
   if (i < n_rays) {
     const int e = q[i].owner;
@@ -293,10 +303,10 @@ __global__ void k_tree_update(const __grid_constant__ DevParams P, long long n_r
                         (unsigned long long)(first_event + chunk_base + e), chunk_base + e, sink);
     if (T.active) {
       push = true;
-      species = T.cur.species;
       r.in.x0[0] = T.cur.x; r.in.x0[1] = T.cur.y; r.in.x0[2] = T.cur.z;
       r.in.k0[0] = T.cur.kx; r.in.k0[1] = T.cur.ky; r.in.k0[2] = T.cur.kz;
       r.in.erg = E.erg_inf; r.in.t_start = T.cur.t; r.in.dOmega = T.cur.dw; r.in.max_cross = -1;
+      r.in.species = T.cur.species;
       r.owner = e; r.pad_ = 0;
     } else {
       atomicAdd(tot_count, (unsigned long long)T.tree_len);
@@ -305,12 +315,9 @@ __global__ void k_tree_update(const __grid_constant__ DevParams P, long long n_r
     }
     ts[e] = T;
   }
-  // warp-aggregated append to the two species queues
-  for (int sp = 0; sp < 2; ++sp) {
-    const bool mine = push && species == sp;
-    const long long slot = warp_pop(next_counts + (sp == SPECIES_PHOTON ? 0 : 1), mine);
-    if (mine) (sp == SPECIES_PHOTON ? next_ph : next_ax)[slot] = r;
-  }
+  // warp-aggregated append to the next generation's queue (stream compaction of survivors)
+  const long long slot = warp_pop(next_count, push);
+  if (push) next_q[slot] = r;
 }
 
 // save_mode ≥ 1: columns c (20) and info (21) are known only when the tree is complete

@@ -16,8 +16,6 @@
 
 namespace art {
 
-enum { SPECIES_AXION = 0, SPECIES_PHOTON = 1 };
-
 struct TreeNode {  // RT.node, RayTracer.jl:126-163 (fields that reach the outputs)
   double x, y, z, kx, ky, kz, t, dw;
   double prob, weight, prob_conv, prob_conv0;

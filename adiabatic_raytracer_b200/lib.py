@@ -11,7 +11,7 @@ import numpy as np
 from .params import ArtParams, ArtStats, CROSS_REC
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libart_b200.so")
+SO_PATH = os.environ.get("ART_SO", os.path.join(_HERE, "libart_b200.so"))  # ART_SO: tuning variants only
 
 _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 _ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")

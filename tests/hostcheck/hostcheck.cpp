@@ -19,11 +19,12 @@ static int dev(const art_params* p, DevParams& d) {
   return make_dev_params(*p, d, e);
 }
 
-template <bool AX>
 static void trace_one(const DevParams& P, const RayIn& in, double* rec, int cap, RayOut& o) {
-  Ray<AX> R;
+  Ray R;
+  double kbuf[42];
+  KStore K{kbuf, 1};
   R.init(P, in, rec, cap);
-  while (!R.done) R.step(P);
+  while (!R.done) R.step(P, K);
   R.finish(P, o);
 }
 
@@ -129,10 +130,10 @@ int hc_propagate(const art_params* p, int64_t n, const int32_t* species, const d
     RayIn in;
     for (int c = 0; c < 3; ++c) { in.x0[c] = x0[c * n + i]; in.k0[c] = k0[c * n + i]; }
     in.erg = erg[i]; in.t_start = t_start[i]; in.dOmega = dOmega[i]; in.max_cross = max_crossings;
+    in.species = species[i];
     RayOut o;
     double* rec = cross_rec + (size_t)i * cross_cap * 8;
-    if (species[i] == SPECIES_PHOTON) trace_one<false>(P, in, rec, cross_cap, o);
-    else trace_one<true>(P, in, rec, cross_cap, o);
+    trace_one(P, in, rec, cross_cap, o);
     for (int c = 0; c < 3; ++c) { x_f[c * n + i] = o.xf[c]; k_f[c * n + i] = o.kf[c]; }
     u7_f[i] = o.u7f; status[i] = o.status; n_cross[i] = o.n_cross;
     if (counters) { counters[4 * i] = o.n_acc; counters[4 * i + 1] = o.n_rej; counters[4 * i + 2] = o.n_rhs; counters[4 * i + 3] = o.n_cond; }
@@ -169,9 +170,9 @@ int hc_run(const art_params* p, uint64_t seed, int64_t first_event, int64_t n_ev
     E.erg_inf = W.erg_inf; E.vel_eng = W.vel_eng; E.sln_prob = W.sln_prob; E.cos_w = W.cos_w;
     RayIn in;
     for (int c = 0; c < 3; ++c) { in.x0[c] = E.x[c]; in.k0[c] = -E.k_init[c]; }
-    in.erg = E.erg_inf; in.t_start = 0.0; in.dOmega = -1.0; in.max_cross = 100000;
+    in.erg = E.erg_inf; in.t_start = 0.0; in.dOmega = -1.0; in.max_cross = 100000; in.species = SPECIES_AXION;
     RayOut o;
-    trace_one<true>(P, in, rec.data(), p->cross_cap, o);
+    trace_one(P, in, rec.data(), p->cross_cap, o);
     tree_backward(P, E, o, rec.data(), p->cross_cap);
     TreeState T;
     tree_forward_start(P, E, T);
@@ -181,9 +182,8 @@ int hc_run(const art_params* p, uint64_t seed, int64_t first_event, int64_t n_ev
         in.x0[c] = (&T.cur.x)[c];
         in.k0[c] = (&T.cur.kx)[c];
       }
-      in.t_start = T.cur.t; in.dOmega = T.cur.dw; in.max_cross = -1;
-      if (T.cur.species == SPECIES_PHOTON) trace_one<false>(P, in, rec.data(), p->cross_cap, o);
-      else trace_one<true>(P, in, rec.data(), p->cross_cap, o);
+      in.t_start = T.cur.t; in.dOmega = T.cur.dw; in.max_cross = -1; in.species = T.cur.species;
+      trace_one(P, in, rec.data(), p->cross_cap, o);
       tree_forward_update(P, E, T, stack.data(), o, rec.data(), seed, ev, e, S);
     }
     tc += T.tree_len;
@@ -210,19 +210,19 @@ extern "C" int hc_trace_ray(const art_params* p, int32_t species, const double* 
   if (rc) return rc;
   RayIn in;
   for (int c = 0; c < 3; ++c) { in.x0[c] = x0[c]; in.k0[c] = k0[c]; }
-  in.erg = erg; in.t_start = t_start; in.dOmega = dOmega; in.max_cross = max_crossings;
+  in.erg = erg; in.t_start = t_start; in.dOmega = dOmega; in.max_cross = max_crossings; in.species = species;
   std::vector<double> rec((size_t)p->cross_cap * 8);
   int n = 0;
-  auto run = [&](auto& R) {
-    R.init(P, in, rec.data(), p->cross_cap);
-    while (!R.done) {
-      double s = R.s, dt = R.dt;
-      int acc = R.n_acc;
-      R.step(P);
-      if (n < cap) { out[4 * n] = s; out[4 * n + 1] = dt; out[4 * n + 2] = R.n_acc - acc; out[4 * n + 3] = R.n_cross; }
-      n++;
-    }
-  };
-  if (species == SPECIES_PHOTON) { Ray<false> R; run(R); } else { Ray<true> R; run(R); }
+  Ray R;
+  double kbuf[42];
+  KStore K{kbuf, 1};
+  R.init(P, in, rec.data(), p->cross_cap);
+  while (!R.done) {
+    double s = R.s, dt = R.dt;
+    int acc = R.n_acc;
+    R.step(P, K);
+    if (n < cap) { out[4 * n] = s; out[4 * n + 1] = dt; out[4 * n + 2] = R.n_acc - acc; out[4 * n + 3] = R.n_cross; }
+    n++;
+  }
   return n;
 }
