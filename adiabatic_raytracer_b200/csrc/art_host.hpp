@@ -32,7 +32,7 @@ inline int make_dev_params(const art_params& p, DevParams& d, std::string& err) 
     err = "n_maxSample must be in 1..8";
     return ART_ERR_ARG;
   }
-  if (p.max_nodes < 1 || p.max_nodes > 250 || p.interp_points_ray < 2 || p.interp_points_sampler < 2 ||
+  if (p.max_nodes < 1 || p.max_nodes > 250 || p.interp_points_ray < 2 || p.interp_points_ray > 64 || p.interp_points_sampler < 2 ||
       p.cross_cap < 1 || p.cross_cap > 64 || !(p.reltol > 0) || !(p.ode_err > 0) || !(p.sampler_dt > 0)) {
     err = "numerics parameter out of range";
     return ART_ERR_ARG;
@@ -71,6 +71,8 @@ inline int make_dev_params(const art_params& p, DevParams& d, std::string& err) 
   d.MC_nodes = p.MC_nodes;
   d.max_nodes = p.max_nodes;
   d.prob_cutoff = p.prob_cutoff;
+  d.inv_Mrm1 = 1.0 / (double)(p.interp_points_ray - 1);
+  d.inv_Msm1 = 1.0 / (double)(p.interp_points_sampler - 1);
   // Find_Conversion_Surface, RT.jl:1250-1263: ωp at r = rNS, θ* = θm/2 (or (θm+π)/2), φ = 0, t = fix_time
   const double thE = (p.theta_m < PI / 2.0) ? p.theta_m / 2.0 : (p.theta_m + PI) / 2.0;
   const Fld f = field<false>(d, thE, 0.0 - p.omega_pul * p.fix_time);

@@ -58,21 +58,97 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 // ------------------------------------------------------------------------------------------
 // K3: ray tracer.  Persistent threads; every lane owns one ray at a time and pulls the next
 // one from the device queue when its ray retires (ballot + popc + one atomic per warp), so
-// survivors never move and no separate compaction pass exists.  Stage derivatives live in
-// shared memory: 7 × 6 doubles per thread, column-major over threads (conflict-free).
+// survivors never move and no separate compaction pass exists.
+//
+// Shared memory per CTA (TRACE_THREADS = 128 → 96 KB, two CTAs per SM):
+//   K    [42][T] doubles   stage derivatives k1..k7, one column per thread (conflict-free)
+//   SEG  [35][T] doubles   dense-output segment of the accepted step, readable by the warp
+//   SIGN [T][64] u8        sign of the crossing condition per (ray, point)
+//   LIST [T/32][2048] u16  per-warp work list of (lane, point) pairs for the cooperative scan
 // ------------------------------------------------------------------------------------------
-constexpr size_t TRACE_SMEM = (size_t)42 * TRACE_THREADS * sizeof(double);
+constexpr int SCAN_LIST = 32 * 64;
+constexpr size_t TRACE_SMEM = (size_t)(42 + SEG_N) * TRACE_THREADS * sizeof(double) +
+                              (size_t)TRACE_THREADS * 64 +
+                              (size_t)(TRACE_THREADS / 32) * SCAN_LIST * sizeof(unsigned short);
 #ifndef ART_TRACE_MINBLOCKS
 #define ART_TRACE_MINBLOCKS 2  // resident CTAs per SM the register allocation is tuned for
 #endif
+
+// Cooperative crossing scan of one warp.  Lanes whose step was accepted (`pending`) classify
+// their own M−1 dense-output points with the far-field test (cheap); the points that need the
+// full condition are pooled into the warp's work list and dealt out round-robin, so lanes
+// whose step was rejected, whose ray is in the far field, or that hold no ray at all evaluate
+// points of OTHER lanes' rays.  Results come back as sign masks in shared memory.
+__device__ __forceinline__ ScanMasks warp_scan(const DevParams& P, bool pending, bool nudge, double* seg_w, int stride,
+                                               unsigned char* sign_w, unsigned short* list) {
+  const unsigned lane = threadIdx.x & 31;
+  const int M = P.M_ray;
+  unsigned long long need = 0ull, neg = 0ull;
+  if (pending) {
+    const SegStore D{seg_w + lane, stride};
+    for (int i = nudge ? 0 : 1; i < M; ++i) {
+      const int qk = seg_quick(P, D, seg_theta(P, i));
+      if (qk == 0) need |= 1ull << i;
+      else if (qk == -1) neg |= 1ull << i;
+    }
+  }
+  const int cnt = __popcll(need);
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(FULL, incl, o);
+    if ((int)lane >= o) incl += t;
+  }
+  const int N = __shfl_sync(FULL, incl, 31);
+  ScanMasks out{0ull, neg, 0ull};
+  if (N == 0) return out;
+  {
+    int c = incl - cnt;
+    unsigned long long m = need;
+    while (m) {
+      const int i = __ffsll((long long)m) - 1;
+      list[c++] = (unsigned short)((lane << 8) | (unsigned)i);
+      m &= m - 1ull;
+    }
+  }
+  __syncwarp();
+  for (int k = (int)lane; k < N; k += 32) {
+    const unsigned code = list[k];
+    const unsigned l = code >> 8, i = code & 255u;
+    const SegStore Dl{seg_w + l, stride};
+    const double g = seg_cond_full(P, Dl, seg_theta(P, (int)i));
+    sign_w[l * 64 + i] = (g > 0.0) ? 1 : ((g < 0.0) ? 2 : ((g == 0.0) ? 3 : 0));
+  }
+  __syncwarp();
+  {
+    unsigned long long m = need;
+    while (m) {
+      const int i = __ffsll((long long)m) - 1;
+      const unsigned sg = sign_w[lane * 64 + i];
+      if (sg == 1) out.pos |= 1ull << i;
+      else if (sg == 2) out.neg |= 1ull << i;
+      else if (sg == 3) out.zero |= 1ull << i;
+      m &= m - 1ull;
+    }
+  }
+  return out;
+}
 
 __global__ void __launch_bounds__(TRACE_THREADS, ART_TRACE_MINBLOCKS)
 k_trace(const __grid_constant__ DevParams P, const QueuedRay* __restrict__ q, long long n,
         RayOut* __restrict__ out, double* __restrict__ rec, int rec_cap, unsigned long long* head,
         DevStats* stats) {
   extern __shared__ double ksm[];
-  const KStore K{ksm + threadIdx.x, (int)blockDim.x};
+  const int T = (int)blockDim.x;
+  const int warp0 = (int)(threadIdx.x & ~31u);
+  const KStore K{ksm + threadIdx.x, T};
+  double* seg_base = ksm + (size_t)42 * T;
+  const SegStore D{seg_base + threadIdx.x, T};
+  unsigned char* sign_base = (unsigned char*)(seg_base + (size_t)SEG_N * T);
+  unsigned short* list = (unsigned short*)(sign_base + (size_t)T * 64) + (size_t)(threadIdx.x >> 5) * SCAN_LIST;
   Ray R;
+  R.done = true;
+  R.event_last = false;
   bool have = false, exhausted = false;
   long long idx = -1;
   unsigned long long c_acc = 0, c_rej = 0, c_rhs = 0, c_cond = 0, c_rays = 0, c_ph = 0;
@@ -89,17 +165,19 @@ k_trace(const __grid_constant__ DevParams P, const QueuedRay* __restrict__ q, lo
       }
     }
     if (__ballot_sync(FULL, have) == 0) break;
-    if (have) {
-      if (!R.done) R.step(P, K);
-      if (R.done) {
-        RayOut o;
-        R.finish(P, o);
-        out[idx] = o;
-        c_acc += o.n_acc; c_rej += o.n_rej; c_rhs += o.n_rhs; c_cond += o.n_cond; c_rays++;
-        c_ph += R.axion ? 0 : 1;
-        c_st[o.status]++;
-        have = false;
-      }
+    bool pending = false;
+    if (have && !R.done) pending = R.stages(P, K, D);
+    // warp-cooperative: every lane takes part, whether or not it owns a pending step
+    const ScanMasks m = warp_scan(P, pending, pending && R.event_last, seg_base + warp0, T, sign_base + (size_t)warp0 * 64, list);
+    if (pending) R.finish_step(P, K, D, m);
+    if (have && R.done) {
+      RayOut o;
+      R.finish(P, o);
+      out[idx] = o;
+      c_acc += o.n_acc; c_rej += o.n_rej; c_rhs += o.n_rhs; c_cond += o.n_cond; c_rays++;
+      c_ph += R.axion ? 0 : 1;
+      c_st[o.status]++;
+      have = false;
     }
   }
   c_acc = warp_sum(c_acc); c_rej = warp_sum(c_rej); c_rhs = warp_sum(c_rhs); c_cond = warp_sum(c_cond);

@@ -54,6 +54,7 @@ struct DevParams {
   int32_t isotropic, flat;
   int32_t num_cutoff, MC_nodes, max_nodes;
   double prob_cutoff;
+  double inv_Mrm1, inv_Msm1;  // 1/(M_ray − 1), 1/(M_samp − 1): dense-output grid spacing
 };
 
 struct Met {

@@ -170,7 +170,7 @@ struct Sampler {
     if (phase == 0) {
       const int M = P.M_samp;
       const bool end = (i == M - 1);
-      const double th = end ? 1.0 : (double)i / (double)(M - 1);
+      const double th = end ? 1.0 : (double)i * P.inv_Msm1;
       const double g = cond(P, end ? tau_new : tau + th * h);
       const int sg = (g > 0.0) - (g < 0.0);
       if (sgn_prev != 0 && sgn_prev * sg < 0) {

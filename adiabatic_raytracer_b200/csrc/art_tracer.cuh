@@ -72,15 +72,85 @@ struct KStore {
   ART_HD double& operator()(int j, int i) const { return base[(j * 6 + i) * stride]; }
 };
 
+// Dense-output segment of an accepted step, published (device: in shared memory, one column
+// per thread) so that ANY lane of the warp can evaluate the crossing condition on it.
+enum { SEG_U = 0, SEG_R1 = 6, SEG_R2 = 12, SEG_R3 = 18, SEG_R4 = 24, SEG_S = 30, SEG_H = 31, SEG_U70 = 32,
+       SEG_FAC7 = 33, SEG_U60 = 34, SEG_N = 35 };
+struct SegStore {
+  double* base;
+  int stride;
+  ART_HD double& operator()(int f) const { return base[f * stride]; }
+};
+ART_HD int ffs64(unsigned long long v) {  // 1-based index of the lowest set bit
+#if defined(__CUDA_ARCH__)
+  return __ffsll((long long)v);
+#else
+  return __builtin_ffsll((long long)v);
+#endif
+}
+ART_HD int clz64(unsigned long long v) {
+#if defined(__CUDA_ARCH__)
+  return __clzll((long long)v);
+#else
+  return __builtin_clzll(v);
+#endif
+}
+
+struct ScanMasks {
+  unsigned long long pos, neg, zero;  // bit i: sign of the condition at grid point i (bit 0: nudge point)
+};
+
+// dense-output grid of the crossing scan: θ_i = i/(M−1), i = 1..M−1; index 0 = the repeat-nudge point 0.01
+ART_HD double seg_theta(const DevParams& P, int i) { return i == 0 ? 0.01 : ((i == P.M_ray - 1) ? 1.0 : (double)i * P.inv_Mrm1); }
+
+ART_HD double seg_comp(const SegStore D, int i, double th, double th1) {
+  return D(SEG_U + i) + th * (D(SEG_R1 + i) + th1 * (D(SEG_R2 + i) + th * (D(SEG_R3 + i) + th1 * D(SEG_R4 + i))));
+}
+ART_HD void seg_state(const SegStore D, double th, double w[6]) {
+  const double th1 = 1.0 - th;
+  for (int i = 0; i < 6; ++i) w[i] = seg_comp(D, i, th, th1);
+}
+
+// Far-field classification of a dense-output point: −1 the condition is provably negative
+// (r > Rcut ⇒ ωp < m_a in every direction, and NrmSq ≥ 0 ⇔ E² r ≥ m_a² (r − rs)), 2 it is NaN
+// (NrmSq < 0, only reachable in flat mode), 0 it has to be evaluated.
+ART_HD int seg_quick(const DevParams& P, const SegStore D, double th) {
+  const double th1 = 1.0 - th;
+  const double r = seg_comp(D, 0, th, th1);
+  if (!(r > P.Rcut && r > P.r_int)) return 0;
+  const double E = D(SEG_U70) + D(SEG_FAC7) * (seg_comp(D, 5, th, th1) - D(SEG_U60));
+  return (E * E * r >= P.ma2 * (r - P.rs_ray)) ? -1 : 2;
+}
+
+// `condition` of propagate (RT.jl:254-298) at dense-output parameter th of a published segment
+ART_HD double seg_cond_full(const DevParams& P, const SegStore D, double th) {
+  double w[6];
+  seg_state(D, th, w);
+  const double E = D(SEG_U70) + D(SEG_FAC7) * (w[5] - D(SEG_U60));
+  const double t = exp(D(SEG_S) + th * D(SEG_H));
+  return thick_condition(P, w[0], w[1], w[2] - P.Omega * t, w[3], w[4], w[5], E, P.rs_ray, true);
+}
+ART_HD double seg_cond(const DevParams& P, const SegStore D, double th) {
+  const int qk = seg_quick(P, D, th);
+  if (qk == -1) return -1.0;
+  if (qk == 2) return NAN;
+  double w[6];
+  seg_state(D, th, w);
+  const double E = D(SEG_U70) + D(SEG_FAC7) * (w[5] - D(SEG_U60));
+  const double t = exp(D(SEG_S) + th * D(SEG_H));
+  return thick_condition(P, w[0], w[1], w[2] - P.Omega * t, w[3], w[4], w[5], E, P.rs_ray, true);
+}
+
 struct Ray {
-  double u[6];
-  double s, dt, qold, g_prev;
+  double u[6], un[6];
+  double s, dt, qold, s_new, dt_new;
   double erg, fac7, u7_0, u6_0;
   double x0[3];
   double* rec;  // crossing records, ART_CROSS_REC doubles each
   int rec_cap, max_cross;
   int n_cross, iters, status;
   int n_acc, n_rej, n_rhs, n_cond;
+  int sgn_end;  // sign of the condition at the end of the last accepted step (= start of the next)
   bool axion, starting, need_k1, event_last, done;
 
   ART_HD double u7_of(double u6) const { return u7_0 + fac7 * (u6 - u6_0); }
@@ -99,7 +169,9 @@ struct Ray {
     fac7 = axion ? 0.0 : P.Omega * erg / C_KM;
     s = log(fmax(in.t_start, P.t_floor));  // MR.jl:166
     dt = 0.0;
-    g_prev = 0.0;
+    s_new = s;
+    dt_new = 0.0;
+    sgn_end = 0;
     n_cross = iters = n_acc = n_rej = n_rhs = n_cond = 0;
     status = RAY_END;
     event_last = false;
@@ -165,13 +237,24 @@ struct Ray {
     return false;
   }
 
-  // ---- one iteration: (first call) start-up, or one attempted step with error control,
-  // event scan and callbacks ------------------------------------------------------------------
-  ART_HD void step(const DevParams& P, const KStore K) {
+  // ---------------------------------------------------------------------------------------
+  // One iteration = stages() → crossing scan of the accepted step → finish_step().
+  // The scan is separated out because on the GPU it is done COOPERATIVELY by the warp: the
+  // (ray, dense-output point) pairs that really need an evaluation — the step was accepted
+  // and the point is not in the provably negative far field — are pooled over the 32 lanes
+  // and dealt out evenly (art_kernels.cuh: warp_scan).  Only SIGNS of the condition are kept
+  // (three 64-bit masks per ray: positive / negative / exactly zero; neither = NaN); the two
+  // bracket values the root finder starts from are re-evaluated, which gives the same numbers.
+  // ---------------------------------------------------------------------------------------
+
+  // stages(): start-up on the first call, otherwise one attempted DP5 step with error control.
+  // Returns true if the step was accepted; its dense-output segment has then been published
+  // in D and must be scanned before finish_step().
+  ART_HD bool stages(const DevParams& P, const KStore K, const SegStore D) {
     if (++iters > P.maxiters) {
       status = RAY_MAXITERS;
       done = true;
-      return;
+      return false;
     }
     const double s1 = P.ln_tend;
     double h = dt;
@@ -180,8 +263,7 @@ struct Ray {
       h = s1 - s;
       last = true;
     }
-    const double s_new = last ? s1 : s + h;
-    double un[6];
+    s_new = last ? s1 : s + h;
     double sk[6], sk7 = 0.0, d1 = 0.0, dt0 = 0.0;  // start-up only
 
     // ---- stages (rolled: one copy of the right-hand side) ----------------------------------
@@ -230,142 +312,146 @@ struct Ray {
     }
     need_k1 = false;
 
-    // ---- error control (normal step) -------------------------------------------------------
-    double dt_new = dt;
-    bool scan = false;
-    if (!starting) {
-      double q = 0.0, e6 = 0.0;
-      for (int i = 0; i < 6; ++i) {
-        double e = 0.0;
-        for (int j = 0; j < 7; ++j) e += DP_E[j] * K(j, i);
-        e *= h;
-        if (i == 5) e6 = e;
-        const double r_ = e / (P.atol + fmax(fabs(u[i]), fabs(un[i])) * P.rtol);
-        q += r_ * r_;
-      }
-      const double r7 = fac7 * e6 / (P.atol + fmax(fabs(u7_of(u[5])), fabs(u7_of(un[5]))) * P.rtol);
-      q += r7 * r7;
-      const double EEst = sqrt(q / 7.0);
-      // PI controller: q11 = EEst^β1, q = q11 / qold^β2
-      double q11 = exp(dp::beta1 * log(EEst));
-      double qq = q11 * exp(-dp::beta2 * log(qold));
-      qq = fmax(1.0 / dp::qmax, fmin(1.0 / dp::qmin, qq / dp::gamma));
-      if (EEst == 0.0) qq = 1.0 / dp::qmax;
-      bool accept = (EEst <= 1.0) || (h <= P.dtmin);  // force_dtmin
-      if (!(EEst == EEst)) {
-        accept = false;
-        q11 = 1e30;
-      }
-      if (!accept) {
-        n_rej++;
-        dt = h / fmin(1.0 / dp::qmin, q11 / dp::gamma);
-        if (dt < P.dtmin) dt = P.dtmin;
-        return;
-      }
-      n_acc++;
-      if (qq <= dp::qsteady_max && qq >= dp::qsteady_min) qq = 1.0;
-      qold = fmax(EEst, dp::qoldinit);
-      dt_new = h / qq;
-      scan = true;
+    if (starting) {  // reference sign of the crossing condition at the start point
+      const double g = cond(P, u, s);
+      n_cond++;
+      sgn_end = (g > 0.0) - (g < 0.0);
+      starting = false;
+      return false;
     }
 
-    // ---- crossing events on the dense output: ONE loop, one condition evaluation per turn ---
-    // phases: 0 scan point i, 1 repeat-nudge point, 2 root-finder iterate, 3 start-up value.
-    double r1[6], r2[6], r3[6], r4[6];  // Hairer contd5 (rcont2..rcont5); rcont1 = u
-    if (scan) {
-      for (int i = 0; i < 6; ++i) {
-        double d = 0.0;
-        for (int j = 0; j < 7; ++j) d += DP_D[j] * K(j, i);
-        r1[i] = un[i] - u[i];
-        r2[i] = h * K(0, i) - r1[i];
-        r3[i] = r1[i] - h * K(6, i) - r2[i];
-        r4[i] = h * d;
-      }
-    } else {
-      for (int i = 0; i < 6; ++i) r1[i] = r2[i] = r3[i] = r4[i] = 0.0;
+    // ---- error control ---------------------------------------------------------------------
+    double q = 0.0, e6 = 0.0;
+    for (int i = 0; i < 6; ++i) {
+      double e = 0.0;
+      for (int j = 0; j < 7; ++j) e += DP_E[j] * K(j, i);
+      e *= h;
+      if (i == 5) e6 = e;
+      const double r_ = e / (P.atol + fmax(fabs(u[i]), fabs(un[i])) * P.rtol);
+      q += r_ * r_;
     }
+    const double r7 = fac7 * e6 / (P.atol + fmax(fabs(u7_of(u[5])), fabs(u7_of(un[5]))) * P.rtol);
+    q += r7 * r7;
+    const double EEst = sqrt(q / 7.0);
+    // PI controller: q11 = EEst^β1, q = q11 / qold^β2
+    double q11 = exp(dp::beta1 * log(EEst));
+    double qq = q11 * exp(-dp::beta2 * log(qold));
+    qq = fmax(1.0 / dp::qmax, fmin(1.0 / dp::qmin, qq / dp::gamma));
+    if (EEst == 0.0) qq = 1.0 / dp::qmax;
+    bool accept = (EEst <= 1.0) || (h <= P.dtmin);  // force_dtmin
+    if (!(EEst == EEst)) {
+      accept = false;
+      q11 = 1e30;
+    }
+    if (!accept) {
+      n_rej++;
+      dt = h / fmin(1.0 / dp::qmin, q11 / dp::gamma);
+      if (dt < P.dtmin) dt = P.dtmin;
+      return false;
+    }
+    n_acc++;
+    if (qq <= dp::qsteady_max && qq >= dp::qsteady_min) qq = 1.0;
+    qold = fmax(EEst, dp::qoldinit);
+    dt_new = h / qq;
+
+    // ---- publish the dense-output segment (Hairer contd5: rcont1 = u, rcont2..5 = r1..r4) ----
+    for (int i = 0; i < 6; ++i) {
+      double d = 0.0;
+      for (int j = 0; j < 7; ++j) d += DP_D[j] * K(j, i);
+      const double a1 = un[i] - u[i];
+      const double a2 = h * K(0, i) - a1;
+      D(SEG_U + i) = u[i];
+      D(SEG_R1 + i) = a1;
+      D(SEG_R2 + i) = a2;
+      D(SEG_R3 + i) = a1 - h * K(6, i) - a2;
+      D(SEG_R4 + i) = h * d;
+    }
+    D(SEG_S) = s;
+    D(SEG_H) = h;
+    D(SEG_U70) = u7_0;
+    D(SEG_FAC7) = fac7;
+    D(SEG_U60) = u6_0;
+    n_cond += P.M_ray - 1 + (event_last ? 1 : 0);
+    return true;
+  }
+
+  // is the dense-output point th still inside the ±0.01 % box around the start point (RT.jl:307-311)?
+  ART_HD bool in_start_box(const DevParams& P, const SegStore D, double th) const {
+    double w[6], x[3], k[3];
+    seg_state(D, th, w);
+    state_to_cartesian(P, w, erg, false, x, k);
+    const double sb = 1.0001;
+    bool in = true;
+    for (int c = 0; c < 3; ++c) in = in && (fabs(x[c]) < fabs(x0[c]) * sb) && (fabs(x[c]) > fabs(x0[c]) / sb);
+    return in;
+  }
+
+  // finish_step(): first sign change of the scanned step → root → callbacks → state update.
+  ART_HD void finish_step(const DevParams& P, const KStore K, const SegStore D, const ScanMasks m) {
     const int M = P.M_ray;
-    int phase = starting ? 3 : (event_last ? 1 : 0);
-    int ip = 1, side = 0, it = 0;
-    int sgn_prev = (g_prev > 0.0) - (g_prev < 0.0);
-    double th_a = 0.0, g_a = g_prev, th_ev = -1.0, g_end = 0.0;
-    double ra = 0.0, fa = 0.0, rb = 0.0, fb = 0.0;
-    bool looping = true;
-    while (looping) {
-      double th;
-      if (phase == 0 && event_last && ip < M - 1 && (double)ip / (double)(M - 1) <= 0.01) {
-        ip++;  // grid points at or before the nudge point are not compared (interp_points > 100 only)
+    int cur = sgn_end;
+    if (event_last)  // DiffEqBase repeat_nudge = 1/100: reference sign taken just after the event
+      cur = (int)(m.pos & 1ull) - (int)(m.neg & 1ull);
+    // grid points that take part in the comparison: 1..M−1 (after an event only those beyond the nudge)
+    unsigned long long valid = ((M >= 64) ? ~0ull : ((1ull << M) - 1ull)) & ~1ull;
+    if (event_last)
+      for (int i = 1; i < M - 1 && (double)i * P.inv_Mrm1 <= 0.01; ++i) valid &= ~(1ull << i);
+    int ia = 0, ib = -1;  // bracket indices; ia = 0 stands for the left end (θ = 0, or 0.01 after an event)
+    unsigned long long from = valid;
+    while (cur != 0) {
+      const unsigned long long opp = (cur > 0 ? m.neg : m.pos) & from;
+      if (!opp) break;
+      const int i = ffs64(opp) - 1;
+      const unsigned long long below = (cur > 0 ? m.pos : m.neg) & from & ((1ull << i) - 1ull);
+      if (below) ia = 63 - clz64(below);
+      // start-box rule: a sign change whose grid point is still inside the box
+      // around the start point is discarded without locating it; the reference sign flips
+      if (n_cross == 0 && in_start_box(P, D, seg_theta(P, i))) {
+        cur = -cur;
+        ia = i;
+        from &= ~((2ull << i) - 1ull);
         continue;
       }
-      if (phase == 0) th = (ip == M - 1) ? 1.0 : (double)ip / (double)(M - 1);
-      else if (phase == 1) th = 0.01;  // DiffEqBase repeat_nudge = 1/100
-      else if (phase == 2) {
-        th = (ra * fb - rb * fa) / (fb - fa);
-        const double lo = fmin(ra, rb), hi = fmax(ra, rb);
-        if (!(th > lo && th < hi) || it >= 60) th = 0.5 * (ra + rb);
-        it++;
-      } else th = 0.0;
-      double w_[6];
-      {
-        const double th1 = 1.0 - th;
-        for (int i = 0; i < 6; ++i) w_[i] = u[i] + th * (r1[i] + th1 * (r2[i] + th * (r3[i] + th1 * r4[i])));
-        if (th >= 1.0)
-          for (int i = 0; i < 6; ++i) w_[i] = un[i];
-      }
-      const double g = cond(P, w_, (th >= 1.0) ? s_new : s + th * h);
-      n_cond++;
-      if (phase == 3) {  // start-up: reference value at the start point
-        g_prev = g;
-        looping = false;
-      } else if (phase == 1) {
-        sgn_prev = (g > 0.0) - (g < 0.0);
-        th_a = 0.01;
-        g_a = g;
-        phase = 0;
-      } else if (phase == 0) {
-        const int sg = (g > 0.0) - (g < 0.0);
-        if (ip == M - 1) g_end = g;
-        if (sgn_prev != 0 && sgn_prev * sg < 0) {
-          ra = th_a; fa = g_a; rb = th; fb = g;
-          side = 0; it = 0; phase = 2;
-        } else {
-          if (sg == sgn_prev) {
-            th_a = th;
-            g_a = g;
-          }
-          if (ip == M - 1) {
-            if (sgn_prev != 0 && g == 0.0) th_ev = 1.0;
-            looping = false;
-          }
-          ip++;
-        }
-      } else {  // root finder: Illinois regula falsi, bisection safeguard, left-biased result
-        if (g == 0.0) {
-          th_ev = th;
-          looping = false;
-        } else {
-          if ((g < 0.0) != (fb < 0.0)) {
-            ra = rb; fa = fb; side = 0;
-          } else {
-            if (side == 1) fa *= 0.5;
-            side = 1;
-          }
-          rb = th; fb = g;
-        }
-      }
-      if (phase == 2 && looping) {
-        const double tol = 4.0 * 2.220446049250313e-16 * fmax(fabs(ra), fabs(rb)) + 1e-300;
-        if (fabs(rb - ra) <= tol || it >= 200) {
-          th_ev = fmin(ra, rb);
-          looping = false;
-        }
-      }
+      ib = i;
+      break;
     }
-    if (starting) {
-      starting = false;
-      return;
+    const int sg_last = (int)((m.pos >> (M - 1)) & 1ull) - (int)((m.neg >> (M - 1)) & 1ull);
+    const bool zero_last = ((m.zero >> (M - 1)) & 1ull) != 0;
+    double th_ev = -1.0;
+    if (ib >= 0) {
+      // Illinois regula falsi with bisection safeguard, to floating precision; left-biased
+      double ra = (ia == 0) ? (event_last ? 0.01 : 0.0) : seg_theta(P, ia), rb = seg_theta(P, ib);
+      double fa = seg_cond(P, D, ra), fb = seg_cond(P, D, rb);
+      n_cond += 2;
+      int side = 0;
+      bool exact = false;
+      for (int it = 0; it < 200; ++it) {
+        const double tol = 4.0 * 2.220446049250313e-16 * fmax(fabs(ra), fabs(rb)) + 1e-300;
+        if (fabs(rb - ra) <= tol) break;
+        double c = (ra * fb - rb * fa) / (fb - fa);
+        const double lo = fmin(ra, rb), hi = fmax(ra, rb);
+        if (!(c > lo && c < hi) || it >= 60) c = 0.5 * (ra + rb);
+        const double fc = seg_cond(P, D, c);
+        n_cond++;
+        if (fc == 0.0) {
+          th_ev = c;
+          exact = true;
+          break;
+        }
+        if ((fc < 0.0) != (fb < 0.0)) {
+          ra = rb; fa = fb; side = 0;
+        } else {
+          if (side == 1) fa *= 0.5;
+          side = 1;
+        }
+        rb = c; fb = fc;
+      }
+      if (!exact) th_ev = fmin(ra, rb);
+    } else if (cur != 0 && zero_last) {
+      th_ev = 1.0;  // prev_sign · next_sign ≤ 0 with the end point exactly on the surface
     }
 
+    const double h = D(SEG_H);
     bool terminated = false;
     if (th_ev >= 0.0) {
       double ue[6];
@@ -374,8 +460,7 @@ struct Ray {
         for (int i = 0; i < 6; ++i) ue[i] = un[i];
         se = s_new;
       } else {
-        const double th1 = 1.0 - th_ev;
-        for (int i = 0; i < 6; ++i) ue[i] = u[i] + th_ev * (r1[i] + th1 * (r2[i] + th_ev * (r3[i] + th1 * r4[i])));
+        seg_state(D, th_ev, ue);
         se = s + th_ev * h;
       }
       terminated = on_crossing(P, ue, se);
@@ -389,7 +474,7 @@ struct Ray {
         K(0, i) = K(6, i);  // FSAL
       }
       s = s_new;
-      g_prev = g_end;
+      sgn_end = sg_last;
       event_last = false;
     }
     dt = dt_new;
@@ -402,7 +487,21 @@ struct Ray {
       done = true;
       return;
     }
-    if (!(s < s1)) done = true;
+    if (!(s < P.ln_tend)) done = true;
+  }
+
+  // sequential form (host check, and the definition the cooperative GPU scan must reproduce)
+  ART_HD void step(const DevParams& P, const KStore K, const SegStore D) {
+    if (!stages(P, K, D)) return;
+    ScanMasks m = {0ull, 0ull, 0ull};
+    const int M = P.M_ray;
+    for (int i = event_last ? 0 : 1; i < M; ++i) {
+      const double g = seg_cond(P, D, seg_theta(P, i));
+      if (g > 0.0) m.pos |= 1ull << i;
+      else if (g < 0.0) m.neg |= 1ull << i;
+      else if (g == 0.0) m.zero |= 1ull << i;
+    }
+    finish_step(P, K, D, m);
   }
 
   ART_HD void finish(const DevParams& P, RayOut& o) const {

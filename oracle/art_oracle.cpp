@@ -115,7 +115,7 @@ static SampleOut find_sample(const double U[10], double maxR, const art_params& 
     int sgn_prev = (prev > 0) - (prev < 0);
     double th_a = th_left, g_a = prev, th_ev = -1.0, g_end = 0.0;
     for (int i = 1; i < M; ++i) {
-      double th = (i == M - 1) ? 1.0 : (double)i / (double)(M - 1);
+      double th = (i == M - 1) ? 1.0 : (double)i * (1.0 / (double)(M - 1));
       double gv = cond(th >= 1.0 ? tau_new : tau + th * dt);
       if (i == M - 1) g_end = gv;
       int sg = (gv > 0) - (gv < 0);
@@ -593,6 +593,8 @@ int orc_trace_ray(const art_params* p, int32_t species, const double* x0, const 
   }
   return (int)tr.size();
 }
+
+void orc_set_literal_start_events(int on) { g_literal_start_events = on != 0; }
 
 int orc_num_threads(void) {
 #ifdef _OPENMP

@@ -152,5 +152,10 @@ def sampler_uniforms(seed, event, attempt):
     return U
 
 
+def set_literal_start_events(on):
+    """True: locate-then-discard start-point events like the reference; False (default): start-box rule."""
+    lib().orc_set_literal_start_events(int(bool(on)))
+
+
 def num_threads():
     return lib().orc_num_threads()

@@ -107,6 +107,10 @@ struct Crossing {
   double x, y, z, kx, ky, kz, t, dw;
 };
 
+// false (default): start-box rule on.  true: locate and then discard start-point events exactly like
+// the reference does (used by tests/test_oracle_invariants.py to bound the effect of the rule).
+static bool g_literal_start_events = false;
+
 struct StepTrace {
   double s, dt, EEst;
   int accepted, event;
@@ -326,12 +330,34 @@ inline RayResult propagate(const double x0[3], const double k0_in[3], const RayP
       int sgn_prev = (prev > 0) - (prev < 0);
       double th_ev = -1.0;
       for (int i = 1; i < M; ++i) {
-        double th = (i == M - 1) ? 1.0 : (double)i / (double)(M - 1);
+        double th = (i == M - 1) ? 1.0 : (double)i * (1.0 / (double)(M - 1));
         double gv = cond_at(th);
         R.n_cond++;
         if (i == M - 1) g_end = gv;
         if (th <= th_left) continue;
         int sg = (gv > 0) - (gv < 0);
+        if (sgn_prev != 0 && sgn_prev * sg < 0 && callback_count == 0 && !g_literal_start_events) {
+          // Start-box rule (this project's integrator specification): a ray starts ON
+          // the conversion surface, so while it has not moved the condition is round-off noise and
+          // flips sign at random.  The reference locates every such flip with the root finder and then
+          // discards it in affect! (RT.jl:303-314, the ±0.01 % box around the start point).  Here a sign
+          // change whose grid point still lies inside that box is discarded WITHOUT locating it: the
+          // reference sign flips and the scan continues.  Recorded crossings are the same; only the
+          // (noise-driven, irreproducible) step truncations at discarded events disappear.
+          double v[7];
+          if (th >= 1.0) for (int c = 0; c < 7; ++c) v[c] = un[c]; else dense(th, v);
+          double pos[3] = {v[0] * std::sin(v[1]) * std::cos(v[2]), v[0] * std::sin(v[1]) * std::sin(v[2]), v[0] * std::cos(v[1])};
+          const double sb = 1.0001;
+          bool in = true;
+          for (int c = 0; c < 3; ++c)
+            in = in && (std::fabs(pos[c]) < std::fabs(x0[c]) * sb) && (std::fabs(pos[c]) > std::fabs(x0[c]) / sb);
+          if (in) {
+            sgn_prev = sg;
+            th_a = th;
+            g_a = gv;
+            continue;
+          }
+        }
         if (sgn_prev != 0 && sgn_prev * sg < 0) {
           int ne = 0;
           th_ev = find_root(cond_at, th_a, g_a, th, gv, &ne);

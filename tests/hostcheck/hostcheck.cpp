@@ -21,10 +21,11 @@ static int dev(const art_params* p, DevParams& d) {
 
 static void trace_one(const DevParams& P, const RayIn& in, double* rec, int cap, RayOut& o) {
   Ray R;
-  double kbuf[42];
+  double kbuf[42], sbuf[SEG_N];
   KStore K{kbuf, 1};
+  SegStore D{sbuf, 1};
   R.init(P, in, rec, cap);
-  while (!R.done) R.step(P, K);
+  while (!R.done) R.step(P, K, D);
   R.finish(P, o);
 }
 
@@ -214,13 +215,14 @@ extern "C" int hc_trace_ray(const art_params* p, int32_t species, const double* 
   std::vector<double> rec((size_t)p->cross_cap * 8);
   int n = 0;
   Ray R;
-  double kbuf[42];
+  double kbuf[42], sbuf[SEG_N];
   KStore K{kbuf, 1};
+  SegStore D{sbuf, 1};
   R.init(P, in, rec.data(), p->cross_cap);
   while (!R.done) {
     double s = R.s, dt = R.dt;
     int acc = R.n_acc;
-    R.step(P, K);
+    R.step(P, K, D);
     if (n < cap) { out[4 * n] = s; out[4 * n + 1] = dt; out[4 * n + 2] = R.n_acc - acc; out[4 * n + 3] = R.n_cross; }
     n++;
   }
