@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -19,6 +20,7 @@
 #include "../../include/art.h"
 #include "art_host.hpp"
 #include "art_kernels.cuh"
+#include "art_wavefront.cuh"
 
 using namespace art;
 
@@ -98,6 +100,9 @@ struct art_handle {
   // pipeline buffers (per chunk)
   DBuf samples, events, tstate, stacks, q[2], rout, rec, counters, stats, fin_count, fin_info;
   DBuf rows, keys, hist, scratch[12];
+  DBuf wf_ray, wf_kf, wf_seg, wf_need, wf_neg, wf_pend, wf_sign, wf_act[4], wf_items, wf_roots, wf_fin, wf_ctr;
+  int use_wavefront = 1;  // ART_TRACER=persistent selects the one-kernel tracer (k_trace)
+  long long tail_switch = 0;  // active rays below which the persistent tail kernel takes over
   long long rows_cap = 0;   // rows held on device
   long long n_rows_dev = 0;
   int ncols = 13;
@@ -132,14 +137,94 @@ int upload(art_handle* h, DBuf& b, const void* src, size_t bytes) {
 }
 
 // launches the tracer over a device queue; zeroes the queue head first
+int launch_trace_wf(art_handle* h, const QueuedRay* q, long long n, RayOut* out, double* rec, int rec_cap,
+                    DevStats* stats, const WfTree* tree);
 int launch_trace(art_handle* h, const QueuedRay* q, long long n, RayOut* out, double* rec, int rec_cap,
                  unsigned long long* head, DevStats* stats) {
   if (n <= 0) return ART_OK;
+  if (h->use_wavefront) return launch_trace_wf(h, q, n, out, rec, rec_cap, stats, nullptr);
   CU(cudaMemsetAsync(head, 0, sizeof(unsigned long long), h->stream));
   const int blocks = (int)std::min<long long>(h->blocks_trace, (n + TRACE_THREADS - 1) / TRACE_THREADS);
   k_trace<<<blocks, TRACE_THREADS, TRACE_SMEM, h->stream>>>(h->dp, q, n, out, rec, rec_cap, head, stats);
   h->launches++;
   CU(cudaGetLastError());
+  return ART_OK;
+}
+
+// step-batched tracer over a device queue (art_wavefront.cuh).  With a tree context the loop also
+// walks every event's tree: finished rays spawn the next node of their event in place.
+int launch_trace_wf(art_handle* h, const QueuedRay* q, long long n, RayOut* out, double* rec, int rec_cap,
+                    DevStats* stats, const WfTree* tree) {
+  if (n <= 0) return ART_OK;
+  const int M = h->params.interp_points_ray;
+  CU(h->wf_ray.ensure((size_t)n * sizeof(Ray)));
+  CU(h->wf_kf.ensure((size_t)n * KF_PAD * sizeof(double)));
+  CU(h->wf_seg.ensure((size_t)n * SEG_PAD * sizeof(double)));
+  CU(h->wf_need.ensure((size_t)n * 8));
+  CU(h->wf_neg.ensure((size_t)n * 8));
+  CU(h->wf_pend.ensure((size_t)n));
+  CU(h->wf_sign.ensure((size_t)n * 64));
+  for (int k = 0; k < 4; ++k) CU(h->wf_act[k].ensure((size_t)n * 4));
+  CU(h->wf_items.ensure((size_t)n * M * 4));
+  CU(h->wf_roots.ensure((size_t)n * 4));
+  CU(h->wf_fin.ensure((size_t)n * 4));
+  CU(h->wf_ctr.ensure(WC_N * 8));
+  WfPool W;
+  W.ray = h->wf_ray.as<Ray>(); W.kf = h->wf_kf.as<double>(); W.seg = h->wf_seg.as<double>();
+  W.need = h->wf_need.as<unsigned long long>(); W.neg = h->wf_neg.as<unsigned long long>();
+  W.pend = h->wf_pend.as<unsigned char>(); W.sign = h->wf_sign.as<unsigned char>();
+  for (int par = 0; par < 2; ++par)
+    for (int sp = 0; sp < 2; ++sp) W.act[par][sp] = h->wf_act[par * 2 + sp].as<int>();
+  W.items = h->wf_items.as<unsigned>(); W.roots = h->wf_roots.as<int>(); W.fin = h->wf_fin.as<int>();
+  W.ctr = h->wf_ctr.as<unsigned long long>();
+  const size_t ksmem = (size_t)42 * WF_THREADS * sizeof(double);
+  CU(cudaMemsetAsync(W.ctr, 0, WC_N * 8, h->stream));
+  const int gmax = h->n_sm * 8;
+  auto grid = [&](long long work, int threads) { return (int)std::max<long long>(1, std::min<long long>(gmax, (work + threads - 1) / threads)); };
+  k_wf_init<<<grid(n, WF_THREADS), WF_THREADS, 0, h->stream>>>(h->dp, q, n, W, out, rec, rec_cap, stats);
+  h->launches++;
+  CU(cudaGetLastError());
+  long long n_act = n;  // upper bound of the active count, refreshed at every host check
+  int cur = 0;
+  for (long long iter = 0;;) {
+    const int burst = n_act > 65536 ? 4 : (n_act > 2048 ? 8 : 24);  // steps between host checks
+    for (int b = 0; b < burst; ++b, ++iter) {
+      const int next = 1 - cur;
+      const int g1 = grid(n_act, WF_THREADS);
+      k_wf_reset<<<1, 32, 0, h->stream>>>(W, next);
+      k_wf_stages<SPECIES_AXION><<<g1, WF_THREADS, ksmem, h->stream>>>(h->dp, W, cur);
+      k_wf_stages<SPECIES_PHOTON><<<g1, WF_THREADS, ksmem, h->stream>>>(h->dp, W, cur);
+      k_wf_scan<<<grid(n_act * 24, 256), 256, 0, h->stream>>>(h->dp, W);
+      k_wf_detect<<<g1, WF_THREADS, 0, h->stream>>>(h->dp, W, cur, out, stats);
+      k_wf_root<<<grid(n_act / 8 + 1, WF_THREADS), WF_THREADS, 0, h->stream>>>(h->dp, W, next, out, stats);
+      h->launches += 6;
+      if (tree) {
+        k_wf_tree<<<grid(n_act / 4 + 1, WF_THREADS), WF_THREADS, 0, h->stream>>>(h->dp, W, *tree, next, out, rec, rec_cap, stats);
+        h->launches++;
+      }
+      cur = next;
+    }
+    CU(cudaGetLastError());
+    unsigned long long na[2] = {0, 0};
+    CU(cudaMemcpyAsync(na, W.ctr + WC_ACT + cur * 2, 16, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    n_act = (long long)(na[0] + na[1]);
+    if (n_act == 0) break;
+    if (iter > 64LL * h->params.maxiters) return fail(h, ART_ERR_CUDA, "wavefront tracer did not terminate");
+    if (n_act <= h->tail_switch) {
+      // latency-bound tail: one persistent kernel finishes the remaining rays and their trees
+      WfTree none;
+      memset(&none, 0, sizeof(none));
+      k_wf_reset<<<1, 32, 0, h->stream>>>(W, 1 - cur);  // zeroes the item counter = the tail's queue head
+      const int blocks = grid(n_act, WF_THREADS);
+      k_wf_tail<<<std::min(blocks, h->n_sm * 2), WF_THREADS, ksmem, h->stream>>>(h->dp, W, tree ? *tree : none, cur, out, rec,
+                                                                               rec_cap, stats);
+      h->launches += 2;
+      CU(cudaGetLastError());
+      CU(cudaStreamSynchronize(h->stream));
+      break;
+    }
+  }
   return ART_OK;
 }
 
@@ -195,6 +280,8 @@ int art_create(const art_params* p, int device_id, art_handle** out) {
   h->dp = d;
   h->device = device_id;
   h->ncols = p->save_mode > 0 ? ART_ROW_COLS_LONG : ART_ROW_COLS_SHORT;
+  if (const char* t = getenv("ART_TRACER")) h->use_wavefront = strcmp(t, "persistent") != 0;
+  if (const char* t = getenv("ART_TAIL_SWITCH")) h->tail_switch = atoll(t);
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, device_id);
   h->n_sm = prop.multiProcessorCount;
@@ -219,6 +306,9 @@ void art_destroy(art_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  DBuf* wf[] = {&h->wf_ray, &h->wf_kf, &h->wf_seg, &h->wf_need, &h->wf_neg, &h->wf_pend, &h->wf_sign, &h->wf_act[0],
+                &h->wf_act[1], &h->wf_act[2], &h->wf_act[3], &h->wf_items, &h->wf_roots, &h->wf_fin, &h->wf_ctr};
+  for (DBuf* b : wf) b->release();
   DBuf* all[] = {&h->samples, &h->events, &h->tstate, &h->stacks, &h->q[0], &h->q[1], &h->rout, &h->rec,
                  &h->counters, &h->stats, &h->fin_count, &h->fin_info, &h->rows, &h->keys, &h->hist};
   for (DBuf* b : all) b->release();
@@ -488,6 +578,15 @@ int art_run_device(art_handle* h, uint64_t seed, int64_t first_event, int64_t n_
     h->launches++;
     CU(cudaGetLastError());
     CU(cudaEventRecord(ev[2], h->stream));
+    if (h->use_wavefront) {
+      // K3+K4 fused: n back-traced axions (slots 0..n) + the n forward trees (slots n..2n) in ONE loop
+      WfTree T;
+      T.ev = h->events.as<EventData>(); T.ts = h->tstate.as<TreeState>(); T.stacks = h->stacks.as<TreeNode>();
+      T.stack_stride = stack_stride; T.seed = seed; T.first_event = first_event; T.chunk_base = base; T.n_events = n;
+      T.sink = sink; T.tot_count = ctr + 3; T.fin_count = h->fin_count.as<int>(); T.fin_info = h->fin_info.as<int>();
+      if (int rc = launch_trace_wf(h, h->q[0].as<QueuedRay>(), 2 * n, rout, rec, cap, dstats, &T)) return rc;
+      CU(cudaEventRecord(ev[3], h->stream));
+    } else {
     // K3 first launch: n back-traced axions (slots 0..n) + n first forward photons (slots n..2n)
     if (int rc = launch_trace(h, h->q[0].as<QueuedRay>(), 2 * n, rout, rec, cap, ctr + 1, dstats)) return rc;
     CU(cudaEventRecord(ev[3], h->stream));
@@ -525,6 +624,7 @@ int art_run_device(art_handle* h, uint64_t seed, int64_t first_event, int64_t n_
       CU(cudaEventRecord(e_tr, h->stream));
       gen_ev.push_back(e_tr);
     }
+    }
     // failed sampler attempts of this chunk (→ f_inx)
     {
       std::vector<EventSample> hs((size_t)n);
@@ -541,13 +641,11 @@ int art_run_device(art_handle* h, uint64_t seed, int64_t first_event, int64_t n_
     }
     const long long nr = (long long)rows_after - (long long)rows_before;
     if (nr > 0) {
-      if (ncols > 13) {
-        k_patch_rows<<<nblk(nr, 256), 256, 0, h->stream>>>((long long)rows_after, h->rows.as<double>(), h->keys.as<long long>(),
-                                                           ncols, base, h->fin_count.as<int>(), h->fin_info.as<int>(),
-                                                           (long long)rows_before);
-        h->launches++;
-        CU(cudaGetLastError());
-      }
+      k_patch_rows<<<nblk(nr, 256), 256, 0, h->stream>>>((long long)rows_after, h->rows.as<double>(), h->keys.as<long long>(),
+                                                         ncols, base, h->events.as<EventData>(), h->fin_count.as<int>(),
+                                                         h->fin_info.as<int>(), (long long)rows_before);
+      h->launches++;
+      CU(cudaGetLastError());
       const int nb = 2 * h->n_ct * h->n_ph * 4;
       const int use_smem = nb * (int)sizeof(double) <= 48 * 1024;
       const int blocks = (int)std::min<long long>(h->n_sm * 4, (nr + 255) / 256);

@@ -86,8 +86,9 @@ __device__ __forceinline__ ScanMasks warp_scan(const DevParams& P, bool pending,
   unsigned long long need = 0ull, neg = 0ull;
   if (pending) {
     const SegStore D{seg_w + lane, stride};
+    const SegQuick Q(D);
     for (int i = nudge ? 0 : 1; i < M; ++i) {
-      const int qk = seg_quick(P, D, seg_theta(P, i));
+      const int qk = Q.classify(P, seg_theta(P, i));
       if (qk == 0) need |= 1ull << i;
       else if (qk == -1) neg |= 1ull << i;
     }
@@ -398,14 +399,14 @@ __global__ void k_tree_update(const __grid_constant__ DevParams P, long long n_r
   if (push) next_q[slot] = r;
 }
 
-// save_mode ≥ 1: columns c (20) and info (21) are known only when the tree is complete
+// rows are completed (back-traced weight, tree count / info) when their event is finished
 __global__ void k_patch_rows(long long n_rows, double* rows, const long long* keys, int ncols, long long chunk_base,
-                             const int* fin_count, const int* fin_info, long long row_begin) {
+                             const EventData* __restrict__ ev, const int* fin_count, const int* fin_info,
+                             long long row_begin) {
   const long long i = row_begin + blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n_rows) return;
   const long long e = (keys[i] >> 8) - chunk_base;
-  rows[i * ncols + 20] = (double)fin_count[e];
-  rows[i * ncols + 21] = (double)fin_info[e];
+  patch_row(rows + i * ncols, ncols, ev[e], fin_count[e], fin_info[e]);
 }
 
 // ------------------------------------------------------------------------------------------

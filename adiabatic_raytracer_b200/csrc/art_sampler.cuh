@@ -31,6 +31,7 @@ struct Sampler {
   double xs[3], va[3], vl[3];  // line origin, line direction, local velocity direction
   double erg_inf, vI[3], vI_mag;
   double cpsi0, spsi0;         // cos/sin of Ω t0
+  double mh[3], mv;            // magnetic axis m̂ at the field time t0, and m̂·v
   double tau, tau_new, h, T, tau_out;
   double g_prev, th_a, g_a, a, fa, b, fb;
   double taus[SAMP_KEEP];
@@ -42,22 +43,50 @@ struct Sampler {
     for (int c = 0; c < 3; ++c) u[c] = xs[c] + t_ * va[c];
   }
 
-  // condition of find_samples_new, RT.jl:1554-1581
+  // condition of find_samples_new, RT.jl:1554-1581, as a division-light equivalent.
+  //
+  // The reference builds covariant components of the unit vector v (vvec_loc), normalises them to
+  // the axion mass shell and forms Ham = ½(−m_a² + ωp²(1 − g^rr k∥²/E²))/E².  With physical
+  // components, k∥²·g^rr/E² = g^rr·NrmSq·N²/(D·E²), NrmSq = (−E² g^tt − m_a²)/ww, and for a point
+  // outside the star (AA = g^rr = A, g^tt = −1/A):
+  //     ww = v_r² + v_θ² + v_φ² = 1,   N = v·b,   b = 3(m̂·r̂) r̂ − m̂   (dipole direction, |b|² = D),
+  //     b_z = 3(m̂·r̂)(ẑ·r̂) − cosθm,   m̂ = (sinθm cosΩt0, sinθm sinΩt0, cosθm)
+  // so everything is a dot product of the Cartesian point with two fixed vectors:
+  //     F = Q|b_z| r⁻³ (D E² − N² (E² − m_a² A)) − m_a² D E²   has the sign (and the roots) of Ham.
+  // One sqrt, one reciprocal, no trigonometry (the literal form costs 14 divisions and 5 square
+  // roots per evaluation — profiles/r01_sampler_v1_hotlines.txt: 60 % stall_wait on those chains).
+  // Inside the star (r < rNS: AA = 1 quirk RT.jl:1558-1560; r ≤ r_int: interior metric) the same
+  // algebra is kept with the general g^tt, g^rr:  ww = 1 − (1 − g^rr/AA') v_r² …, see below.
   ART_HD double cond(const DevParams& P, double t_) {
-    double u[3];
-    point(t_, u);
-    const double rho2 = u[0] * u[0] + u[1] * u[1];
-    const double r = sqrt(rho2 + u[2] * u[2]);
-    const double rho = sqrt(rho2);
-    const double c = u[2] / r, s = rho / r;
-    const double cph = u[0] / rho, sph = u[1] / rho;
-    const Fld f = field_cs<false>(P, c, s, cph * cpsi0 + sph * spsi0, sph * cpsi0 - cph * spsi0);
-    double AA = 1.0 - P.rs_real / r;
-    if (r < P.rNS) AA = 1.0;  // RT.jl:1558-1560
-    double w[3];
-    celerity(u, r, s, vl, AA, w);
     n_cond++;
-    return thick_condition_f(P, r, f, w[0], w[1], w[2], erg_inf, P.rs_real, false);
+    const double x = xs[0] + t_ * va[0], y = xs[1] + t_ * va[1], z = xs[2] + t_ * va[2];
+    const double r2 = x * x + y * y + z * z;
+    const double r = sqrt(r2);
+    const double rinv = 1.0 / r;
+    const double mx = (mh[0] * x + mh[1] * y + mh[2] * z) * rinv;  // m̂·r̂
+    const double vx = (vl[0] * x + vl[1] * y + vl[2] * z) * rinv;  // v·r̂  (= v_r)
+    const double cz = z * rinv;                                    // ẑ·r̂
+    const double D = 3.0 * mx * mx + 1.0;
+    const double bz = 3.0 * mx * cz - P.cm;
+    const double Pq = P.Q * fabs(bz) * rinv * rinv * rinv;         // ωp²
+    const double E2 = erg_inf * erg_inf;
+    if (r >= P.rNS && r > P.r_int) {
+      const double N = 3.0 * mx * vx - mv;                         // v·b
+      const double A = 1.0 - P.rs_real * rinv;
+      return Pq * (D * E2 - N * N * (E2 - P.ma2 * A)) - P.ma2 * D * E2;
+    }
+    // general form: covariant w = (v_r/(√AA·AA), v_θ r/AA, v_φ r s/AA); the common 1/AA drops out
+    const Met m = metric(r, P.rs_real, P.r_int);
+    const double AA = (r < P.rNS) ? 1.0 : 1.0 - P.rs_real * rinv;
+    const double br = 2.0 * mx;
+    const double vt2 = 1.0 - vx * vx;                              // v_θ² + v_φ²
+    const double wr2 = vx * vx / AA;                               // (v_r/√AA)²
+    const double ww = m.grr * wr2 + vt2;
+    // N = √g^rr w_r b_r + v_θ b_θ + v_φ b_φ,  v_θ b_θ + v_φ b_φ = v·b − v_r b_r
+    const double N = sqrt(m.grr / AA) * vx * br + ((3.0 * mx * vx - mv) - vx * br);
+    const double nrm = -E2 * m.gtt - P.ma2;                        // NrmSq·ww
+    if (nrm < 0.0) return NAN;
+    return Pq * (ww * D * E2 - m.grr * N * N * nrm) - P.ma2 * ww * D * E2;
   }
 
   // affect!, RT.jl:1585-1597
@@ -127,6 +156,8 @@ struct Sampler {
     erg_inf = P.ma * sqrt(1.0 + bc * bc / (1.0 - bc * bc));  // RT.jl:1537-1538
     for (int c = 0; c < 3; ++c) xs[c] += va[c] * (-P.maxR * 1.1);  // RT.jl:1542
     sincos(P.Omega * P.t0, &spsi0, &cpsi0);
+    mh[0] = P.sm * cpsi0; mh[1] = P.sm * spsi0; mh[2] = P.cm;
+    mv = mh[0] * vl[0] + mh[1] * vl[1] + mh[2] * vl[2];
     n_cross = 0;
     n_cond = 0;
     event_last = false;

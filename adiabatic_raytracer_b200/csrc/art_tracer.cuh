@@ -122,6 +122,25 @@ ART_HD int seg_quick(const DevParams& P, const SegStore D, double th) {
   return (E * E * r >= P.ma2 * (r - P.rs_ray)) ? -1 : 2;
 }
 
+// The same test with the two polynomials it needs (r and u6) held in registers — used where all
+// M−1 points of a segment are classified in a row.
+struct SegQuick {
+  double a0[5], a5[5], u70, fac7, u60;
+  ART_HD explicit SegQuick(const SegStore D) {
+    a0[0] = D(SEG_U + 0); a0[1] = D(SEG_R1 + 0); a0[2] = D(SEG_R2 + 0); a0[3] = D(SEG_R3 + 0); a0[4] = D(SEG_R4 + 0);
+    a5[0] = D(SEG_U + 5); a5[1] = D(SEG_R1 + 5); a5[2] = D(SEG_R2 + 5); a5[3] = D(SEG_R3 + 5); a5[4] = D(SEG_R4 + 5);
+    u70 = D(SEG_U70); fac7 = D(SEG_FAC7); u60 = D(SEG_U60);
+  }
+  ART_HD int classify(const DevParams& P, double th) const {
+    const double th1 = 1.0 - th;
+    const double r = a0[0] + th * (a0[1] + th1 * (a0[2] + th * (a0[3] + th1 * a0[4])));
+    if (!(r > P.Rcut && r > P.r_int)) return 0;
+    const double u6 = a5[0] + th * (a5[1] + th1 * (a5[2] + th * (a5[3] + th1 * a5[4])));
+    const double E = u70 + fac7 * (u6 - u60);
+    return (E * E * r >= P.ma2 * (r - P.rs_ray)) ? -1 : 2;
+  }
+};
+
 // `condition` of propagate (RT.jl:254-298) at dense-output parameter th of a published segment
 ART_HD double seg_cond_full(const DevParams& P, const SegStore D, double th) {
   double w[6];
@@ -150,6 +169,7 @@ struct Ray {
   int rec_cap, max_cross;
   int n_cross, iters, status;
   int n_acc, n_rej, n_rhs, n_cond;
+  int br_a, br_b, br_sg;  // bracket found by detect(), waiting for the root kernel (wavefront path)
   int sgn_end;  // sign of the condition at the end of the last accepted step (= start of the next)
   bool axion, starting, need_k1, event_last, done;
 
@@ -182,9 +202,12 @@ struct Ray {
   }
 
   // func! / func_axion!, RT.jl:71-123
+  // SP = −1: species from the ray (mixed batches); 0 / 1: compile-time axion / photon
+  template <int SP = -1>
   ART_HD void f(const DevParams& P, const double v[6], double lnt, double dv[6]) const {
     const double t = exp(lnt);
-    if (axion)
+    const bool ax = SP < 0 ? axion : (SP == SPECIES_AXION);
+    if (ax)
       rhs_axion(P, v[0], v[1], v[3] * erg, v[4] * erg, v[5] * erg, t, erg, dv);
     else
       rhs_photon(P, v[0], v[1], v[2], v[3] * erg, v[4] * erg, v[5] * erg, -u7_of(v[5]), t, erg, dv);
@@ -250,6 +273,7 @@ struct Ray {
   // stages(): start-up on the first call, otherwise one attempted DP5 step with error control.
   // Returns true if the step was accepted; its dense-output segment has then been published
   // in D and must be scanned before finish_step().
+  template <int SP = -1>
   ART_HD bool stages(const DevParams& P, const KStore K, const SegStore D) {
     if (++iters > P.maxiters) {
       status = RAY_MAXITERS;
@@ -295,7 +319,7 @@ struct Ray {
         ts = (st == 6) ? s_new : s + DP_C[st] * h;
       }
       double dv[6];
-      f(P, v, ts, dv);
+      f<SP>(P, v, ts, dv);
       n_rhs++;
       if (starting && st == 1) {
         double a[6];
@@ -388,6 +412,21 @@ struct Ray {
 
   // finish_step(): first sign change of the scanned step → root → callbacks → state update.
   ART_HD void finish_step(const DevParams& P, const KStore K, const SegStore D, const ScanMasks m) {
+    finish_step_t(P, K, D, m);
+  }
+  template <class KS>
+  ART_HD void finish_step_t(const DevParams& P, const KS K, const SegStore D, const ScanMasks m) {
+    int ia = 0, ib = -1, sg_last = 0;
+    const int ev = detect(P, D, m, ia, ib, sg_last);
+    double th_ev = -1.0;
+    if (ev == 1) th_ev = locate(P, D, ia, ib);
+    else if (ev == 2) th_ev = 1.0;
+    apply(P, K, D, th_ev, sg_last);
+  }
+
+  // detect(): first sign change of the scanned step.  0 = none, 1 = bracket (ia, ib) found,
+  // 2 = the end point lies exactly on the surface (prev_sign · next_sign ≤ 0).
+  ART_HD int detect(const DevParams& P, const SegStore D, const ScanMasks m, int& ia, int& ib, int& sg_last) const {
     const int M = P.M_ray;
     int cur = sgn_end;
     if (event_last)  // DiffEqBase repeat_nudge = 1/100: reference sign taken just after the event
@@ -396,7 +435,8 @@ struct Ray {
     unsigned long long valid = ((M >= 64) ? ~0ull : ((1ull << M) - 1ull)) & ~1ull;
     if (event_last)
       for (int i = 1; i < M - 1 && (double)i * P.inv_Mrm1 <= 0.01; ++i) valid &= ~(1ull << i);
-    int ia = 0, ib = -1;  // bracket indices; ia = 0 stands for the left end (θ = 0, or 0.01 after an event)
+    ia = 0;   // 0 stands for the left end (θ = 0, or 0.01 after an event)
+    ib = -1;
     unsigned long long from = valid;
     while (cur != 0) {
       const unsigned long long opp = (cur > 0 ? m.neg : m.pos) & from;
@@ -415,42 +455,41 @@ struct Ray {
       ib = i;
       break;
     }
-    const int sg_last = (int)((m.pos >> (M - 1)) & 1ull) - (int)((m.neg >> (M - 1)) & 1ull);
-    const bool zero_last = ((m.zero >> (M - 1)) & 1ull) != 0;
-    double th_ev = -1.0;
-    if (ib >= 0) {
-      // Illinois regula falsi with bisection safeguard, to floating precision; left-biased
-      double ra = (ia == 0) ? (event_last ? 0.01 : 0.0) : seg_theta(P, ia), rb = seg_theta(P, ib);
-      double fa = seg_cond(P, D, ra), fb = seg_cond(P, D, rb);
-      n_cond += 2;
-      int side = 0;
-      bool exact = false;
-      for (int it = 0; it < 200; ++it) {
-        const double tol = 4.0 * 2.220446049250313e-16 * fmax(fabs(ra), fabs(rb)) + 1e-300;
-        if (fabs(rb - ra) <= tol) break;
-        double c = (ra * fb - rb * fa) / (fb - fa);
-        const double lo = fmin(ra, rb), hi = fmax(ra, rb);
-        if (!(c > lo && c < hi) || it >= 60) c = 0.5 * (ra + rb);
-        const double fc = seg_cond(P, D, c);
-        n_cond++;
-        if (fc == 0.0) {
-          th_ev = c;
-          exact = true;
-          break;
-        }
-        if ((fc < 0.0) != (fb < 0.0)) {
-          ra = rb; fa = fb; side = 0;
-        } else {
-          if (side == 1) fa *= 0.5;
-          side = 1;
-        }
-        rb = c; fb = fc;
-      }
-      if (!exact) th_ev = fmin(ra, rb);
-    } else if (cur != 0 && zero_last) {
-      th_ev = 1.0;  // prev_sign · next_sign ≤ 0 with the end point exactly on the surface
-    }
+    sg_last = (int)((m.pos >> (M - 1)) & 1ull) - (int)((m.neg >> (M - 1)) & 1ull);
+    if (ib >= 0) return 1;
+    if (cur != 0 && ((m.zero >> (M - 1)) & 1ull)) return 2;
+    return 0;
+  }
 
+  // locate(): Illinois regula falsi with bisection safeguard, to floating precision; left-biased
+  ART_HD double locate(const DevParams& P, const SegStore D, int ia, int ib) {
+    double ra = (ia == 0) ? (event_last ? 0.01 : 0.0) : seg_theta(P, ia), rb = seg_theta(P, ib);
+    double fa = seg_cond(P, D, ra), fb = seg_cond(P, D, rb);
+    n_cond += 2;
+    int side = 0;
+    for (int it = 0; it < 200; ++it) {
+      const double tol = 4.0 * 2.220446049250313e-16 * fmax(fabs(ra), fabs(rb)) + 1e-300;
+      if (fabs(rb - ra) <= tol) break;
+      double c = (ra * fb - rb * fa) / (fb - fa);
+      const double lo = fmin(ra, rb), hi = fmax(ra, rb);
+      if (!(c > lo && c < hi) || it >= 60) c = 0.5 * (ra + rb);
+      const double fc = seg_cond(P, D, c);
+      n_cond++;
+      if (fc == 0.0) return c;
+      if ((fc < 0.0) != (fb < 0.0)) {
+        ra = rb; fa = fb; side = 0;
+      } else {
+        if (side == 1) fa *= 0.5;
+        side = 1;
+      }
+      rb = c; fb = fc;
+    }
+    return fmin(ra, rb);
+  }
+
+  // apply(): callbacks and state update at the end of an accepted step (th_ev < 0: no event)
+  template <class KS>
+  ART_HD void apply(const DevParams& P, const KS K, const SegStore D, double th_ev, int sg_last) {
     const double h = D(SEG_H);
     bool terminated = false;
     if (th_ev >= 0.0) {

@@ -134,7 +134,7 @@ ART_HD void emit_row(const DevParams& P, const EventData& E, const TreeState& T,
   const double absf = sqrt(R.kf[0] * R.kf[0] + R.kf[1] * R.kf[1] + R.kf[2] * R.kf[2]);
   const double absfX = sqrt(R.xf[0] * R.xf[0] + R.xf[1] * R.xf[1] + R.xf[2] * R.xf[2]);
   const int id = n.species == SPECIES_PHOTON ? 1 : 0;
-  const double w = n.weight * E.back_weight;  // MR.jl:686
+  const double w = n.weight;  // × samp_back_weight (MR.jl:686) is applied by patch_row once the back-trace is in
   sink_add(S.n_final + (id == 1 ? 0 : 1), 1ULL);
   const unsigned long long slot = sink_add(S.n_rows, 1ULL);
   if (slot >= S.cap) return;
@@ -166,8 +166,23 @@ ART_HD void emit_row(const DevParams& P, const EventData& E, const TreeState& T,
     row[22] = n.prob;
     row[23] = n.prob_conv;
     row[24] = n.prob_conv0;
-    row[25] = E.back_weight;
+    row[25] = 0.0;  // samp_back_weight — patch_row
     row[26] = absfX;
+    row[27] = 0.0;  // c_bck            — patch_row
+    row[28] = 0.0;  // Prob_nonAD_0     — patch_row
+  }
+}
+
+// Completes a row once its event is finished: the forward tree and the back-trace of an event run
+// concurrently, so the back-traced weight (MR.jl:630,686) and the tree's final count / info
+// (MR.jl:715, columns c and info) are filled in afterwards.
+ART_HD void patch_row(double* row, int ncols, const EventData& E, int count, int info) {
+  row[8] *= E.back_weight;
+  if (ncols > 13) {
+    row[13] *= E.back_weight;
+    row[20] = (double)count;
+    row[21] = (double)info;
+    row[25] = E.back_weight;
     row[27] = (double)E.c_bck;
     row[28] = E.prob0;
   }

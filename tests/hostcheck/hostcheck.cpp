@@ -188,11 +188,8 @@ int hc_run(const art_params* p, uint64_t seed, int64_t first_event, int64_t n_ev
       tree_forward_update(P, E, T, stack.data(), o, rec.data(), seed, ev, e, S);
     }
     tc += T.tree_len;
-    if (ncols > 13)
-      for (unsigned long long r = row0; r < nr && r < (unsigned long long)rows_cap; ++r) {
-        rows[r * ncols + 20] = T.count;
-        rows[r * ncols + 21] = T.info;
-      }
+    for (unsigned long long r = row0; r < nr && r < (unsigned long long)rows_cap; ++r)
+      patch_row(rows + r * ncols, ncols, E, T.count, T.info);
   }
   if (nr > (unsigned long long)rows_cap) return ART_ERR_CAPACITY;
   *n_rows = (int64_t)nr;
