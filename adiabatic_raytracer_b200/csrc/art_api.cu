@@ -12,6 +12,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <string>
@@ -209,6 +210,14 @@ int launch_trace_wf(art_handle* h, const QueuedRay* q, long long n, RayOut* out,
     CU(cudaMemcpyAsync(na, W.ctr + WC_ACT + cur * 2, 16, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     n_act = (long long)(na[0] + na[1]);
+    if (getenv("ART_WF_TRACE")) {
+      static double t_prev = 0;
+      struct timespec ts;
+      clock_gettime(CLOCK_MONOTONIC, &ts);
+      const double now = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+      fprintf(stderr, "[wf] iter %lld active %lld (ax %llu ph %llu) +%.2f ms\n", iter, n_act, na[0], na[1], t_prev ? now - t_prev : 0.0);
+      t_prev = now;
+    }
     if (n_act == 0) break;
     if (iter > 64LL * h->params.maxiters) return fail(h, ART_ERR_CUDA, "wavefront tracer did not terminate");
     if (n_act <= h->tail_switch) {

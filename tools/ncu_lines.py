@@ -1,10 +1,13 @@
 """Per-source-line hot spots from an ncu report: python tools/ncu_lines.py report.ncu-rep [top]"""
 import csv, subprocess, sys, io
 rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
+kfilter = sys.argv[3] if len(sys.argv) > 3 else None; kname = ""
 txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 fname = "?"; hdr = None; out = []
 for r in csv.reader(io.StringIO(txt)):
     if not r: continue
+    if r[0] in ("Kernel Name", "Function Name"): kname = r[1]; continue
+    if kfilter and kfilter not in kname: continue
     if r[0] == "File Name": fname = (r[1] or "?").split("/")[-1]; continue
     if r[0] == "Line No": hdr = r; continue
     if hdr is None or r[0] == "" or len(r) < 10: continue
