@@ -8,6 +8,7 @@
 // The host only reads two queue counters per generation.  There is no CPU compute path: every
 // entry point that computes needs a CUDA device and fails with ART_ERR_CUDA otherwise.
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 #include <dlfcn.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -15,7 +16,10 @@
 #include <time.h>
 
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/art.h"
@@ -91,34 +95,59 @@ bool nccl_load(std::string& err) {
 
 }  // namespace
 
+// Per-stream working set: one "lane" traces one sub-chunk of events at a time.  Several lanes run
+// concurrently (host thread + CUDA stream each) so that the thin tail of one sub-chunk's wavefront loop
+// overlaps the sampler and the bulk steps of the others.
+struct Lane {
+  cudaStream_t stream = nullptr;
+  DBuf samples, tstate, stacks, q0, rout, rec, ctr;
+  DBuf wf_ray, wf_kf, wf_seg, wf_need, wf_neg, wf_pend, wf_sign, wf_act[4], wf_items, wf_roots, wf_fin, wf_ctr;
+  float ms_sampler = 0, ms_weights = 0, ms_tracer = 0;
+  void release() {
+    DBuf* all[] = {&samples, &tstate, &stacks, &q0, &rout, &rec, &ctr, &wf_ray, &wf_kf, &wf_seg, &wf_need, &wf_neg,
+                   &wf_pend, &wf_sign, &wf_act[0], &wf_act[1], &wf_act[2], &wf_act[3], &wf_items, &wf_roots, &wf_fin, &wf_ctr};
+    for (DBuf* b : all) b->release();
+    if (stream) cudaStreamDestroy(stream);
+    stream = nullptr;
+  }
+};
+
 struct art_handle {
   art_params params;
   DevParams dp;
   int device = 0, n_sm = 0;
   int blocks_trace = 0, blocks_sample = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;  // main stream (fine-grained entry points, patch / histogram / collectives)
   std::string err;
-  // pipeline buffers (per chunk)
-  DBuf samples, events, tstate, stacks, q[2], rout, rec, counters, stats, fin_count, fin_info;
+  std::mutex err_mu;
+  std::vector<Lane> lanes;
+  // shared by all lanes of a pipeline call
+  DBuf events, fin_count, fin_info, gctr, stats;
   DBuf rows, keys, hist, scratch[12];
-  DBuf wf_ray, wf_kf, wf_seg, wf_need, wf_neg, wf_pend, wf_sign, wf_act[4], wf_items, wf_roots, wf_fin, wf_ctr;
-  int use_wavefront = 1;  // ART_TRACER=persistent selects the one-kernel tracer (k_trace)
-  long long tail_switch = 0;  // active rays below which the persistent tail kernel takes over
-  long long rows_cap = 0;   // rows held on device
+  DBuf q[2];                      // fine-grained art_propagate queue
+  long long rows_cap = 0;         // rows held on device
   long long n_rows_dev = 0;
   int ncols = 13;
   int n_ct = 16, n_ph = 16;
   double host_counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   void* comm = nullptr;
   int nranks = 1, rank = 0;
-  long long launches = 0;  // kernels launched since the current pipeline call began
+  std::atomic<long long> launches{0};  // kernels launched since the current pipeline call began
+  int use_wavefront = 1;          // ART_TRACER=persistent: art_propagate uses the one-kernel tracer (k_trace)
+  long long tail_switch = 0;      // active rays below which the persistent tail kernel takes over (0 = never)
+  int n_lanes = 1;                // concurrent sub-chunks (ART_LANES); measured: one big chunk beats overlapped small ones
+  long long sub_chunk = 1 << 21;  // events per sub-chunk (ART_SUBCHUNK)
 };
 
 namespace {
 
 int fail(art_handle* h, int code, const std::string& msg) {
-  if (h) h->err = msg;
-  else g_create_error = msg;
+  if (h) {
+    std::lock_guard<std::mutex> g(h->err_mu);
+    h->err = msg;
+  } else {
+    g_create_error = msg;
+  }
   return code;
 }
 
@@ -137,100 +166,103 @@ int upload(art_handle* h, DBuf& b, const void* src, size_t bytes) {
   return ART_OK;
 }
 
-// launches the tracer over a device queue; zeroes the queue head first
-int launch_trace_wf(art_handle* h, const QueuedRay* q, long long n, RayOut* out, double* rec, int rec_cap,
-                    DevStats* stats, const WfTree* tree);
-int launch_trace(art_handle* h, const QueuedRay* q, long long n, RayOut* out, double* rec, int rec_cap,
-                 unsigned long long* head, DevStats* stats) {
+int ensure_lanes(art_handle* h, int n) {
+  while ((int)h->lanes.size() < n) {
+    h->lanes.emplace_back();
+    CU(cudaStreamCreateWithFlags(&h->lanes.back().stream, cudaStreamNonBlocking));
+  }
+  return ART_OK;
+}
+
+// persistent one-kernel tracer over a device queue (kept for comparison / profiling)
+int launch_trace_persistent(art_handle* h, Lane& L, const QueuedRay* q, long long n, RayOut* out, double* rec, int rec_cap,
+                            DevStats* stats) {
   if (n <= 0) return ART_OK;
-  if (h->use_wavefront) return launch_trace_wf(h, q, n, out, rec, rec_cap, stats, nullptr);
-  CU(cudaMemsetAsync(head, 0, sizeof(unsigned long long), h->stream));
+  CU(L.ctr.ensure(64));
+  unsigned long long* head = L.ctr.as<unsigned long long>();
+  CU(cudaMemsetAsync(head, 0, sizeof(unsigned long long), L.stream));
   const int blocks = (int)std::min<long long>(h->blocks_trace, (n + TRACE_THREADS - 1) / TRACE_THREADS);
-  k_trace<<<blocks, TRACE_THREADS, TRACE_SMEM, h->stream>>>(h->dp, q, n, out, rec, rec_cap, head, stats);
+  k_trace<<<blocks, TRACE_THREADS, TRACE_SMEM, L.stream>>>(h->dp, q, n, out, rec, rec_cap, head, stats);
   h->launches++;
   CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(L.stream));
   return ART_OK;
 }
 
 // step-batched tracer over a device queue (art_wavefront.cuh).  With a tree context the loop also
 // walks every event's tree: finished rays spawn the next node of their event in place.
-int launch_trace_wf(art_handle* h, const QueuedRay* q, long long n, RayOut* out, double* rec, int rec_cap,
+int launch_trace_wf(art_handle* h, Lane& L, const QueuedRay* q, long long n, RayOut* out, double* rec, int rec_cap,
                     DevStats* stats, const WfTree* tree) {
   if (n <= 0) return ART_OK;
   const int M = h->params.interp_points_ray;
-  CU(h->wf_ray.ensure((size_t)n * sizeof(Ray)));
-  CU(h->wf_kf.ensure((size_t)n * KF_PAD * sizeof(double)));
-  CU(h->wf_seg.ensure((size_t)n * SEG_PAD * sizeof(double)));
-  CU(h->wf_need.ensure((size_t)n * 8));
-  CU(h->wf_neg.ensure((size_t)n * 8));
-  CU(h->wf_pend.ensure((size_t)n));
-  CU(h->wf_sign.ensure((size_t)n * 64));
-  for (int k = 0; k < 4; ++k) CU(h->wf_act[k].ensure((size_t)n * 4));
-  CU(h->wf_items.ensure((size_t)n * M * 4));
-  CU(h->wf_roots.ensure((size_t)n * 4));
-  CU(h->wf_fin.ensure((size_t)n * 4));
-  CU(h->wf_ctr.ensure(WC_N * 8));
+  cudaStream_t st = L.stream;
+  CU(L.wf_ray.ensure((size_t)n * sizeof(Ray)));
+  CU(L.wf_kf.ensure((size_t)n * KF_PAD * sizeof(double)));
+  CU(L.wf_seg.ensure((size_t)n * SEG_PAD * sizeof(double)));
+  CU(L.wf_need.ensure((size_t)n * 8));
+  CU(L.wf_neg.ensure((size_t)n * 8));
+  CU(L.wf_pend.ensure((size_t)n));
+  CU(L.wf_sign.ensure((size_t)n * 64));
+  for (int k = 0; k < 4; ++k) CU(L.wf_act[k].ensure((size_t)n * 4));
+  CU(L.wf_items.ensure((size_t)n * M * 4));
+  CU(L.wf_roots.ensure((size_t)n * 4));
+  CU(L.wf_fin.ensure((size_t)n * 4));
+  CU(L.wf_ctr.ensure(WC_N * 8));
   WfPool W;
-  W.ray = h->wf_ray.as<Ray>(); W.kf = h->wf_kf.as<double>(); W.seg = h->wf_seg.as<double>();
-  W.need = h->wf_need.as<unsigned long long>(); W.neg = h->wf_neg.as<unsigned long long>();
-  W.pend = h->wf_pend.as<unsigned char>(); W.sign = h->wf_sign.as<unsigned char>();
+  W.ray = L.wf_ray.as<Ray>(); W.kf = L.wf_kf.as<double>(); W.seg = L.wf_seg.as<double>();
+  W.need = L.wf_need.as<unsigned long long>(); W.neg = L.wf_neg.as<unsigned long long>();
+  W.pend = L.wf_pend.as<unsigned char>(); W.sign = L.wf_sign.as<unsigned char>();
   for (int par = 0; par < 2; ++par)
-    for (int sp = 0; sp < 2; ++sp) W.act[par][sp] = h->wf_act[par * 2 + sp].as<int>();
-  W.items = h->wf_items.as<unsigned>(); W.roots = h->wf_roots.as<int>(); W.fin = h->wf_fin.as<int>();
-  W.ctr = h->wf_ctr.as<unsigned long long>();
+    for (int sp = 0; sp < 2; ++sp) W.act[par][sp] = L.wf_act[par * 2 + sp].as<int>();
+  W.items = L.wf_items.as<unsigned>(); W.roots = L.wf_roots.as<int>(); W.fin = L.wf_fin.as<int>();
+  W.ctr = L.wf_ctr.as<unsigned long long>();
   const size_t ksmem = (size_t)42 * WF_THREADS * sizeof(double);
-  CU(cudaMemsetAsync(W.ctr, 0, WC_N * 8, h->stream));
+  CU(cudaMemsetAsync(W.ctr, 0, WC_N * 8, st));
   const int gmax = h->n_sm * 8;
   auto grid = [&](long long work, int threads) { return (int)std::max<long long>(1, std::min<long long>(gmax, (work + threads - 1) / threads)); };
-  k_wf_init<<<grid(n, WF_THREADS), WF_THREADS, 0, h->stream>>>(h->dp, q, n, W, out, rec, rec_cap, stats);
+  k_wf_init<<<grid(n, WF_THREADS), WF_THREADS, 0, st>>>(h->dp, q, n, W, out, rec, rec_cap, stats);
   h->launches++;
   CU(cudaGetLastError());
   long long n_act = n;  // upper bound of the active count, refreshed at every host check
   int cur = 0;
+  const bool trace = getenv("ART_WF_TRACE") != nullptr;
   for (long long iter = 0;;) {
     const int burst = n_act > 65536 ? 4 : (n_act > 2048 ? 8 : 24);  // steps between host checks
     for (int b = 0; b < burst; ++b, ++iter) {
       const int next = 1 - cur;
       const int g1 = grid(n_act, WF_THREADS);
-      k_wf_reset<<<1, 32, 0, h->stream>>>(W, next);
-      k_wf_stages<SPECIES_AXION><<<g1, WF_THREADS, ksmem, h->stream>>>(h->dp, W, cur);
-      k_wf_stages<SPECIES_PHOTON><<<g1, WF_THREADS, ksmem, h->stream>>>(h->dp, W, cur);
-      k_wf_scan<<<grid(n_act * 24, 256), 256, 0, h->stream>>>(h->dp, W);
-      k_wf_detect<<<g1, WF_THREADS, 0, h->stream>>>(h->dp, W, cur, out, stats);
-      k_wf_root<<<grid(n_act / 8 + 1, WF_THREADS), WF_THREADS, 0, h->stream>>>(h->dp, W, next, out, stats);
+      k_wf_reset<<<1, 32, 0, st>>>(W, next);
+      k_wf_stages<SPECIES_AXION><<<g1, WF_THREADS, ksmem, st>>>(h->dp, W, cur);
+      k_wf_stages<SPECIES_PHOTON><<<g1, WF_THREADS, ksmem, st>>>(h->dp, W, cur);
+      k_wf_scan<<<grid(n_act * 24, 256), 256, 0, st>>>(h->dp, W);
+      k_wf_detect<<<g1, WF_THREADS, 0, st>>>(h->dp, W, cur, out, stats);
+      k_wf_root<<<grid(n_act / 8 + 1, WF_THREADS), WF_THREADS, 0, st>>>(h->dp, W, next, out, stats);
       h->launches += 6;
       if (tree) {
-        k_wf_tree<<<grid(n_act / 4 + 1, WF_THREADS), WF_THREADS, 0, h->stream>>>(h->dp, W, *tree, next, out, rec, rec_cap, stats);
+        k_wf_tree<<<grid(n_act / 4 + 1, WF_THREADS), WF_THREADS, 0, st>>>(h->dp, W, *tree, next, out, rec, rec_cap, stats);
         h->launches++;
       }
       cur = next;
     }
     CU(cudaGetLastError());
     unsigned long long na[2] = {0, 0};
-    CU(cudaMemcpyAsync(na, W.ctr + WC_ACT + cur * 2, 16, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpyAsync(na, W.ctr + WC_ACT + cur * 2, 16, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     n_act = (long long)(na[0] + na[1]);
-    if (getenv("ART_WF_TRACE")) {
-      static double t_prev = 0;
-      struct timespec ts;
-      clock_gettime(CLOCK_MONOTONIC, &ts);
-      const double now = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
-      fprintf(stderr, "[wf] iter %lld active %lld (ax %llu ph %llu) +%.2f ms\n", iter, n_act, na[0], na[1], t_prev ? now - t_prev : 0.0);
-      t_prev = now;
-    }
+    if (trace) fprintf(stderr, "[wf %p] iter %lld active %lld (ax %llu ph %llu)\n", (void*)&L, iter, n_act, na[0], na[1]);
     if (n_act == 0) break;
     if (iter > 64LL * h->params.maxiters) return fail(h, ART_ERR_CUDA, "wavefront tracer did not terminate");
     if (n_act <= h->tail_switch) {
       // latency-bound tail: one persistent kernel finishes the remaining rays and their trees
       WfTree none;
       memset(&none, 0, sizeof(none));
-      k_wf_reset<<<1, 32, 0, h->stream>>>(W, 1 - cur);  // zeroes the item counter = the tail's queue head
+      k_wf_reset<<<1, 32, 0, st>>>(W, 1 - cur);  // zeroes the item counter = the tail's queue head
       const int blocks = grid(n_act, WF_THREADS);
-      k_wf_tail<<<std::min(blocks, h->n_sm * 2), WF_THREADS, ksmem, h->stream>>>(h->dp, W, tree ? *tree : none, cur, out, rec,
-                                                                               rec_cap, stats);
+      k_wf_tail<<<std::min(blocks, h->n_sm * 2), WF_THREADS, ksmem, st>>>(h->dp, W, tree ? *tree : none, cur, out, rec, rec_cap,
+                                                                          stats);
       h->launches += 2;
       CU(cudaGetLastError());
-      CU(cudaStreamSynchronize(h->stream));
+      CU(cudaStreamSynchronize(st));
       break;
     }
   }
@@ -301,6 +333,8 @@ int art_create(const art_params* p, int device_id, art_handle** out) {
   h->blocks_trace = h->n_sm * std::max(occ, 1);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sample_events, SAMPLE_THREADS, 0);
   h->blocks_sample = h->n_sm * std::max(occ, 1);
+  if (const char* t = getenv("ART_LANES")) h->n_lanes = std::max(1, std::min(16, atoi(t)));
+  if (const char* t = getenv("ART_SUBCHUNK")) h->sub_chunk = std::max(1024LL, atoll(t));
   ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (ce != cudaSuccess) {
     std::string m = cudaGetErrorString(ce);
@@ -315,11 +349,8 @@ void art_destroy(art_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-  DBuf* wf[] = {&h->wf_ray, &h->wf_kf, &h->wf_seg, &h->wf_need, &h->wf_neg, &h->wf_pend, &h->wf_sign, &h->wf_act[0],
-                &h->wf_act[1], &h->wf_act[2], &h->wf_act[3], &h->wf_items, &h->wf_roots, &h->wf_fin, &h->wf_ctr};
-  for (DBuf* b : wf) b->release();
-  DBuf* all[] = {&h->samples, &h->events, &h->tstate, &h->stacks, &h->q[0], &h->q[1], &h->rout, &h->rec,
-                 &h->counters, &h->stats, &h->fin_count, &h->fin_info, &h->rows, &h->keys, &h->hist};
+  for (Lane& L : h->lanes) L.release();
+  DBuf* all[] = {&h->events, &h->fin_count, &h->fin_info, &h->gctr, &h->stats, &h->rows, &h->keys, &h->hist, &h->q[0], &h->q[1]};
   for (DBuf* b : all) b->release();
   for (DBuf& b : h->scratch) b.release();
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -355,15 +386,17 @@ int art_sample(art_handle* h, uint64_t seed, int64_t first_event, int64_t n, dou
   if (!h || n < 0) return ART_ERR_ARG;
   CU(cudaSetDevice(h->device));
   if (n == 0) return ART_OK;
-  CU(h->samples.ensure(n * sizeof(EventSample)));
-  CU(h->counters.ensure(64));
-  CU(cudaMemsetAsync(h->counters.p, 0, 64, h->stream));
+  if (int rc = ensure_lanes(h, 1)) return rc;
+  Lane& L = h->lanes[0];
+  CU(L.samples.ensure(n * sizeof(EventSample)));
+  CU(L.ctr.ensure(64));
+  CU(cudaMemsetAsync(L.ctr.p, 0, 64, h->stream));
   const int blocks = (int)std::min<long long>(h->blocks_sample, (n + SAMPLE_THREADS - 1) / SAMPLE_THREADS);
-  k_sample_events<<<blocks, SAMPLE_THREADS, 0, h->stream>>>(h->dp, seed, first_event, n, h->samples.as<EventSample>(),
-                                                            h->counters.as<unsigned long long>(), nullptr);
+  k_sample_events<<<blocks, SAMPLE_THREADS, 0, h->stream>>>(h->dp, seed, first_event, n, L.samples.as<EventSample>(),
+                                                            L.ctr.as<unsigned long long>(), nullptr, nullptr);
   CU(cudaGetLastError());
   std::vector<EventSample> host((size_t)n);
-  CU(cudaMemcpyAsync(host.data(), h->samples.p, n * sizeof(EventSample), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(host.data(), L.samples.p, n * sizeof(EventSample), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   for (int64_t i = 0; i < n; ++i) {
     for (int c = 0; c < 3; ++c) {
@@ -447,17 +480,20 @@ int art_propagate(art_handle* h, int64_t n, const int32_t* species, const double
     r.in.species = species[i] == ART_SPECIES_PHOTON ? SPECIES_PHOTON : SPECIES_AXION;
     r.owner = (int)i; r.pad_ = 0;
   }
-  CU(h->counters.ensure(64));
+  if (int rc = ensure_lanes(h, 1)) return rc;
+  Lane& L = h->lanes[0];
   if (upload(h, h->q[0], qs.data(), n * sizeof(QueuedRay))) return ART_ERR_CUDA;
-  CU(h->rout.ensure(n * sizeof(RayOut)));
-  CU(h->rec.ensure((size_t)n * cross_cap * 8 * sizeof(double)));
-  CU(cudaMemsetAsync(h->rec.p, 0, (size_t)n * cross_cap * 8 * sizeof(double), h->stream));
-  if (int rc = launch_trace(h, h->q[0].as<QueuedRay>(), n, h->rout.as<RayOut>(), h->rec.as<double>(), cross_cap,
-                            h->counters.as<unsigned long long>(), nullptr))
+  CU(L.rout.ensure(n * sizeof(RayOut)));
+  CU(L.rec.ensure((size_t)n * cross_cap * 8 * sizeof(double)));
+  CU(cudaMemsetAsync(L.rec.p, 0, (size_t)n * cross_cap * 8 * sizeof(double), h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (int rc = h->use_wavefront
+                   ? launch_trace_wf(h, L, h->q[0].as<QueuedRay>(), n, L.rout.as<RayOut>(), L.rec.as<double>(), cross_cap, nullptr, nullptr)
+                   : launch_trace_persistent(h, L, h->q[0].as<QueuedRay>(), n, L.rout.as<RayOut>(), L.rec.as<double>(), cross_cap, nullptr))
     return rc;
   std::vector<RayOut> ro((size_t)n);
-  CU(cudaMemcpyAsync(ro.data(), h->rout.p, n * sizeof(RayOut), cudaMemcpyDeviceToHost, h->stream));
-  CU(cudaMemcpyAsync(cross_rec, h->rec.p, (size_t)n * cross_cap * 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(ro.data(), L.rout.p, n * sizeof(RayOut), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(cross_rec, L.rec.p, (size_t)n * cross_cap * 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   for (int64_t i = 0; i < n; ++i) {
     const RayOut& o = ro[(size_t)i];
@@ -514,31 +550,79 @@ int art_hist_get(art_handle* h, double* out, int64_t cap) {
   return ART_OK;
 }
 
+// One sub-chunk of events on one lane: sampler → weights → fused wavefront loop (back-traces + trees).
+static int run_subchunk(art_handle* h, Lane& L, uint64_t seed, int64_t first_event, long long base, long long n,
+                        const RowSink& sink, unsigned long long* gctr, DevStats* dstats) {
+  CU(cudaSetDevice(h->device));
+  const DevParams& P = h->dp;
+  const int cap = h->params.cross_cap;
+  const int stack_stride = h->params.max_nodes + 4;
+  cudaStream_t st = L.stream;
+  CU(L.samples.ensure(n * sizeof(EventSample)));
+  CU(L.tstate.ensure(n * sizeof(TreeState)));
+  CU(L.stacks.ensure((size_t)n * stack_stride * sizeof(TreeNode)));
+  CU(L.q0.ensure(2 * n * sizeof(QueuedRay)));
+  CU(L.rout.ensure(2 * n * sizeof(RayOut)));
+  CU(L.rec.ensure((size_t)2 * n * cap * 8 * sizeof(double)));
+  CU(L.ctr.ensure(64));
+  cudaEvent_t ev[4];
+  for (auto& e : ev) CU(cudaEventCreate(&e));
+  EventData* events = h->events.as<EventData>() + base;
+  // K1 sampler
+  CU(cudaEventRecord(ev[0], st));
+  CU(cudaMemsetAsync(L.ctr.p, 0, 64, st));
+  {
+    const int blocks = (int)std::min<long long>(h->blocks_sample, (n + SAMPLE_THREADS - 1) / SAMPLE_THREADS);
+    k_sample_events<<<blocks, SAMPLE_THREADS, 0, st>>>(P, seed, first_event + base, n, L.samples.as<EventSample>(),
+                                                       L.ctr.as<unsigned long long>(), dstats, gctr + 0);
+    h->launches++;
+    CU(cudaGetLastError());
+  }
+  CU(cudaEventRecord(ev[1], st));
+  // K2 weights: EventData, first tree node, and the 2n rays of the loop (n back-traces + n forward photons)
+  k_weights_events<<<nblk(n, 128), 128, 0, st>>>(P, n, L.samples.as<EventSample>(), events, L.tstate.as<TreeState>(),
+                                                 L.q0.as<QueuedRay>());
+  h->launches++;
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(ev[2], st));
+  // K3+K4 fused wavefront loop
+  WfTree T;
+  T.ev = events; T.ts = L.tstate.as<TreeState>(); T.stacks = L.stacks.as<TreeNode>();
+  T.stack_stride = stack_stride; T.seed = seed; T.first_event = first_event; T.chunk_base = base; T.n_events = n;
+  T.sink = sink; T.tot_count = gctr + 1; T.fin_count = h->fin_count.as<int>() + base; T.fin_info = h->fin_info.as<int>() + base;
+  if (int rc = launch_trace_wf(h, L, L.q0.as<QueuedRay>(), 2 * n, L.rout.as<RayOut>(), L.rec.as<double>(), cap, dstats, &T))
+    return rc;
+  CU(cudaEventRecord(ev[3], st));
+  CU(cudaStreamSynchronize(st));
+  float t01 = 0, t12 = 0, t23 = 0;
+  cudaEventElapsedTime(&t01, ev[0], ev[1]);
+  cudaEventElapsedTime(&t12, ev[1], ev[2]);
+  cudaEventElapsedTime(&t23, ev[2], ev[3]);
+  L.ms_sampler += t01; L.ms_weights += t12; L.ms_tracer += t23;
+  for (auto& e : ev) cudaEventDestroy(e);
+  return ART_OK;
+}
+
 int art_run_device(art_handle* h, uint64_t seed, int64_t first_event, int64_t n_events, int64_t* n_rows_out,
                    int64_t* f_inx_out, int64_t* tot_count_out, art_stats* st_out) {
   if (!h || n_events < 0) return ART_ERR_ARG;
   CU(cudaSetDevice(h->device));
-  const DevParams& P = h->dp;
   const int ncols = h->ncols;
-  const int cap = h->params.cross_cap;
-  const int stack_stride = h->params.max_nodes + 4;
-  const long long CH = std::min<long long>(std::max<long long>(n_events, 1), 1LL << 20);
   if (!h->hist.p) {
     int rc = art_hist_reset(h);
     if (rc) return rc;
   }
-  // buffers (per chunk of CH events; the first launch propagates 2 rays per event)
-  CU(h->samples.ensure(CH * sizeof(EventSample)));
-  CU(h->events.ensure(CH * sizeof(EventData)));
-  CU(h->tstate.ensure(CH * sizeof(TreeState)));
-  CU(h->stacks.ensure((size_t)CH * stack_stride * sizeof(TreeNode)));
-  CU(h->q[0].ensure(2 * CH * sizeof(QueuedRay)));
-  CU(h->q[1].ensure(CH * sizeof(QueuedRay)));
-  CU(h->rout.ensure(2 * CH * sizeof(RayOut)));
-  CU(h->rec.ensure((size_t)2 * CH * cap * 8 * sizeof(double)));
-  CU(h->fin_count.ensure(CH * sizeof(int)));
-  CU(h->fin_info.ensure(CH * sizeof(int)));
-  CU(h->counters.ensure(16 * sizeof(unsigned long long)));
+  const long long ne = std::max<long long>(n_events, 1);
+  // sub-chunks: at most n_lanes in flight; small runs use a single one
+  long long sub = std::min<long long>(h->sub_chunk, ne);
+  if (ne > sub && ne < sub * h->n_lanes) sub = (ne + h->n_lanes - 1) / h->n_lanes;
+  const long long n_sub = (ne + sub - 1) / sub;
+  const int n_workers = (int)std::min<long long>(h->n_lanes, n_sub);
+  if (int rc = ensure_lanes(h, n_workers)) return rc;
+  CU(h->events.ensure(ne * sizeof(EventData)));
+  CU(h->fin_count.ensure(ne * sizeof(int)));
+  CU(h->fin_info.ensure(ne * sizeof(int)));
+  CU(h->gctr.ensure(16 * sizeof(unsigned long long)));
   CU(h->stats.ensure(sizeof(DevStats)));
   // rows: the reference appends without bound; start with 3 rows/event and report overflow
   const long long want_rows = n_events * 3 + 1024;
@@ -549,152 +633,76 @@ int art_run_device(art_handle* h, uint64_t seed, int64_t first_event, int64_t n_
   }
   h->n_rows_dev = 0;
   h->launches = 0;
-  unsigned long long* ctr = h->counters.as<unsigned long long>();
-  // ctr layout: [0] sampler head, [1] trace head, [3] tot_count, [4] next-queue count,
-  //             [6] n_rows, [7,8] n_final (photon, axion)
-  CU(cudaMemsetAsync(ctr, 0, 16 * sizeof(unsigned long long), h->stream));
+  unsigned long long* gctr = h->gctr.as<unsigned long long>();
+  // gctr layout: [0] failed sampler attempts, [1] tot_count, [6] n_rows, [7,8] n_final (photon, axion)
+  CU(cudaMemsetAsync(gctr, 0, 16 * sizeof(unsigned long long), h->stream));
   CU(cudaMemsetAsync(h->stats.p, 0, sizeof(DevStats), h->stream));
   DevStats* dstats = h->stats.as<DevStats>();
-  RowSink sink{h->rows.as<double>(), h->keys.as<long long>(), ctr + 6, (unsigned long long)h->rows_cap, ncols, ctr + 7};
-  RayOut* rout = h->rout.as<RayOut>();
-  double* rec = h->rec.as<double>();
-
-  cudaEvent_t ev[6];
-  for (auto& e : ev) CU(cudaEventCreate(&e));
-  std::vector<cudaEvent_t> gen_ev;  // (start, after trace, after tree) per generation
-  float ms_s = 0, ms_w = 0, ms_t = 0, ms_tree = 0, ms_tot = 0;
-  long long failed_total = 0;
-  CU(cudaEventRecord(ev[4], h->stream));
-
-  for (long long base = 0; base < n_events; base += CH) {
-    const long long n = std::min(CH, n_events - base);
-    unsigned long long rows_before = 0;
-    CU(cudaMemcpyAsync(&rows_before, ctr + 6, 8, cudaMemcpyDeviceToHost, h->stream));
-    // K1 sampler
-    CU(cudaEventRecord(ev[0], h->stream));
-    CU(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), h->stream));
-    {
-      const int blocks = (int)std::min<long long>(h->blocks_sample, (n + SAMPLE_THREADS - 1) / SAMPLE_THREADS);
-      k_sample_events<<<blocks, SAMPLE_THREADS, 0, h->stream>>>(P, seed, first_event + base, n, h->samples.as<EventSample>(),
-                                                                ctr, dstats);
-      h->launches++;
-      CU(cudaGetLastError());
-    }
-    CU(cudaEventRecord(ev[1], h->stream));
-    // K2 weights: EventData, first tree node, and the 2n rays of the first launch
-    k_weights_events<<<nblk(n, 128), 128, 0, h->stream>>>(P, n, h->samples.as<EventSample>(), h->events.as<EventData>(),
-                                                          h->tstate.as<TreeState>(), h->q[0].as<QueuedRay>());
-    h->launches++;
-    CU(cudaGetLastError());
-    CU(cudaEventRecord(ev[2], h->stream));
-    if (h->use_wavefront) {
-      // K3+K4 fused: n back-traced axions (slots 0..n) + the n forward trees (slots n..2n) in ONE loop
-      WfTree T;
-      T.ev = h->events.as<EventData>(); T.ts = h->tstate.as<TreeState>(); T.stacks = h->stacks.as<TreeNode>();
-      T.stack_stride = stack_stride; T.seed = seed; T.first_event = first_event; T.chunk_base = base; T.n_events = n;
-      T.sink = sink; T.tot_count = ctr + 3; T.fin_count = h->fin_count.as<int>(); T.fin_info = h->fin_info.as<int>();
-      if (int rc = launch_trace_wf(h, h->q[0].as<QueuedRay>(), 2 * n, rout, rec, cap, dstats, &T)) return rc;
-      CU(cudaEventRecord(ev[3], h->stream));
-    } else {
-    // K3 first launch: n back-traced axions (slots 0..n) + n first forward photons (slots n..2n)
-    if (int rc = launch_trace(h, h->q[0].as<QueuedRay>(), 2 * n, rout, rec, cap, ctr + 1, dstats)) return rc;
-    CU(cudaEventRecord(ev[3], h->stream));
-    // K4 back-finish (samp_back_weight), then the tree update of the first forward photons
-    k_back_finish<<<nblk(n, 128), 128, 0, h->stream>>>(P, n, h->events.as<EventData>(), rout, rec, cap,
-                                                       h->tstate.as<TreeState>());
-    h->launches++;
-    CU(cudaGetLastError());
-    int cur = 0;  // queue holding the rays that were just propagated
-    long long q_off = n, n_rays = n;  // forward rays of the first launch start at slot n
-    for (;;) {
-      QueuedRay* qc = h->q[cur].as<QueuedRay>() + q_off;
-      QueuedRay* qn = h->q[1 - cur].as<QueuedRay>();
-      CU(cudaMemsetAsync(ctr + 4, 0, sizeof(unsigned long long), h->stream));
-      k_tree_update<<<nblk(n_rays, 128), 128, 0, h->stream>>>(
-          P, n_rays, qc, rout + q_off, rec + (size_t)q_off * cap * 8, cap, h->events.as<EventData>(),
-          h->tstate.as<TreeState>(), h->stacks.as<TreeNode>(), stack_stride, seed, first_event, base, sink, qn,
-          ctr + 4, ctr + 3, h->fin_count.as<int>(), h->fin_info.as<int>());
-      h->launches++;
-      CU(cudaGetLastError());
-      cudaEvent_t e_tree;
-      CU(cudaEventCreate(&e_tree));
-      CU(cudaEventRecord(e_tree, h->stream));
-      gen_ev.push_back(e_tree);
-      unsigned long long nxt = 0;
-      CU(cudaMemcpyAsync(&nxt, ctr + 4, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
-      CU(cudaStreamSynchronize(h->stream));
-      n_rays = (long long)nxt;
-      if (n_rays == 0) break;
-      cur = 1 - cur;
-      q_off = 0;
-      if (int rc = launch_trace(h, h->q[cur].as<QueuedRay>(), n_rays, rout, rec, cap, ctr + 1, dstats)) return rc;
-      cudaEvent_t e_tr;
-      CU(cudaEventCreate(&e_tr));
-      CU(cudaEventRecord(e_tr, h->stream));
-      gen_ev.push_back(e_tr);
-    }
-    }
-    // failed sampler attempts of this chunk (→ f_inx)
-    {
-      std::vector<EventSample> hs((size_t)n);
-      CU(cudaMemcpyAsync(hs.data(), h->samples.p, n * sizeof(EventSample), cudaMemcpyDeviceToHost, h->stream));
-      CU(cudaStreamSynchronize(h->stream));
-      for (auto& s : hs) failed_total += s.n_failed;
-    }
-    unsigned long long rows_after = 0;
-    CU(cudaMemcpy(&rows_after, ctr + 6, 8, cudaMemcpyDeviceToHost));
-    if ((long long)rows_after > h->rows_cap) {
-      for (auto& e : ev) cudaEventDestroy(e);
-      for (auto& e : gen_ev) cudaEventDestroy(e);
-      return fail(h, ART_ERR_CAPACITY, "device row buffer overflow (more than 3 rows per event on average)");
-    }
-    const long long nr = (long long)rows_after - (long long)rows_before;
-    if (nr > 0) {
-      k_patch_rows<<<nblk(nr, 256), 256, 0, h->stream>>>((long long)rows_after, h->rows.as<double>(), h->keys.as<long long>(),
-                                                         ncols, base, h->events.as<EventData>(), h->fin_count.as<int>(),
-                                                         h->fin_info.as<int>(), (long long)rows_before);
-      h->launches++;
-      CU(cudaGetLastError());
-      const int nb = 2 * h->n_ct * h->n_ph * 4;
-      const int use_smem = nb * (int)sizeof(double) <= 48 * 1024;
-      const int blocks = (int)std::min<long long>(h->n_sm * 4, (nr + 255) / 256);
-      k_hist<<<blocks, 256, use_smem ? nb * sizeof(double) : 0, h->stream>>>((long long)rows_before, (long long)rows_after,
-                                                                             h->rows.as<double>(), ncols, h->n_ct, h->n_ph,
-                                                                             h->hist.as<double>(), use_smem);
-      h->launches++;
-      CU(cudaGetLastError());
-    }
-    CU(cudaStreamSynchronize(h->stream));
-    float t01, t12, t23;
-    cudaEventElapsedTime(&t01, ev[0], ev[1]);
-    cudaEventElapsedTime(&t12, ev[1], ev[2]);
-    cudaEventElapsedTime(&t23, ev[2], ev[3]);
-    ms_s += t01; ms_w += t12; ms_t += t23;
-    // generation events alternate: tree, trace, tree, trace, …, tree  (first "tree" follows ev[3])
-    cudaEvent_t prev = ev[3];
-    for (size_t k = 0; k < gen_ev.size(); ++k) {
-      float x = 0;
-      cudaEventElapsedTime(&x, prev, gen_ev[k]);
-      if (k % 2 == 0) ms_tree += x; else ms_t += x;
-      prev = gen_ev[k];
-    }
-    for (auto& e : gen_ev) cudaEventDestroy(e);
-    gen_ev.clear();
-  }
-  CU(cudaEventRecord(ev[5], h->stream));
+  RowSink sink{h->rows.as<double>(), h->keys.as<long long>(), gctr + 6, (unsigned long long)h->rows_cap, ncols, gctr + 7};
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  CU(cudaEventRecord(e0, h->stream));
   CU(cudaStreamSynchronize(h->stream));
-  cudaEventElapsedTime(&ms_tot, ev[4], ev[5]);
-  for (auto& e : ev) cudaEventDestroy(e);
+  for (Lane& L : h->lanes) L.ms_sampler = L.ms_weights = L.ms_tracer = 0;
 
+  if (n_events > 0) {
+    std::atomic<long long> next_sub{0};
+    std::vector<int> rcs((size_t)n_workers, ART_OK);
+    auto worker = [&](int w) {
+      for (;;) {
+        const long long k = next_sub.fetch_add(1);
+        if (k >= n_sub) break;
+        const long long base = k * sub, n = std::min(sub, n_events - base);
+        const int rc = run_subchunk(h, h->lanes[(size_t)w], seed, first_event, base, n, sink, gctr, dstats);
+        if (rc) {
+          rcs[(size_t)w] = rc;
+          break;
+        }
+      }
+    };
+    if (n_workers == 1) {
+      worker(0);
+    } else {
+      std::vector<std::thread> th;
+      for (int w = 0; w < n_workers; ++w) th.emplace_back(worker, w);
+      for (auto& t : th) t.join();
+    }
+    for (int rc : rcs)
+      if (rc) return rc;
+  }
+  // all lanes are synchronised (run_subchunk ends with a stream sync): finish on the main stream
   unsigned long long hc[16];
+  CU(cudaMemcpy(hc, gctr, sizeof(hc), cudaMemcpyDeviceToHost));
+  if ((long long)hc[6] > h->rows_cap)
+    return fail(h, ART_ERR_CAPACITY, "device row buffer overflow (more than 3 rows per event on average)");
+  const long long nr = (long long)hc[6];
+  if (nr > 0) {
+    k_patch_rows<<<nblk(nr, 256), 256, 0, h->stream>>>(nr, h->rows.as<double>(), h->keys.as<long long>(), ncols, 0,
+                                                       h->events.as<EventData>(), h->fin_count.as<int>(),
+                                                       h->fin_info.as<int>(), 0);
+    const int nb = 2 * h->n_ct * h->n_ph * 4;
+    const int use_smem = nb * (int)sizeof(double) <= 48 * 1024;
+    const int blocks = (int)std::min<long long>(h->n_sm * 4, (nr + 255) / 256);
+    k_hist<<<blocks, 256, use_smem ? nb * sizeof(double) : 0, h->stream>>>(0, nr, h->rows.as<double>(), ncols, h->n_ct, h->n_ph,
+                                                                           h->hist.as<double>(), use_smem);
+    h->launches += 2;
+    CU(cudaGetLastError());
+  }
+  CU(cudaEventRecord(e1, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  float ms_tot = 0;
+  cudaEventElapsedTime(&ms_tot, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+
   DevStats ds;
-  CU(cudaMemcpy(hc, ctr, sizeof(hc), cudaMemcpyDeviceToHost));
   CU(cudaMemcpy(&ds, dstats, sizeof(ds), cudaMemcpyDeviceToHost));
-  h->n_rows_dev = (long long)hc[6];
-  const long long f_inx = failed_total + (long long)hc[7];
+  h->n_rows_dev = nr;
+  const long long f_inx = (long long)hc[0] + (long long)hc[7];
   if (n_rows_out) *n_rows_out = h->n_rows_dev;
   if (f_inx_out) *f_inx_out = f_inx;
-  if (tot_count_out) *tot_count_out = (long long)hc[3];
+  if (tot_count_out) *tot_count_out = (long long)hc[1];
   art_stats S;
   memset(&S, 0, sizeof(S));
   S.n_events = n_events; S.n_attempts = (long long)ds.n_attempts; S.n_sampler_cond = (long long)ds.n_sampler_cond;
@@ -702,8 +710,11 @@ int art_run_device(art_handle* h, uint64_t seed, int64_t first_event, int64_t n_
   S.n_rej = (long long)ds.n_rej; S.n_rhs = (long long)ds.n_rhs; S.n_cond = (long long)ds.n_cond;
   S.n_final_photon = (long long)hc[7]; S.n_final_axion = (long long)hc[8];
   for (int k = 0; k < 5; ++k) S.n_status[k] = (long long)ds.n_status[k];
-  S.ms_sampler = ms_s; S.ms_weights = ms_w; S.ms_tracer = ms_t; S.ms_tree = ms_tree; S.ms_total = ms_tot;
-  S.n_launches = h->launches;
+  // stage times are summed over lanes (lanes overlap, so they can add up to more than ms_total)
+  for (Lane& L : h->lanes) { S.ms_sampler += L.ms_sampler; S.ms_weights += L.ms_weights; S.ms_tracer += L.ms_tracer; }
+  S.ms_tree = 0.0;
+  S.ms_total = ms_tot;
+  S.n_launches = h->launches.load();
   if (st_out) *st_out = S;
   // trailing histogram counters: [f_inx, n_rows, n_events, n_acc, n_rej, n_rhs, n_cond, n_rays]
   h->host_counters[0] += (double)f_inx; h->host_counters[1] += (double)h->n_rows_dev; h->host_counters[2] += (double)n_events;
@@ -720,16 +731,24 @@ int art_fetch_rows(art_handle* h, double* rows, int64_t rows_cap, int64_t* n_row
   if (n > rows_cap) return fail(h, ART_ERR_CAPACITY, "rows_cap too small");
   if (n == 0) return ART_OK;
   const int ncols = h->ncols;
-  std::vector<double> tmp((size_t)n * ncols);
-  std::vector<long long> keys((size_t)n);
-  CU(cudaMemcpy(tmp.data(), h->rows.p, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
-  CU(cudaMemcpy(keys.data(), h->keys.p, keys.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-  // order rows as the reference writes them: by event, then by position in the tree
-  std::vector<long long> order((size_t)n);
-  for (long long i = 0; i < n; ++i) order[(size_t)i] = i;
-  std::sort(order.begin(), order.end(), [&](long long a, long long b) { return keys[(size_t)a] < keys[(size_t)b]; });
-  for (long long i = 0; i < n; ++i)
-    memcpy(rows + (size_t)i * ncols, tmp.data() + (size_t)order[(size_t)i] * ncols, (size_t)ncols * sizeof(double));
+  // order rows as the reference writes them — by event, then by position in the tree — on the device:
+  // radix sort of (key, row index) pairs (CUB, a utility outside the hot path), gather, one copy out
+  DBuf* s = h->scratch;
+  CU(s[0].ensure((size_t)n * 8));            // keys out
+  CU(s[1].ensure((size_t)n * 4));            // index in
+  CU(s[2].ensure((size_t)n * 4));            // index out
+  CU(s[3].ensure((size_t)n * ncols * 8));    // ordered rows
+  k_iota<<<nblk(n, 256), 256, 0, h->stream>>>(s[1].as<int>(), n);
+  size_t tmp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->keys.as<long long>(), s[0].as<long long>(), s[1].as<int>(),
+                                  s[2].as<int>(), (int)n, 0, 64, h->stream);
+  CU(s[4].ensure(tmp_bytes));
+  CU(cub::DeviceRadixSort::SortPairs(s[4].p, tmp_bytes, h->keys.as<long long>(), s[0].as<long long>(), s[1].as<int>(),
+                                     s[2].as<int>(), (int)n, 0, 64, h->stream));
+  k_gather_rows<<<nblk(n * ncols, 256), 256, 0, h->stream>>>(h->rows.as<double>(), s[2].as<int>(), n, ncols, s[3].as<double>());
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(rows, s[3].p, (size_t)n * ncols * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
   return ART_OK;
 }
 

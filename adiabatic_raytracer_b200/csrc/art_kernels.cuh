@@ -204,13 +204,14 @@ struct EventSample {
 
 __global__ void __launch_bounds__(SAMPLE_THREADS)
 k_sample_events(const __grid_constant__ DevParams P, unsigned long long seed, long long first_event, long long n,
-                EventSample* __restrict__ out, unsigned long long* head, DevStats* stats) {
+                EventSample* __restrict__ out, unsigned long long* head, DevStats* stats,
+                unsigned long long* n_failed_total) {
   Sampler S;
   bool have = false, exhausted = false;
   long long idx = -1;
   unsigned attempt = 0;
   double u_idx = 0.0;
-  unsigned long long c_att = 0, c_cond = 0;
+  unsigned long long c_att = 0, c_cond = 0, c_fail = 0;
   for (;;) {
     const long long got = warp_pop(head, !have && !exhausted);
     if (!have && !exhausted) {
@@ -239,6 +240,7 @@ k_sample_events(const __grid_constant__ DevParams P, unsigned long long seed, lo
           for (int c = 0; c < 3; ++c) { e.x[c] = R.x[c]; e.vloc[c] = R.vloc[c]; e.vinf[c] = R.vinf[c]; }
           e.n_cross = R.n_cross;
           e.n_failed = (int)attempt;
+          c_fail += attempt;
           out[idx] = e;
           have = false;
         } else {  // MainRunner.jl:463-494: try again (f_inx counts the failure)
@@ -253,9 +255,13 @@ k_sample_events(const __grid_constant__ DevParams P, unsigned long long seed, lo
   }
   c_att = warp_sum(c_att);
   c_cond = warp_sum(c_cond);
-  if ((threadIdx.x & 31) == 0 && stats) {
-    atomicAdd(&stats->n_attempts, c_att);
-    atomicAdd(&stats->n_sampler_cond, c_cond);
+  c_fail = warp_sum(c_fail);
+  if ((threadIdx.x & 31) == 0) {
+    if (stats) {
+      atomicAdd(&stats->n_attempts, c_att);
+      atomicAdd(&stats->n_sampler_cond, c_cond);
+    }
+    if (n_failed_total && c_fail) atomicAdd(n_failed_total, c_fail);
   }
 }
 
@@ -407,6 +413,20 @@ __global__ void k_patch_rows(long long n_rows, double* rows, const long long* ke
   if (i >= n_rows) return;
   const long long e = (keys[i] >> 8) - chunk_base;
   patch_row(rows + i * ncols, ncols, ev[e], fin_count[e], fin_info[e]);
+}
+
+__global__ void k_iota(int* idx, long long n) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) idx[i] = (int)i;
+}
+
+__global__ void k_gather_rows(const double* __restrict__ rows, const int* __restrict__ order, long long n, int ncols,
+                              double* __restrict__ out) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= n * ncols) return;
+  const long long r = t / ncols;
+  const int c = (int)(t - r * ncols);
+  out[t] = rows[(long long)order[r] * ncols + c];
 }
 
 // ------------------------------------------------------------------------------------------

@@ -71,6 +71,12 @@ struct KStore {
   int stride;
   ART_HD double& operator()(int j, int i) const { return base[(j * 6 + i) * stride]; }
 };
+// same with the stride known at compile time (device: STRIDE = CTA size ⇒ addresses fold into immediates)
+template <int STRIDE>
+struct KStoreT {
+  double* base;
+  ART_HD double& operator()(int j, int i) const { return base[(j * 6 + i) * STRIDE]; }
+};
 
 // Dense-output segment of an accepted step, published (device: in shared memory, one column
 // per thread) so that ANY lane of the warp can evaluate the crossing condition on it.
@@ -80,6 +86,10 @@ struct SegStore {
   double* base;
   int stride;
   ART_HD double& operator()(int f) const { return base[f * stride]; }
+};
+struct SegAoS {  // contiguous record (stride 1)
+  double* base;
+  ART_HD double& operator()(int f) const { return base[f]; }
 };
 ART_HD int ffs64(unsigned long long v) {  // 1-based index of the lowest set bit
 #if defined(__CUDA_ARCH__)
@@ -103,10 +113,12 @@ struct ScanMasks {
 // dense-output grid of the crossing scan: θ_i = i/(M−1), i = 1..M−1; index 0 = the repeat-nudge point 0.01
 ART_HD double seg_theta(const DevParams& P, int i) { return i == 0 ? 0.01 : ((i == P.M_ray - 1) ? 1.0 : (double)i * P.inv_Mrm1); }
 
-ART_HD double seg_comp(const SegStore D, int i, double th, double th1) {
+template <class DS>
+ART_HD double seg_comp(const DS D, int i, double th, double th1) {
   return D(SEG_U + i) + th * (D(SEG_R1 + i) + th1 * (D(SEG_R2 + i) + th * (D(SEG_R3 + i) + th1 * D(SEG_R4 + i))));
 }
-ART_HD void seg_state(const SegStore D, double th, double w[6]) {
+template <class DS>
+ART_HD void seg_state(const DS D, double th, double w[6]) {
   const double th1 = 1.0 - th;
   for (int i = 0; i < 6; ++i) w[i] = seg_comp(D, i, th, th1);
 }
@@ -114,7 +126,8 @@ ART_HD void seg_state(const SegStore D, double th, double w[6]) {
 // Far-field classification of a dense-output point: −1 the condition is provably negative
 // (r > Rcut ⇒ ωp < m_a in every direction, and NrmSq ≥ 0 ⇔ E² r ≥ m_a² (r − rs)), 2 it is NaN
 // (NrmSq < 0, only reachable in flat mode), 0 it has to be evaluated.
-ART_HD int seg_quick(const DevParams& P, const SegStore D, double th) {
+template <class DS>
+ART_HD int seg_quick(const DevParams& P, const DS D, double th) {
   const double th1 = 1.0 - th;
   const double r = seg_comp(D, 0, th, th1);
   if (!(r > P.Rcut && r > P.r_int)) return 0;
@@ -126,10 +139,23 @@ ART_HD int seg_quick(const DevParams& P, const SegStore D, double th) {
 // M−1 points of a segment are classified in a row.
 struct SegQuick {
   double a0[5], a5[5], u70, fac7, u60;
-  ART_HD explicit SegQuick(const SegStore D) {
+  template <class DS>
+  ART_HD explicit SegQuick(const DS D) {
     a0[0] = D(SEG_U + 0); a0[1] = D(SEG_R1 + 0); a0[2] = D(SEG_R2 + 0); a0[3] = D(SEG_R3 + 0); a0[4] = D(SEG_R4 + 0);
     a5[0] = D(SEG_U + 5); a5[1] = D(SEG_R1 + 5); a5[2] = D(SEG_R2 + 5); a5[3] = D(SEG_R3 + 5); a5[4] = D(SEG_R4 + 5);
     u70 = D(SEG_U70); fac7 = D(SEG_FAC7); u60 = D(SEG_U60);
+  }
+  // Rigorous whole-segment test: θ(1−θ) ≤ ¼ on [0,1] bounds the deviation of the dense-output polynomial
+  // from its chord, so min r over the step ≥ min(r₀, r₁) − ¼(|r2| + |r3| + ¼|r4|); if that clears Rcut
+  // (with a 1e-9 margin against Horner round-off) and E² ≥ m_a² over the step, every scan point is
+  // in the provably negative far field and the per-point classification is skipped.
+  ART_HD bool all_far(const DevParams& P) const {
+    const double lo = fmin(a0[0], a0[0] + a0[1]) - 0.25 * (fabs(a0[2]) + fabs(a0[3]) + 0.25 * fabs(a0[4]));
+    if (!(lo > fmax(P.Rcut, P.r_int) * (1.0 + 1e-9))) return false;
+    const double e0 = u70 + fac7 * (a5[0] - u60), e1 = e0 + fac7 * a5[1];
+    const double de = fabs(fac7) * 0.25 * (fabs(a5[2]) + fabs(a5[3]) + 0.25 * fabs(a5[4]));
+    const double emin = fmin(fabs(e0), fabs(e1)) - de;
+    return emin > 0.0 && emin * emin >= P.ma2 * (1.0 + 1e-12);
   }
   ART_HD int classify(const DevParams& P, double th) const {
     const double th1 = 1.0 - th;
@@ -142,14 +168,16 @@ struct SegQuick {
 };
 
 // `condition` of propagate (RT.jl:254-298) at dense-output parameter th of a published segment
-ART_HD double seg_cond_full(const DevParams& P, const SegStore D, double th) {
+template <class DS>
+ART_HD double seg_cond_full(const DevParams& P, const DS D, double th) {
   double w[6];
   seg_state(D, th, w);
   const double E = D(SEG_U70) + D(SEG_FAC7) * (w[5] - D(SEG_U60));
   const double t = exp(D(SEG_S) + th * D(SEG_H));
   return thick_condition(P, w[0], w[1], w[2] - P.Omega * t, w[3], w[4], w[5], E, P.rs_ray, true);
 }
-ART_HD double seg_cond(const DevParams& P, const SegStore D, double th) {
+template <class DS>
+ART_HD double seg_cond(const DevParams& P, const DS D, double th) {
   const int qk = seg_quick(P, D, th);
   if (qk == -1) return -1.0;
   if (qk == 2) return NAN;
@@ -160,7 +188,7 @@ ART_HD double seg_cond(const DevParams& P, const SegStore D, double th) {
   return thick_condition(P, w[0], w[1], w[2] - P.Omega * t, w[3], w[4], w[5], E, P.rs_ray, true);
 }
 
-struct Ray {
+struct alignas(16) Ray {
   double u[6], un[6];
   double s, dt, qold, s_new, dt_new;
   double erg, fac7, u7_0, u6_0;
@@ -273,8 +301,8 @@ struct Ray {
   // stages(): start-up on the first call, otherwise one attempted DP5 step with error control.
   // Returns true if the step was accepted; its dense-output segment has then been published
   // in D and must be scanned before finish_step().
-  template <int SP = -1>
-  ART_HD bool stages(const DevParams& P, const KStore K, const SegStore D) {
+  template <int SP = -1, class KS = KStore, class DS = SegStore>
+  ART_HD bool stages(const DevParams& P, const KS K, const DS D) {
     if (++iters > P.maxiters) {
       status = RAY_MAXITERS;
       done = true;
@@ -400,7 +428,8 @@ struct Ray {
   }
 
   // is the dense-output point th still inside the ±0.01 % box around the start point (RT.jl:307-311)?
-  ART_HD bool in_start_box(const DevParams& P, const SegStore D, double th) const {
+  template <class DS>
+  ART_HD bool in_start_box(const DevParams& P, const DS D, double th) const {
     double w[6], x[3], k[3];
     seg_state(D, th, w);
     state_to_cartesian(P, w, erg, false, x, k);
@@ -414,8 +443,8 @@ struct Ray {
   ART_HD void finish_step(const DevParams& P, const KStore K, const SegStore D, const ScanMasks m) {
     finish_step_t(P, K, D, m);
   }
-  template <class KS>
-  ART_HD void finish_step_t(const DevParams& P, const KS K, const SegStore D, const ScanMasks m) {
+  template <class KS, class DS>
+  ART_HD void finish_step_t(const DevParams& P, const KS K, const DS D, const ScanMasks m) {
     int ia = 0, ib = -1, sg_last = 0;
     const int ev = detect(P, D, m, ia, ib, sg_last);
     double th_ev = -1.0;
@@ -426,7 +455,8 @@ struct Ray {
 
   // detect(): first sign change of the scanned step.  0 = none, 1 = bracket (ia, ib) found,
   // 2 = the end point lies exactly on the surface (prev_sign · next_sign ≤ 0).
-  ART_HD int detect(const DevParams& P, const SegStore D, const ScanMasks m, int& ia, int& ib, int& sg_last) const {
+  template <class DS>
+  ART_HD int detect(const DevParams& P, const DS D, const ScanMasks m, int& ia, int& ib, int& sg_last) const {
     const int M = P.M_ray;
     int cur = sgn_end;
     if (event_last)  // DiffEqBase repeat_nudge = 1/100: reference sign taken just after the event
@@ -462,7 +492,8 @@ struct Ray {
   }
 
   // locate(): Illinois regula falsi with bisection safeguard, to floating precision; left-biased
-  ART_HD double locate(const DevParams& P, const SegStore D, int ia, int ib) {
+  template <class DS>
+  ART_HD double locate(const DevParams& P, const DS D, int ia, int ib) {
     double ra = (ia == 0) ? (event_last ? 0.01 : 0.0) : seg_theta(P, ia), rb = seg_theta(P, ib);
     double fa = seg_cond(P, D, ra), fb = seg_cond(P, D, rb);
     n_cond += 2;
@@ -488,8 +519,8 @@ struct Ray {
   }
 
   // apply(): callbacks and state update at the end of an accepted step (th_ev < 0: no event)
-  template <class KS>
-  ART_HD void apply(const DevParams& P, const KS K, const SegStore D, double th_ev, int sg_last) {
+  template <class KS, class DS>
+  ART_HD void apply(const DevParams& P, const KS K, const DS D, double th_ev, int sg_last) {
     const double h = D(SEG_H);
     bool terminated = false;
     if (th_ev >= 0.0) {

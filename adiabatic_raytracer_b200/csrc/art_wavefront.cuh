@@ -160,7 +160,7 @@ template <int SP>
 __global__ void __launch_bounds__(WF_THREADS, ART_STAGE_MINBLOCKS)
 k_wf_stages(const __grid_constant__ DevParams P, WfPool W, int cur) {
   extern __shared__ double ksm[];
-  const KStore K{ksm + threadIdx.x, (int)blockDim.x};
+  const KStoreT<WF_THREADS> K{ksm + threadIdx.x};
   const long long n = (long long)W.ctr[WC_ACT + cur * 2 + SP];
   const int* __restrict__ act = W.act[cur][SP];
   const long long nthreads = (long long)gridDim.x * blockDim.x;
@@ -176,7 +176,7 @@ k_wf_stages(const __grid_constant__ DevParams P, WfPool W, int cur) {
       const bool had_k1 = !R.need_k1;
       if (had_k1)
         for (int k = 0; k < 6; ++k) K(0, k) = kf[k];
-      const SegStore D{W.seg + (size_t)id * SEG_PAD, 1};
+      const SegAoS D{W.seg + (size_t)id * SEG_PAD};
       const bool pending = R.template stages<SP>(P, K, D);
       if (!had_k1)
         for (int k = 0; k < 6; ++k) kf[k] = K(0, k);
@@ -185,10 +185,14 @@ k_wf_stages(const __grid_constant__ DevParams P, WfPool W, int cur) {
         for (int k = 0; k < 6; ++k) kf[6 + k] = K(6, k);
         const int M = P.M_ray;
         const SegQuick Q(D);
-        for (int i = R.event_last ? 0 : 1; i < M; ++i) {
-          const int qk = Q.classify(P, seg_theta(P, i));
-          if (qk == 0) need |= 1ull << i;
-          else if (qk == -1) neg |= 1ull << i;
+        if (Q.all_far(P)) {
+          neg = ((M >= 64) ? ~0ull : ((1ull << M) - 1ull)) & (R.event_last ? ~0ull : ~1ull);
+        } else {
+          for (int i = R.event_last ? 0 : 1; i < M; ++i) {
+            const int qk = Q.classify(P, seg_theta(P, i));
+            if (qk == 0) need |= 1ull << i;
+            else if (qk == -1) neg |= 1ull << i;
+          }
         }
         W.need[id] = need;
         W.neg[id] = neg;
@@ -228,7 +232,7 @@ k_wf_scan(const __grid_constant__ DevParams P, WfPool W) {
   for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += nthreads) {
     const unsigned code = W.items[k];
     const unsigned id = code >> 6, i = code & 63u;
-    const SegStore D{W.seg + (size_t)id * SEG_PAD, 1};
+    const SegAoS D{W.seg + (size_t)id * SEG_PAD};
     const double g = seg_cond_full(P, D, seg_theta(P, (int)i));
     W.sign[(size_t)id * 64 + i] = (g > 0.0) ? 1 : ((g < 0.0) ? 2 : ((g == 0.0) ? 3 : 0));
   }
@@ -264,7 +268,7 @@ k_wf_detect(const __grid_constant__ DevParams P, WfPool W, int cur, RayOut* __re
           else if (v == 3) m.zero |= 1ull << i;
           need &= need - 1ull;
         }
-        const SegStore D{W.seg + (size_t)id * SEG_PAD, 1};
+        const SegAoS D{W.seg + (size_t)id * SEG_PAD};
         int ia, ib, sgl;
         const int ev = R.detect(P, D, m, ia, ib, sgl);
         if (ev == 1) {
@@ -306,7 +310,7 @@ k_wf_root(const __grid_constant__ DevParams P, WfPool W, int next, RayOut* __res
 #pragma unroll
         for (int k = 0; k < SEG_PAD; ++k) segl[k] = sgp[k];
       }
-      const SegStore D{segl, 1};
+      const SegAoS D{segl};
       const KfView K{W.kf + (size_t)id * KF_PAD};
       const double th = R.locate(P, D, R.br_a, R.br_b);
       R.apply(P, K, D, th, R.br_sg);
