@@ -101,10 +101,10 @@ bool nccl_load(std::string& err) {
 struct Lane {
   cudaStream_t stream = nullptr;
   DBuf samples, tstate, stacks, q0, rout, rec, ctr;
-  DBuf wf_ray, wf_kf, wf_seg, wf_need, wf_neg, wf_pend, wf_sign, wf_act[4], wf_items, wf_roots, wf_fin, wf_ctr;
+  DBuf wf_hot, wf_cold, wf_seg, wf_need, wf_neg, wf_pend, wf_sign, wf_act[4], wf_items, wf_roots, wf_fin, wf_ctr;
   float ms_sampler = 0, ms_weights = 0, ms_tracer = 0;
   void release() {
-    DBuf* all[] = {&samples, &tstate, &stacks, &q0, &rout, &rec, &ctr, &wf_ray, &wf_kf, &wf_seg, &wf_need, &wf_neg,
+    DBuf* all[] = {&samples, &tstate, &stacks, &q0, &rout, &rec, &ctr, &wf_hot, &wf_cold, &wf_seg, &wf_need, &wf_neg,
                    &wf_pend, &wf_sign, &wf_act[0], &wf_act[1], &wf_act[2], &wf_act[3], &wf_items, &wf_roots, &wf_fin, &wf_ctr};
     for (DBuf* b : all) b->release();
     if (stream) cudaStreamDestroy(stream);
@@ -116,7 +116,7 @@ struct art_handle {
   art_params params;
   DevParams dp;
   int device = 0, n_sm = 0;
-  int blocks_trace = 0, blocks_sample = 0;
+  int blocks_sample = 0;
   cudaStream_t stream = nullptr;  // main stream (fine-grained entry points, patch / histogram / collectives)
   std::string err;
   std::mutex err_mu;
@@ -133,8 +133,6 @@ struct art_handle {
   void* comm = nullptr;
   int nranks = 1, rank = 0;
   std::atomic<long long> launches{0};  // kernels launched since the current pipeline call began
-  int use_wavefront = 1;          // ART_TRACER=persistent: art_propagate uses the one-kernel tracer (k_trace)
-  long long tail_switch = 0;      // active rays below which the persistent tail kernel takes over (0 = never)
   int n_lanes = 1;                // concurrent sub-chunks (ART_LANES); measured: one big chunk beats overlapped small ones
   long long sub_chunk = 1 << 21;  // events per sub-chunk (ART_SUBCHUNK)
 };
@@ -174,21 +172,6 @@ int ensure_lanes(art_handle* h, int n) {
   return ART_OK;
 }
 
-// persistent one-kernel tracer over a device queue (kept for comparison / profiling)
-int launch_trace_persistent(art_handle* h, Lane& L, const QueuedRay* q, long long n, RayOut* out, double* rec, int rec_cap,
-                            DevStats* stats) {
-  if (n <= 0) return ART_OK;
-  CU(L.ctr.ensure(64));
-  unsigned long long* head = L.ctr.as<unsigned long long>();
-  CU(cudaMemsetAsync(head, 0, sizeof(unsigned long long), L.stream));
-  const int blocks = (int)std::min<long long>(h->blocks_trace, (n + TRACE_THREADS - 1) / TRACE_THREADS);
-  k_trace<<<blocks, TRACE_THREADS, TRACE_SMEM, L.stream>>>(h->dp, q, n, out, rec, rec_cap, head, stats);
-  h->launches++;
-  CU(cudaGetLastError());
-  CU(cudaStreamSynchronize(L.stream));
-  return ART_OK;
-}
-
 // step-batched tracer over a device queue (art_wavefront.cuh).  With a tree context the loop also
 // walks every event's tree: finished rays spawn the next node of their event in place.
 int launch_trace_wf(art_handle* h, Lane& L, const QueuedRay* q, long long n, RayOut* out, double* rec, int rec_cap,
@@ -196,38 +179,39 @@ int launch_trace_wf(art_handle* h, Lane& L, const QueuedRay* q, long long n, Ray
   if (n <= 0) return ART_OK;
   const int M = h->params.interp_points_ray;
   cudaStream_t st = L.stream;
-  CU(L.wf_ray.ensure((size_t)n * sizeof(Ray)));
-  CU(L.wf_kf.ensure((size_t)n * KF_PAD * sizeof(double)));
+  CU(L.wf_hot.ensure((size_t)n * sizeof(RayHot)));
+  CU(L.wf_cold.ensure((size_t)n * sizeof(RayCold)));
   CU(L.wf_seg.ensure((size_t)n * SEG_PAD * sizeof(double)));
   CU(L.wf_need.ensure((size_t)n * 8));
   CU(L.wf_neg.ensure((size_t)n * 8));
-  CU(L.wf_pend.ensure((size_t)n));
   CU(L.wf_sign.ensure((size_t)n * 64));
   for (int k = 0; k < 4; ++k) CU(L.wf_act[k].ensure((size_t)n * 4));
+  CU(L.wf_pend.ensure((size_t)n * 4));
   CU(L.wf_items.ensure((size_t)n * M * 4));
   CU(L.wf_roots.ensure((size_t)n * 4));
   CU(L.wf_fin.ensure((size_t)n * 4));
   CU(L.wf_ctr.ensure(WC_N * 8));
   WfPool W;
-  W.ray = L.wf_ray.as<Ray>(); W.kf = L.wf_kf.as<double>(); W.seg = L.wf_seg.as<double>();
+  W.hot = L.wf_hot.as<RayHot>(); W.cold = L.wf_cold.as<RayCold>(); W.seg = L.wf_seg.as<double>();
   W.need = L.wf_need.as<unsigned long long>(); W.neg = L.wf_neg.as<unsigned long long>();
-  W.pend = L.wf_pend.as<unsigned char>(); W.sign = L.wf_sign.as<unsigned char>();
+  W.sign = L.wf_sign.as<unsigned char>();
   for (int par = 0; par < 2; ++par)
     for (int sp = 0; sp < 2; ++sp) W.act[par][sp] = L.wf_act[par * 2 + sp].as<int>();
+  W.pend = L.wf_pend.as<int>();
   W.items = L.wf_items.as<unsigned>(); W.roots = L.wf_roots.as<int>(); W.fin = L.wf_fin.as<int>();
   W.ctr = L.wf_ctr.as<unsigned long long>();
   const size_t ksmem = (size_t)42 * WF_THREADS * sizeof(double);
   CU(cudaMemsetAsync(W.ctr, 0, WC_N * 8, st));
   const int gmax = h->n_sm * 8;
   auto grid = [&](long long work, int threads) { return (int)std::max<long long>(1, std::min<long long>(gmax, (work + threads - 1) / threads)); };
-  k_wf_init<<<grid(n, WF_THREADS), WF_THREADS, 0, st>>>(h->dp, q, n, W, out, rec, rec_cap, stats);
+  k_wf_init<<<grid(n, WF_THREADS), WF_THREADS, 0, st>>>(h->dp, q, n, W, rec, rec_cap);
   h->launches++;
   CU(cudaGetLastError());
   long long n_act = n;  // upper bound of the active count, refreshed at every host check
   int cur = 0;
   const bool trace = getenv("ART_WF_TRACE") != nullptr;
   for (long long iter = 0;;) {
-    const int burst = n_act > 65536 ? 4 : (n_act > 2048 ? 8 : 24);  // steps between host checks
+    const int burst = n_act > 65536 ? 4 : (n_act > 2048 ? 8 : 16);  // steps between host checks
     for (int b = 0; b < burst; ++b, ++iter) {
       const int next = 1 - cur;
       const int g1 = grid(n_act, WF_THREADS);
@@ -235,13 +219,13 @@ int launch_trace_wf(art_handle* h, Lane& L, const QueuedRay* q, long long n, Ray
       k_wf_stages<SPECIES_AXION><<<g1, WF_THREADS, ksmem, st>>>(h->dp, W, cur);
       k_wf_stages<SPECIES_PHOTON><<<g1, WF_THREADS, ksmem, st>>>(h->dp, W, cur);
       k_wf_scan<<<grid(n_act * 24, 256), 256, 0, st>>>(h->dp, W);
-      k_wf_detect<<<g1, WF_THREADS, 0, st>>>(h->dp, W, cur, out, stats);
-      k_wf_root<<<grid(n_act / 8 + 1, WF_THREADS), WF_THREADS, 0, st>>>(h->dp, W, next, out, stats);
-      h->launches += 6;
-      if (tree) {
-        k_wf_tree<<<grid(n_act / 4 + 1, WF_THREADS), WF_THREADS, 0, st>>>(h->dp, W, *tree, next, out, rec, rec_cap, stats);
-        h->launches++;
-      }
+      k_wf_detect<<<g1, WF_THREADS, 0, st>>>(h->dp, W, next);
+      k_wf_root<<<grid(n_act / 8 + 1, WF_THREADS), WF_THREADS, 0, st>>>(h->dp, W, next);
+      if (tree)
+        k_wf_tree<<<grid(n_act / 4 + 1, WF_THREADS), WF_THREADS, 0, st>>>(h->dp, W, *tree, next, rec, rec_cap, stats);
+      else
+        k_wf_collect<<<grid(n_act / 4 + 1, WF_THREADS), WF_THREADS, 0, st>>>(h->dp, W, out, stats);
+      h->launches += 7;
       cur = next;
     }
     CU(cudaGetLastError());
@@ -252,19 +236,6 @@ int launch_trace_wf(art_handle* h, Lane& L, const QueuedRay* q, long long n, Ray
     if (trace) fprintf(stderr, "[wf %p] iter %lld active %lld (ax %llu ph %llu)\n", (void*)&L, iter, n_act, na[0], na[1]);
     if (n_act == 0) break;
     if (iter > 64LL * h->params.maxiters) return fail(h, ART_ERR_CUDA, "wavefront tracer did not terminate");
-    if (n_act <= h->tail_switch) {
-      // latency-bound tail: one persistent kernel finishes the remaining rays and their trees
-      WfTree none;
-      memset(&none, 0, sizeof(none));
-      k_wf_reset<<<1, 32, 0, st>>>(W, 1 - cur);  // zeroes the item counter = the tail's queue head
-      const int blocks = grid(n_act, WF_THREADS);
-      k_wf_tail<<<std::min(blocks, h->n_sm * 2), WF_THREADS, ksmem, st>>>(h->dp, W, tree ? *tree : none, cur, out, rec, rec_cap,
-                                                                          stats);
-      h->launches += 2;
-      CU(cudaGetLastError());
-      CU(cudaStreamSynchronize(st));
-      break;
-    }
   }
   return ART_OK;
 }
@@ -321,16 +292,14 @@ int art_create(const art_params* p, int device_id, art_handle** out) {
   h->dp = d;
   h->device = device_id;
   h->ncols = p->save_mode > 0 ? ART_ROW_COLS_LONG : ART_ROW_COLS_SHORT;
-  if (const char* t = getenv("ART_TRACER")) h->use_wavefront = strcmp(t, "persistent") != 0;
-  if (const char* t = getenv("ART_TAIL_SWITCH")) h->tail_switch = atoll(t);
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, device_id);
   h->n_sm = prop.multiProcessorCount;
   int occ = 0;
-  cudaFuncSetAttribute(k_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRACE_SMEM);
-  cudaFuncSetAttribute(k_trace, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace, TRACE_THREADS, TRACE_SMEM);
-  h->blocks_trace = h->n_sm * std::max(occ, 1);
+  for (auto fn : {(const void*)k_wf_stages<SPECIES_AXION>, (const void*)k_wf_stages<SPECIES_PHOTON>}) {
+    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(42 * WF_THREADS * sizeof(double)));
+    cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  }
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sample_events, SAMPLE_THREADS, 0);
   h->blocks_sample = h->n_sm * std::max(occ, 1);
   if (const char* t = getenv("ART_LANES")) h->n_lanes = std::max(1, std::min(16, atoi(t)));
@@ -487,9 +456,7 @@ int art_propagate(art_handle* h, int64_t n, const int32_t* species, const double
   CU(L.rec.ensure((size_t)n * cross_cap * 8 * sizeof(double)));
   CU(cudaMemsetAsync(L.rec.p, 0, (size_t)n * cross_cap * 8 * sizeof(double), h->stream));
   CU(cudaStreamSynchronize(h->stream));
-  if (int rc = h->use_wavefront
-                   ? launch_trace_wf(h, L, h->q[0].as<QueuedRay>(), n, L.rout.as<RayOut>(), L.rec.as<double>(), cross_cap, nullptr, nullptr)
-                   : launch_trace_persistent(h, L, h->q[0].as<QueuedRay>(), n, L.rout.as<RayOut>(), L.rec.as<double>(), cross_cap, nullptr))
+  if (int rc = launch_trace_wf(h, L, h->q[0].as<QueuedRay>(), n, L.rout.as<RayOut>(), L.rec.as<double>(), cross_cap, nullptr, nullptr))
     return rc;
   std::vector<RayOut> ro((size_t)n);
   CU(cudaMemcpyAsync(ro.data(), L.rout.p, n * sizeof(RayOut), cudaMemcpyDeviceToHost, h->stream));

@@ -3,11 +3,9 @@
 //   K1 k_sample_events    surface sampler, persistent threads, one attempt per lane, events
 //                         pulled from a device queue by warp-aggregated atomics (FP64 ALU)
 //   K2 k_weights          per-sample flux weights (FP64, pointwise)
-//   K3 k_trace<AXION>     adaptive ray integrator, one ray per lane, RK stages in registers,
-//                         finished lanes are retired and refilled in place by ballot/popc
-//                         (the "compaction" is the refill: survivors never move) (FP64 ALU)
-//   K4 k_tree_update      get_tree loop body per event + next-generation queue build
-//                         (warp-aggregated append = stream compaction; HBM bound)
+//   K3 k_wf_*             adaptive ray integrator, step-batched over compacted ray lists
+//                         (art_wavefront.cuh) (FP64 ALU)
+//   K4 k_wf_tree          get_tree loop body per finished ray, next node spawned in place
 //   K5 k_hist             binned flux with shared-memory privatised bins (atomics)
 //
 // None of this has a dense contraction: tensor cores / TMA are deliberately not used
@@ -23,7 +21,6 @@
 namespace art {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int TRACE_THREADS = 128;
 constexpr int SAMPLE_THREADS = 128;
 
 struct DevStats {  // accumulated with atomics; mirrors the counters of art_stats
@@ -53,145 +50,6 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL, v, o);
   return v;
-}
-
-// ------------------------------------------------------------------------------------------
-// K3: ray tracer.  Persistent threads; every lane owns one ray at a time and pulls the next
-// one from the device queue when its ray retires (ballot + popc + one atomic per warp), so
-// survivors never move and no separate compaction pass exists.
-//
-// Shared memory per CTA (TRACE_THREADS = 128 → 96 KB, two CTAs per SM):
-//   K    [42][T] doubles   stage derivatives k1..k7, one column per thread (conflict-free)
-//   SEG  [35][T] doubles   dense-output segment of the accepted step, readable by the warp
-//   SIGN [T][64] u8        sign of the crossing condition per (ray, point)
-//   LIST [T/32][2048] u16  per-warp work list of (lane, point) pairs for the cooperative scan
-// ------------------------------------------------------------------------------------------
-constexpr int SCAN_LIST = 32 * 64;
-constexpr size_t TRACE_SMEM = (size_t)(42 + SEG_N) * TRACE_THREADS * sizeof(double) +
-                              (size_t)TRACE_THREADS * 64 +
-                              (size_t)(TRACE_THREADS / 32) * SCAN_LIST * sizeof(unsigned short);
-#ifndef ART_TRACE_MINBLOCKS
-#define ART_TRACE_MINBLOCKS 2  // resident CTAs per SM the register allocation is tuned for
-#endif
-
-// Cooperative crossing scan of one warp.  Lanes whose step was accepted (`pending`) classify
-// their own M−1 dense-output points with the far-field test (cheap); the points that need the
-// full condition are pooled into the warp's work list and dealt out round-robin, so lanes
-// whose step was rejected, whose ray is in the far field, or that hold no ray at all evaluate
-// points of OTHER lanes' rays.  Results come back as sign masks in shared memory.
-__device__ __forceinline__ ScanMasks warp_scan(const DevParams& P, bool pending, bool nudge, double* seg_w, int stride,
-                                               unsigned char* sign_w, unsigned short* list) {
-  const unsigned lane = threadIdx.x & 31;
-  const int M = P.M_ray;
-  unsigned long long need = 0ull, neg = 0ull;
-  if (pending) {
-    const SegStore D{seg_w + lane, stride};
-    const SegQuick Q(D);
-    for (int i = nudge ? 0 : 1; i < M; ++i) {
-      const int qk = Q.classify(P, seg_theta(P, i));
-      if (qk == 0) need |= 1ull << i;
-      else if (qk == -1) neg |= 1ull << i;
-    }
-  }
-  const int cnt = __popcll(need);
-  int incl = cnt;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(FULL, incl, o);
-    if ((int)lane >= o) incl += t;
-  }
-  const int N = __shfl_sync(FULL, incl, 31);
-  ScanMasks out{0ull, neg, 0ull};
-  if (N == 0) return out;
-  {
-    int c = incl - cnt;
-    unsigned long long m = need;
-    while (m) {
-      const int i = __ffsll((long long)m) - 1;
-      list[c++] = (unsigned short)((lane << 8) | (unsigned)i);
-      m &= m - 1ull;
-    }
-  }
-  __syncwarp();
-  for (int k = (int)lane; k < N; k += 32) {
-    const unsigned code = list[k];
-    const unsigned l = code >> 8, i = code & 255u;
-    const SegStore Dl{seg_w + l, stride};
-    const double g = seg_cond_full(P, Dl, seg_theta(P, (int)i));
-    sign_w[l * 64 + i] = (g > 0.0) ? 1 : ((g < 0.0) ? 2 : ((g == 0.0) ? 3 : 0));
-  }
-  __syncwarp();
-  {
-    unsigned long long m = need;
-    while (m) {
-      const int i = __ffsll((long long)m) - 1;
-      const unsigned sg = sign_w[lane * 64 + i];
-      if (sg == 1) out.pos |= 1ull << i;
-      else if (sg == 2) out.neg |= 1ull << i;
-      else if (sg == 3) out.zero |= 1ull << i;
-      m &= m - 1ull;
-    }
-  }
-  return out;
-}
-
-__global__ void __launch_bounds__(TRACE_THREADS, ART_TRACE_MINBLOCKS)
-k_trace(const __grid_constant__ DevParams P, const QueuedRay* __restrict__ q, long long n,
-        RayOut* __restrict__ out, double* __restrict__ rec, int rec_cap, unsigned long long* head,
-        DevStats* stats) {
-  extern __shared__ double ksm[];
-  const int T = (int)blockDim.x;
-  const int warp0 = (int)(threadIdx.x & ~31u);
-  const KStore K{ksm + threadIdx.x, T};
-  double* seg_base = ksm + (size_t)42 * T;
-  const SegStore D{seg_base + threadIdx.x, T};
-  unsigned char* sign_base = (unsigned char*)(seg_base + (size_t)SEG_N * T);
-  unsigned short* list = (unsigned short*)(sign_base + (size_t)T * 64) + (size_t)(threadIdx.x >> 5) * SCAN_LIST;
-  Ray R;
-  R.done = true;
-  R.event_last = false;
-  bool have = false, exhausted = false;
-  long long idx = -1;
-  unsigned long long c_acc = 0, c_rej = 0, c_rhs = 0, c_cond = 0, c_rays = 0, c_ph = 0;
-  unsigned long long c_st[5] = {0, 0, 0, 0, 0};
-  for (;;) {
-    const long long got = warp_pop(head, !have && !exhausted);
-    if (!have && !exhausted) {
-      if (got >= 0 && got < n) {
-        idx = got;
-        R.init(P, q[idx].in, rec + (size_t)idx * rec_cap * 8, rec_cap);
-        have = true;
-      } else {
-        exhausted = true;
-      }
-    }
-    if (__ballot_sync(FULL, have) == 0) break;
-    bool pending = false;
-    if (have && !R.done) pending = R.stages(P, K, D);
-    // warp-cooperative: every lane takes part, whether or not it owns a pending step
-    const ScanMasks m = warp_scan(P, pending, pending && R.event_last, seg_base + warp0, T, sign_base + (size_t)warp0 * 64, list);
-    if (pending) R.finish_step(P, K, D, m);
-    if (have && R.done) {
-      RayOut o;
-      R.finish(P, o);
-      out[idx] = o;
-      c_acc += o.n_acc; c_rej += o.n_rej; c_rhs += o.n_rhs; c_cond += o.n_cond; c_rays++;
-      c_ph += R.axion ? 0 : 1;
-      c_st[o.status]++;
-      have = false;
-    }
-  }
-  c_acc = warp_sum(c_acc); c_rej = warp_sum(c_rej); c_rhs = warp_sum(c_rhs); c_cond = warp_sum(c_cond);
-  c_rays = warp_sum(c_rays); c_ph = warp_sum(c_ph);
-#pragma unroll
-  for (int k = 0; k < 5; ++k) c_st[k] = warp_sum(c_st[k]);
-  if ((threadIdx.x & 31) == 0 && stats) {
-    atomicAdd(&stats->n_acc, c_acc); atomicAdd(&stats->n_rej, c_rej); atomicAdd(&stats->n_rhs, c_rhs);
-    atomicAdd(&stats->n_cond, c_cond); atomicAdd(&stats->n_rays, c_rays);
-    atomicAdd(&stats->n_rays_photon, c_ph);
-    for (int k = 0; k < 5; ++k)
-      if (c_st[k]) atomicAdd(&stats->n_status[k], c_st[k]);
-  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -356,55 +214,6 @@ __global__ void k_rhs_api(const __grid_constant__ DevParams P, long long n, cons
 // ------------------------------------------------------------------------------------------
 // K4: tree
 // ------------------------------------------------------------------------------------------
-// after the first launch: samp_back_weight from the back-traced axion (slot i)
-__global__ void k_back_finish(const __grid_constant__ DevParams P, long long n, EventData* __restrict__ ev,
-                              const RayOut* __restrict__ bout, const double* __restrict__ rec, int rec_cap,
-                              TreeState* __restrict__ ts) {
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  EventData E = ev[i];
-  const RayOut R = bout[i];
-  tree_backward(P, E, R, rec + (size_t)i * rec_cap * 8, rec_cap);
-  ev[i] = E;
-  ts[i].back_status = R.status;
-}
-
-// one thread per just-propagated node: get_tree loop body, rows, next-generation queues
-__global__ void k_tree_update(const __grid_constant__ DevParams P, long long n_rays, const QueuedRay* __restrict__ q,
-                              const RayOut* __restrict__ out, const double* __restrict__ rec, int rec_cap,
-                              const EventData* __restrict__ ev, TreeState* __restrict__ ts,
-                              TreeNode* __restrict__ stacks, int stack_stride, unsigned long long seed,
-                              long long first_event, long long chunk_base, RowSink sink,
-                              QueuedRay* __restrict__ next_q, unsigned long long* next_count,
-                              unsigned long long* tot_count, int* fin_count, int* fin_info) {
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  bool push = false;
-  QueuedRay r;
-  if (i < n_rays) {
-    const int e = q[i].owner;
-    const EventData E = ev[e];
-    TreeState T = ts[e];
-    tree_forward_update(P, E, T, stacks + (size_t)e * stack_stride, out[i], rec + (size_t)i * rec_cap * 8, seed,
-                        (unsigned long long)(first_event + chunk_base + e), chunk_base + e, sink);
-    if (T.active) {
-      push = true;
-      r.in.x0[0] = T.cur.x; r.in.x0[1] = T.cur.y; r.in.x0[2] = T.cur.z;
-      r.in.k0[0] = T.cur.kx; r.in.k0[1] = T.cur.ky; r.in.k0[2] = T.cur.kz;
-      r.in.erg = E.erg_inf; r.in.t_start = T.cur.t; r.in.dOmega = T.cur.dw; r.in.max_cross = -1;
-      r.in.species = T.cur.species;
-      r.owner = e; r.pad_ = 0;
-    } else {
-      atomicAdd(tot_count, (unsigned long long)T.tree_len);
-      fin_count[e] = T.count;
-      fin_info[e] = T.info;
-    }
-    ts[e] = T;
-  }
-  // warp-aggregated append to the next generation's queue (stream compaction of survivors)
-  const long long slot = warp_pop(next_count, push);
-  if (push) next_q[slot] = r;
-}
-
 // rows are completed (back-traced weight, tree count / info) when their event is finished
 __global__ void k_patch_rows(long long n_rows, double* rows, const long long* keys, int ncols, long long chunk_base,
                              const EventData* __restrict__ ev, const int* fin_count, const int* fin_info,

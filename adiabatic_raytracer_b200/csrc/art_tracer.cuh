@@ -188,23 +188,38 @@ ART_HD double seg_cond(const DevParams& P, const DS D, double th) {
   return thick_condition(P, w[0], w[1], w[2] - P.Omega * t, w[3], w[4], w[5], E, P.rs_ray, true);
 }
 
-struct alignas(16) Ray {
-  double u[6], un[6];
-  double s, dt, qold, s_new, dt_new;
+// Ray state, split by access pattern: the HOT record is what an attempted step reads
+// and writes (one 192-byte, 16-byte-aligned record per ray: 12 vector loads); the COLD record is only
+// touched by callbacks (start-box test, crossing records, root brackets).
+struct alignas(16) RayHot {
+  double u[6];    // state at the start of the next step
+  double k1[6];   // f(u, s): FSAL derivative, always valid between steps
+  double s, dt, qold;
   double erg, fac7, u7_0, u6_0;
+  int iters, n_cross, status;
+  int sgn_end;    // sign of the condition at the end of the last accepted step (= start of the next)
+  int n_acc, n_rej, n_rhs, n_cond;
+  bool axion, starting, event_last, done;
+  int pad_;
+};
+struct alignas(16) RayCold {
   double x0[3];
   double* rec;  // crossing records, ART_CROSS_REC doubles each
   int rec_cap, max_cross;
-  int n_cross, iters, status;
-  int n_acc, n_rej, n_rhs, n_cond;
   int br_a, br_b, br_sg;  // bracket found by detect(), waiting for the root kernel (wavefront path)
-  int sgn_end;  // sign of the condition at the end of the last accepted step (= start of the next)
-  bool axion, starting, need_k1, event_last, done;
+  int pad2_;
+};
+static_assert(sizeof(RayHot) == 192, "RayHot layout");
+static_assert(sizeof(RayCold) == 64, "RayCold layout");
+
+struct Ray : RayHot, RayCold {
+  // transient: the attempted step between attempt() and apply()
+  double un[6], s_new, dt_new, h;
 
   ART_HD double u7_of(double u6) const { return u7_0 + fac7 * (u6 - u6_0); }
 
-  // ---- set-up: IC transform (RT.jl:179-216).  The first RHS, the initial step size and the
-  // first condition value are produced by the first call of step() (starting = true).
+  // ---- set-up: IC transform (RT.jl:179-216).  startup() then produces the first RHS, the initial
+  // step size and the first condition value.
   ART_HD void init(const DevParams& P, const RayIn& in, double* rec_, int rec_cap_) {
     rec = rec_;
     rec_cap = rec_cap_;
@@ -219,12 +234,15 @@ struct alignas(16) Ray {
     dt = 0.0;
     s_new = s;
     dt_new = 0.0;
+    h = 0.0;
     sgn_end = 0;
     n_cross = iters = n_acc = n_rej = n_rhs = n_cond = 0;
+    br_a = br_b = br_sg = 0;
+    pad_ = pad2_ = 0;
     status = RAY_END;
     event_last = false;
     starting = true;
-    need_k1 = true;
+    for (int i = 0; i < 6; ++i) k1[i] = 0.0;
     qold = dp::qoldinit;
     done = !(s < P.ln_tend);
   }
@@ -289,88 +307,82 @@ struct alignas(16) Ray {
   }
 
   // ---------------------------------------------------------------------------------------
-  // One iteration = stages() → crossing scan of the accepted step → finish_step().
-  // The scan is separated out because on the GPU it is done COOPERATIVELY by the warp: the
-  // (ray, dense-output point) pairs that really need an evaluation — the step was accepted
-  // and the point is not in the provably negative far field — are pooled over the 32 lanes
-  // and dealt out evenly (art_kernels.cuh: warp_scan).  Only SIGNS of the condition are kept
-  // (three 64-bit masks per ray: positive / negative / exactly zero; neither = NaN); the two
-  // bracket values the root finder starts from are re-evaluated, which gives the same numbers.
+  // One iteration = [startup() once] → attempt() → publish() → crossing scan of the accepted step →
+  // finish_step().  On the GPU these are separate kernels over compacted ray lists
+  // (art_wavefront.cuh); step() below is the sequential definition they must reproduce.
+  // Only SIGNS of the condition are kept by the scan (three 64-bit masks per ray: positive /
+  // negative / exactly zero; neither = NaN); the two bracket values the root finder starts from are
+  // re-evaluated, which gives the same numbers.
   // ---------------------------------------------------------------------------------------
 
-  // stages(): start-up on the first call, otherwise one attempted DP5 step with error control.
-  // Returns true if the step was accepted; its dense-output segment has then been published
-  // in D and must be scanned before finish_step().
-  template <int SP = -1, class KS = KStore, class DS = SegStore>
-  ART_HD bool stages(const DevParams& P, const KS K, const DS D) {
+  // guard shared by start-up and attempted steps (OrdinaryDiffEq maxiters)
+  ART_HD bool iter_guard(const DevParams& P) {
     if (++iters > P.maxiters) {
       status = RAY_MAXITERS;
       done = true;
       return false;
     }
+    return true;
+  }
+
+  // startup(): first RHS, OrdinaryDiffEq ode_determine_initdt (Hairer II.4; order 5, 7-component RMS
+  // norm), reference sign of the crossing condition at the start point.
+  template <int SP = -1>
+  ART_HD void startup(const DevParams& P) {
     const double s1 = P.ln_tend;
-    double h = dt;
+    f<SP>(P, u, s, k1);
+    double sk[6], a[6], v[6], dv[6];
+    for (int i = 0; i < 6; ++i) sk[i] = P.atol + fabs(u[i]) * P.rtol;
+    const double sk7 = P.atol + fabs(u7_0) * P.rtol;
+    for (int i = 0; i < 6; ++i) a[i] = u[i] / sk[i];
+    const double d0 = rms7(a, u7_0 / sk7);
+    for (int i = 0; i < 6; ++i) a[i] = k1[i] / sk[i];
+    const double d1 = rms7(a, fac7 * k1[5] / sk7);
+    double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
+    dt0 = fmin(dt0, s1 - s);
+    for (int i = 0; i < 6; ++i) v[i] = u[i] + dt0 * k1[i];
+    f<SP>(P, v, s + dt0, dv);
+    n_rhs += 2;
+    for (int i = 0; i < 6; ++i) a[i] = (dv[i] - k1[i]) / sk[i];
+    const double d2 = rms7(a, fac7 * (dv[5] - k1[5]) / sk7) / dt0;
+    const double dm = fmax(d1, d2);
+    const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : exp(-(2.0 + log10(dm)) / 5.0 * 2.302585092994046);
+    dt = fmin(fmin(100.0 * dt0, dt1), s1 - s);
+    const double g = cond(P, u, s);
+    n_cond++;
+    sgn_end = (g > 0.0) - (g < 0.0);
+    starting = false;
+  }
+
+  // attempt(): one attempted DP5 step with error control (stage loop rolled: one copy of the
+  // right-hand side).  Returns true if the step was accepted; un, s_new, dt_new, h and K then
+  // describe it until apply().
+  template <int SP = -1, class KS = KStore>
+  ART_HD bool attempt(const DevParams& P, const KS K) {
+    const double s1 = P.ln_tend;
+    h = dt;
     bool last = false;
-    if (!starting && s + h >= s1) {
+    if (s + h >= s1) {
       h = s1 - s;
       last = true;
     }
     s_new = last ? s1 : s + h;
-    double sk[6], sk7 = 0.0, d1 = 0.0, dt0 = 0.0;  // start-up only
-
-    // ---- stages (rolled: one copy of the right-hand side) ----------------------------------
-    const int n_stage = starting ? 1 : 6;
-    for (int st = need_k1 ? 0 : 1; st <= n_stage; ++st) {
+    for (int i = 0; i < 6; ++i) K(0, i) = k1[i];
+    for (int st = 1; st <= 6; ++st) {
       double v[6];
-      double ts;
       for (int i = 0; i < 6; ++i) v[i] = u[i];
-      if (st == 0) {
-        ts = s;
-      } else if (starting) {
-        // OrdinaryDiffEq ode_determine_initdt (Hairer II.4), order 5, 7-component RMS norm
-        double a[6];
-        for (int i = 0; i < 6; ++i) sk[i] = P.atol + fabs(u[i]) * P.rtol;
-        sk7 = P.atol + fabs(u7_0) * P.rtol;
-        for (int i = 0; i < 6; ++i) a[i] = u[i] / sk[i];
-        const double d0 = rms7(a, u7_0 / sk7);
-        for (int i = 0; i < 6; ++i) a[i] = K(0, i) / sk[i];
-        d1 = rms7(a, fac7 * K(0, 5) / sk7);
-        dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
-        dt0 = fmin(dt0, s1 - s);
-        for (int i = 0; i < 6; ++i) v[i] += dt0 * K(0, i);
-        ts = s + dt0;
-      } else {
-        for (int j = 0; j < st; ++j) {
-          const double c = h * DP_A[st][j];
-          for (int i = 0; i < 6; ++i) v[i] += c * K(j, i);
-        }
-        ts = (st == 6) ? s_new : s + DP_C[st] * h;
+      for (int j = 0; j < st; ++j) {
+        const double c = h * DP_A[st][j];
+        for (int i = 0; i < 6; ++i) v[i] += c * K(j, i);
       }
+      const double ts = (st == 6) ? s_new : s + DP_C[st] * h;
       double dv[6];
       f<SP>(P, v, ts, dv);
-      n_rhs++;
-      if (starting && st == 1) {
-        double a[6];
-        for (int i = 0; i < 6; ++i) a[i] = (dv[i] - K(0, i)) / sk[i];
-        const double d2 = rms7(a, fac7 * (dv[5] - K(0, 5)) / sk7) / dt0;
-        const double dm = fmax(d1, d2);
-        const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : exp(-(2.0 + log10(dm)) / 5.0 * 2.302585092994046);
-        dt = fmin(fmin(100.0 * dt0, dt1), s1 - s);
-      } else {
-        for (int i = 0; i < 6; ++i) K(st, i) = dv[i];
-        if (st == 6)
-          for (int i = 0; i < 6; ++i) un[i] = v[i];
-      }
+      for (int i = 0; i < 6; ++i) K(st, i) = dv[i];
+      if (st == 6)
+        for (int i = 0; i < 6; ++i) un[i] = v[i];
     }
-    need_k1 = false;
-
-    if (starting) {  // reference sign of the crossing condition at the start point
-      const double g = cond(P, u, s);
-      n_cond++;
-      sgn_end = (g > 0.0) - (g < 0.0);
-      starting = false;
-      return false;
-    }
+    n_rhs += 6;
 
     // ---- error control ---------------------------------------------------------------------
     double q = 0.0, e6 = 0.0;
@@ -405,25 +417,70 @@ struct alignas(16) Ray {
     if (qq <= dp::qsteady_max && qq >= dp::qsteady_min) qq = 1.0;
     qold = fmax(EEst, dp::qoldinit);
     dt_new = h / qq;
+    n_cond += P.M_ray - 1 + (event_last ? 1 : 0);
+    return true;
+  }
 
-    // ---- publish the dense-output segment (Hairer contd5: rcont1 = u, rcont2..5 = r1..r4) ----
+  // Dense-output coefficients of component i of the accepted step (Hairer contd5: rcont1 = u,
+  // rcont2..5 = r1..r4)
+  template <class KS>
+  ART_HD void dense_comp(const KS K, int i, double r[4]) const {
+    double d = 0.0;
+    for (int j = 0; j < 7; ++j) d += DP_D[j] * K(j, i);
+    const double a1 = un[i] - u[i];
+    const double a2 = h * K(0, i) - a1;
+    r[0] = a1;
+    r[1] = a2;
+    r[2] = a1 - h * K(6, i) - a2;
+    r[3] = h * d;
+  }
+
+  // publish the dense-output segment of the accepted step
+  template <class KS, class DS>
+  ART_HD void publish(const KS K, const DS D) const {
     for (int i = 0; i < 6; ++i) {
-      double d = 0.0;
-      for (int j = 0; j < 7; ++j) d += DP_D[j] * K(j, i);
-      const double a1 = un[i] - u[i];
-      const double a2 = h * K(0, i) - a1;
+      double r[4];
+      dense_comp(K, i, r);
       D(SEG_U + i) = u[i];
-      D(SEG_R1 + i) = a1;
-      D(SEG_R2 + i) = a2;
-      D(SEG_R3 + i) = a1 - h * K(6, i) - a2;
-      D(SEG_R4 + i) = h * d;
+      D(SEG_R1 + i) = r[0];
+      D(SEG_R2 + i) = r[1];
+      D(SEG_R3 + i) = r[2];
+      D(SEG_R4 + i) = r[3];
     }
     D(SEG_S) = s;
     D(SEG_H) = h;
     D(SEG_U70) = u7_0;
     D(SEG_FAC7) = fac7;
     D(SEG_U60) = u6_0;
-    n_cond += P.M_ray - 1 + (event_last ? 1 : 0);
+  }
+
+  // Whole-step far-field test straight from the stage store (no segment needed): true ⇒ every scan
+  // point of the accepted step, the nudge point included, is provably negative (SegQuick::all_far).
+  template <class KS>
+  ART_HD bool step_all_far(const DevParams& P, const KS K) const {
+    double r0[4], r5[4];
+    dense_comp(K, 0, r0);
+    const double lo = fmin(u[0], u[0] + r0[0]) - 0.25 * (fabs(r0[1]) + fabs(r0[2]) + 0.25 * fabs(r0[3]));
+    if (!(lo > fmax(P.Rcut, P.r_int) * (1.0 + 1e-9))) return false;
+    dense_comp(K, 5, r5);
+    const double e0 = u7_0 + fac7 * (u[5] - u6_0), e1 = e0 + fac7 * r5[0];
+    const double de = fabs(fac7) * 0.25 * (fabs(r5[1]) + fabs(r5[2]) + 0.25 * fabs(r5[3]));
+    const double emin = fmin(fabs(e0), fabs(e1)) - de;
+    return emin > 0.0 && emin * emin >= P.ma2 * (1.0 + 1e-12);
+  }
+
+  // stages(): sequential form of start-up / attempted step (host check).  Returns true if a step was
+  // accepted; its dense-output segment has then been published in D and must be scanned before
+  // finish_step().
+  template <int SP = -1, class KS = KStore, class DS = SegStore>
+  ART_HD bool stages(const DevParams& P, const KS K, const DS D) {
+    if (!iter_guard(P)) return false;
+    if (starting) {
+      startup<SP>(P);
+      return false;
+    }
+    if (!attempt<SP>(P, K)) return false;
+    publish(K, D);
     return true;
   }
 
@@ -440,11 +497,8 @@ struct alignas(16) Ray {
   }
 
   // finish_step(): first sign change of the scanned step → root → callbacks → state update.
-  ART_HD void finish_step(const DevParams& P, const KStore K, const SegStore D, const ScanMasks m) {
-    finish_step_t(P, K, D, m);
-  }
   template <class KS, class DS>
-  ART_HD void finish_step_t(const DevParams& P, const KS K, const DS D, const ScanMasks m) {
+  ART_HD void finish_step(const DevParams& P, const KS K, const DS D, const ScanMasks m) {
     int ia = 0, ib = -1, sg_last = 0;
     const int ev = detect(P, D, m, ia, ib, sg_last);
     double th_ev = -1.0;
@@ -518,10 +572,22 @@ struct alignas(16) Ray {
     return fmin(ra, rb);
   }
 
-  // apply(): callbacks and state update at the end of an accepted step (th_ev < 0: no event)
+  // termination checks at the end of an accepted step: DiscreteCallback (photon hits the star,
+  // RT.jl:352-359) and the end of the span
+  ART_HD void settle(const DevParams& P) {
+    if (!axion && u[0] < P.rNS101) {
+      status = RAY_HIT_NS;
+      done = true;
+      return;
+    }
+    if (!(s < P.ln_tend)) done = true;
+  }
+
+  // apply(): callbacks and state update at the end of an accepted step (th_ev < 0: no event).
+  // K(6, ·) = k7 of the step (FSAL).  After an event the derivative at the event point is recomputed
+  // here unless the ray is finished (the reference's solver does it at the start of its next step).
   template <class KS, class DS>
   ART_HD void apply(const DevParams& P, const KS K, const DS D, double th_ev, int sg_last) {
-    const double h = D(SEG_H);
     bool terminated = false;
     if (th_ev >= 0.0) {
       double ue[6];
@@ -536,31 +602,26 @@ struct alignas(16) Ray {
       terminated = on_crossing(P, ue, se);
       for (int i = 0; i < 6; ++i) u[i] = ue[i];
       s = se;
-      need_k1 = !terminated;  // FSAL invalidated: k1 is recomputed at the start of the next step
       event_last = true;
     } else {
       for (int i = 0; i < 6; ++i) {
         u[i] = un[i];
-        K(0, i) = K(6, i);  // FSAL
+        k1[i] = K(6, i);  // FSAL
       }
       s = s_new;
       sgn_end = sg_last;
       event_last = false;
     }
     dt = dt_new;
-    if (terminated) {
-      done = true;
-      return;
+    if (terminated) done = true;
+    else settle(P);
+    if (th_ev >= 0.0 && !done) {  // FSAL invalidated by the event
+      f<-1>(P, u, s, k1);
+      n_rhs++;
     }
-    if (!axion && u[0] < P.rNS101) {  // DiscreteCallback, RT.jl:352-359
-      status = RAY_HIT_NS;
-      done = true;
-      return;
-    }
-    if (!(s < P.ln_tend)) done = true;
   }
 
-  // sequential form (host check, and the definition the cooperative GPU scan must reproduce)
+  // sequential form (host check, and the definition the GPU kernels must reproduce)
   ART_HD void step(const DevParams& P, const KStore K, const SegStore D) {
     if (!stages(P, K, D)) return;
     ScanMasks m = {0ull, 0ull, 0ull};

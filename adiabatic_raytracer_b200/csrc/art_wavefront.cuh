@@ -38,22 +38,24 @@ namespace art {
 
 constexpr int WF_THREADS = 128;
 #ifndef ART_STAGE_MINBLOCKS
-#define ART_STAGE_MINBLOCKS 2  // resident CTAs per SM the stage kernels' register allocation is tuned for
+#define ART_STAGE_MINBLOCKS 3  // resident CTAs per SM the stage kernels' register allocation is tuned for
+#endif
+#ifndef ART_STAGE_NSTEP
+#define ART_STAGE_NSTEP 4      // attempted steps a ray may take inside one k_wf_stages launch
 #endif
 constexpr int SEG_PAD = 36;  // doubles per published segment (SEG_N = 35, padded)
-constexpr int KF_PAD = 12;   // k1 and k7 of the last accepted step (FSAL), 6 doubles each
 
-enum { WC_ITEMS = 0, WC_ROOTS = 1, WC_FIN = 2, WC_ACT = 3 /* + parity*2 + species */, WC_N = 8 };
+enum { WC_ITEMS = 0, WC_ROOTS = 1, WC_FIN = 2, WC_PEND = 3, WC_ACT = 4 /* + parity*2 + species */, WC_N = 8 };
 
 struct WfPool {
-  Ray* ray;                   // [cap] ray state between kernels
-  double* kf;                 // [cap][12]
-  double* seg;                // [cap][36]
+  RayHot* hot;                // [cap] per-step ray state
+  RayCold* cold;              // [cap] callback-only ray state
+  double* seg;                // [cap][36] dense-output segment of a pending (accepted, unscanned) step
   unsigned long long* need;   // [cap] scan points awaiting the full condition
   unsigned long long* neg;    // [cap] scan points proven negative by the far-field test
-  unsigned char* pend;        // [cap] 1 = accepted step waiting for k_wf_detect
   unsigned char* sign;        // [cap][64]
   int* act[2][2];             // [parity][species][cap] ray ids
+  int* pend;                  // [cap] rays with a pending step
   unsigned* items;            // [cap * (M−1+1)] work list: (ray << 6) | point
   int* roots;                 // [cap]
   int* fin;                   // [cap]
@@ -73,10 +75,10 @@ struct WfTree {  // per-event tree context (null ev ⇒ plain ray batch, art_pro
   int* fin_info;
 };
 
-// FSAL copy K(0) ← K(6) of Ray::apply goes through a view of which only rows 0 and 6 exist
-struct KfView {
-  double* kf;
-  __device__ __forceinline__ double& operator()(int j, int i) const { return kf[(j == 0 ? 0 : 6) + i]; }
+// apply()'s FSAL copy k1 ← K(6): on the device k7 is already in the hot record
+struct K7View {
+  const double* k7;
+  __device__ __forceinline__ double operator()(int, int i) const { return k7[i]; }
 };
 
 struct WfStat {
@@ -105,22 +107,19 @@ struct WfStat {
   }
 };
 
-// Every lane of the warp calls this: finished rays write their result and join the finished list,
-// live rays join the next step's active list of their species (stream compaction of survivors).
-__device__ __forceinline__ void wf_route(const DevParams& P, const WfPool& W, int next, bool valid, int id,
-                                         const Ray& R, RayOut* out, WfStat& st) {
-  const bool fin = valid && R.done;
-  if (fin) {
-    RayOut o;
-    R.finish(P, o);
-    out[id] = o;
-    st.add(o, R.axion);
-  }
+// Stream compaction of survivors.  Every lane of the warp calls this: finished rays join the finished
+// list (their result is written by k_wf_tree / k_wf_collect), rays with a pending step the pending
+// list, live rays the next step's active list of their species — one atomic per warp and list.
+__device__ __forceinline__ void wf_route(const WfPool& W, int next, bool valid, int id, bool done, bool pending, bool axion) {
+  const bool fin = valid && done;
   const long long sf = warp_pop(W.ctr + WC_FIN, fin);
   if (fin) W.fin[sf] = id;
+  const bool pd = valid && !done && pending;
+  const long long sp_ = warp_pop(W.ctr + WC_PEND, pd);
+  if (pd) W.pend[sp_] = id;
 #pragma unroll
   for (int sp = 0; sp < 2; ++sp) {
-    const bool mine = valid && !R.done && ((R.axion ? SPECIES_AXION : SPECIES_PHOTON) == sp);
+    const bool mine = valid && !done && !pending && ((axion ? SPECIES_AXION : SPECIES_PHOTON) == sp);
     const long long s = warp_pop(W.ctr + WC_ACT + next * 2 + sp, mine);
     if (mine) W.act[next][sp][s] = id;
   }
@@ -128,16 +127,15 @@ __device__ __forceinline__ void wf_route(const DevParams& P, const WfPool& W, in
 
 __global__ void k_wf_reset(WfPool W, int next) {
   if (threadIdx.x == 0) {
-    W.ctr[WC_ITEMS] = 0; W.ctr[WC_ROOTS] = 0; W.ctr[WC_FIN] = 0;
+    W.ctr[WC_ITEMS] = 0; W.ctr[WC_ROOTS] = 0; W.ctr[WC_FIN] = 0; W.ctr[WC_PEND] = 0;
     W.ctr[WC_ACT + next * 2] = 0; W.ctr[WC_ACT + next * 2 + 1] = 0;
   }
 }
 
-// ---- start-up of a batch: IC transform; the first stages() call of a ray does the rest --------
+// ---- start-up of a batch: IC transform, first RHS, initial step size, starting sign ----------------
 __global__ void __launch_bounds__(WF_THREADS)
 k_wf_init(const __grid_constant__ DevParams P, const QueuedRay* __restrict__ q, long long n, WfPool W,
-          RayOut* __restrict__ out, double* __restrict__ rec, int rec_cap, DevStats* stats) {
-  WfStat st;
+          double* __restrict__ rec, int rec_cap) {
   const long long nthreads = (long long)gridDim.x * blockDim.x;
   const long long nround = ((n + nthreads - 1) / nthreads) * nthreads;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nround; i += nthreads) {
@@ -147,20 +145,31 @@ k_wf_init(const __grid_constant__ DevParams P, const QueuedRay* __restrict__ q, 
     const bool valid = i < n;
     if (valid) {
       R.init(P, q[i].in, rec + (size_t)i * rec_cap * 8, rec_cap);
-      W.pend[i] = 0;
-      W.ray[i] = R;
+      if (!R.done && R.iter_guard(P)) R.startup<-1>(P);
+      W.hot[i] = static_cast<const RayHot&>(R);
+      W.cold[i] = static_cast<const RayCold&>(R);
     }
-    wf_route(P, W, 0, valid, (int)i, R, out, st);
+    // rays that start past the end of the span stay `done`: the first k_wf_stages launch retires them
+    wf_route(W, 0, valid, (int)i, false, false, R.axion);
   }
-  st.flush(stats);
 }
 
-// ---- one iteration (start-up or attempted step) per active ray of species SP --------------------
+// ---- attempted steps of the active rays of species SP ------------------------------------------------
+// One thread per ray: 6 right-hand sides per attempt with the stage derivatives in shared memory (one
+// column per thread), error control, then one of three outcomes —
+//   rejected                       → new dt, try again
+//   accepted, whole step provably in the far field and no sign change possible
+//                                  → state advanced in registers, try the next step
+//   accepted otherwise             → state advanced optimistically, dense-output segment published,
+//                                    scan points classified and listed; ray joins the pending list
+// A warp keeps stepping (at most ART_STAGE_NSTEP attempts) while at least half of its lanes can go on,
+// so far-field rays and rejected steps do not pay a state round trip per attempt.
 template <int SP>
 __global__ void __launch_bounds__(WF_THREADS, ART_STAGE_MINBLOCKS)
 k_wf_stages(const __grid_constant__ DevParams P, WfPool W, int cur) {
   extern __shared__ double ksm[];
   const KStoreT<WF_THREADS> K{ksm + threadIdx.x};
+  const int next = 1 - cur;
   const long long n = (long long)W.ctr[WC_ACT + cur * 2 + SP];
   const int* __restrict__ act = W.act[cur][SP];
   const long long nthreads = (long long)gridDim.x * blockDim.x;
@@ -169,37 +178,63 @@ k_wf_stages(const __grid_constant__ DevParams P, WfPool W, int cur) {
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nround; t += nthreads) {
     unsigned long long need = 0ull;
     int id = -1;
-    if (t < n) {
-      id = act[t];
-      Ray R = W.ray[id];
-      double* kf = W.kf + (size_t)id * KF_PAD;
-      const bool had_k1 = !R.need_k1;
-      if (had_k1)
-        for (int k = 0; k < 6; ++k) K(0, k) = kf[k];
-      const SegAoS D{W.seg + (size_t)id * SEG_PAD};
-      const bool pending = R.template stages<SP>(P, K, D);
-      if (!had_k1)
-        for (int k = 0; k < 6; ++k) kf[k] = K(0, k);
-      if (pending) {
-        unsigned long long neg = 0ull;
-        for (int k = 0; k < 6; ++k) kf[6 + k] = K(6, k);
-        const int M = P.M_ray;
-        const SegQuick Q(D);
-        if (Q.all_far(P)) {
-          neg = ((M >= 64) ? ~0ull : ((1ull << M) - 1ull)) & (R.event_last ? ~0ull : ~1ull);
-        } else {
-          for (int i = R.event_last ? 0 : 1; i < M; ++i) {
-            const int qk = Q.classify(P, seg_theta(P, i));
-            if (qk == 0) need |= 1ull << i;
-            else if (qk == -1) neg |= 1ull << i;
+    bool pending = false, done = false;
+    const bool valid = t < n;
+    if (valid) id = act[t];
+    Ray R;
+    if (valid) static_cast<RayHot&>(R) = W.hot[id];
+    bool go = valid && !R.done;
+    done = valid && R.done;
+    for (int it = 0; it < ART_STAGE_NSTEP; ++it) {
+      if (go) {
+        if (!R.iter_guard(P)) {
+          go = false;
+          done = true;
+        } else if (R.template attempt<SP>(P, K)) {
+          if ((R.event_last || R.sgn_end <= 0) && R.step_all_far(P, K)) {
+            // no crossing possible: apply(th_ev < 0, sg_last = −1)
+            for (int i = 0; i < 6; ++i) {
+              R.u[i] = R.un[i];
+              R.k1[i] = K(6, i);
+            }
+            R.s = R.s_new;
+            R.sgn_end = -1;
+            R.event_last = false;
+            R.dt = R.dt_new;
+            R.settle(P);
+            if (R.done) {
+              go = false;
+              done = true;
+            }
+          } else {
+            const SegAoS D{W.seg + (size_t)id * SEG_PAD};
+            R.publish(K, D);
+            unsigned long long neg = 0ull;
+            const int M = P.M_ray;
+            const SegQuick Q(D);
+            for (int i = R.event_last ? 0 : 1; i < M; ++i) {
+              const int qk = Q.classify(P, seg_theta(P, i));
+              if (qk == 0) need |= 1ull << i;
+              else if (qk == -1) neg |= 1ull << i;
+            }
+            W.need[id] = need;
+            W.neg[id] = neg;
+            // optimistic advance; k_wf_detect / k_wf_root complete or override it
+            for (int i = 0; i < 6; ++i) {
+              R.u[i] = R.un[i];
+              R.k1[i] = K(6, i);
+            }
+            R.s = R.s_new;
+            R.dt = R.dt_new;
+            go = false;
+            pending = true;
           }
         }
-        W.need[id] = need;
-        W.neg[id] = neg;
       }
-      W.pend[id] = pending ? 1 : 0;
-      W.ray[id] = R;
+      if (it + 1 < ART_STAGE_NSTEP && __popc(__ballot_sync(FULL, go)) < 16) break;
     }
+    if (valid) W.hot[id] = static_cast<const RayHot&>(R);
+    wf_route(W, next, valid, id, done, pending, SP == SPECIES_AXION);
     // append this warp's scan points to the global work list: one atomic per warp
     const int cnt = __popcll(need);
     int incl = cnt;
@@ -238,72 +273,89 @@ k_wf_scan(const __grid_constant__ DevParams P, WfPool W) {
   }
 }
 
-// ---- events: detection, no-crossing update, routing --------------------------------------------------
+// Rebuilds the transient view of a pending step from the hot record (optimistically advanced) and the
+// published segment (state at the start of the step).
+__device__ __forceinline__ void wf_load_pending(Ray& R, const SegAoS D) {
+  for (int i = 0; i < 6; ++i) {
+    R.un[i] = R.u[i];
+    R.u[i] = D(SEG_U + i);
+  }
+  R.s_new = R.s;
+  R.s = D(SEG_S);
+  R.h = D(SEG_H);
+  R.dt_new = R.dt;
+}
+
+// ---- events: detection over the pending rays; no crossing ⇒ the optimistic advance stands ------------
 __global__ void __launch_bounds__(WF_THREADS)
-k_wf_detect(const __grid_constant__ DevParams P, WfPool W, int cur, RayOut* __restrict__ out, DevStats* stats) {
-  WfStat st;
-  const int next = 1 - cur;
-  const long long n0 = (long long)W.ctr[WC_ACT + cur * 2 + 0], n1 = (long long)W.ctr[WC_ACT + cur * 2 + 1];
-  const long long n = n0 + n1;
+k_wf_detect(const __grid_constant__ DevParams P, WfPool W, int next) {
+  const long long n = (long long)W.ctr[WC_PEND];
   const long long nthreads = (long long)gridDim.x * blockDim.x;
   const long long nround = ((n + nthreads - 1) / nthreads) * nthreads;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nround; t += nthreads) {
-    Ray R;
-    R.done = false;
-    R.axion = false;
-    bool valid = t < n, to_root = false;
+    const bool valid = t < n;
+    bool to_root = false, done = false, axion = false;
     int id = -1;
     if (valid) {
-      id = (t < n0) ? W.act[cur][0][t] : W.act[cur][1][t - n0];
-      R = W.ray[id];
-      if (W.pend[id]) {
-        ScanMasks m{0ull, W.neg[id], 0ull};
-        unsigned long long need = W.need[id];
-        const unsigned char* sg = W.sign + (size_t)id * 64;
-        while (need) {
-          const int i = __ffsll((long long)need) - 1;
-          const unsigned v = sg[i];
-          if (v == 1) m.pos |= 1ull << i;
-          else if (v == 2) m.neg |= 1ull << i;
-          else if (v == 3) m.zero |= 1ull << i;
-          need &= need - 1ull;
-        }
-        const SegAoS D{W.seg + (size_t)id * SEG_PAD};
-        int ia, ib, sgl;
-        const int ev = R.detect(P, D, m, ia, ib, sgl);
-        if (ev == 1) {
-          R.br_a = ia; R.br_b = ib; R.br_sg = sgl;
-          to_root = true;
-        } else {
-          const KfView K{W.kf + (size_t)id * KF_PAD};
-          R.apply(P, K, D, ev == 2 ? 1.0 : -1.0, sgl);
-        }
-        W.pend[id] = 0;
-        W.ray[id] = R;
+      id = W.pend[t];
+      Ray R;
+      static_cast<RayHot&>(R) = W.hot[id];
+      axion = R.axion;
+      ScanMasks m{0ull, W.neg[id], 0ull};
+      unsigned long long need = W.need[id];
+      const unsigned char* sg = W.sign + (size_t)id * 64;
+      while (need) {
+        const int i = __ffsll((long long)need) - 1;
+        const unsigned v = sg[i];
+        if (v == 1) m.pos |= 1ull << i;
+        else if (v == 2) m.neg |= 1ull << i;
+        else if (v == 3) m.zero |= 1ull << i;
+        need &= need - 1ull;
+      }
+      const SegAoS D{W.seg + (size_t)id * SEG_PAD};
+      // detect() only reads the start-box reference point from the cold record (first crossing only)
+      if (R.n_cross == 0) {
+        const RayCold& C = W.cold[id];
+        R.x0[0] = C.x0[0]; R.x0[1] = C.x0[1]; R.x0[2] = C.x0[2];
+      }
+      int ia, ib, sgl;
+      const int ev = R.detect(P, D, m, ia, ib, sgl);
+      if (ev != 0) {
+        RayCold& C = W.cold[id];
+        C.br_a = ia; C.br_b = (ev == 2) ? -2 : ib; C.br_sg = sgl;
+        to_root = true;
+      } else {
+        // apply(th_ev < 0): state, FSAL derivative, s and dt were advanced by k_wf_stages
+        R.sgn_end = sgl;
+        R.event_last = false;
+        R.settle(P);
+        done = R.done;
+        RayHot& H = W.hot[id];
+        H.sgn_end = R.sgn_end; H.status = R.status;
+        H.event_last = false; H.done = R.done;
       }
     }
     const long long sr = warp_pop(W.ctr + WC_ROOTS, to_root);
     if (to_root) W.roots[sr] = id;
-    wf_route(P, W, next, valid && !to_root, id, R, out, st);
+    wf_route(W, next, valid && !to_root, id, done, false, axion);
   }
-  st.flush(stats);
 }
 
+// ---- root finder (all lanes iterate together), crossing callback, state update ------------------------
 __global__ void __launch_bounds__(WF_THREADS)
-k_wf_root(const __grid_constant__ DevParams P, WfPool W, int next, RayOut* __restrict__ out, DevStats* stats) {
-  WfStat st;
+k_wf_root(const __grid_constant__ DevParams P, WfPool W, int next) {
   const long long n = (long long)W.ctr[WC_ROOTS];
   const long long nthreads = (long long)gridDim.x * blockDim.x;
   const long long nround = ((n + nthreads - 1) / nthreads) * nthreads;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nround; t += nthreads) {
-    Ray R;
-    R.done = false;
-    R.axion = false;
     const bool valid = t < n;
+    bool done = false, axion = false;
     int id = -1;
     if (valid) {
       id = W.roots[t];
-      R = W.ray[id];
+      Ray R;
+      static_cast<RayHot&>(R) = W.hot[id];
+      static_cast<RayCold&>(R) = W.cold[id];
       double segl[SEG_PAD];  // the root finder evaluates the segment ~12 times: keep it on chip
       {
         const double* sgp = W.seg + (size_t)id * SEG_PAD;
@@ -311,12 +363,36 @@ k_wf_root(const __grid_constant__ DevParams P, WfPool W, int next, RayOut* __res
         for (int k = 0; k < SEG_PAD; ++k) segl[k] = sgp[k];
       }
       const SegAoS D{segl};
-      const KfView K{W.kf + (size_t)id * KF_PAD};
-      const double th = R.locate(P, D, R.br_a, R.br_b);
+      wf_load_pending(R, D);
+      const K7View K{R.k1};
+      const double th = (R.br_b == -2) ? 1.0 : R.locate(P, D, R.br_a, R.br_b);
       R.apply(P, K, D, th, R.br_sg);
-      W.ray[id] = R;
+      W.hot[id] = static_cast<const RayHot&>(R);
+      done = R.done;
+      axion = R.axion;
     }
-    wf_route(P, W, next, valid, id, R, out, st);
+    wf_route(W, next, valid, id, done, false, axion);
+  }
+}
+
+// result of a finished ray
+__device__ __forceinline__ RayOut wf_result(const DevParams& P, const RayHot& H, WfStat& st) {
+  Ray R;
+  static_cast<RayHot&>(R) = H;
+  RayOut o;
+  R.finish(P, o);
+  st.add(o, R.axion);
+  return o;
+}
+
+// plain ray batches (art_propagate): results of the finished rays
+__global__ void __launch_bounds__(WF_THREADS)
+k_wf_collect(const __grid_constant__ DevParams P, WfPool W, RayOut* __restrict__ out, DevStats* stats) {
+  WfStat st;
+  const long long n = (long long)W.ctr[WC_FIN];
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const int id = W.fin[t];
+    out[id] = wf_result(P, W.hot[id], st);
   }
   st.flush(stats);
 }
@@ -357,8 +433,8 @@ __device__ __forceinline__ bool wf_tree_step(const DevParams& P, const WfTree& T
 }
 
 __global__ void __launch_bounds__(WF_THREADS)
-k_wf_tree(const __grid_constant__ DevParams P, WfPool W, WfTree T, int next, RayOut* __restrict__ out,
-          double* __restrict__ rec, int rec_cap, DevStats* stats) {
+k_wf_tree(const __grid_constant__ DevParams P, WfPool W, WfTree T, int next, double* __restrict__ rec, int rec_cap,
+          DevStats* stats) {
   WfStat st;
   const long long n = (long long)W.ctr[WC_FIN];
   const long long nthreads = (long long)gridDim.x * blockDim.x;
@@ -371,60 +447,23 @@ k_wf_tree(const __grid_constant__ DevParams P, WfPool W, WfTree T, int next, Ray
     int id = -1;
     if (t < n) {
       id = W.fin[t];
-      spawn = wf_tree_step(P, T, id, out[id], rec, rec_cap, R);
+      const RayOut o = wf_result(P, W.hot[id], st);
+      spawn = wf_tree_step(P, T, id, o, rec, rec_cap, R);
       if (spawn) {
-        W.pend[id] = 0;
-        W.ray[id] = R;
+        // a re-initialised ray that is already past the end of the span stays `done`: the next
+        // k_wf_stages launch routes it back here (never happens for t < 1/Ω)
+        if (!R.done && R.iter_guard(P)) R.startup<-1>(P);
+        W.hot[id] = static_cast<const RayHot&>(R);
+        W.cold[id] = static_cast<const RayCold&>(R);
       }
     }
-    // a re-initialised ray that is already past the end of the span retires at once (never for t < 1/Ω)
-    wf_route(P, W, next, spawn, id, R, out, st);
-  }
-  st.flush(stats);
-}
-
-// ---- tail: when few rays are left the step-batched loop is latency bound (six kernels per step
-// for a handful of warps), so ONE persistent kernel finishes them: every lane takes an active ray,
-// steps it sequentially to its end, walks on through its event's tree in place, then takes the next.
-__global__ void __launch_bounds__(WF_THREADS)
-k_wf_tail(const __grid_constant__ DevParams P, WfPool W, WfTree T, int cur, RayOut* __restrict__ out,
-          double* __restrict__ rec, int rec_cap, DevStats* stats) {
-  extern __shared__ double ksm[];
-  const KStore K{ksm + threadIdx.x, (int)blockDim.x};
-  WfStat st;
-  const long long n0 = (long long)W.ctr[WC_ACT + cur * 2 + 0], n1 = (long long)W.ctr[WC_ACT + cur * 2 + 1];
-  const long long n = n0 + n1;
-  Ray R;
-  R.done = true;
-  bool have = false, exhausted = false;
-  int id = -1;
-  for (;;) {
-    const long long got = warp_pop(W.ctr + WC_ITEMS, !have && !exhausted);
-    if (!have && !exhausted) {
-      if (got >= 0 && got < n) {
-        id = (got < n0) ? W.act[cur][0][got] : W.act[cur][1][got - n0];
-        R = W.ray[id];
-        if (!R.need_k1)
-          for (int k = 0; k < 6; ++k) K(0, k) = W.kf[(size_t)id * KF_PAD + k];
-        have = true;
-      } else {
-        exhausted = true;
-      }
-    }
-    if (__ballot_sync(FULL, have) == 0) break;
-    if (have) {
-      if (!R.done) {
-        const SegStore D{W.seg + (size_t)id * SEG_PAD, 1};
-        R.step(P, K, D);
-      }
-      if (R.done) {
-        RayOut o;
-        R.finish(P, o);
-        out[id] = o;
-        st.add(o, R.axion);
-        have = false;
-        if (T.ev) have = wf_tree_step(P, T, id, o, rec, rec_cap, R);
-      }
+    // spawned rays join the next step's active list even when already done (see above)
+    const bool ax = R.axion;
+#pragma unroll
+    for (int sp = 0; sp < 2; ++sp) {
+      const bool mine = spawn && ((ax ? SPECIES_AXION : SPECIES_PHOTON) == sp);
+      const long long s = warp_pop(W.ctr + WC_ACT + next * 2 + sp, mine);
+      if (mine) W.act[next][sp][s] = id;
     }
   }
   st.flush(stats);
