@@ -202,10 +202,10 @@ __global__ void k_rhs_api(const __grid_constant__ DevParams P, long long n, cons
   double o[6];
   const double t = exp(lnt[i]);
   if (species[i] == SPECIES_PHOTON) {
-    rhs_photon(P, v[0], v[1], v[2], v[3] * erg[i], v[4] * erg[i], v[5] * erg[i], -v[6], t, erg[i], o);
+    rhs_photon(P, v[0], v[1], v[2], v[3] * erg[i], v[4] * erg[i], v[5] * erg[i], -v[6], t, 1.0 / erg[i], o);
     du[7 * i + 6] = P.Omega * erg[i] / C_KM * o[5];
   } else {
-    rhs_axion(P, v[0], v[1], v[3] * erg[i], v[4] * erg[i], v[5] * erg[i], t, erg[i], o);
+    rhs_axion(P, v[0], v[1], v[3] * erg[i], v[4] * erg[i], v[5] * erg[i], t, erg[i], 1.0 / erg[i], o);
     du[7 * i + 6] = 0.0;
   }
   for (int c = 0; c < 6; ++c) du[7 * i + c] = o[c];

@@ -32,6 +32,73 @@ constexpr double HBAR = 6.582119e-16;
 constexpr double GNEW = 1.32712e11;
 constexpr double PI = 3.14159265358979323846;
 
+// ---------------------------------------------------------------------------------------
+// Branch-free FP64 helpers for the hot loops.  CUDA's IEEE `/`, sqrt() and sincos() each carry a
+// special-case branch (and sincos a Payne–Hanek path with a local-memory frame); on the ray equations
+// those made 63 % of the executed instructions non-FP64 (profiles/r01_wf5_*).  Arguments here are
+// finite, normal and of moderate size, so: MUFU seed + two Newton steps (≤ 1–2 ulp), and a
+// Cody–Waite reduction with fdlibm's kernel polynomials for |x| < 1e5 (≤ 1 ulp).
+// The host build (tests/hostcheck) uses the plain operators for 1/x and sqrt.
+// ---------------------------------------------------------------------------------------
+ART_HD double frcp(double x) {
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+#else
+  return 1.0 / x;
+#endif
+}
+ART_HD double frsqrt(double x) {  // x > 0
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  double e = fma(-hx * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-hx * y, y, 0.5);
+  return fma(y, e, y);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+ART_HD double fsqrt(double x) {  // x > 0
+#if defined(__CUDA_ARCH__)
+  const double y = frsqrt(x);
+  double s = x * y;
+  const double r = fma(-s, s, x);
+  return fma(r, 0.5 * y, s);
+#else
+  return sqrt(x);
+#endif
+}
+ART_HD void fsincos(double x, double* sn, double* cs) {
+  const double k = rint(x * 0.63661977236758134308);  // 2/π
+  double r = fma(-k, 1.57079632679489655800e+00, x);
+  r = fma(-k, 6.12323399573676603587e-17, r);
+  r = fma(-k, 8.4784276603688985e-32, r);
+  const double z = r * r;
+  double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+  ps = fma(z, ps, 2.75573137070700676789e-06);
+  ps = fma(z, ps, -1.98412698298579493134e-04);
+  ps = fma(z, ps, 8.33333333332248946124e-03);
+  ps = fma(z, ps, -1.66666666666666324348e-01);
+  const double S = fma(r * z, ps, r);
+  double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+  pc = fma(z, pc, -2.75573143513906633035e-07);
+  pc = fma(z, pc, 2.48015872894767294178e-05);
+  pc = fma(z, pc, -1.38888888888741095749e-03);
+  pc = fma(z, pc, 4.16666666666666019037e-02);
+  const double C = fma(z * z, pc, fma(-0.5, z, 1.0));
+  const int n = (int)k;
+  const double a = (n & 1) ? C : S, b = (n & 1) ? S : C;
+  *sn = (n & 2) ? -a : a;
+  *cs = ((n + 1) & 2) ? -b : b;
+}
+
 // Run constants, derived once on the host from art_params (art_api.cu: make_dev_params).
 struct DevParams {
   double cm, sm;      // cos θm, sin θm
@@ -127,59 +194,89 @@ ART_HD Fld field_cs(const DevParams& P, double c, double s, double cp, double sp
 template <bool DERIV>
 ART_HD Fld field(const DevParams& P, double th, double psi) {
   double c, s, cp, sp;
-  sincos(th, &s, &c);
-  sincos(psi, &sp, &cp);
+  fsincos(th, &s, &c);
+  fsincos(psi, &sp, &cp);
   return field_cs<DERIV>(P, c, s, cp, sp);
+}
+
+// Metric for the hot loops: as metric(), from 1/r, plus √g^rr and 1/√g^rr; the exterior branch has
+// one rsqrt and no division.
+struct MetHot {
+  double gtt, grr, dgtt, dgrr, sq, isq;
+};
+ART_HD MetHot metric_hot(double r, double rinv, double rs, double R) {
+  MetHot m;
+  if (r > R) {
+    const double A = 1.0 - rs * rinv;
+    const double y = frsqrt(A);
+    const double Ainv = y * y;
+    m.grr = A;
+    m.gtt = -Ainv;
+    m.dgrr = rs * rinv * rinv;
+    m.dgtt = m.dgrr * Ainv * Ainv;
+    m.sq = A * y;
+    m.isq = y;
+  } else {
+    const Met g = metric(r, rs, R);
+    m.gtt = g.gtt; m.grr = g.grr; m.dgtt = g.dgtt; m.dgrr = g.dgrr;
+    m.sq = sqrt(g.grr);
+    m.isq = 1.0 / m.sq;
+  }
+  return m;
 }
 
 // ---------------------------------------------------------------------------------------
 // Photon right-hand side: func!, RT.jl:71-91, components 1..6 (du7 = (Ω·erg/c_km)·du6, see
 // DESIGN.md §3.2 — H depends on t only through ψ = φ − Ωt, so ∂H/∂t = −Ω ∂H/∂φ).
-// k = (k_r,k_θ,k_φ) = u[4:6]·erg, om = −u7, t = e^{ln t}.
+// k = (k_r,k_θ,k_φ) = u[4:6]·erg, om = −u7, t = e^{ln t}, einv = 1/erg.
+// Five reciprocals (r, sinθ, D, ω, via rsqrt: g^rr), no division.
 // ---------------------------------------------------------------------------------------
 ART_HD void rhs_photon(const DevParams& P, double r, double th, double ph, double kr, double kt,
-                       double kp, double om, double t, double erg, double du[6]) {
+                       double kp, double om, double t, double einv, double du[6]) {
   if (r <= P.rNS101) {  // RT.jl:86
     for (int i = 0; i < 6; ++i) du[i] = 0.0;
     return;
   }
-  const Met m = metric(r, P.rs_ray, P.r_int);
+  const double rinv = frcp(r);
+  const MetHot m = metric_hot(r, rinv, P.rs_ray, P.r_int);
   const Fld f = field<true>(P, th, ph - P.Omega * t);
-  const double rinv = 1.0 / r, sinv = 1.0 / f.s;
+  const double sinv = frcp(f.s);
   const double rinv2 = rinv * rinv, rinv3 = rinv2 * rinv;
   const double q3 = P.Q * rinv3;
   const double Pp = q3 * fabs(f.bz);
   const double sg = signbit(f.bz) ? -q3 : q3;  // ForwardDiff abs: signbit ? −d : d
-  const double sq = sqrt(m.grr);
-  const double om2 = om * om;
+  const double sq = m.sq;
+  const double ominv = frcp(om);
+  const double om2inv = ominv * ominv;
   const double n_r = sq * f.br, n_t = f.bt * rinv, n_p = f.bp * rinv * sinv;
   const double N = kr * n_r + kt * n_t + kp * n_p;
-  const double Dinv = 1.0 / f.D;
-  double W = Pp * Dinv / om2;  // ωp² / (D ω²)
-  double X = 1.0 - m.grr * N * N * Dinv / om2;
+  const double Dinv = frcp(f.D);
+  double W = Pp * Dinv * om2inv;  // ωp² / (D ω²)
+  double X = 1.0 - m.grr * N * N * Dinv * om2inv;
   if (P.isotropic) {  // hamiltonian iso branch, RT.jl:542-544
     W = 0.0;
     X = 1.0;
   }
   const double gN = W * m.grr * N;
-  const double kp2 = kp * kp * rinv2 * sinv * sinv;  // k_φ² /(r² s²)
+  const double s2inv = rinv2 * sinv * sinv;
+  const double kp2 = kp * kp * s2inv;  // k_φ² /(r² s²)
   const double kt2 = kt * kt * rinv2;
   // ∂H/∂k
   const double Hk_r = m.grr * kr - gN * n_r;
   const double Hk_t = kt * rinv2 - gN * n_t;
-  const double Hk_p = kp * rinv2 * sinv * sinv - gN * n_p;
+  const double Hk_p = kp * s2inv - gN * n_p;
   // ∂N/∂x
-  const double N_r = (0.5 * m.dgrr / sq) * kr * f.br - (kt * n_t + kp * n_p) * rinv;
+  const double N_r = (0.5 * m.dgrr * m.isq) * kr * f.br - (kt * n_t + kp * n_p) * rinv;
   const double N_t = kr * sq * f.br_t + kt * f.bt_t * rinv - kp * n_p * f.c * sinv;
   const double N_p = kr * sq * f.br_p + kt * f.bt_p * rinv + kp * f.bp_p * rinv * sinv;
   // ∂H/∂x
-  const double H_r = 0.5 * (m.dgtt * om2 + m.dgrr * kr * kr - 2.0 * (kt2 + kp2) * rinv - 3.0 * Pp * rinv * X -
+  const double H_r = 0.5 * (m.dgtt * om * om + m.dgrr * kr * kr - 2.0 * (kt2 + kp2) * rinv - 3.0 * Pp * rinv * X -
                             W * (m.dgrr * N * N + 2.0 * m.grr * N * N_r));
   const double H_t = 0.5 * (-2.0 * f.c * sinv * kp2 + sg * f.bz_t * X -
                             W * m.grr * (2.0 * N * N_t - N * N * f.D_t * Dinv));
   const double H_p = 0.5 * (sg * f.bz_p * X - W * m.grr * (2.0 * N * N_p - N * N * f.D_p * Dinv));
-  const double fac = C_KM * t * m.grr / om;
-  const double face = fac / erg;
+  const double fac = C_KM * t * m.grr * ominv;
+  const double face = fac * einv;
   du[0] = Hk_r * fac;
   du[1] = Hk_t * fac;
   du[2] = Hk_p * fac;
@@ -190,21 +287,23 @@ ART_HD void rhs_photon(const DevParams& P, double r, double th, double ph, doubl
 
 // Axion right-hand side: func_axion!, RT.jl:95-123 (geodesic; interior metric inside the star).
 ART_HD void rhs_axion(const DevParams& P, double r, double th, double kr, double kt, double kp,
-                      double t, double erg, double du[6]) {
-  const Met m = metric(r, P.rs_ray, P.r_int);
+                      double t, double erg, double einv, double du[6]) {
+  const double rinv = frcp(r);
+  const MetHot m = metric_hot(r, rinv, P.rs_ray, P.r_int);
   double s, c;
-  sincos(th, &s, &c);
-  const double rinv = 1.0 / r, sinv = 1.0 / s;
+  fsincos(th, &s, &c);
+  const double sinv = frcp(s);
   const double rinv2 = rinv * rinv;
-  const double kp2 = kp * kp * rinv2 * sinv * sinv;
+  const double s2inv = rinv2 * sinv * sinv;
+  const double kp2 = kp * kp * s2inv;
   const double kt2 = kt * kt * rinv2;
   const double H_r = 0.5 * (m.dgtt * erg * erg + m.dgrr * kr * kr - 2.0 * (kt2 + kp2) * rinv);
   const double H_t = -c * sinv * kp2;
-  const double fac = C_KM * t * m.grr / erg;
-  const double face = fac / erg;
+  const double fac = C_KM * t * m.grr * einv;
+  const double face = fac * einv;
   du[0] = m.grr * kr * fac;
   du[1] = kt * rinv2 * fac;
-  du[2] = kp * rinv2 * sinv * sinv * fac;
+  du[2] = kp * s2inv * fac;
   du[3] = -H_r * face;
   du[4] = -H_t * face;
   du[5] = 0.0;
@@ -242,6 +341,42 @@ ART_HD double thick_condition(const DevParams& P, double r, double th, double ps
                               double wt, double wp, double E, double rs, bool zero_in) {
   const Fld f = field<false>(P, th, psi);
   return thick_condition_f(P, r, f, wr, wt, wp, E, rs, zero_in);
+}
+
+// Division-free form of the same condition for the ray tracer's crossing scan and root finder:
+//   F = Q|b_z| (E² ww' D − g^rr NrmSq·ww N'²) − m_a² E² ww' D r³,   ww' = ww (r s)²,  N' = N r s,
+// i.e. F = Ham · 2E² · (E² ww D) (r s)² r³ — a strictly positive multiple, so F has the sign, the zeros
+// and the NaN set of Ham (same algebra as the sampler's condition, art_sampler.cuh).  Exterior metric:
+// g^rr NrmSq·ww = E² − m_a² A.  One reciprocal, one square root, two sincos.
+ART_HD double thick_F(const DevParams& P, double r, double th, double psi, double wr, double wt,
+                      double wp, double E, double rs, bool zero_in) {
+  double c, s, cp, sp;
+  fsincos(th, &s, &c);
+  fsincos(psi, &sp, &cp);
+  const Fld f = field_cs<false>(P, c, s, cp, sp);
+  const double E2 = E * E;
+  double grr, sq, gn;
+  if (r > P.r_int) {
+    grr = 1.0 - rs * frcp(r);
+    sq = fsqrt(grr);
+    gn = E2 - P.ma2 * grr;
+    if (gn < 0.0) return NAN;  // NrmSq < 0
+  } else {
+    const Met m = metric(r, rs, P.r_int);
+    const double nrm = -E2 * m.gtt - P.ma2;
+    if (nrm < 0.0) return NAN;
+    grr = m.grr;
+    sq = sqrt(grr);
+    gn = grr * nrm;
+  }
+  const double a = wr * r * s, b = wt * s;
+  const double wwp = grr * a * a + b * b + wp * wp;
+  const double Np = a * sq * f.br + b * f.bt + wp * f.bp;
+  double Pq = P.Q * fabs(f.bz);
+  if (zero_in && r <= P.rNS) Pq = 0.0;
+  const double base = E2 * wwp * f.D;
+  const double aniso = P.isotropic ? 0.0 : gn * Np * Np;
+  return Pq * (base - aniso) - P.ma2 * base * (r * r * r);
 }
 
 // Cartesian → spherical

@@ -167,14 +167,16 @@ struct SegQuick {
   }
 };
 
-// `condition` of propagate (RT.jl:254-298) at dense-output parameter th of a published segment
+// `condition` of propagate (RT.jl:254-298) at dense-output parameter th of a published segment, as the
+// sign-equivalent division-free thick_F (art_physics.cuh); the scan keeps only its sign, the root finder
+// its zero
 template <class DS>
 ART_HD double seg_cond_full(const DevParams& P, const DS D, double th) {
   double w[6];
   seg_state(D, th, w);
   const double E = D(SEG_U70) + D(SEG_FAC7) * (w[5] - D(SEG_U60));
   const double t = exp(D(SEG_S) + th * D(SEG_H));
-  return thick_condition(P, w[0], w[1], w[2] - P.Omega * t, w[3], w[4], w[5], E, P.rs_ray, true);
+  return thick_F(P, w[0], w[1], w[2] - P.Omega * t, w[3], w[4], w[5], E, P.rs_ray, true);
 }
 template <class DS>
 ART_HD double seg_cond(const DevParams& P, const DS D, double th) {
@@ -253,10 +255,11 @@ struct Ray : RayHot, RayCold {
   ART_HD void f(const DevParams& P, const double v[6], double lnt, double dv[6]) const {
     const double t = exp(lnt);
     const bool ax = SP < 0 ? axion : (SP == SPECIES_AXION);
+    const double einv = frcp(erg);
     if (ax)
-      rhs_axion(P, v[0], v[1], v[3] * erg, v[4] * erg, v[5] * erg, t, erg, dv);
+      rhs_axion(P, v[0], v[1], v[3] * erg, v[4] * erg, v[5] * erg, t, erg, einv, dv);
     else
-      rhs_photon(P, v[0], v[1], v[2], v[3] * erg, v[4] * erg, v[5] * erg, -u7_of(v[5]), t, erg, dv);
+      rhs_photon(P, v[0], v[1], v[2], v[3] * erg, v[4] * erg, v[5] * erg, -u7_of(v[5]), t, einv, dv);
   }
 
   // `condition` of propagate (RT.jl:254-298) at a state v, time lnt.  Exact shortcut: for
@@ -268,7 +271,7 @@ struct Ray : RayHot, RayCold {
     const double r = v[0];
     if (r > P.Rcut && r > P.r_int) return (E * E * r >= P.ma2 * (r - P.rs_ray)) ? -1.0 : NAN;
     const double t = exp(lnt);
-    return thick_condition(P, r, v[1], v[2] - P.Omega * t, v[3], v[4], v[5], E, P.rs_ray, true);
+    return thick_F(P, r, v[1], v[2] - P.Omega * t, v[3], v[4], v[5], E, P.rs_ray, true);
   }
 
   ART_HD static double rms7(const double a[6], double a7) {
@@ -545,20 +548,24 @@ struct Ray : RayHot, RayCold {
     return 0;
   }
 
-  // locate(): Illinois regula falsi with bisection safeguard, to floating precision; left-biased
+  // locate(): Illinois regula falsi with bisection safeguard and Brent's minimum step, to floating
+  // precision; left-biased.  Values come from seg_cond_full (far-field shortcut values would not be on
+  // the scale of thick_F).
   template <class DS>
   ART_HD double locate(const DevParams& P, const DS D, int ia, int ib) {
     double ra = (ia == 0) ? (event_last ? 0.01 : 0.0) : seg_theta(P, ia), rb = seg_theta(P, ib);
-    double fa = seg_cond(P, D, ra), fb = seg_cond(P, D, rb);
+    double fa = seg_cond_full(P, D, ra), fb = seg_cond_full(P, D, rb);
     n_cond += 2;
     int side = 0;
     for (int it = 0; it < 200; ++it) {
       const double tol = 4.0 * 2.220446049250313e-16 * fmax(fabs(ra), fabs(rb)) + 1e-300;
-      if (fabs(rb - ra) <= tol) break;
+      const double width = fabs(rb - ra);
+      if (width <= tol) break;
       double c = (ra * fb - rb * fa) / (fb - fa);
       const double lo = fmin(ra, rb), hi = fmax(ra, rb);
-      if (!(c > lo && c < hi) || it >= 60) c = 0.5 * (ra + rb);
-      const double fc = seg_cond(P, D, c);
+      if (!(c > lo && c < hi) || it >= 60 || width <= 2.0 * tol) c = 0.5 * (ra + rb);
+      else if (fabs(c - rb) < tol) c = rb + copysign(tol, ra - rb);  // a converged iterate collapses the bracket
+      const double fc = seg_cond_full(P, D, c);
       n_cond++;
       if (fc == 0.0) return c;
       if ((fc < 0.0) != (fb < 0.0)) {

@@ -171,7 +171,7 @@ k_wf_stages(const __grid_constant__ DevParams P, WfPool W, int cur) {
   const KStoreT<WF_THREADS> K{ksm + threadIdx.x};
   const int next = 1 - cur;
   const long long n = (long long)W.ctr[WC_ACT + cur * 2 + SP];
-  const int* __restrict__ act = W.act[cur][SP];
+  const int* __restrict__ act = cur ? W.act[1][SP] : W.act[0][SP];  // (a dynamic index would copy the parameter struct to local memory)
   const long long nthreads = (long long)gridDim.x * blockDim.x;
   const long long nround = ((n + nthreads - 1) / nthreads) * nthreads;
   const unsigned lane = threadIdx.x & 31;

@@ -145,7 +145,9 @@ constexpr double qsteady_min = 1.0, qsteady_max = 1.2, qoldinit = 1e-4;
 }  // namespace dp
 
 // Bracketing root finder of the event location (stand-in for DiffEqBase's find_callback_time):
-// Illinois-modified regula falsi with a bisection safeguard, run to floating precision.
+// Illinois-modified regula falsi with a bisection safeguard and Brent's minimum step (an iterate that
+// has converged moves by the tolerance towards the other end, which collapses the bracket), run to
+// floating precision.
 // Returns the LEFT end (in time) of the final bracket, like DiffEqBase's left-biased root.
 template <class F>
 inline double find_root(F&& f, double a, double fa, double b, double fb, int* n_eval) {
@@ -157,7 +159,8 @@ inline double find_root(F&& f, double a, double fa, double b, double fb, int* n_
     if (width <= tol) break;
     double c = (a * fb - b * fa) / (fb - fa);
     double lo = std::min(a, b), hi = std::max(a, b);
-    if (!(c > lo && c < hi) || it >= 60) c = 0.5 * (a + b);
+    if (!(c > lo && c < hi) || it >= 60 || width <= 2.0 * tol) c = 0.5 * (a + b);
+    else if (std::fabs(c - b) < tol) c = b + std::copysign(tol, a - b);  // Brent's minimum step
     double fc = f(c);
     ++*n_eval;
     if (fc == 0.0) return c;

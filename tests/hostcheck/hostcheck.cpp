@@ -49,10 +49,10 @@ int hc_rhs(const art_params* p, int64_t n, const int32_t* species, const double*
     double* o = du + 7 * i;
     double t = exp(lnt[i]);
     if (species[i] == SPECIES_PHOTON) {
-      rhs_photon(P, v[0], v[1], v[2], v[3] * erg[i], v[4] * erg[i], v[5] * erg[i], -v[6], t, erg[i], o);
+      rhs_photon(P, v[0], v[1], v[2], v[3] * erg[i], v[4] * erg[i], v[5] * erg[i], -v[6], t, 1.0 / erg[i], o);
       o[6] = P.Omega * erg[i] / C_KM * o[5];
     } else {
-      rhs_axion(P, v[0], v[1], v[3] * erg[i], v[4] * erg[i], v[5] * erg[i], t, erg[i], o);
+      rhs_axion(P, v[0], v[1], v[3] * erg[i], v[4] * erg[i], v[5] * erg[i], t, erg[i], 1.0 / erg[i], o);
       o[6] = 0.0;
     }
   }
