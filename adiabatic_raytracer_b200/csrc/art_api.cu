@@ -212,12 +212,12 @@ int launch_trace_wf(art_handle* h, Lane& L, const QueuedRay* q, long long n, Ray
   const bool trace = getenv("ART_WF_TRACE") != nullptr;
   for (long long iter = 0;;) {
     const int burst = n_act > 65536 ? 4 : (n_act > 2048 ? 8 : 16);  // steps between host checks
+    const bool tail = n_act < 8LL * h->n_sm * WF_THREADS;               // fewer rays than one resident wave
     for (int b = 0; b < burst; ++b, ++iter) {
       const int next = 1 - cur;
       const int g1 = grid(n_act, WF_THREADS);
       k_wf_reset<<<1, 32, 0, st>>>(W, next);
-      k_wf_stages<SPECIES_AXION><<<g1, WF_THREADS, ksmem, st>>>(h->dp, W, cur);
-      k_wf_stages<SPECIES_PHOTON><<<g1, WF_THREADS, ksmem, st>>>(h->dp, W, cur);
+      k_wf_stages<<<2 * g1, WF_THREADS, ksmem, st>>>(h->dp, W, cur, tail ? 16 : ART_STAGE_NSTEP, tail ? 1 : 16);
       k_wf_scan<<<grid(n_act * 24, 256), 256, 0, st>>>(h->dp, W);
       k_wf_detect<<<g1, WF_THREADS, 0, st>>>(h->dp, W, next);
       k_wf_root<<<grid(n_act / 8 + 1, WF_THREADS), WF_THREADS, 0, st>>>(h->dp, W, next);
@@ -225,7 +225,7 @@ int launch_trace_wf(art_handle* h, Lane& L, const QueuedRay* q, long long n, Ray
         k_wf_tree<<<grid(n_act / 4 + 1, WF_THREADS), WF_THREADS, 0, st>>>(h->dp, W, *tree, next, rec, rec_cap, stats);
       else
         k_wf_collect<<<grid(n_act / 4 + 1, WF_THREADS), WF_THREADS, 0, st>>>(h->dp, W, out, stats);
-      h->launches += 7;
+      h->launches += 6;
       cur = next;
     }
     CU(cudaGetLastError());
@@ -296,10 +296,8 @@ int art_create(const art_params* p, int device_id, art_handle** out) {
   cudaGetDeviceProperties(&prop, device_id);
   h->n_sm = prop.multiProcessorCount;
   int occ = 0;
-  for (auto fn : {(const void*)k_wf_stages<SPECIES_AXION>, (const void*)k_wf_stages<SPECIES_PHOTON>}) {
-    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(42 * WF_THREADS * sizeof(double)));
-    cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  }
+  cudaFuncSetAttribute(k_wf_stages, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(42 * WF_THREADS * sizeof(double)));
+  cudaFuncSetAttribute(k_wf_stages, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sample_events, SAMPLE_THREADS, 0);
   h->blocks_sample = h->n_sm * std::max(occ, 1);
   if (const char* t = getenv("ART_LANES")) h->n_lanes = std::max(1, std::min(16, atoi(t)));

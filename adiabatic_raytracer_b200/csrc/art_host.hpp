@@ -80,6 +80,12 @@ inline int make_dev_params(const art_params& p, DevParams& d, std::string& err) 
   d.maxR = 1.01 * p.rNS * pow(om_test / p.Mass_a, 2.0 / 3.0);
   // radius beyond which ωp < m_a for every direction: max |b_z| = (3 + |cos θm|)/2
   d.Rcut = cbrt(d.Q * 0.5 * (3.0 + fabs(d.cm)) / d.ma2) * (1.0 + 1e-9);
+  d.cpsi0 = cos(p.omega_pul * p.t0_sample);
+  d.spsi0 = sin(p.omega_pul * p.t0_sample);
+  d.mh[0] = d.sm * d.cpsi0;
+  d.mh[1] = d.sm * d.spsi0;
+  d.mh[2] = d.cm;
+  d.T_samp = 2.2 * d.maxR;
   if (d.maxR < p.rNS) {
     err = "Too small Max R (no conversion surface outside the star), MainRunner.jl:389-396";
     return ART_ERR_NO_SURFACE;

@@ -64,7 +64,11 @@ __global__ void __launch_bounds__(SAMPLE_THREADS)
 k_sample_events(const __grid_constant__ DevParams P, unsigned long long seed, long long first_event, long long n,
                 EventSample* __restrict__ out, unsigned long long* head, DevStats* stats,
                 unsigned long long* n_failed_total) {
+  __shared__ double taus_sm[SAMP_KEEP * SAMPLE_THREADS];
   Sampler S;
+  S.taus = taus_sm + threadIdx.x;
+  S.taus_stride = SAMPLE_THREADS;
+  S.done = true;
   bool have = false, exhausted = false;
   long long idx = -1;
   unsigned attempt = 0;

@@ -122,6 +122,8 @@ struct DevParams {
   int32_t num_cutoff, MC_nodes, max_nodes;
   double prob_cutoff;
   double inv_Mrm1, inv_Msm1;  // 1/(M_ray − 1), 1/(M_samp − 1): dense-output grid spacing
+  double cpsi0, spsi0, mh[3];  // cos/sin Ω t0 and the magnetic axis m̂ at the field time t0 (sampler)
+  double T_samp;               // length of the sampler's line march, 2.2 maxR (RT.jl:1611)
 };
 
 struct Met {

@@ -20,6 +20,11 @@
 
 namespace art {
 
+#ifndef ART_ROOT_RTOL_DEFINED
+#define ART_ROOT_RTOL_DEFINED
+constexpr double ROOT_RTOL = 1e-13;  // event tolerance of the root finders, relative to the step
+#endif
+
 constexpr int SAMP_KEEP = 8;  // crossings remembered per line (n_maxSample ≤ 8)
 
 struct SampleResult {
@@ -27,17 +32,22 @@ struct SampleResult {
   int accepted, n_cross, n_cond;
 };
 
+// Attempt state.  Kept small enough to live in registers: the field orientation at t0 (m̂, cos/sin Ωt0)
+// and the march length are run constants (DevParams), the crossing list lives outside the struct (device:
+// a shared-memory column; a dynamically indexed member would push the whole struct to local memory —
+// profiles/r01_sampler_v2_hotlines.txt: 1.2e10 local sectors per launch, 10 active threads per
+// instruction).
 struct Sampler {
   double xs[3], va[3], vl[3];  // line origin, line direction, local velocity direction
-  double erg_inf, vI[3], vI_mag;
-  double cpsi0, spsi0;         // cos/sin of Ω t0
-  double mh[3], mv;            // magnetic axis m̂ at the field time t0, and m̂·v
-  double tau, tau_new, h, T, tau_out;
-  double g_prev, th_a, g_a, a, fa, b, fb;
-  double taus[SAMP_KEEP];
-  int i, sgn_prev, side, it, phase;  // phase: 0 scan, 1 nudge, 2 root
+  double E2, vI[3];            // E∞², v∞ components [km/s]
+  double mv;                   // m̂·v
+  double tau, tau_new, h, tau_out;
+  double g_prev, th_a, g_a, a, fa, b, fb, f0, w1, w2;
+  double* taus;    // crossing list, SAMP_KEEP entries `taus_stride` apart (device: shared memory column)
+  int taus_stride;
+  int i, sgn_prev, side, it, phase;  // phase: 0 scan, 1 nudge, 2 root, 3 first point of the march
   int n_cross, n_cond;
-  bool event_last, done;
+  bool event_last, done, pure;
 
   ART_HD void point(double t_, double u[3]) const {
     for (int c = 0; c < 3; ++c) u[c] = xs[c] + t_ * va[c];
@@ -47,49 +57,59 @@ struct Sampler {
   //
   // The reference builds covariant components of the unit vector v (vvec_loc), normalises them to
   // the axion mass shell and forms Ham = ½(−m_a² + ωp²(1 − g^rr k∥²/E²))/E².  With physical
-  // components, k∥²·g^rr/E² = g^rr·NrmSq·N²/(D·E²), NrmSq = (−E² g^tt − m_a²)/ww, and for a point
-  // outside the star (AA = g^rr = A, g^tt = −1/A):
-  //     ww = v_r² + v_θ² + v_φ² = 1,   N = v·b,   b = 3(m̂·r̂) r̂ − m̂   (dipole direction, |b|² = D),
-  //     b_z = 3(m̂·r̂)(ẑ·r̂) − cosθm,   m̂ = (sinθm cosΩt0, sinθm sinΩt0, cosθm)
-  // so everything is a dot product of the Cartesian point with two fixed vectors:
-  //     F = Q|b_z| r⁻³ (D E² − N² (E² − m_a² A)) − m_a² D E²   has the sign (and the roots) of Ham.
-  // One sqrt, one reciprocal, no trigonometry (the literal form costs 14 divisions and 5 square
-  // roots per evaluation — profiles/r01_sampler_v1_hotlines.txt: 60 % stall_wait on those chains).
-  // Inside the star (r < rNS: AA = 1 quirk RT.jl:1558-1560; r ≤ r_int: interior metric) the same
-  // algebra is kept with the general g^tt, g^rr:  ww = 1 − (1 − g^rr/AA') v_r² …, see below.
+  // components, k∥²·g^rr/E² = g^rr·NrmSq·N²/(D·E²), NrmSq = (−E² g^tt − m_a²)/ww, and
+  //     b = 3(m̂·r̂) r̂ − m̂   (dipole direction, |b|² = D),   b_z = 3(m̂·r̂)(ẑ·r̂) − cosθm,
+  //     covariant w = (v_r/(√AA·AA), v_θ r/AA, v_φ r s/AA)  (the common 1/AA drops out)
+  //     ww = g^rr v_r²/AA + v_θ² + v_φ²,   N = √(g^rr/AA) v_r b_r + (v·b − v_r b_r)
+  //     F = Q|b_z| r⁻³ (ww D E² − g^rr NrmSq·ww N²) − m_a² ww D E²   has the sign (and the roots) of Ham.
+  // Outside the star AA = g^rr = A and g^tt = −1/A, so ww = 1, N = v·b, g^rr NrmSq·ww = E² − m_a² A:
+  // one rsqrt, no division, no trigonometry.  Inside (r < rNS: AA = 1 quirk RT.jl:1558-1560; r ≤ r_int:
+  // interior metric) only the three metric scalars differ; the formula is shared, so lanes inside and
+  // outside the star stay converged except for the few instructions of the interior metric.
   ART_HD double cond(const DevParams& P, double t_) {
     n_cond++;
     const double x = xs[0] + t_ * va[0], y = xs[1] + t_ * va[1], z = xs[2] + t_ * va[2];
     const double r2 = x * x + y * y + z * z;
-    const double r = sqrt(r2);
-    const double rinv = 1.0 / r;
-    const double mx = (mh[0] * x + mh[1] * y + mh[2] * z) * rinv;  // m̂·r̂
-    const double vx = (vl[0] * x + vl[1] * y + vl[2] * z) * rinv;  // v·r̂  (= v_r)
-    const double cz = z * rinv;                                    // ẑ·r̂
+    const double rinv = frsqrt(r2);
+    const double r = r2 * rinv;
+    const double mx = (P.mh[0] * x + P.mh[1] * y + P.mh[2] * z) * rinv;  // m̂·r̂
+    const double vx = (vl[0] * x + vl[1] * y + vl[2] * z) * rinv;        // v·r̂  (= v_r)
+    const double cz = z * rinv;                                          // ẑ·r̂
     const double D = 3.0 * mx * mx + 1.0;
     const double bz = 3.0 * mx * cz - P.cm;
-    const double Pq = P.Q * fabs(bz) * rinv * rinv * rinv;         // ωp²
-    const double E2 = erg_inf * erg_inf;
-    if (r >= P.rNS && r > P.r_int) {
-      const double N = 3.0 * mx * vx - mv;                         // v·b
-      const double A = 1.0 - P.rs_real * rinv;
-      return Pq * (D * E2 - N * N * (E2 - P.ma2 * A)) - P.ma2 * D * E2;
+    const double Pq = P.Q * fabs(bz) * rinv * rinv * rinv;               // ωp²
+    const double vb = 3.0 * mx * vx - mv;                                // v·b
+    double ww = 1.0, N = vb, gn = E2 - P.ma2 * (1.0 - P.rs_real * rinv);
+    if (!(r >= P.rNS && r > P.r_int)) {
+      double grr, gtt;
+      if (r > P.r_int) {
+        grr = 1.0 - P.rs_real * rinv;
+        gtt = -frcp(grr);
+      } else {  // g_schwartz interior branch (RT.jl:463, 496-497), see metric()
+        const double q = r / P.r_int;
+        const double q3 = q * q * q;
+        const double aa = P.rs_real * q3 / P.r_int;
+        const double bb = aa * q * q;
+        const double den = 3.0 * fsqrt(1.0 - aa) - fsqrt(1.0 - bb);
+        grr = 1.0 - bb;
+        gtt = -4.0 * frcp(den * den);
+      }
+      const double AA = (r < P.rNS) ? 1.0 : 1.0 - P.rs_real * rinv;
+      const double AAinv = frcp(AA);
+      const double br = 2.0 * mx;
+      ww = grr * vx * vx * AAinv + (1.0 - vx * vx);
+      N = fsqrt(grr * AAinv) * vx * br + (vb - vx * br);
+      const double nrm = -E2 * gtt - P.ma2;  // NrmSq·ww
+      gn = grr * nrm;
+      if (nrm < 0.0) gn = NAN;
     }
-    // general form: covariant w = (v_r/(√AA·AA), v_θ r/AA, v_φ r s/AA); the common 1/AA drops out
-    const Met m = metric(r, P.rs_real, P.r_int);
-    const double AA = (r < P.rNS) ? 1.0 : 1.0 - P.rs_real * rinv;
-    const double br = 2.0 * mx;
-    const double vt2 = 1.0 - vx * vx;                              // v_θ² + v_φ²
-    const double wr2 = vx * vx / AA;                               // (v_r/√AA)²
-    const double ww = m.grr * wr2 + vt2;
-    // N = √g^rr w_r b_r + v_θ b_θ + v_φ b_φ,  v_θ b_θ + v_φ b_φ = v·b − v_r b_r
-    const double N = sqrt(m.grr / AA) * vx * br + ((3.0 * mx * vx - mv) - vx * br);
-    const double nrm = -E2 * m.gtt - P.ma2;                        // NrmSq·ww
-    if (nrm < 0.0) return NAN;
-    return Pq * (ww * D * E2 - m.grr * N * N * nrm) - P.ma2 * ww * D * E2;
+    // NrmSq < 0 (E below the local mass shell): the reference would throw; NaN = "no crossing"
+    if (gn < 0.0) gn = NAN;
+    const double base = ww * D * E2;
+    return Pq * (base - gn * N * N) - P.ma2 * base;
   }
 
-  // affect!, RT.jl:1585-1597
+  // affect!, RT.jl:1585-1597: keep the crossing iff r > rNS and E/√g^rr > ωp
   ART_HD void affect(const DevParams& P, double t_) {
     double u[3];
     point(t_, u);
@@ -97,25 +117,25 @@ struct Sampler {
     const double r = sqrt(rho2 + u[2] * u[2]);
     const double rho = sqrt(rho2);
     const double cph = u[0] / rho, sph = u[1] / rho;
-    const Fld f = field_cs<false>(P, u[2] / r, rho / r, cph * cpsi0 + sph * spsi0, sph * cpsi0 - cph * spsi0);
+    const Fld f = field_cs<false>(P, u[2] / r, rho / r, cph * P.cpsi0 + sph * P.spsi0, sph * P.cpsi0 - cph * P.spsi0);
     const double wp = sqrt(P.Q / (r * r * r) * fabs(f.bz));
     const Met m = metric(r, P.rs_real, P.r_int);
-    if (r > P.rNS && erg_inf / sqrt(m.grr) > wp) {
-      if (n_cross < SAMP_KEEP) taus[n_cross] = t_;
+    if (r > P.rNS && sqrt(E2) / sqrt(m.grr) > wp) {
+      if (n_cross < SAMP_KEEP) taus[n_cross * taus_stride] = t_;
       n_cross++;
     }
   }
 
   ART_HD void next_step(const DevParams& P) {
-    if (!(tau < T) || !(tau < tau_out)) {
+    if (!(tau < P.T_samp) || !(tau < tau_out)) {
       done = true;
       return;
     }
     h = P.samp_dt;
     tau_new = tau + h;
-    if (tau_new >= T) {
-      h = T - tau;
-      tau_new = T;
+    if (tau_new >= P.T_samp) {
+      h = P.T_samp - tau;
+      tau_new = P.T_samp;
     }
     i = 1;
     if (event_last) {
@@ -133,11 +153,11 @@ struct Sampler {
     double sti, cti, spi, cpi, stl, ctl, spl, cpl, sR, cR;
     cti = 1.0 - 2.0 * U[0];                 // θi = acos(1 − 2u)
     sti = sqrt(fmax(0.0, 1.0 - cti * cti));
-    sincos(U[1] * 2.0 * PI, &spi, &cpi);
+    fsincos(U[1] * 2.0 * PI, &spi, &cpi);
     ctl = 1.0 - 2.0 * U[2];
     stl = sqrt(fmax(0.0, 1.0 - ctl * ctl));
-    sincos(U[3] * 2.0 * PI, &spl, &cpl);
-    sincos(U[4] * 2.0 * PI, &sR, &cR);
+    fsincos(U[3] * 2.0 * PI, &spl, &cpl);
+    fsincos(U[4] * 2.0 * PI, &sR, &cR);
     const double rR = sqrt(U[5]) * P.maxR;
     va[0] = sti * cpi; va[1] = sti * spi; va[2] = cti;
     vl[0] = stl * cpl; vl[1] = stl * spl; vl[2] = ctl;
@@ -151,22 +171,25 @@ struct Sampler {
       vI[c] = (220.0 + U[6 + c] * 1.0e-5) / sqrt(3.0);  // RT.jl:1531
       v2 += vI[c] * vI[c];
     }
-    vI_mag = sqrt(v2);
-    const double bc = vI_mag / C_KM;
-    erg_inf = P.ma * sqrt(1.0 + bc * bc / (1.0 - bc * bc));  // RT.jl:1537-1538
+    const double bc = sqrt(v2) / C_KM;
+    const double erg_inf = P.ma * sqrt(1.0 + bc * bc / (1.0 - bc * bc));  // RT.jl:1537-1538
+    E2 = erg_inf * erg_inf;
     for (int c = 0; c < 3; ++c) xs[c] += va[c] * (-P.maxR * 1.1);  // RT.jl:1542
-    sincos(P.Omega * P.t0, &spsi0, &cpsi0);
-    mh[0] = P.sm * cpsi0; mh[1] = P.sm * spsi0; mh[2] = P.cm;
-    mv = mh[0] * vl[0] + mh[1] * vl[1] + mh[2] * vl[2];
+    mv = P.mh[0] * vl[0] + P.mh[1] * vl[1] + P.mh[2] * vl[2];
     n_cross = 0;
     n_cond = 0;
     event_last = false;
     done = false;
-    T = 2.2 * P.maxR;
+    pure = false;
+    phase = 3;
+    i = 1; sgn_prev = 0; side = 0; it = 0;
+    tau_new = h = g_prev = th_a = g_a = a = fa = b = fb = f0 = w1 = w2 = 0.0;
     // chord of the line inside the sphere r = Rcut
     const double bq = xs[0] * va[0] + xs[1] * va[1] + xs[2] * va[2];
     const double cq = xs[0] * xs[0] + xs[1] * xs[1] + xs[2] * xs[2] - P.Rcut * P.Rcut;
     const double disc = bq * bq - cq;
+    tau = 0.0;
+    tau_out = 0.0;
     if (!(disc > 0.0)) {
       done = true;
       return;
@@ -175,9 +198,7 @@ struct Sampler {
     const double tau_in = -bq - sd;
     tau_out = -bq + sd;
     const double n0 = floor(fmax(tau_in, 0.0) / P.samp_dt);
-    tau = n0 * P.samp_dt;
-    g_prev = cond(P, tau);
-    next_step(P);
+    tau = n0 * P.samp_dt;  // the first advance() evaluates the condition here (phase 3)
   }
 
   ART_HD void event(const DevParams& P, double th) {
@@ -188,24 +209,43 @@ struct Sampler {
     next_step(P);
   }
 
-  // exactly one condition evaluation
+  // Exactly one condition evaluation, at ONE call site: every lane of a warp — whatever the phase of
+  // its attempt — first picks its evaluation point, then all lanes evaluate together, then each
+  // finishes its phase's bookkeeping.
   ART_HD void advance(const DevParams& P) {
-    if (phase == 1) {  // repeat-nudge reference sign after an event (DiffEqBase repeat_nudge = 1/100)
-      const double g = cond(P, tau + 0.01 * h);
-      sgn_prev = (g > 0.0) - (g < 0.0);
-      th_a = 0.01;
-      g_a = g;
-      phase = 0;
-      return;
+    const int M = P.M_samp;
+    double tq, th = 0.0, c = 0.0;
+    bool end = false;
+    if (phase == 2) {
+      const double tol = ROOT_RTOL * fmax(fabs(a), fabs(b)) + 1e-300;
+      const double width = fabs(b - a);
+      if (width <= tol || it >= 200) {
+        event(P, fmin(a, b));
+        return;
+      }
+      if (it == 3 && fmin(fabs(fa), fabs(fb)) > 0.25 * f0) pure = true;
+      c = (a * fb - b * fa) / (fb - fa);
+      const double lo = fmin(a, b), hi = fmax(a, b);
+      if (pure || (it >= 3 && width > 0.5 * w2) || !(c > lo && c < hi) || width <= 2.0 * tol) c = 0.5 * (a + b);
+      else if (fabs(c - b) < tol) c = b + copysign(tol, a - b);
+      w2 = w1;
+      w1 = width;
+      tq = tau + c * h;
+    } else if (phase == 0) {
+      end = (i == M - 1);
+      th = end ? 1.0 : (double)i * P.inv_Msm1;
+      tq = end ? tau_new : tau + th * h;
+    } else if (phase == 1) {  // repeat-nudge reference sign after an event (DiffEqBase repeat_nudge = 1/100)
+      tq = tau + 0.01 * h;
+    } else {
+      tq = tau;
     }
+    const double g = cond(P, tq);
     if (phase == 0) {
-      const int M = P.M_samp;
-      const bool end = (i == M - 1);
-      const double th = end ? 1.0 : (double)i * P.inv_Msm1;
-      const double g = cond(P, end ? tau_new : tau + th * h);
       const int sg = (g > 0.0) - (g < 0.0);
       if (sgn_prev != 0 && sgn_prev * sg < 0) {
         a = th_a; fa = g_a; b = th; fb = g;
+        f0 = fmin(fabs(fa), fabs(fb)); w1 = w2 = 2.0; pure = false;
         side = 0; it = 0; phase = 2;
         return;
       }
@@ -225,31 +265,27 @@ struct Sampler {
       } else {
         i++;
       }
-      return;
-    }
-    // phase 2: Illinois regula falsi with bisection safeguard (same rule as the ray tracer)
-    {
-      const double tol = 4.0 * 2.220446049250313e-16 * fmax(fabs(a), fabs(b)) + 1e-300;
-      if (fabs(b - a) <= tol || it >= 200) {
-        event(P, fmin(a, b));
-        return;
-      }
-      double c = (a * fb - b * fa) / (fb - fa);
-      const double lo = fmin(a, b), hi = fmax(a, b);
-      if (!(c > lo && c < hi) || it >= 60) c = 0.5 * (a + b);
-      const double fc = cond(P, tau + c * h);
+    } else if (phase == 2) {
       it++;
-      if (fc == 0.0) {
+      if (g == 0.0) {
         event(P, c);
         return;
       }
-      if ((fc < 0.0) != (fb < 0.0)) {
+      if ((g < 0.0) != (fb < 0.0)) {
         a = b; fa = fb; side = 0;
       } else {
         if (side == 1) fa *= 0.5;
         side = 1;
       }
-      b = c; fb = fc;
+      b = c; fb = g;
+    } else if (phase == 1) {
+      sgn_prev = (g > 0.0) - (g < 0.0);
+      th_a = 0.01;
+      g_a = g;
+      phase = 0;
+    } else {
+      g_prev = g;
+      next_step(P);
     }
   }
 
@@ -263,8 +299,9 @@ struct Sampler {
     int randInx = 1 + (int)floor(u_idx * P.n_max);
     if (randInx > P.n_max) randInx = P.n_max;
     if (n_cross < randInx) return;
-    point(taus[randInx - 1], R.x);
+    point(taus[(randInx - 1) * taus_stride], R.x);
     const double rmag = sqrt(R.x[0] * R.x[0] + R.x[1] * R.x[1] + R.x[2] * R.x[2]);
+    const double vI_mag = sqrt(vI[0] * vI[0] + vI[1] * vI[1] + vI[2] * vI[2]);
     const double vmag_loc = sqrt(vI_mag * vI_mag + P.rs_real * C_KM * C_KM / rmag) / C_KM;  // 2GM/r
     R.accepted = 1;
     for (int c = 0; c < 3; ++c) {
@@ -277,6 +314,9 @@ struct Sampler {
 // whole attempt on one thread (fine-grained API, host check)
 ART_HD void sample_attempt(const DevParams& P, const double U[10], SampleResult& R) {
   Sampler S;
+  double taus[SAMP_KEEP];
+  S.taus = taus;
+  S.taus_stride = 1;
   S.begin(P, U);
   while (!S.done) S.advance(P);
   S.finish(P, U[9], R);

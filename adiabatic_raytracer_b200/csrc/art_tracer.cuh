@@ -106,6 +106,11 @@ ART_HD int clz64(unsigned long long v) {
 #endif
 }
 
+#ifndef ART_ROOT_RTOL_DEFINED
+#define ART_ROOT_RTOL_DEFINED
+constexpr double ROOT_RTOL = 1e-13;  // event tolerance of the root finders, relative to the step
+#endif
+
 struct ScanMasks {
   unsigned long long pos, neg, zero;  // bit i: sign of the condition at grid point i (bit 0: nudge point)
 };
@@ -548,23 +553,31 @@ struct Ray : RayHot, RayCold {
     return 0;
   }
 
-  // locate(): Illinois regula falsi with bisection safeguard and Brent's minimum step, to floating
-  // precision; left-biased.  Values come from seg_cond_full (far-field shortcut values would not be on
-  // the scale of thick_F).
+  // locate(): bracketing root finder of the event time — Illinois regula falsi with Brent's minimum
+  // step; bisection whenever the bracket has not halved over two iterations, and for good once three
+  // iterations have not brought |f| down (a jump, e.g. ωp switched off at r = rNS, has no zero to
+  // converge to).  Run to 1e-13 of the step (the condition's own round-off noise is wider); left-biased.
+  // Values come from seg_cond_full (far-field shortcut values would not be on the scale of thick_F).
   template <class DS>
   ART_HD double locate(const DevParams& P, const DS D, int ia, int ib) {
     double ra = (ia == 0) ? (event_last ? 0.01 : 0.0) : seg_theta(P, ia), rb = seg_theta(P, ib);
     double fa = seg_cond_full(P, D, ra), fb = seg_cond_full(P, D, rb);
     n_cond += 2;
+    const double f0 = fmin(fabs(fa), fabs(fb));
+    double w1 = 2.0, w2 = 2.0;
+    bool pure = false;
     int side = 0;
     for (int it = 0; it < 200; ++it) {
-      const double tol = 4.0 * 2.220446049250313e-16 * fmax(fabs(ra), fabs(rb)) + 1e-300;
+      const double tol = ROOT_RTOL * fmax(fabs(ra), fabs(rb)) + 1e-300;
       const double width = fabs(rb - ra);
       if (width <= tol) break;
+      if (it == 3 && fmin(fabs(fa), fabs(fb)) > 0.25 * f0) pure = true;
       double c = (ra * fb - rb * fa) / (fb - fa);
       const double lo = fmin(ra, rb), hi = fmax(ra, rb);
-      if (!(c > lo && c < hi) || it >= 60 || width <= 2.0 * tol) c = 0.5 * (ra + rb);
+      if (pure || (it >= 3 && width > 0.5 * w2) || !(c > lo && c < hi) || width <= 2.0 * tol) c = 0.5 * (ra + rb);
       else if (fabs(c - rb) < tol) c = rb + copysign(tol, ra - rb);  // a converged iterate collapses the bracket
+      w2 = w1;
+      w1 = width;
       const double fc = seg_cond_full(P, D, c);
       n_cond++;
       if (fc == 0.0) return c;

@@ -121,7 +121,7 @@ __device__ __forceinline__ void wf_route(const WfPool& W, int next, bool valid, 
   for (int sp = 0; sp < 2; ++sp) {
     const bool mine = valid && !done && !pending && ((axion ? SPECIES_AXION : SPECIES_PHOTON) == sp);
     const long long s = warp_pop(W.ctr + WC_ACT + next * 2 + sp, mine);
-    if (mine) W.act[next][sp][s] = id;
+    if (mine) (next ? W.act[1][sp] : W.act[0][sp])[s] = id;
   }
 }
 
@@ -162,30 +162,41 @@ k_wf_init(const __grid_constant__ DevParams P, const QueuedRay* __restrict__ q, 
 //                                  → state advanced in registers, try the next step
 //   accepted otherwise             → state advanced optimistically, dense-output segment published,
 //                                    scan points classified and listed; ray joins the pending list
-// A warp keeps stepping (at most ART_STAGE_NSTEP attempts) while at least half of its lanes can go on,
-// so far-field rays and rejected steps do not pay a state round trip per attempt.
+// A warp keeps stepping (at most `nstep` attempts) while at least `min_go` of its lanes can go on, so
+// far-field rays and rejected steps do not pay a state round trip per attempt (bulk: 4 attempts, half
+// the warp; thin tail of a batch: 16 attempts, any lane — there only latency counts).
 template <int SP>
-__global__ void __launch_bounds__(WF_THREADS, ART_STAGE_MINBLOCKS)
-k_wf_stages(const __grid_constant__ DevParams P, WfPool W, int cur) {
-  extern __shared__ double ksm[];
+__device__ __forceinline__ void wf_stages_body(const DevParams& P, const WfPool& W, int cur, int nstep, int min_go,
+                                               unsigned bid, unsigned nblocks, double* ksm) {
   const KStoreT<WF_THREADS> K{ksm + threadIdx.x};
   const int next = 1 - cur;
   const long long n = (long long)W.ctr[WC_ACT + cur * 2 + SP];
   const int* __restrict__ act = cur ? W.act[1][SP] : W.act[0][SP];  // (a dynamic index would copy the parameter struct to local memory)
-  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  const long long nthreads = (long long)nblocks * blockDim.x;
   const long long nround = ((n + nthreads - 1) / nthreads) * nthreads;
   const unsigned lane = threadIdx.x & 31;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nround; t += nthreads) {
+  // the ids of this thread's next two trips are kept in flight and the hot record of the next trip is
+  // pulled into L2 while the current ray is being stepped (12 resident warps cannot hide an HBM miss)
+  long long t = bid * (long long)blockDim.x + threadIdx.x;
+  int id_a = t < n ? act[t] : -1;
+  int id_b = t + nthreads < n ? act[t + nthreads] : -1;
+  for (; t < nround; t += nthreads) {
     unsigned long long need = 0ull;
-    int id = -1;
+    const int id = id_a;
     bool pending = false, done = false;
-    const bool valid = t < n;
-    if (valid) id = act[t];
+    const bool valid = id >= 0;
+    id_a = id_b;
+    if (id_a >= 0) {
+      const char* nx = (const char*)(W.hot + id_a);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 128));
+    }
+    id_b = t + 2 * nthreads < n ? act[t + 2 * nthreads] : -1;
     Ray R;
     if (valid) static_cast<RayHot&>(R) = W.hot[id];
     bool go = valid && !R.done;
     done = valid && R.done;
-    for (int it = 0; it < ART_STAGE_NSTEP; ++it) {
+    for (int it = 0; it < nstep; ++it) {
       if (go) {
         if (!R.iter_guard(P)) {
           go = false;
@@ -231,7 +242,7 @@ k_wf_stages(const __grid_constant__ DevParams P, WfPool W, int cur) {
           }
         }
       }
-      if (it + 1 < ART_STAGE_NSTEP && __popc(__ballot_sync(FULL, go)) < 16) break;
+      if (it + 1 < nstep && __popc(__ballot_sync(FULL, go)) < min_go) break;
     }
     if (valid) W.hot[id] = static_cast<const RayHot&>(R);
     wf_route(W, next, valid, id, done, pending, SP == SPECIES_AXION);
@@ -257,6 +268,17 @@ k_wf_stages(const __grid_constant__ DevParams P, WfPool W, int cur) {
       }
     }
   }
+}
+
+// One launch steps both species: the first half of the grid walks the axion list, the second half the
+// photon list (a warp never executes both right-hand sides; in the thin tail of a batch the two lists
+// are stepped concurrently instead of one launch after the other).
+__global__ void __launch_bounds__(WF_THREADS, ART_STAGE_MINBLOCKS)
+k_wf_stages(const __grid_constant__ DevParams P, WfPool W, int cur, int nstep, int min_go) {
+  extern __shared__ double ksm[];
+  const unsigned half = gridDim.x >> 1;
+  if (blockIdx.x < half) wf_stages_body<SPECIES_AXION>(P, W, cur, nstep, min_go, blockIdx.x, half, ksm);
+  else wf_stages_body<SPECIES_PHOTON>(P, W, cur, nstep, min_go, blockIdx.x - half, half, ksm);
 }
 
 // ---- crossing condition at every listed (ray, point) -----------------------------------------------
@@ -463,7 +485,7 @@ k_wf_tree(const __grid_constant__ DevParams P, WfPool W, WfTree T, int next, dou
     for (int sp = 0; sp < 2; ++sp) {
       const bool mine = spawn && ((ax ? SPECIES_AXION : SPECIES_PHOTON) == sp);
       const long long s = warp_pop(W.ctr + WC_ACT + next * 2 + sp, mine);
-      if (mine) W.act[next][sp][s] = id;
+      if (mine) (next ? W.act[1][sp] : W.act[0][sp])[s] = id;
     }
   }
   st.flush(stats);

@@ -145,22 +145,30 @@ constexpr double qsteady_min = 1.0, qsteady_max = 1.2, qoldinit = 1e-4;
 }  // namespace dp
 
 // Bracketing root finder of the event location (stand-in for DiffEqBase's find_callback_time):
-// Illinois-modified regula falsi with a bisection safeguard and Brent's minimum step (an iterate that
-// has converged moves by the tolerance towards the other end, which collapses the bracket), run to
-// floating precision.
-// Returns the LEFT end (in time) of the final bracket, like DiffEqBase's left-biased root.
+// Illinois-modified regula falsi with Brent's minimum step (an iterate that has converged moves by the
+// tolerance towards the other end, which collapses the bracket); bisection whenever the bracket has not
+// halved over two iterations, and for good once three iterations have not brought |f| down (a jump has
+// no zero to converge to).  Tolerance 1e-13 of the step.  Returns the LEFT end (in time) of the final
+// bracket, like DiffEqBase's left-biased root.
+constexpr double ROOT_RTOL = 1e-13;
 template <class F>
 inline double find_root(F&& f, double a, double fa, double b, double fb, int* n_eval) {
   // invariant: fa*fb < 0 ; a is the "old" end, b the most recent iterate
   int side = 0;
+  const double f0 = std::min(std::fabs(fa), std::fabs(fb));
+  double w1 = 2.0, w2 = 2.0;
+  bool pure = false;
   for (int it = 0; it < 200; ++it) {
     double width = std::fabs(b - a);
-    double tol = 4.0 * 2.220446049250313e-16 * std::max(std::fabs(a), std::fabs(b)) + 1e-300;
+    double tol = ROOT_RTOL * std::max(std::fabs(a), std::fabs(b)) + 1e-300;
     if (width <= tol) break;
+    if (it == 3 && std::min(std::fabs(fa), std::fabs(fb)) > 0.25 * f0) pure = true;
     double c = (a * fb - b * fa) / (fb - fa);
     double lo = std::min(a, b), hi = std::max(a, b);
-    if (!(c > lo && c < hi) || it >= 60 || width <= 2.0 * tol) c = 0.5 * (a + b);
-    else if (std::fabs(c - b) < tol) c = b + std::copysign(tol, a - b);  // Brent's minimum step
+    if (pure || (it >= 3 && width > 0.5 * w2) || !(c > lo && c < hi) || width <= 2.0 * tol) c = 0.5 * (a + b);
+    else if (std::fabs(c - b) < tol) c = b + std::copysign(tol, a - b);
+    w2 = w1;
+    w1 = width;
     double fc = f(c);
     ++*n_eval;
     if (fc == 0.0) return c;
