@@ -177,28 +177,26 @@ int ensure_lanes(art_handle* h, int n) {
 int launch_trace_wf(art_handle* h, Lane& L, const QueuedRay* q, long long n, RayOut* out, double* rec, int rec_cap,
                     DevStats* stats, const WfTree* tree) {
   if (n <= 0) return ART_OK;
-  const int M = h->params.interp_points_ray;
   cudaStream_t st = L.stream;
   CU(L.wf_hot.ensure((size_t)n * sizeof(RayHot)));
   CU(L.wf_cold.ensure((size_t)n * sizeof(RayCold)));
   CU(L.wf_seg.ensure((size_t)n * SEG_PAD * sizeof(double)));
   CU(L.wf_need.ensure((size_t)n * 8));
   CU(L.wf_neg.ensure((size_t)n * 8));
-  CU(L.wf_sign.ensure((size_t)n * 64));
+  CU(L.wf_sign.ensure((size_t)n * 8));
   for (int k = 0; k < 4; ++k) CU(L.wf_act[k].ensure((size_t)n * 4));
   CU(L.wf_pend.ensure((size_t)n * 4));
-  CU(L.wf_items.ensure((size_t)n * M * 4));
   CU(L.wf_roots.ensure((size_t)n * 4));
   CU(L.wf_fin.ensure((size_t)n * 4));
   CU(L.wf_ctr.ensure(WC_N * 8));
   WfPool W;
   W.hot = L.wf_hot.as<RayHot>(); W.cold = L.wf_cold.as<RayCold>(); W.seg = L.wf_seg.as<double>();
-  W.need = L.wf_need.as<unsigned long long>(); W.neg = L.wf_neg.as<unsigned long long>();
-  W.sign = L.wf_sign.as<unsigned char>();
+  W.mpos = L.wf_need.as<unsigned long long>(); W.mneg = L.wf_neg.as<unsigned long long>();
+  W.mzero = L.wf_sign.as<unsigned long long>();
   for (int par = 0; par < 2; ++par)
     for (int sp = 0; sp < 2; ++sp) W.act[par][sp] = L.wf_act[par * 2 + sp].as<int>();
   W.pend = L.wf_pend.as<int>();
-  W.items = L.wf_items.as<unsigned>(); W.roots = L.wf_roots.as<int>(); W.fin = L.wf_fin.as<int>();
+  W.roots = L.wf_roots.as<int>(); W.fin = L.wf_fin.as<int>();
   W.ctr = L.wf_ctr.as<unsigned long long>();
   const size_t ksmem = (size_t)42 * WF_THREADS * sizeof(double);
   CU(cudaMemsetAsync(W.ctr, 0, WC_N * 8, st));
@@ -218,7 +216,7 @@ int launch_trace_wf(art_handle* h, Lane& L, const QueuedRay* q, long long n, Ray
       const int g1 = grid(n_act, WF_THREADS);
       k_wf_reset<<<1, 32, 0, st>>>(W, next);
       k_wf_stages<<<2 * g1, WF_THREADS, ksmem, st>>>(h->dp, W, cur, tail ? 16 : ART_STAGE_NSTEP, tail ? 1 : 16);
-      k_wf_scan<<<grid(n_act * 24, 256), 256, 0, st>>>(h->dp, W);
+      k_wf_scan<<<grid(n_act * 32, SCAN_THREADS), SCAN_THREADS, 0, st>>>(h->dp, W);
       k_wf_detect<<<g1, WF_THREADS, 0, st>>>(h->dp, W, next);
       k_wf_root<<<grid(n_act / 8 + 1, WF_THREADS), WF_THREADS, 0, st>>>(h->dp, W, next);
       if (tree)

@@ -86,6 +86,7 @@ inline int make_dev_params(const art_params& p, DevParams& d, std::string& err) 
   d.mh[1] = d.sm * d.spsi0;
   d.mh[2] = d.cm;
   d.T_samp = 2.2 * d.maxR;
+  d.inv_r_int = 1.0 / d.r_int;
   if (d.maxR < p.rNS) {
     err = "Too small Max R (no conversion surface outside the star), MainRunner.jl:389-396";
     return ART_ERR_NO_SURFACE;

@@ -75,28 +75,88 @@ ART_HD double fsqrt(double x) {  // x > 0
   return sqrt(x);
 #endif
 }
+// Polynomial coefficients live in the constant bank: a 64-bit literal costs two move instructions per
+// use (17 % of the stage kernel's instructions were IMAD.MOV/UMOV pairs feeding DFMA), a constant-bank
+// operand none.
+// (Host code compiled by nvcc must not read a __constant__ symbol — it would see the host shadow — so
+// each table exists twice and the name resolves per compilation pass.)
+#define ART_FM_SIN {-1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04, \
+                    2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10}
+#define ART_FM_COS {4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05, \
+                    -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11}
+#define ART_FM_PIO2 {0.63661977236758134308, 1.57079632679489655800e+00, 6.12323399573676603587e-17, 8.4784276603688985e-32}
+// 1/n!, n = 2..13
+#define ART_FM_EXP {1.0 / 2, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320, 1.0 / 362880, \
+                    1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600, 1.0 / 6227020800.0}
+#define ART_FM_LN2 {1.4426950408889634074, 6.93147180369123816490e-01, 1.90821492927058770002e-10}
+#if defined(__CUDACC__)
+__device__ __constant__ double FM_SIN_D[6] = ART_FM_SIN;
+__device__ __constant__ double FM_COS_D[6] = ART_FM_COS;
+__device__ __constant__ double FM_PIO2_D[4] = ART_FM_PIO2;
+__device__ __constant__ double FM_EXP_D[12] = ART_FM_EXP;
+__device__ __constant__ double FM_LN2_D[3] = ART_FM_LN2;
+#endif
+#if defined(__CUDA_ARCH__)
+#define FM_SIN FM_SIN_D
+#define FM_COS FM_COS_D
+#define FM_PIO2 FM_PIO2_D
+#define FM_EXP FM_EXP_D
+#define FM_LN2 FM_LN2_D
+#else
+static const double FM_SIN[6] = ART_FM_SIN;
+static const double FM_COS[6] = ART_FM_COS;
+static const double FM_PIO2[4] = ART_FM_PIO2;
+static const double FM_EXP[12] = ART_FM_EXP;
+static const double FM_LN2[3] = ART_FM_LN2;
+#endif
+
 ART_HD void fsincos(double x, double* sn, double* cs) {
-  const double k = rint(x * 0.63661977236758134308);  // 2/π
-  double r = fma(-k, 1.57079632679489655800e+00, x);
-  r = fma(-k, 6.12323399573676603587e-17, r);
-  r = fma(-k, 8.4784276603688985e-32, r);
+  const double k = rint(x * FM_PIO2[0]);  // 2/π
+  double r = fma(-k, FM_PIO2[1], x);
+  r = fma(-k, FM_PIO2[2], r);
+  r = fma(-k, FM_PIO2[3], r);
   const double z = r * r;
-  double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-  ps = fma(z, ps, 2.75573137070700676789e-06);
-  ps = fma(z, ps, -1.98412698298579493134e-04);
-  ps = fma(z, ps, 8.33333333332248946124e-03);
-  ps = fma(z, ps, -1.66666666666666324348e-01);
+  double ps = fma(z, FM_SIN[5], FM_SIN[4]);
+  ps = fma(z, ps, FM_SIN[3]);
+  ps = fma(z, ps, FM_SIN[2]);
+  ps = fma(z, ps, FM_SIN[1]);
+  ps = fma(z, ps, FM_SIN[0]);
   const double S = fma(r * z, ps, r);
-  double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-  pc = fma(z, pc, -2.75573143513906633035e-07);
-  pc = fma(z, pc, 2.48015872894767294178e-05);
-  pc = fma(z, pc, -1.38888888888741095749e-03);
-  pc = fma(z, pc, 4.16666666666666019037e-02);
+  double pc = fma(z, FM_COS[5], FM_COS[4]);
+  pc = fma(z, pc, FM_COS[3]);
+  pc = fma(z, pc, FM_COS[2]);
+  pc = fma(z, pc, FM_COS[1]);
+  pc = fma(z, pc, FM_COS[0]);
   const double C = fma(z * z, pc, fma(-0.5, z, 1.0));
   const int n = (int)k;
   const double a = (n & 1) ? C : S, b = (n & 1) ? S : C;
   *sn = (n & 2) ? -a : a;
   *cs = ((n + 1) & 2) ? -b : b;
+}
+
+// e^x for |x| < 700: x = k ln2 + r, |r| ≤ ln2/2, Taylor to r¹³ (truncation 4e-18), scaled through the
+// exponent field.  Branch-free; ≤ 1 ulp.
+ART_HD double fexp(double x) {
+  const double k = rint(x * FM_LN2[0]);
+  double r = fma(-k, FM_LN2[1], x);
+  r = fma(-k, FM_LN2[2], r);
+  double p = fma(r, FM_EXP[11], FM_EXP[10]);
+  p = fma(r, p, FM_EXP[9]);
+  p = fma(r, p, FM_EXP[8]);
+  p = fma(r, p, FM_EXP[7]);
+  p = fma(r, p, FM_EXP[6]);
+  p = fma(r, p, FM_EXP[5]);
+  p = fma(r, p, FM_EXP[4]);
+  p = fma(r, p, FM_EXP[3]);
+  p = fma(r, p, FM_EXP[2]);
+  p = fma(r, p, FM_EXP[1]);
+  p = fma(r, p, FM_EXP[0]);
+  p = fma(r * r, p, r) + 1.0;
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double(__double2hiint(p) + ((int)k << 20), __double2loint(p));
+#else
+  return ldexp(p, (int)k);
+#endif
 }
 
 // Run constants, derived once on the host from art_params (art_api.cu: make_dev_params).
@@ -124,6 +184,7 @@ struct DevParams {
   double inv_Mrm1, inv_Msm1;  // 1/(M_ray − 1), 1/(M_samp − 1): dense-output grid spacing
   double cpsi0, spsi0, mh[3];  // cos/sin Ω t0 and the magnetic axis m̂ at the field time t0 (sampler)
   double T_samp;               // length of the sampler's line march, 2.2 maxR (RT.jl:1611)
+  double inv_r_int;            // 1 / r_int
 };
 
 struct Met {

@@ -81,24 +81,29 @@ struct Sampler {
     const double vb = 3.0 * mx * vx - mv;                                // v·b
     double ww = 1.0, N = vb, gn = E2 - P.ma2 * (1.0 - P.rs_real * rinv);
     if (!(r >= P.rNS && r > P.r_int)) {
-      double grr, gtt;
+      double grr, sq, gtt;  // g^rr, √g^rr, g^tt
       if (r > P.r_int) {
         grr = 1.0 - P.rs_real * rinv;
-        gtt = -frcp(grr);
+        const double y = frsqrt(grr);
+        sq = grr * y;
+        gtt = -(y * y);
       } else {  // g_schwartz interior branch (RT.jl:463, 496-497), see metric()
-        const double q = r / P.r_int;
-        const double q3 = q * q * q;
-        const double aa = P.rs_real * q3 / P.r_int;
-        const double bb = aa * q * q;
-        const double den = 3.0 * fsqrt(1.0 - aa) - fsqrt(1.0 - bb);
+        const double q = r * P.inv_r_int;
+        const double q2 = q * q;
+        const double aa = P.rs_real * P.inv_r_int * q2 * q;
+        const double bb = aa * q2;
         grr = 1.0 - bb;
+        sq = fsqrt(grr);
+        const double den = 3.0 * fsqrt(1.0 - aa) - sq;
         gtt = -4.0 * frcp(den * den);
       }
-      const double AA = (r < P.rNS) ? 1.0 : 1.0 - P.rs_real * rinv;
-      const double AAinv = frcp(AA);
+      // AA = 1 inside the star (RT.jl:1558-1560 quirk), 1 − rs/r outside
+      const bool in = r < P.rNS;
+      const double A = 1.0 - P.rs_real * rinv;
+      const double yA = in ? 1.0 : frsqrt(A);  // 1/√AA
       const double br = 2.0 * mx;
-      ww = grr * vx * vx * AAinv + (1.0 - vx * vx);
-      N = fsqrt(grr * AAinv) * vx * br + (vb - vx * br);
+      ww = grr * vx * vx * yA * yA + (1.0 - vx * vx);
+      N = sq * yA * vx * br + (vb - vx * br);
       const double nrm = -E2 * gtt - P.ma2;  // NrmSq·ww
       gn = grr * nrm;
       if (nrm < 0.0) gn = NAN;

@@ -180,7 +180,7 @@ ART_HD double seg_cond_full(const DevParams& P, const DS D, double th) {
   double w[6];
   seg_state(D, th, w);
   const double E = D(SEG_U70) + D(SEG_FAC7) * (w[5] - D(SEG_U60));
-  const double t = exp(D(SEG_S) + th * D(SEG_H));
+  const double t = fexp(D(SEG_S) + th * D(SEG_H));
   return thick_F(P, w[0], w[1], w[2] - P.Omega * t, w[3], w[4], w[5], E, P.rs_ray, true);
 }
 template <class DS>
@@ -191,7 +191,7 @@ ART_HD double seg_cond(const DevParams& P, const DS D, double th) {
   double w[6];
   seg_state(D, th, w);
   const double E = D(SEG_U70) + D(SEG_FAC7) * (w[5] - D(SEG_U60));
-  const double t = exp(D(SEG_S) + th * D(SEG_H));
+  const double t = fexp(D(SEG_S) + th * D(SEG_H));
   return thick_condition(P, w[0], w[1], w[2] - P.Omega * t, w[3], w[4], w[5], E, P.rs_ray, true);
 }
 
@@ -258,7 +258,7 @@ struct Ray : RayHot, RayCold {
   // SP = −1: species from the ray (mixed batches); 0 / 1: compile-time axion / photon
   template <int SP = -1>
   ART_HD void f(const DevParams& P, const double v[6], double lnt, double dv[6]) const {
-    const double t = exp(lnt);
+    const double t = fexp(lnt);
     const bool ax = SP < 0 ? axion : (SP == SPECIES_AXION);
     const double einv = frcp(erg);
     if (ax)
@@ -275,7 +275,7 @@ struct Ray : RayHot, RayCold {
     const double E = u7_of(v[5]);
     const double r = v[0];
     if (r > P.Rcut && r > P.r_int) return (E * E * r >= P.ma2 * (r - P.rs_ray)) ? -1.0 : NAN;
-    const double t = exp(lnt);
+    const double t = fexp(lnt);
     return thick_F(P, r, v[1], v[2] - P.Omega * t, v[3], v[4], v[5], E, P.rs_ray, true);
   }
 
@@ -406,8 +406,8 @@ struct Ray : RayHot, RayCold {
     q += r7 * r7;
     const double EEst = sqrt(q / 7.0);
     // PI controller: q11 = EEst^β1, q = q11 / qold^β2
-    double q11 = exp(dp::beta1 * log(EEst));
-    double qq = q11 * exp(-dp::beta2 * log(qold));
+    double q11 = fexp(dp::beta1 * log(EEst));
+    double qq = q11 * fexp(-dp::beta2 * log(qold));
     qq = fmax(1.0 / dp::qmax, fmin(1.0 / dp::qmin, qq / dp::gamma));
     if (EEst == 0.0) qq = 1.0 / dp::qmax;
     bool accept = (EEst <= 1.0) || (h <= P.dtmin);  // force_dtmin

@@ -44,19 +44,19 @@ constexpr int WF_THREADS = 128;
 #define ART_STAGE_NSTEP 4      // attempted steps a ray may take inside one k_wf_stages launch
 #endif
 constexpr int SEG_PAD = 36;  // doubles per published segment (SEG_N = 35, padded)
+constexpr int SEG_NUDGE = 35;  // padding slot: 1.0 if the step follows an event (the scan then includes the nudge point)
 
-enum { WC_ITEMS = 0, WC_ROOTS = 1, WC_FIN = 2, WC_PEND = 3, WC_ACT = 4 /* + parity*2 + species */, WC_N = 8 };
+enum { WC_SPARE = 0, WC_ROOTS = 1, WC_FIN = 2, WC_PEND = 3, WC_ACT = 4 /* + parity*2 + species */, WC_N = 8 };
 
 struct WfPool {
   RayHot* hot;                // [cap] per-step ray state
   RayCold* cold;              // [cap] callback-only ray state
   double* seg;                // [cap][36] dense-output segment of a pending (accepted, unscanned) step
-  unsigned long long* need;   // [cap] scan points awaiting the full condition
-  unsigned long long* neg;    // [cap] scan points proven negative by the far-field test
-  unsigned char* sign;        // [cap][64]
+  unsigned long long* mpos;   // [cap] scan points with a positive condition (bit i = grid point i)
+  unsigned long long* mneg;   // [cap] … negative (far-field points included)
+  unsigned long long* mzero;  // [cap] … exactly zero
   int* act[2][2];             // [parity][species][cap] ray ids
   int* pend;                  // [cap] rays with a pending step
-  unsigned* items;            // [cap * (M−1+1)] work list: (ray << 6) | point
   int* roots;                 // [cap]
   int* fin;                   // [cap]
   unsigned long long* ctr;    // WC_*
@@ -127,7 +127,7 @@ __device__ __forceinline__ void wf_route(const WfPool& W, int next, bool valid, 
 
 __global__ void k_wf_reset(WfPool W, int next) {
   if (threadIdx.x == 0) {
-    W.ctr[WC_ITEMS] = 0; W.ctr[WC_ROOTS] = 0; W.ctr[WC_FIN] = 0; W.ctr[WC_PEND] = 0;
+    W.ctr[WC_ROOTS] = 0; W.ctr[WC_FIN] = 0; W.ctr[WC_PEND] = 0;
     W.ctr[WC_ACT + next * 2] = 0; W.ctr[WC_ACT + next * 2 + 1] = 0;
   }
 }
@@ -174,14 +174,12 @@ __device__ __forceinline__ void wf_stages_body(const DevParams& P, const WfPool&
   const int* __restrict__ act = cur ? W.act[1][SP] : W.act[0][SP];  // (a dynamic index would copy the parameter struct to local memory)
   const long long nthreads = (long long)nblocks * blockDim.x;
   const long long nround = ((n + nthreads - 1) / nthreads) * nthreads;
-  const unsigned lane = threadIdx.x & 31;
   // the ids of this thread's next two trips are kept in flight and the hot record of the next trip is
   // pulled into L2 while the current ray is being stepped (12 resident warps cannot hide an HBM miss)
   long long t = bid * (long long)blockDim.x + threadIdx.x;
   int id_a = t < n ? act[t] : -1;
   int id_b = t + nthreads < n ? act[t + nthreads] : -1;
   for (; t < nround; t += nthreads) {
-    unsigned long long need = 0ull;
     const int id = id_a;
     bool pending = false, done = false;
     const bool valid = id >= 0;
@@ -220,16 +218,7 @@ __device__ __forceinline__ void wf_stages_body(const DevParams& P, const WfPool&
           } else {
             const SegAoS D{W.seg + (size_t)id * SEG_PAD};
             R.publish(K, D);
-            unsigned long long neg = 0ull;
-            const int M = P.M_ray;
-            const SegQuick Q(D);
-            for (int i = R.event_last ? 0 : 1; i < M; ++i) {
-              const int qk = Q.classify(P, seg_theta(P, i));
-              if (qk == 0) need |= 1ull << i;
-              else if (qk == -1) neg |= 1ull << i;
-            }
-            W.need[id] = need;
-            W.neg[id] = neg;
+            D(SEG_NUDGE) = R.event_last ? 1.0 : 0.0;
             // optimistic advance; k_wf_detect / k_wf_root complete or override it
             for (int i = 0; i < 6; ++i) {
               R.u[i] = R.un[i];
@@ -246,27 +235,6 @@ __device__ __forceinline__ void wf_stages_body(const DevParams& P, const WfPool&
     }
     if (valid) W.hot[id] = static_cast<const RayHot&>(R);
     wf_route(W, next, valid, id, done, pending, SP == SPECIES_AXION);
-    // append this warp's scan points to the global work list: one atomic per warp
-    const int cnt = __popcll(need);
-    int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(FULL, incl, o);
-      if ((int)lane >= o) incl += v;
-    }
-    const int total = __shfl_sync(FULL, incl, 31);
-    if (total) {
-      unsigned long long base = 0;
-      if (lane == 31) base = atomicAdd(W.ctr + WC_ITEMS, (unsigned long long)total);
-      base = __shfl_sync(FULL, base, 31);
-      unsigned long long pos = base + (unsigned long long)(incl - cnt);
-      unsigned long long m = need;
-      while (m) {
-        const int i = __ffsll((long long)m) - 1;
-        W.items[pos++] = ((unsigned)id << 6) | (unsigned)i;
-        m &= m - 1ull;
-      }
-    }
   }
 }
 
@@ -281,17 +249,59 @@ k_wf_stages(const __grid_constant__ DevParams P, WfPool W, int cur, int nstep, i
   else wf_stages_body<SPECIES_PHOTON>(P, W, cur, nstep, min_go, blockIdx.x - half, half, ksm);
 }
 
-// ---- crossing condition at every listed (ray, point) -----------------------------------------------
-__global__ void __launch_bounds__(256)
+// ---- crossing scan: one warp per pending step -----------------------------------------------------------
+// The M−1 grid points of the step (and the nudge point after an event) are dealt to the lanes, 32 per
+// round.  Every lane first classifies its point with the far-field test (two polynomials); the lanes
+// whose point needs it then evaluate the full condition together; three ballots per round turn the
+// signs into the bit masks k_wf_detect works on.  No per-ray work list, no per-point sign bytes: the
+// segment is read once (staged in shared memory) and 24 bytes of masks are written per step.
+constexpr int SCAN_THREADS = 256;
+__global__ void __launch_bounds__(SCAN_THREADS, 3)
 k_wf_scan(const __grid_constant__ DevParams P, WfPool W) {
-  const long long n = (long long)W.ctr[WC_ITEMS];
-  const long long nthreads = (long long)gridDim.x * blockDim.x;
-  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += nthreads) {
-    const unsigned code = W.items[k];
-    const unsigned id = code >> 6, i = code & 63u;
-    const SegAoS D{W.seg + (size_t)id * SEG_PAD};
-    const double g = seg_cond_full(P, D, seg_theta(P, (int)i));
-    W.sign[(size_t)id * 64 + i] = (g > 0.0) ? 1 : ((g < 0.0) ? 2 : ((g == 0.0) ? 3 : 0));
+  __shared__ double seg_sm[SCAN_THREADS / 32][SEG_PAD];
+  const long long n = (long long)W.ctr[WC_PEND];
+  const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const long long nwarps = (long long)gridDim.x * (SCAN_THREADS / 32);
+  const int M = P.M_ray;
+  double* sg = seg_sm[wib];
+  for (long long p = blockIdx.x * (long long)(SCAN_THREADS / 32) + wib; p < n; p += nwarps) {
+    const int id = W.pend[p];
+    const double* src = W.seg + (size_t)id * SEG_PAD;
+    __syncwarp();
+    sg[lane] = src[lane];
+    if (lane < SEG_PAD - 32) sg[32 + lane] = src[32 + lane];
+    __syncwarp();
+    const SegAoS D{sg};
+    const bool nudge = D(SEG_NUDGE) != 0.0;
+    unsigned long long mp = 0ull, mn = 0ull, mz = 0ull;
+    const int rounds = (M - 1 > 32 || nudge) ? 2 : 1;
+    for (int rd = 0; rd < rounds; ++rd) {
+      const int slot = rd * 32 + (int)lane;   // slot s ↔ grid point s + 1; slot 63 ↔ the nudge point 0
+      int i = -1;
+      if (slot + 1 <= M - 1) i = slot + 1;
+      else if (slot == 63 && nudge) i = 0;
+      int code = 0;  // 1 positive, 2 negative, 3 zero, 0 NaN / no point
+      if (i >= 0) {
+        const double th = seg_theta(P, i);
+        const int qk = seg_quick(P, D, th);
+        if (qk == -1) code = 2;
+        else if (qk == 0) {
+          const double g = seg_cond_full(P, D, th);
+          code = (g > 0.0) ? 1 : ((g < 0.0) ? 2 : ((g == 0.0) ? 3 : 0));
+        }
+      }
+      unsigned bp = __ballot_sync(FULL, code == 1), bn = __ballot_sync(FULL, code == 2), bz = __ballot_sync(FULL, code == 3);
+      if (rd == 0) {
+        mp |= (unsigned long long)bp << 1; mn |= (unsigned long long)bn << 1; mz |= (unsigned long long)bz << 1;
+      } else {
+        mp |= (unsigned long long)(bp >> 31); mn |= (unsigned long long)(bn >> 31); mz |= (unsigned long long)(bz >> 31);
+        mp |= (unsigned long long)(bp & 0x7fffffffu) << 33; mn |= (unsigned long long)(bn & 0x7fffffffu) << 33;
+        mz |= (unsigned long long)(bz & 0x7fffffffu) << 33;
+      }
+    }
+    if (lane == 0) {
+      W.mpos[id] = mp; W.mneg[id] = mn; W.mzero[id] = mz;
+    }
   }
 }
 
@@ -323,17 +333,7 @@ k_wf_detect(const __grid_constant__ DevParams P, WfPool W, int next) {
       Ray R;
       static_cast<RayHot&>(R) = W.hot[id];
       axion = R.axion;
-      ScanMasks m{0ull, W.neg[id], 0ull};
-      unsigned long long need = W.need[id];
-      const unsigned char* sg = W.sign + (size_t)id * 64;
-      while (need) {
-        const int i = __ffsll((long long)need) - 1;
-        const unsigned v = sg[i];
-        if (v == 1) m.pos |= 1ull << i;
-        else if (v == 2) m.neg |= 1ull << i;
-        else if (v == 3) m.zero |= 1ull << i;
-        need &= need - 1ull;
-      }
+      const ScanMasks m{W.mpos[id], W.mneg[id], W.mzero[id]};
       const SegAoS D{W.seg + (size_t)id * SEG_PAD};
       // detect() only reads the start-box reference point from the cold record (first crossing only)
       if (R.n_cross == 0) {

@@ -31,6 +31,27 @@ static void trace_one(const DevParams& P, const RayIn& in, double* rec, int cap,
 
 extern "C" {
 
+// branch-free helpers of art_physics.cuh (portable parts: fsincos, fexp; thick_F vs thick_condition)
+int hc_fastmath(int64_t n, const double* x, double* sn, double* cs, double* ex) {
+  for (int64_t i = 0; i < n; ++i) {
+    fsincos(x[i], sn + i, cs + i);
+    ex[i] = fexp(x[i]);
+  }
+  return 0;
+}
+
+// sign-equivalent division-free condition (same argument layout as hc_condition)
+int hc_condition_F(const art_params* p, int64_t n, const double* in, double* out) {
+  DevParams P;
+  int rc = dev(p, P);
+  if (rc) return rc;
+  for (int64_t i = 0; i < n; ++i) {
+    const double* a = in + 8 * i;
+    out[i] = thick_F(P, a[0], a[1], a[2] - P.Omega * exp(a[7]), a[3], a[4], a[5], a[6], P.rs_ray, true);
+  }
+  return 0;
+}
+
 int hc_max_radius(const art_params* p, double* maxR, double* Rcut) {
   DevParams d;
   int rc = dev(p, d);

@@ -24,6 +24,8 @@ def lib():
         L.hc_max_radius.argtypes = [PP, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.hc_rhs.argtypes = [PP, C.c_int64, _ip, _dp, _dp, _dp, _dp]
         L.hc_condition.argtypes = [PP, C.c_int64, _dp, _dp]
+        L.hc_condition_F.argtypes = [PP, C.c_int64, _dp, _dp]
+        L.hc_fastmath.argtypes = [C.c_int64, _dp, _dp, _dp, _dp]
         L.hc_sample_from_uniforms.argtypes = [PP, C.c_int64, _dp, _dp, _dp, _dp, _ip, _ip, _ip]
         L.hc_weights.argtypes = [PP, C.c_int64, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]
         L.hc_conv_prob.argtypes = [PP, C.c_int64, _dp, _dp, _dp, C.c_int32, _dp]
@@ -52,6 +54,20 @@ def rhs(p, species, u, erg, lnt):
     _chk(lib().hc_rhs(C.byref(p), u.shape[0], np.ascontiguousarray(species, np.int32), u,
                       np.ascontiguousarray(erg, np.float64), np.ascontiguousarray(lnt, np.float64), du))
     return du
+
+
+def fastmath(x):
+    x = np.ascontiguousarray(x, np.float64)
+    sn, cs, ex = np.zeros_like(x), np.zeros_like(x), np.zeros_like(x)
+    _chk(lib().hc_fastmath(x.size, x, sn, cs, ex))
+    return sn, cs, ex
+
+
+def condition_F(p, inp):
+    inp = np.ascontiguousarray(inp, np.float64)
+    out = np.zeros(inp.shape[0])
+    _chk(lib().hc_condition_F(C.byref(p), inp.shape[0], inp, out))
+    return out
 
 
 def condition(p, inp):

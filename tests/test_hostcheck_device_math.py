@@ -1,0 +1,92 @@
+"""CPU checks of the product's device arithmetic: the `__host__ __device__` headers under
+adiabatic_raytracer_b200/csrc are compiled for the host (tests/hostcheck, test infrastructure) and compared
+with the oracle and with libm.  No GPU needed; the GPU parity tests repeat the comparisons through the C ABI."""
+import math
+
+import numpy as np
+import pytest
+
+from adiabatic_raytracer_b200.params import ArtParams
+from tests.hostcheck import loader as hc
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    from oracle import loader
+    return loader
+
+
+def test_branch_free_sincos_and_exp_match_libm():
+    rng = np.random.default_rng(3)
+    x = np.concatenate([rng.uniform(-7, 7, 20000), rng.uniform(-1e4, 1e4, 20000), rng.uniform(-40, 5, 20000),
+                        [0.0, math.pi / 2, math.pi, -math.pi / 4, 1e-300, 3.0e4]])
+    sn, cs, ex = hc.fastmath(x)
+    # |error| ≤ 2 ulp of the larger of |value| and the reduction error k·2⁻⁵³ (arguments up to 1e4)
+    assert np.max(np.abs(sn - np.sin(x))) < 4e-16 * 2
+    assert np.max(np.abs(cs - np.cos(x))) < 4e-16 * 2
+    small = np.abs(x) < 100
+    assert np.max(np.abs(ex[small] / np.exp(x[small]) - 1.0)) < 5e-16
+
+
+def test_division_free_condition_has_the_sign_and_zeros_of_the_reference_condition(oracle):
+    """thick_F = Ham · (positive factor): same sign everywhere, same NaN set, and the ratio is positive."""
+    p = ArtParams.default(theta_m=0.2)
+    rng = np.random.default_rng(11)
+    n = 20000
+    r = rng.uniform(9.0, 40.0, n)
+    th = np.arccos(rng.uniform(-1, 1, n))
+    ph = rng.uniform(-math.pi, math.pi, n)
+    w = rng.normal(size=(n, 3))
+    w[:, 1] *= r
+    w[:, 2] *= r * np.sin(th)
+    E = p.Mass_a * rng.uniform(1.0, 1.2, n)
+    lnt = rng.uniform(-30, 0, n)
+    inp = np.column_stack([r, th, ph, w[:, 0], w[:, 1], w[:, 2], E, lnt])
+    a = hc.condition(p, inp)
+    f = hc.condition_F(p, inp)
+    assert np.array_equal(np.isnan(a), np.isnan(f))
+    ok = ~np.isnan(a)
+    assert np.array_equal(np.sign(a[ok]), np.sign(f[ok]))
+    big = ok & (np.abs(a) > 1e-6)
+    assert np.all(f[big] / a[big] > 0)
+
+
+@pytest.mark.parametrize("kw", [dict(theta_m=0.2), dict(theta_m=0.2, flat=1)])
+def test_host_compiled_tracer_matches_oracle(oracle, kw):
+    p = ArtParams.default(**kw)
+    n = 400
+    s = oracle.sample(p, 5, 1, n)
+    w = oracle.weights(p, s["x"], s["v_loc"], s["v_inf"])
+    x, k, erg = s["x"], w["k_init"], w["erg_inf"]
+    for sp, mc, bs in ((1, -1, 1), (0, 100000, -1)):
+        k0 = k if bs == 1 else -k
+        a = hc.propagate(p, np.full(n, sp, np.int32), x, k0, erg, np.zeros(n), -np.ones(n), bs, mc)
+        b = oracle.propagate(p, np.full(n, sp, np.int32), x, k0, erg, np.zeros(n), -np.ones(n), bs, mc)
+        same = (a["status"] == b["status"]) & (a["n_cross"] == b["n_cross"])
+        assert same.mean() > 0.99
+        steps = same & (a["counters"][:, 0] == b["counters"][:, 0]) & (a["counters"][:, 1] == b["counters"][:, 1])
+        assert steps.mean() > 0.98
+        dx = np.linalg.norm(a["x_f"] - b["x_f"], axis=0) / np.linalg.norm(b["x_f"], axis=0)
+        assert np.median(dx[steps]) < 1e-10
+        assert dx[steps].max() < 2e-3  # round-off amplified at the |B_z| kink, bounded by the scheme's truncation error
+
+
+def test_host_compiled_sampler_matches_oracle(oracle):
+    for kw in (dict(theta_m=0.2), dict(theta_m=0.2, rNS=12.0), dict(theta_m=0.2, rNS=8.0)):
+        p = ArtParams.default(**kw)
+        u = np.random.default_rng(1).random((6000, 10))
+        a = hc.sample_from_uniforms(p, u)
+        b = oracle.sample_from_uniforms(p, u)
+        assert np.array_equal(a["accepted"], b["accepted"])
+        assert np.array_equal(a["n_cross"], b["n_cross"])
+        m = a["accepted"] == 1
+        assert np.abs(a["x"] - b["x"])[:, m].max() < 1e-10
+
+
+def test_host_compiled_pipeline_matches_oracle(oracle):
+    p = ArtParams.default(theta_m=0.2)
+    a = hc.run(p, 1769, 1, 200)
+    b = oracle.run(p, 1769, 1, 200)
+    assert a["rows"].shape == b["rows"].shape
+    assert np.array_equal(a["rows"][:, :2], b["rows"][:, :2])
+    assert abs(a["f_inx"] - b["f_inx"]) <= 2
