@@ -133,6 +133,8 @@ struct art_handle {
   void* comm = nullptr;
   int nranks = 1, rank = 0;
   std::atomic<long long> launches{0};  // kernels launched since the current pipeline call began
+  int bulk_nstep = ART_STAGE_NSTEP;  // attempts per stage launch in the bulk (ART_BULK_NSTEP)
+  int tail_nstep = 4;             // attempts per stage launch once fewer rays than one resident wave are left (ART_TAIL_NSTEP)
   int n_lanes = 1;                // concurrent sub-chunks (ART_LANES); measured: one big chunk beats overlapped small ones
   long long sub_chunk = 1 << 21;  // events per sub-chunk (ART_SUBCHUNK)
 };
@@ -202,25 +204,25 @@ int launch_trace_wf(art_handle* h, Lane& L, const QueuedRay* q, long long n, Ray
   CU(cudaMemsetAsync(W.ctr, 0, WC_N * 8, st));
   const int gmax = h->n_sm * 8;
   auto grid = [&](long long work, int threads) { return (int)std::max<long long>(1, std::min<long long>(gmax, (work + threads - 1) / threads)); };
-  k_wf_init<<<grid(n, WF_THREADS), WF_THREADS, 0, st>>>(h->dp, q, n, W, rec, rec_cap);
+  k_wf_init<<<grid(n, WF_THREADS), WF_THREADS, 0, st>>>(h->dp, q, n, W, rec, rec_cap, stats);
   h->launches++;
   CU(cudaGetLastError());
   long long n_act = n;  // upper bound of the active count, refreshed at every host check
   int cur = 0;
   const bool trace = getenv("ART_WF_TRACE") != nullptr;
   for (long long iter = 0;;) {
-    const int burst = n_act > 65536 ? 4 : (n_act > 2048 ? 8 : 16);  // steps between host checks
+    const int burst = n_act > 500000 ? 8 : (n_act > 65536 ? 16 : 32);  // steps between host checks (deep queue: host jitter must not idle the GPU)
     const bool tail = n_act < 8LL * h->n_sm * WF_THREADS;               // fewer rays than one resident wave
     for (int b = 0; b < burst; ++b, ++iter) {
       const int next = 1 - cur;
       const int g1 = grid(n_act, WF_THREADS);
       k_wf_reset<<<1, 32, 0, st>>>(W, next);
-      k_wf_stages<<<2 * g1, WF_THREADS, ksmem, st>>>(h->dp, W, cur, tail ? 16 : ART_STAGE_NSTEP, tail ? 1 : 16);
-      k_wf_scan<<<grid(n_act * 32, SCAN_THREADS), SCAN_THREADS, 0, st>>>(h->dp, W);
+      k_wf_stages<<<2 * g1, WF_THREADS, ksmem, st>>>(h->dp, W, cur, tail ? h->tail_nstep : h->bulk_nstep, tail ? 1 : 16);
+      k_wf_scan<<<grid(n_act * 32, SCAN_THREADS), SCAN_THREADS, 0, st>>>(h->dp, W, stats);
       k_wf_detect<<<g1, WF_THREADS, 0, st>>>(h->dp, W, next);
-      k_wf_root<<<grid(n_act / 8 + 1, WF_THREADS), WF_THREADS, 0, st>>>(h->dp, W, next);
+      k_wf_root<<<grid(n_act / 2 + 1, WF_THREADS), WF_THREADS, 0, st>>>(h->dp, W, next, stats);
       if (tree)
-        k_wf_tree<<<grid(n_act / 4 + 1, WF_THREADS), WF_THREADS, 0, st>>>(h->dp, W, *tree, next, rec, rec_cap, stats);
+        k_wf_tree<<<grid(n_act / 2 + 1, WF_THREADS), WF_THREADS, 0, st>>>(h->dp, W, *tree, next, rec, rec_cap, stats);
       else
         k_wf_collect<<<grid(n_act / 4 + 1, WF_THREADS), WF_THREADS, 0, st>>>(h->dp, W, out, stats);
       h->launches += 6;
@@ -298,6 +300,8 @@ int art_create(const art_params* p, int device_id, art_handle** out) {
   cudaFuncSetAttribute(k_wf_stages, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sample_events, SAMPLE_THREADS, 0);
   h->blocks_sample = h->n_sm * std::max(occ, 1);
+  if (const char* t = getenv("ART_BULK_NSTEP")) h->bulk_nstep = std::max(1, atoi(t));
+  if (const char* t = getenv("ART_TAIL_NSTEP")) h->tail_nstep = std::max(1, atoi(t));
   if (const char* t = getenv("ART_LANES")) h->n_lanes = std::max(1, std::min(16, atoi(t)));
   if (const char* t = getenv("ART_SUBCHUNK")) h->sub_chunk = std::max(1024LL, atoll(t));
   ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
@@ -678,6 +682,7 @@ int art_run_device(art_handle* h, uint64_t seed, int64_t first_event, int64_t n_
   S.ms_tree = 0.0;
   S.ms_total = ms_tot;
   S.n_launches = h->launches.load();
+  S.n_cond_eval = (long long)ds.n_cond_eval;
   if (st_out) *st_out = S;
   // trailing histogram counters: [f_inx, n_rows, n_events, n_acc, n_rej, n_rhs, n_cond, n_rays]
   h->host_counters[0] += (double)f_inx; h->host_counters[1] += (double)h->n_rows_dev; h->host_counters[2] += (double)n_events;

@@ -27,6 +27,7 @@ constexpr int SAMPLE_BURST = 8;
 struct DevStats {  // accumulated with atomics; mirrors the counters of art_stats
   unsigned long long n_attempts, n_sampler_cond, n_rays, n_rays_photon, n_acc, n_rej, n_rhs, n_cond;
   unsigned long long n_status[5];
+  unsigned long long n_cond_eval;  // full evaluations of the crossing condition (scan + root finder + start-up)
 };
 
 struct QueuedRay {  // one node to propagate

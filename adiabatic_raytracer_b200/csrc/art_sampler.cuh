@@ -222,7 +222,7 @@ struct Sampler {
     double tq, th = 0.0, c = 0.0;
     bool end = false;
     if (phase == 2) {
-      const double tol = ROOT_RTOL * fmax(fabs(a), fabs(b)) + 1e-300;
+      const double tol = ROOT_RTOL * fmax(fmax(fabs(a), fabs(b)), 0.01);
       const double width = fabs(b - a);
       if (width <= tol || it >= 200) {
         event(P, fmin(a, b));

@@ -563,12 +563,39 @@ struct Ray : RayHot, RayCold {
     double ra = (ia == 0) ? (event_last ? 0.01 : 0.0) : seg_theta(P, ia), rb = seg_theta(P, ib);
     double fa = seg_cond_full(P, D, ra), fb = seg_cond_full(P, D, rb);
     n_cond += 2;
+    // ωp is switched off inside the star (zeroIn, RT.jl:1165), so the condition JUMPS where the step
+    // crosses r = rNS and a bracketing iteration could only bisect its way there (≈ 40 evaluations of
+    // the field).  A bracket that straddles the stellar surface is therefore split at the surface first,
+    // by bisection on the dense-output polynomial of r alone; two evaluations of the condition either
+    // side then decide whether the jump is the event or which smooth half holds the sign change.
+    {
+      const double ga = seg_comp(D, 0, ra, 1.0 - ra) - P.rNS, gb = seg_comp(D, 0, rb, 1.0 - rb) - P.rNS;
+      if ((ga <= 0.0) != (gb <= 0.0)) {  // inside ⇔ r ≤ rNS, as in thick_F
+        double lo = ra, hi = rb;
+        for (int k = 0; k < 64; ++k) {
+          if (hi - lo <= ROOT_RTOL * fmax(fmax(fabs(lo), fabs(hi)), 0.01)) break;
+          const double mid = 0.5 * (lo + hi);
+          const double gm = seg_comp(D, 0, mid, 1.0 - mid) - P.rNS;
+          if ((gm <= 0.0) == (ga <= 0.0)) lo = mid;
+          else hi = mid;
+        }
+        const double flo = seg_cond_full(P, D, lo), fhi = seg_cond_full(P, D, hi);
+        n_cond += 2;
+        if ((flo < 0.0) != (fa < 0.0)) {
+          rb = lo; fb = flo;
+        } else if ((fhi < 0.0) != (flo < 0.0)) {
+          return lo;
+        } else {
+          ra = hi; fa = fhi;
+        }
+      }
+    }
     const double f0 = fmin(fabs(fa), fabs(fb));
     double w1 = 2.0, w2 = 2.0;
     bool pure = false;
     int side = 0;
     for (int it = 0; it < 200; ++it) {
-      const double tol = ROOT_RTOL * fmax(fabs(ra), fabs(rb)) + 1e-300;
+      const double tol = ROOT_RTOL * fmax(fmax(fabs(ra), fabs(rb)), 0.01);  // 1e-13 of the step, floor 1e-15
       const double width = fabs(rb - ra);
       if (width <= tol) break;
       if (it == 3 && fmin(fabs(fa), fabs(fb)) > 0.25 * f0) pure = true;

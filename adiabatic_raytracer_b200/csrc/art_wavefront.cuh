@@ -125,6 +125,16 @@ __device__ __forceinline__ void wf_route(const WfPool& W, int next, bool valid, 
   }
 }
 
+// Thin lists: when a kernel has fewer items than lanes, its items are dealt one per `spread` lanes, so
+// that a warp holds 1–4 of them instead of 32 — a warp walks the UNION of its lanes' control flow
+// (root-finder iterations, tree branches), and in the thin tail of a batch only latency counts.
+__device__ __forceinline__ int wf_spread(long long n) {
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  int s = 1;
+  while (s < 32 && n * (2LL * s) <= nthreads) s <<= 1;
+  return s;
+}
+
 __global__ void k_wf_reset(WfPool W, int next) {
   if (threadIdx.x == 0) {
     W.ctr[WC_ROOTS] = 0; W.ctr[WC_FIN] = 0; W.ctr[WC_PEND] = 0;
@@ -135,7 +145,8 @@ __global__ void k_wf_reset(WfPool W, int next) {
 // ---- start-up of a batch: IC transform, first RHS, initial step size, starting sign ----------------
 __global__ void __launch_bounds__(WF_THREADS)
 k_wf_init(const __grid_constant__ DevParams P, const QueuedRay* __restrict__ q, long long n, WfPool W,
-          double* __restrict__ rec, int rec_cap) {
+          double* __restrict__ rec, int rec_cap, DevStats* stats) {
+  if (blockIdx.x == 0 && threadIdx.x == 0 && stats) atomicAdd(&stats->n_cond_eval, (unsigned long long)n);  // start-point signs
   const long long nthreads = (long long)gridDim.x * blockDim.x;
   const long long nround = ((n + nthreads - 1) / nthreads) * nthreads;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nround; i += nthreads) {
@@ -257,13 +268,14 @@ k_wf_stages(const __grid_constant__ DevParams P, WfPool W, int cur, int nstep, i
 // segment is read once (staged in shared memory) and 24 bytes of masks are written per step.
 constexpr int SCAN_THREADS = 256;
 __global__ void __launch_bounds__(SCAN_THREADS, 3)
-k_wf_scan(const __grid_constant__ DevParams P, WfPool W) {
+k_wf_scan(const __grid_constant__ DevParams P, WfPool W, DevStats* stats) {
   __shared__ double seg_sm[SCAN_THREADS / 32][SEG_PAD];
   const long long n = (long long)W.ctr[WC_PEND];
   const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const long long nwarps = (long long)gridDim.x * (SCAN_THREADS / 32);
   const int M = P.M_ray;
   double* sg = seg_sm[wib];
+  unsigned long long n_full = 0;
   for (long long p = blockIdx.x * (long long)(SCAN_THREADS / 32) + wib; p < n; p += nwarps) {
     const int id = W.pend[p];
     const double* src = W.seg + (size_t)id * SEG_PAD;
@@ -287,6 +299,7 @@ k_wf_scan(const __grid_constant__ DevParams P, WfPool W) {
         if (qk == -1) code = 2;
         else if (qk == 0) {
           const double g = seg_cond_full(P, D, th);
+          n_full++;
           code = (g > 0.0) ? 1 : ((g < 0.0) ? 2 : ((g == 0.0) ? 3 : 0));
         }
       }
@@ -303,6 +316,8 @@ k_wf_scan(const __grid_constant__ DevParams P, WfPool W) {
       W.mpos[id] = mp; W.mneg[id] = mn; W.mzero[id] = mz;
     }
   }
+  n_full = warp_sum(n_full);
+  if (lane == 0 && stats && n_full) atomicAdd(&stats->n_cond_eval, n_full);
 }
 
 // Rebuilds the transient view of a pending step from the hot record (optimistically advanced) and the
@@ -365,12 +380,15 @@ k_wf_detect(const __grid_constant__ DevParams P, WfPool W, int next) {
 
 // ---- root finder (all lanes iterate together), crossing callback, state update ------------------------
 __global__ void __launch_bounds__(WF_THREADS)
-k_wf_root(const __grid_constant__ DevParams P, WfPool W, int next) {
+k_wf_root(const __grid_constant__ DevParams P, WfPool W, int next, DevStats* stats) {
+  unsigned long long n_full = 0;
   const long long n = (long long)W.ctr[WC_ROOTS];
-  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  const int spread = wf_spread(n);
+  const long long nthreads = (long long)gridDim.x * blockDim.x / spread;
   const long long nround = ((n + nthreads - 1) / nthreads) * nthreads;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nround; t += nthreads) {
-    const bool valid = t < n;
+  const long long t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  for (long long t = t0 / spread; t < nround; t += nthreads) {
+    const bool valid = t < n && (t0 % spread) == 0;
     bool done = false, axion = false;
     int id = -1;
     if (valid) {
@@ -387,7 +405,9 @@ k_wf_root(const __grid_constant__ DevParams P, WfPool W, int next) {
       const SegAoS D{segl};
       wf_load_pending(R, D);
       const K7View K{R.k1};
+      const int c0 = R.n_cond;
       const double th = (R.br_b == -2) ? 1.0 : R.locate(P, D, R.br_a, R.br_b);
+      n_full += (unsigned long long)(R.n_cond - c0);
       R.apply(P, K, D, th, R.br_sg);
       W.hot[id] = static_cast<const RayHot&>(R);
       done = R.done;
@@ -395,6 +415,8 @@ k_wf_root(const __grid_constant__ DevParams P, WfPool W, int next) {
     }
     wf_route(W, next, valid, id, done, false, axion);
   }
+  n_full = warp_sum(n_full);
+  if ((threadIdx.x & 31) == 0 && stats && n_full) atomicAdd(&stats->n_cond_eval, n_full);
 }
 
 // result of a finished ray
@@ -458,23 +480,29 @@ __global__ void __launch_bounds__(WF_THREADS)
 k_wf_tree(const __grid_constant__ DevParams P, WfPool W, WfTree T, int next, double* __restrict__ rec, int rec_cap,
           DevStats* stats) {
   WfStat st;
+  unsigned long long n_start = 0;
   const long long n = (long long)W.ctr[WC_FIN];
-  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  const int spread = wf_spread(n);
+  const long long nthreads = (long long)gridDim.x * blockDim.x / spread;
   const long long nround = ((n + nthreads - 1) / nthreads) * nthreads;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nround; t += nthreads) {
+  const long long t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  for (long long t = t0 / spread; t < nround; t += nthreads) {
     Ray R;
     R.done = true;
     R.axion = false;
     bool spawn = false;
     int id = -1;
-    if (t < n) {
+    if (t < n && (t0 % spread) == 0) {
       id = W.fin[t];
       const RayOut o = wf_result(P, W.hot[id], st);
       spawn = wf_tree_step(P, T, id, o, rec, rec_cap, R);
       if (spawn) {
         // a re-initialised ray that is already past the end of the span stays `done`: the next
         // k_wf_stages launch routes it back here (never happens for t < 1/Ω)
-        if (!R.done && R.iter_guard(P)) R.startup<-1>(P);
+        if (!R.done && R.iter_guard(P)) {
+          R.startup<-1>(P);
+          n_start++;
+        }
         W.hot[id] = static_cast<const RayHot&>(R);
         W.cold[id] = static_cast<const RayCold&>(R);
       }
@@ -489,6 +517,8 @@ k_wf_tree(const __grid_constant__ DevParams P, WfPool W, WfTree T, int next, dou
     }
   }
   st.flush(stats);
+  n_start = warp_sum(n_start);
+  if ((threadIdx.x & 31) == 0 && stats && n_start) atomicAdd(&stats->n_cond_eval, n_start);
 }
 
 }  // namespace art

@@ -94,6 +94,7 @@ class ArtStats(C.Structure):
         ("ms_tree", C.c_double),
         ("ms_total", C.c_double),
         ("n_launches", C.c_int64),
+        ("n_cond_eval", C.c_int64),
     ]
 
     def as_dict(self):

@@ -119,6 +119,8 @@ typedef struct art_stats {
   double ms_tree;
   double ms_total;
   int64_t n_launches;     /* kernels launched by the pipeline call                          */
+  int64_t n_cond_eval;    /* … of n_cond, evaluations actually performed (the rest were decided by the
+                             exact far-field shortcut r > Rcut)                             */
 } art_stats;
 
 typedef struct art_handle art_handle;

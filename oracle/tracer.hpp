@@ -160,7 +160,7 @@ inline double find_root(F&& f, double a, double fa, double b, double fb, int* n_
   bool pure = false;
   for (int it = 0; it < 200; ++it) {
     double width = std::fabs(b - a);
-    double tol = ROOT_RTOL * std::max(std::fabs(a), std::fabs(b)) + 1e-300;
+    double tol = ROOT_RTOL * std::max(std::max(std::fabs(a), std::fabs(b)), 0.01);  // 1e-13 of the step, floor 1e-15
     if (width <= tol) break;
     if (it == 3 && std::min(std::fabs(fa), std::fabs(fb)) > 0.25 * f0) pure = true;
     double c = (a * fb - b * fa) / (fb - fa);
