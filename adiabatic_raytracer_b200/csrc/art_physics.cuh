@@ -411,6 +411,10 @@ ART_HD double thick_condition(const DevParams& P, double r, double th, double ps
 // i.e. F = Ham · 2E² · (E² ww D) (r s)² r³ — a strictly positive multiple, so F has the sign, the zeros
 // and the NaN set of Ham (same algebra as the sampler's condition, art_sampler.cuh).  Exterior metric:
 // g^rr NrmSq·ww = E² − m_a² A.  One reciprocal, one square root, two sincos.
+// SIGN_ONLY: the caller keeps nothing but the sign (crossing scan).  F = base·(Q|b_z| − m_a² r³) − Q|b_z|·aniso
+// with base > 0 and aniso ≥ 0, so wherever the plasma frequency is below the axion mass in THIS direction
+// (Q|b_z| < m_a² r³) the sign is negative whatever the momentum: return before the momentum-dependent half.
+template <bool SIGN_ONLY = false>
 ART_HD double thick_F(const DevParams& P, double r, double th, double psi, double wr, double wt,
                       double wp, double E, double rs, bool zero_in) {
   double c, s, cp, sp;
@@ -418,10 +422,9 @@ ART_HD double thick_F(const DevParams& P, double r, double th, double psi, doubl
   fsincos(psi, &sp, &cp);
   const Fld f = field_cs<false>(P, c, s, cp, sp);
   const double E2 = E * E;
-  double grr, sq, gn;
+  double grr, gn;
   if (r > P.r_int) {
     grr = 1.0 - rs * frcp(r);
-    sq = fsqrt(grr);
     gn = E2 - P.ma2 * grr;
     if (gn < 0.0) return NAN;  // NrmSq < 0
   } else {
@@ -429,17 +432,19 @@ ART_HD double thick_F(const DevParams& P, double r, double th, double psi, doubl
     const double nrm = -E2 * m.gtt - P.ma2;
     if (nrm < 0.0) return NAN;
     grr = m.grr;
-    sq = sqrt(grr);
     gn = grr * nrm;
   }
+  double Pq = P.Q * fabs(f.bz);
+  if (zero_in && r <= P.rNS) Pq = 0.0;
+  const double mr3 = P.ma2 * (r * r * r);
+  if (SIGN_ONLY && Pq < mr3) return -1.0;
+  const double sq = fsqrt(grr);
   const double a = wr * r * s, b = wt * s;
   const double wwp = grr * a * a + b * b + wp * wp;
   const double Np = a * sq * f.br + b * f.bt + wp * f.bp;
-  double Pq = P.Q * fabs(f.bz);
-  if (zero_in && r <= P.rNS) Pq = 0.0;
   const double base = E2 * wwp * f.D;
   const double aniso = P.isotropic ? 0.0 : gn * Np * Np;
-  return Pq * (base - aniso) - P.ma2 * base * (r * r * r);
+  return Pq * (base - aniso) - mr3 * base;
 }
 
 // Cartesian → spherical

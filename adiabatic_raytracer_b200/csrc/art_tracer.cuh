@@ -175,13 +175,13 @@ struct SegQuick {
 // `condition` of propagate (RT.jl:254-298) at dense-output parameter th of a published segment, as the
 // sign-equivalent division-free thick_F (art_physics.cuh); the scan keeps only its sign, the root finder
 // its zero
-template <class DS>
+template <bool SIGN_ONLY = false, class DS>
 ART_HD double seg_cond_full(const DevParams& P, const DS D, double th) {
   double w[6];
   seg_state(D, th, w);
   const double E = D(SEG_U70) + D(SEG_FAC7) * (w[5] - D(SEG_U60));
   const double t = fexp(D(SEG_S) + th * D(SEG_H));
-  return thick_F(P, w[0], w[1], w[2] - P.Omega * t, w[3], w[4], w[5], E, P.rs_ray, true);
+  return thick_F<SIGN_ONLY>(P, w[0], w[1], w[2] - P.Omega * t, w[3], w[4], w[5], E, P.rs_ray, true);
 }
 template <class DS>
 ART_HD double seg_cond(const DevParams& P, const DS D, double th) {
