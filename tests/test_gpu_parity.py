@@ -360,3 +360,71 @@ def test_propagate_tight_tolerance_matches_oracle(lib, oracle):
         assert dx.max() < tol and dk.max() < tol, (sp, dx.max(), dk.max())
         assert np.median(dx) < 1e-9
     h.close()
+
+
+def _binned(rows, n_ct=16):
+    """Σ weight·sln_prob of the final photons in n_ct equal-cosθf viewing-angle bins (plot/flux.py:38-52)."""
+    ph = rows[:, 1] == 1
+    ic = np.clip(np.floor((np.cos(rows[ph, 2]) + 1) * 0.5 * n_ct).astype(int), 0, n_ct - 1)
+    out = np.zeros(n_ct)
+    np.add.at(out, ic, rows[ph, 8] * rows[ph, 7])
+    return out
+
+
+@pytest.mark.parametrize("ma", [2e-6, 1e-5, 3e-5])
+def test_mass_sweep_binned_flux_matches_oracle(lib, oracle, ma):
+    """BASELINE config 3 at test size: axion-mass sweep, 16 viewing-angle bins of the final photon direction.
+    Same seeded events on both sides ⇒ the binned flux agrees far inside its Monte-Carlo error."""
+    p = ArtParams.default(theta_m=0.2, Mass_a=ma)
+    h = lib.Handle(p, 0)
+    h.hist_config(16, 1)
+    n = 1200
+    a = h.run(1769, 1, n)
+    b = oracle.run(p, 1769, 1, n)
+    fa, fb = _binned(a["rows"]), _binned(b["rows"])
+    H = h.hist_get()[:-8].reshape(2, 16, 1, 4)
+    assert np.allclose(H[1, :, 0, 0], fa, rtol=1e-9)             # device histogram = binning of the device rows
+    assert abs(fa.sum() - fb.sum()) <= 0.02 * fb.sum()
+    # per bin: within 3 sigma of the Monte-Carlo error of that bin (sigma² = Σ w², taken from the oracle rows)
+    ph = b["rows"][:, 1] == 1
+    ic = np.clip(np.floor((np.cos(b["rows"][ph, 2]) + 1) * 0.5 * 16).astype(int), 0, 15)
+    var = np.zeros(16)
+    np.add.at(var, ic, (b["rows"][ph, 8] * b["rows"][ph, 7]) ** 2)
+    assert np.all(np.abs(fa - fb) <= 3.0 * np.sqrt(var) + 1e-3 * fb.sum())
+    assert abs(a["f_inx"] - b["f_inx"]) <= 0.01 * b["f_inx"] + 2
+    h.close()
+
+
+def test_mass_above_the_surface_limit_has_no_rays(lib):
+    """Top of the 1e-6…1e-4 eV sweep: maxR < rNS ⇒ "Too small Max R", no output (MainRunner.jl:389-396)."""
+    with pytest.raises(lib.ArtError) as e:
+        lib.Handle(ArtParams.default(theta_m=0.2, Mass_a=6e-5), 0)
+    assert e.value.code == -3
+
+
+@pytest.mark.parametrize("phase", [0, 17, 40])
+def test_rotation_phase_resolved_run_matches_oracle(lib, oracle, phase):
+    """BASELINE config 4 at test size: field time t0 = 2π·phase/(64 Ω) in sampler, weights and conversion
+    probability (generalises the reference's t0 / fix_time knobs, RT.jl:1480, GS.jl:162)."""
+    w = 1.0
+    p = ArtParams.default(theta_m=0.2, omega_pul=w, t0_sample=2 * math.pi * phase / (64 * w))
+    h = lib.Handle(p, 0)
+    n = 600
+    sa, sb = h.sample(7, 1, n), oracle.sample(p, 7, 1, n)
+    assert np.array_equal(sa["n_failed"], sb["n_failed"]) and np.array_equal(sa["n_cross"], sb["n_cross"])
+    assert rel(sa["x"], sb["x"]).max() < 1e-9
+    a, b = h.run(7, 1, n), oracle.run(p, 7, 1, n)
+    ida, idb = a["rows"][:, 0].astype(int), b["rows"][:, 0].astype(int)
+    good = np.bincount(ida, minlength=n + 2) == np.bincount(idb, minlength=n + 2)
+    assert good[1:n + 1].mean() > 0.98
+    A, B = a["rows"][good[ida]], b["rows"][good[idb]]
+    assert np.array_equal(A[:, :2], B[:, :2])
+    assert rel(A[:, 7], B[:, 7]).max() < 1e-9                    # sln_prob (cos_w, g_det at the phase's field)
+    assert np.median(np.abs(A[:, 2] - B[:, 2])) < 1e-7
+    if phase:
+        # a different phase is a different magnetosphere: the sampled points must differ from phase 0
+        s0 = lib.Handle(ArtParams.default(theta_m=0.2, omega_pul=w), 0)
+        x0 = s0.sample(7, 1, n)["x"]
+        s0.close()
+        assert np.abs(x0 - sa["x"]).max() > 1e-3
+    h.close()
