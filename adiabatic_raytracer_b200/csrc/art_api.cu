@@ -200,7 +200,7 @@ int launch_trace_wf(art_handle* h, Lane& L, const QueuedRay* q, long long n, Ray
   W.pend = L.wf_pend.as<int>();
   W.roots = L.wf_roots.as<int>(); W.fin = L.wf_fin.as<int>();
   W.ctr = L.wf_ctr.as<unsigned long long>();
-  const size_t ksmem = (size_t)42 * WF_THREADS * sizeof(double);
+  const size_t ksmem = (size_t)(K_ROWS + K_PARK) * WF_THREADS * sizeof(double);
   CU(cudaMemsetAsync(W.ctr, 0, WC_N * 8, st));
   const int gmax = h->n_sm * 8;
   auto grid = [&](long long work, int threads) { return (int)std::max<long long>(1, std::min<long long>(gmax, (work + threads - 1) / threads)); };
@@ -218,7 +218,7 @@ int launch_trace_wf(art_handle* h, Lane& L, const QueuedRay* q, long long n, Ray
       const int g1 = grid(n_act, WF_THREADS);
       k_wf_reset<<<1, 32, 0, st>>>(W, next);
       k_wf_stages<<<2 * g1, WF_THREADS, ksmem, st>>>(h->dp, W, cur, tail ? h->tail_nstep : h->bulk_nstep, tail ? 1 : 16);
-      k_wf_scan<<<grid(n_act * 32, SCAN_THREADS), SCAN_THREADS, 0, st>>>(h->dp, W, stats);
+      k_wf_scan<<<grid(n_act * 11, SCAN_THREADS), SCAN_THREADS, 0, st>>>(h->dp, W, stats);
       k_wf_detect<<<g1, WF_THREADS, 0, st>>>(h->dp, W, next);
       k_wf_root<<<grid(n_act / 2 + 1, WF_THREADS), WF_THREADS, 0, st>>>(h->dp, W, next, stats);
       if (tree)
@@ -296,7 +296,7 @@ int art_create(const art_params* p, int device_id, art_handle** out) {
   cudaGetDeviceProperties(&prop, device_id);
   h->n_sm = prop.multiProcessorCount;
   int occ = 0;
-  cudaFuncSetAttribute(k_wf_stages, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(42 * WF_THREADS * sizeof(double)));
+  cudaFuncSetAttribute(k_wf_stages, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((K_ROWS + K_PARK) * WF_THREADS * sizeof(double)));
   cudaFuncSetAttribute(k_wf_stages, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sample_events, SAMPLE_THREADS, 0);
   h->blocks_sample = h->n_sm * std::max(occ, 1);

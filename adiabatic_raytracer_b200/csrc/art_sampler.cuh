@@ -114,18 +114,20 @@ struct Sampler {
     return Pq * (base - gn * N * N) - P.ma2 * base;
   }
 
-  // affect!, RT.jl:1585-1597: keep the crossing iff r > rNS and E/√g^rr > ωp
+  // affect!, RT.jl:1585-1597: keep the crossing iff r > rNS and E/√g^rr > ωp, i.e. E² > g^rr ωp² —
+  // evaluated like cond(): dot products with m̂, one rsqrt, no square root of the two sides
   ART_HD void affect(const DevParams& P, double t_) {
     double u[3];
     point(t_, u);
-    const double rho2 = u[0] * u[0] + u[1] * u[1];
-    const double r = sqrt(rho2 + u[2] * u[2]);
-    const double rho = sqrt(rho2);
-    const double cph = u[0] / rho, sph = u[1] / rho;
-    const Fld f = field_cs<false>(P, u[2] / r, rho / r, cph * P.cpsi0 + sph * P.spsi0, sph * P.cpsi0 - cph * P.spsi0);
-    const double wp = sqrt(P.Q / (r * r * r) * fabs(f.bz));
-    const Met m = metric(r, P.rs_real, P.r_int);
-    if (r > P.rNS && sqrt(E2) / sqrt(m.grr) > wp) {
+    const double r2 = u[0] * u[0] + u[1] * u[1] + u[2] * u[2];
+    const double rinv = frsqrt(r2);
+    const double r = r2 * rinv;
+    const double mx = (P.mh[0] * u[0] + P.mh[1] * u[1] + P.mh[2] * u[2]) * rinv;
+    const double bz = 3.0 * mx * (u[2] * rinv) - P.cm;
+    const double wp2 = P.Q * fabs(bz) * rinv * rinv * rinv;
+    double grr = 1.0 - P.rs_real * rinv;
+    if (!(r > P.r_int)) grr = metric(r, P.rs_real, P.r_int).grr;
+    if (r > P.rNS && E2 > grr * wp2) {
       if (n_cross < SAMP_KEEP) taus[n_cross * taus_stride] = t_;
       n_cross++;
     }
@@ -229,7 +231,7 @@ struct Sampler {
         return;
       }
       if (it == 3 && fmin(fabs(fa), fabs(fb)) > 0.25 * f0) pure = true;
-      c = (a * fb - b * fa) / (fb - fa);
+      c = (a * fb - b * fa) * frcp(fb - fa);
       const double lo = fmin(a, b), hi = fmax(a, b);
       if (pure || (it >= 3 && width > 0.5 * w2) || !(c > lo && c < hi) || width <= 2.0 * tol) c = 0.5 * (a + b);
       else if (fabs(c - b) < tol) c = b + copysign(tol, a - b);

@@ -70,12 +70,21 @@ struct KStore {
   double* base;
   int stride;
   ART_HD double& operator()(int j, int i) const { return base[(j * 6 + i) * stride]; }
+  static constexpr bool PARKS = false;  // see KStoreT
+  ART_HD double& park(int) const { return base[0]; }
 };
 // same with the stride known at compile time (device: STRIDE = CTA size ⇒ addresses fold into immediates)
+// Rows 42.. of the device store hold t = e^{ln t} of the six stage times of the attempted step.
+constexpr int K_ROWS = 42, K_PARK = 6;
 template <int STRIDE>
 struct KStoreT {
   double* base;
   ART_HD double& operator()(int j, int i) const { return base[(j * 6 + i) * STRIDE]; }
+#ifndef ART_PRE_T
+#define ART_PRE_T 1
+#endif
+  static constexpr bool PARKS = ART_PRE_T != 0;
+  ART_HD double& park(int k) const { return base[(K_ROWS + k) * STRIDE]; }
 };
 
 // Dense-output segment of an accepted step, published (device: in shared memory, one column
@@ -258,7 +267,10 @@ struct Ray : RayHot, RayCold {
   // SP = −1: species from the ray (mixed batches); 0 / 1: compile-time axion / photon
   template <int SP = -1>
   ART_HD void f(const DevParams& P, const double v[6], double lnt, double dv[6]) const {
-    const double t = fexp(lnt);
+    ft<SP>(P, v, fexp(lnt), dv);
+  }
+  template <int SP = -1>
+  ART_HD void ft(const DevParams& P, const double v[6], double t, double dv[6]) const {
     const bool ax = SP < 0 ? axion : (SP == SPECIES_AXION);
     const double einv = frcp(erg);
     if (ax)
@@ -376,6 +388,12 @@ struct Ray : RayHot, RayCold {
     }
     s_new = last ? s1 : s + h;
     for (int i = 0; i < 6; ++i) K(0, i) = k1[i];
+    // the six stage times are known up front: their exponentials are evaluated together (five independent
+    // chains) instead of heading the dependent chain of every right-hand side
+    if (KS::PARKS) {
+      for (int st = 1; st <= 5; ++st) K.park(st - 1) = fexp(s + DP_C[st] * h);
+      K.park(5) = fexp(s_new);
+    }
     for (int st = 1; st <= 6; ++st) {
       double v[6];
       for (int i = 0; i < 6; ++i) v[i] = u[i];
@@ -383,9 +401,13 @@ struct Ray : RayHot, RayCold {
         const double c = h * DP_A[st][j];
         for (int i = 0; i < 6; ++i) v[i] += c * K(j, i);
       }
-      const double ts = (st == 6) ? s_new : s + DP_C[st] * h;
       double dv[6];
-      f<SP>(P, v, ts, dv);
+      if (KS::PARKS) {
+        ft<SP>(P, v, K.park(st - 1), dv);
+      } else {
+        const double ts = (st == 6) ? s_new : s + DP_C[st] * h;
+        f<SP>(P, v, ts, dv);
+      }
       for (int i = 0; i < 6; ++i) K(st, i) = dv[i];
       if (st == 6)
         for (int i = 0; i < 6; ++i) un[i] = v[i];
@@ -599,7 +621,7 @@ struct Ray : RayHot, RayCold {
       const double width = fabs(rb - ra);
       if (width <= tol) break;
       if (it == 3 && fmin(fabs(fa), fabs(fb)) > 0.25 * f0) pure = true;
-      double c = (ra * fb - rb * fa) / (fb - fa);
+      double c = (ra * fb - rb * fa) * frcp(fb - fa);
       const double lo = fmin(ra, rb), hi = fmax(ra, rb);
       if (pure || (it >= 3 && width > 0.5 * w2) || !(c > lo && c < hi) || width <= 2.0 * tol) c = 0.5 * (ra + rb);
       else if (fabs(c - rb) < tol) c = rb + copysign(tol, ra - rb);  // a converged iterate collapses the bracket

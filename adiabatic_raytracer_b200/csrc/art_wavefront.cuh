@@ -261,60 +261,109 @@ k_wf_stages(const __grid_constant__ DevParams P, WfPool W, int cur, int nstep, i
   else wf_stages_body<SPECIES_PHOTON>(P, W, cur, nstep, min_go, blockIdx.x - half, half, ksm);
 }
 
-// ---- crossing scan: one warp per pending step -----------------------------------------------------------
-// The M−1 grid points of the step (and the nudge point after an event) are dealt to the lanes, 32 per
-// round.  Every lane first classifies its point with the far-field test (two polynomials); the lanes
-// whose point needs it then evaluate the full condition together; three ballots per round turn the
-// signs into the bit masks k_wf_detect works on.  No per-ray work list, no per-point sign bytes: the
-// segment is read once (staged in shared memory) and 24 bytes of masks are written per step.
+// ---- crossing scan: one warp per group of pending steps -----------------------------------------------
+// A step has M slots — its M−1 grid points and the nudge point that is only scanned after an event.  The
+// slots of up to three steps (3·M ≤ 160) are laid end to end and dealt to the lanes, 32 per round, so that
+// 94 % of the lanes hold a point (one step per warp would leave 22 % idle: 50 slots in 64).  Every lane first
+// classifies its point with the far-field test (two polynomials); the lanes whose point needs it then
+// evaluate the condition together; three ballots per round turn the signs into the bit masks k_wf_detect
+// works on.  No per-ray work list, no per-point sign bytes: each segment is read once (staged in shared
+// memory) and 24 bytes of masks are written per step.
 constexpr int SCAN_THREADS = 256;
-__global__ void __launch_bounds__(SCAN_THREADS, 3)
+#ifndef ART_SCAN_PACK
+#define ART_SCAN_PACK 3
+#endif
+constexpr int SCAN_PACK = ART_SCAN_PACK;  // steps per warp and trip (at most)
+constexpr int SCAN_ROUNDS = 5;  // ballot words kept per sign class
+
+__device__ __forceinline__ unsigned scan_pick(const unsigned (&b)[SCAN_ROUNDS], int k) {
+  unsigned v = 0;
+#pragma unroll
+  for (int q = 0; q < SCAN_ROUNDS; ++q) v = (q == k) ? b[q] : v;
+  return v;
+}
+// bits [off, off + M) of the ballot words, re-ordered to grid-point order: slot q < M−1 ↔ point q + 1,
+// slot M−1 ↔ the nudge point 0
+__device__ __forceinline__ unsigned long long scan_extract(const unsigned (&b)[SCAN_ROUNDS], int off, int M) {
+  const int w = off >> 5, sh = off & 31;
+  const unsigned long long lo = (unsigned long long)scan_pick(b, w) | ((unsigned long long)scan_pick(b, w + 1) << 32);
+  const unsigned long long hi = scan_pick(b, w + 2);
+  unsigned long long r = lo >> sh;
+  if (sh) r |= hi << (64 - sh);
+  if (M < 64) r &= (1ull << M) - 1ull;
+  const unsigned long long pts = r & ((1ull << (M - 1)) - 1ull);
+  return (pts << 1) | ((r >> (M - 1)) & 1ull);
+}
+
+#ifndef ART_SCAN_MINBLOCKS
+#define ART_SCAN_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(SCAN_THREADS, ART_SCAN_MINBLOCKS)
 k_wf_scan(const __grid_constant__ DevParams P, WfPool W, DevStats* stats) {
-  __shared__ double seg_sm[SCAN_THREADS / 32][SEG_PAD];
+  __shared__ double seg_sm[SCAN_THREADS / 32][SCAN_PACK][SEG_PAD];
   const long long n = (long long)W.ctr[WC_PEND];
   const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const long long nwarps = (long long)gridDim.x * (SCAN_THREADS / 32);
   const int M = P.M_ray;
-  double* sg = seg_sm[wib];
+  const int pack = min(SCAN_PACK, (32 * SCAN_ROUNDS) / M);  // M ≤ 64 ⇒ pack ≥ 2
+  const int rounds = (pack * M + 31) >> 5;
+  // what this lane does in each round does not depend on the steps: which of the (up to three) staged
+  // segments it reads, at which dense-output parameter, and whether its slot is a nudge slot
+  const double* seg_rd[SCAN_ROUNDS];
+  double th_rd[SCAN_ROUNDS];
+  int j_rd[SCAN_ROUNDS];  // segment index, +8 for a nudge slot, −1 for no slot
+#pragma unroll
+  for (int rd = 0; rd < SCAN_ROUNDS; ++rd) {
+    const int slot = rd * 32 + (int)lane;
+    const int j = slot / M, q = slot - j * M;
+    const bool has = rd < rounds && j < pack;
+    j_rd[rd] = has ? (q < M - 1 ? j : j + 8) : -1;
+    th_rd[rd] = seg_theta(P, (q < M - 1) ? q + 1 : 0);
+    seg_rd[rd] = seg_sm[wib][has ? j : 0];
+  }
   unsigned long long n_full = 0;
-  for (long long p = blockIdx.x * (long long)(SCAN_THREADS / 32) + wib; p < n; p += nwarps) {
-    const int id = W.pend[p];
-    const double* src = W.seg + (size_t)id * SEG_PAD;
+  for (long long p = (blockIdx.x * (long long)(SCAN_THREADS / 32) + wib) * pack; p < n; p += nwarps * pack) {
+    const int cnt = (int)min((long long)pack, n - p);
+    int my_id = -1;
+    if ((int)lane < cnt) my_id = W.pend[p + lane];
     __syncwarp();
-    sg[lane] = src[lane];
-    if (lane < SEG_PAD - 32) sg[32 + lane] = src[32 + lane];
+    for (int j = 0; j < cnt; ++j) {
+      const int id = __shfl_sync(FULL, my_id, j);
+      const double* src = W.seg + (size_t)id * SEG_PAD;
+      seg_sm[wib][j][lane] = src[lane];
+      if (lane < SEG_PAD - 32) seg_sm[wib][j][32 + lane] = src[32 + lane];
+    }
     __syncwarp();
-    const SegAoS D{sg};
-    const bool nudge = D(SEG_NUDGE) != 0.0;
-    unsigned long long mp = 0ull, mn = 0ull, mz = 0ull;
-    const int rounds = (M - 1 > 32 || nudge) ? 2 : 1;
-    for (int rd = 0; rd < rounds; ++rd) {
-      const int slot = rd * 32 + (int)lane;   // slot s ↔ grid point s + 1; slot 63 ↔ the nudge point 0
-      int i = -1;
-      if (slot + 1 <= M - 1) i = slot + 1;
-      else if (slot == 63 && nudge) i = 0;
-      int code = 0;  // 1 positive, 2 negative, 3 zero, 0 NaN / no point
-      if (i >= 0) {
-        const double th = seg_theta(P, i);
-        const int qk = seg_quick(P, D, th);
-        if (qk == -1) code = 2;
-        else if (qk == 0) {
-          const double g = seg_cond_full<true>(P, D, th);
-          n_full++;
-          code = (g > 0.0) ? 1 : ((g < 0.0) ? 2 : ((g == 0.0) ? 3 : 0));
+    unsigned bp[SCAN_ROUNDS], bn[SCAN_ROUNDS], bz[SCAN_ROUNDS];
+#pragma unroll
+    for (int rd = 0; rd < SCAN_ROUNDS; ++rd) {
+      bp[rd] = bn[rd] = bz[rd] = 0u;
+      if (rd < rounds) {
+        int code = 0;  // 1 positive, 2 negative, 3 zero, 0 NaN / no point
+        const int j = j_rd[rd];
+        if (j >= 0 && (j & 7) < cnt) {
+          const SegAoS D{const_cast<double*>(seg_rd[rd])};
+          if (j < 8 || D(SEG_NUDGE) != 0.0) {
+            const double th = th_rd[rd];
+            const int qk = seg_quick(P, D, th);
+            if (qk == -1) code = 2;
+            else if (qk == 0) {
+              const double g = seg_cond_full<true>(P, D, th);
+              n_full++;
+              code = (g > 0.0) ? 1 : ((g < 0.0) ? 2 : ((g == 0.0) ? 3 : 0));
+            }
+          }
         }
-      }
-      unsigned bp = __ballot_sync(FULL, code == 1), bn = __ballot_sync(FULL, code == 2), bz = __ballot_sync(FULL, code == 3);
-      if (rd == 0) {
-        mp |= (unsigned long long)bp << 1; mn |= (unsigned long long)bn << 1; mz |= (unsigned long long)bz << 1;
-      } else {
-        mp |= (unsigned long long)(bp >> 31); mn |= (unsigned long long)(bn >> 31); mz |= (unsigned long long)(bz >> 31);
-        mp |= (unsigned long long)(bp & 0x7fffffffu) << 33; mn |= (unsigned long long)(bn & 0x7fffffffu) << 33;
-        mz |= (unsigned long long)(bz & 0x7fffffffu) << 33;
+        bp[rd] = __ballot_sync(FULL, code == 1);
+        bn[rd] = __ballot_sync(FULL, code == 2);
+        bz[rd] = __ballot_sync(FULL, code == 3);
       }
     }
-    if (lane == 0) {
-      W.mpos[id] = mp; W.mneg[id] = mn; W.mzero[id] = mz;
+    if ((int)lane < cnt) {
+      const int off = (int)lane * M;
+      W.mpos[my_id] = scan_extract(bp, off, M);
+      W.mneg[my_id] = scan_extract(bn, off, M);
+      W.mzero[my_id] = scan_extract(bz, off, M);
     }
   }
   n_full = warp_sum(n_full);
