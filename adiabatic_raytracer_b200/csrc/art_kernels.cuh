@@ -62,7 +62,10 @@ struct EventSample {
   int n_cross, n_failed;
 };
 
-__global__ void __launch_bounds__(SAMPLE_THREADS)
+#ifndef ART_SAMPLE_MINBLOCKS
+#define ART_SAMPLE_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(SAMPLE_THREADS, ART_SAMPLE_MINBLOCKS)
 k_sample_events(const __grid_constant__ DevParams P, unsigned long long seed, long long first_event, long long n,
                 EventSample* __restrict__ out, unsigned long long* head, DevStats* stats,
                 unsigned long long* n_failed_total) {

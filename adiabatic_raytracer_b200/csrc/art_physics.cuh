@@ -17,6 +17,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define ART_HD __host__ __device__ __forceinline__
@@ -89,12 +90,15 @@ ART_HD double fsqrt(double x) {  // x > 0
 #define ART_FM_EXP {1.0 / 2, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320, 1.0 / 362880, \
                     1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600, 1.0 / 6227020800.0}
 #define ART_FM_LN2 {1.4426950408889634074, 6.93147180369123816490e-01, 1.90821492927058770002e-10}
+// 1/(2n+1), n = 1..9 (atanh series)
+#define ART_FM_LOG {1.0 / 3, 1.0 / 5, 1.0 / 7, 1.0 / 9, 1.0 / 11, 1.0 / 13, 1.0 / 15, 1.0 / 17, 1.0 / 19}
 #if defined(__CUDACC__)
 __device__ __constant__ double FM_SIN_D[6] = ART_FM_SIN;
 __device__ __constant__ double FM_COS_D[6] = ART_FM_COS;
 __device__ __constant__ double FM_PIO2_D[4] = ART_FM_PIO2;
 __device__ __constant__ double FM_EXP_D[12] = ART_FM_EXP;
 __device__ __constant__ double FM_LN2_D[3] = ART_FM_LN2;
+__device__ __constant__ double FM_LOG_D[9] = ART_FM_LOG;
 #endif
 #if defined(__CUDA_ARCH__)
 #define FM_SIN FM_SIN_D
@@ -102,12 +106,14 @@ __device__ __constant__ double FM_LN2_D[3] = ART_FM_LN2;
 #define FM_PIO2 FM_PIO2_D
 #define FM_EXP FM_EXP_D
 #define FM_LN2 FM_LN2_D
+#define FM_LOG FM_LOG_D
 #else
 static const double FM_SIN[6] = ART_FM_SIN;
 static const double FM_COS[6] = ART_FM_COS;
 static const double FM_PIO2[4] = ART_FM_PIO2;
 static const double FM_EXP[12] = ART_FM_EXP;
 static const double FM_LN2[3] = ART_FM_LN2;
+static const double FM_LOG[9] = ART_FM_LOG;
 #endif
 
 ART_HD void fsincos(double x, double* sn, double* cs) {
@@ -157,6 +163,39 @@ ART_HD double fexp(double x) {
 #else
   return ldexp(p, (int)k);
 #endif
+}
+
+// ln x for finite x > 0 (0 gives ≈ −709, which every caller clamps): exponent split, m ∈ [√½, √2),
+// ln m = 2 atanh(s), s = (m − 1)/(m + 1), series to s¹⁹ (truncation 2e-17).  Branch-free; ≤ 2 ulp.
+ART_HD double flog(double x) {
+#if defined(__CUDA_ARCH__)
+  const int hi = __double2hiint(x);
+  double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+#else
+  unsigned long long bits;
+  memcpy(&bits, &x, 8);
+  const int hi = (int)(bits >> 32);
+  bits = (bits & 0x000fffffffffffffull) | 0x3ff0000000000000ull;
+  double m;
+  memcpy(&m, &bits, 8);
+#endif
+  int e = (hi >> 20) - 1023;
+  const bool up = m > 1.4142135623730951;
+  m = up ? 0.5 * m : m;
+  e += up ? 1 : 0;
+  const double s = (m - 1.0) * frcp(m + 1.0);
+  const double z = s * s;
+  double p = fma(z, FM_LOG[8], FM_LOG[7]);
+  p = fma(z, p, FM_LOG[6]);
+  p = fma(z, p, FM_LOG[5]);
+  p = fma(z, p, FM_LOG[4]);
+  p = fma(z, p, FM_LOG[3]);
+  p = fma(z, p, FM_LOG[2]);
+  p = fma(z, p, FM_LOG[1]);
+  p = fma(z, p, FM_LOG[0]);
+  const double lm = fma(s * z, p, s);  // atanh(s)
+  const double ed = (double)e;
+  return fma(ed, FM_LN2[1], fma(ed, FM_LN2[2], 2.0 * lm));
 }
 
 // Run constants, derived once on the host from art_params (art_api.cu: make_dev_params).

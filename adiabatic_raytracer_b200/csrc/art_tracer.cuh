@@ -374,6 +374,22 @@ struct Ray : RayHot, RayCold {
     starting = false;
   }
 
+  // v = u + h Σ_{j<ST} a_{ST+1,j+1} k_j with the tableau row as constant-bank operands and the stage store
+  // at static offsets (a j loop with a run-time bound spent 21 % of the stage kernel's instructions on
+  // address and loop arithmetic — profiles/r01_wf10_inst_by_line.txt)
+  template <int ST, class KS>
+  ART_HD void combine(const KS K, double v[6]) const {
+    for (int i = 0; i < 6; ++i) v[i] = u[i];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < ST; ++j) {
+      if (ST == 6 && j == 1) continue;  // b2 = 0: the term is an exact zero
+      const double c = h * DP_A[ST][j];
+      for (int i = 0; i < 6; ++i) v[i] += c * K(j, i);
+    }
+  }
+
   // attempt(): one attempted DP5 step with error control (stage loop rolled: one copy of the
   // right-hand side).  Returns true if the step was accepted; un, s_new, dt_new, h and K then
   // describe it until apply().
@@ -396,10 +412,13 @@ struct Ray : RayHot, RayCold {
     }
     for (int st = 1; st <= 6; ++st) {
       double v[6];
-      for (int i = 0; i < 6; ++i) v[i] = u[i];
-      for (int j = 0; j < st; ++j) {
-        const double c = h * DP_A[st][j];
-        for (int i = 0; i < 6; ++i) v[i] += c * K(j, i);
+      switch (st) {  // warp-uniform: the stage loop stays rolled (one copy of the right-hand side)
+        case 1: combine<1>(K, v); break;
+        case 2: combine<2>(K, v); break;
+        case 3: combine<3>(K, v); break;
+        case 4: combine<4>(K, v); break;
+        case 5: combine<5>(K, v); break;
+        default: combine<6>(K, v); break;
       }
       double dv[6];
       if (KS::PARKS) {
@@ -414,23 +433,27 @@ struct Ray : RayHot, RayCold {
     }
     n_rhs += 6;
 
-    // ---- error control ---------------------------------------------------------------------
+    // ---- error control (divisions as reciprocals, no special-case branches) ---------------------------
     double q = 0.0, e6 = 0.0;
     for (int i = 0; i < 6; ++i) {
-      double e = 0.0;
-      for (int j = 0; j < 7; ++j) e += DP_E[j] * K(j, i);
+      double e = DP_E[0] * K(0, i);  // e2 = 0
+      e += DP_E[2] * K(2, i);
+      e += DP_E[3] * K(3, i);
+      e += DP_E[4] * K(4, i);
+      e += DP_E[5] * K(5, i);
+      e += DP_E[6] * K(6, i);
       e *= h;
       if (i == 5) e6 = e;
-      const double r_ = e / (P.atol + fmax(fabs(u[i]), fabs(un[i])) * P.rtol);
+      const double r_ = e * frcp(P.atol + fmax(fabs(u[i]), fabs(un[i])) * P.rtol);
       q += r_ * r_;
     }
-    const double r7 = fac7 * e6 / (P.atol + fmax(fabs(u7_of(u[5])), fabs(u7_of(un[5]))) * P.rtol);
+    const double r7 = fac7 * e6 * frcp(P.atol + fmax(fabs(u7_of(u[5])), fabs(u7_of(un[5]))) * P.rtol);
     q += r7 * r7;
-    const double EEst = sqrt(q / 7.0);
+    const double EEst = (q > 0.0) ? fsqrt(q * (1.0 / 7.0)) : q;  // 0 stays 0, NaN stays NaN
     // PI controller: q11 = EEst^β1, q = q11 / qold^β2
-    double q11 = fexp(dp::beta1 * log(EEst));
-    double qq = q11 * fexp(-dp::beta2 * log(qold));
-    qq = fmax(1.0 / dp::qmax, fmin(1.0 / dp::qmin, qq / dp::gamma));
+    double q11 = fexp(dp::beta1 * flog(EEst));
+    double qq = q11 * fexp(-dp::beta2 * flog(qold));
+    qq = fmax(1.0 / dp::qmax, fmin(1.0 / dp::qmin, qq * (1.0 / dp::gamma)));
     if (EEst == 0.0) qq = 1.0 / dp::qmax;
     bool accept = (EEst <= 1.0) || (h <= P.dtmin);  // force_dtmin
     if (!(EEst == EEst)) {
@@ -439,14 +462,14 @@ struct Ray : RayHot, RayCold {
     }
     if (!accept) {
       n_rej++;
-      dt = h / fmin(1.0 / dp::qmin, q11 / dp::gamma);
+      dt = h * frcp(fmin(1.0 / dp::qmin, q11 * (1.0 / dp::gamma)));
       if (dt < P.dtmin) dt = P.dtmin;
       return false;
     }
     n_acc++;
     if (qq <= dp::qsteady_max && qq >= dp::qsteady_min) qq = 1.0;
     qold = fmax(EEst, dp::qoldinit);
-    dt_new = h / qq;
+    dt_new = h * frcp(qq);
     n_cond += P.M_ray - 1 + (event_last ? 1 : 0);
     return true;
   }

@@ -38,8 +38,8 @@ namespace art {
 
 constexpr int WF_THREADS = 128;
 #ifndef ART_STAGE_MINBLOCKS
-#define ART_STAGE_MINBLOCKS 2  // resident CTAs per SM the stage kernel's register allocation is tuned for (measured:
-                               // 2 → 234 registers, no spills, 289 ms; 3 → 168 + spills, 298 ms; 5 → 96, 338 ms per 1e6 events)
+#define ART_STAGE_MINBLOCKS 3  // resident CTAs per SM the stage kernel's register allocation is tuned for (measured per 1e6
+                               // events: 2 → 200 registers, 274 ms; 3 → 168 registers, 68 B of spills, 270 ms)
 #endif
 #ifndef ART_STAGE_NSTEP
 #define ART_STAGE_NSTEP 4      // attempted steps a ray may take inside one k_wf_stages launch

@@ -40,6 +40,11 @@ int hc_fastmath(int64_t n, const double* x, double* sn, double* cs, double* ex) 
   return 0;
 }
 
+int hc_flog(int64_t n, const double* x, double* out) {
+  for (int64_t i = 0; i < n; ++i) out[i] = flog(x[i]);
+  return 0;
+}
+
 // sign-equivalent division-free condition (same argument layout as hc_condition)
 int hc_condition_F(const art_params* p, int64_t n, const double* in, double* out) {
   DevParams P;

@@ -26,6 +26,7 @@ def lib():
         L.hc_condition.argtypes = [PP, C.c_int64, _dp, _dp]
         L.hc_condition_F.argtypes = [PP, C.c_int64, _dp, _dp]
         L.hc_fastmath.argtypes = [C.c_int64, _dp, _dp, _dp, _dp]
+        L.hc_flog.argtypes = [C.c_int64, _dp, _dp]
         L.hc_sample_from_uniforms.argtypes = [PP, C.c_int64, _dp, _dp, _dp, _dp, _ip, _ip, _ip]
         L.hc_weights.argtypes = [PP, C.c_int64, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]
         L.hc_conv_prob.argtypes = [PP, C.c_int64, _dp, _dp, _dp, C.c_int32, _dp]
@@ -61,6 +62,13 @@ def fastmath(x):
     sn, cs, ex = np.zeros_like(x), np.zeros_like(x), np.zeros_like(x)
     _chk(lib().hc_fastmath(x.size, x, sn, cs, ex))
     return sn, cs, ex
+
+
+def flog(x):
+    x = np.ascontiguousarray(x, np.float64)
+    out = np.zeros_like(x)
+    _chk(lib().hc_flog(x.size, x, out))
+    return out
 
 
 def condition_F(p, inp):

@@ -26,6 +26,8 @@ def test_branch_free_sincos_and_exp_match_libm():
     assert np.max(np.abs(cs - np.cos(x))) < 4e-16 * 2
     small = np.abs(x) < 100
     assert np.max(np.abs(ex[small] / np.exp(x[small]) - 1.0)) < 5e-16
+    y = np.concatenate([10.0 ** rng.uniform(-30, 30, 20000), rng.uniform(0.5, 2.0, 20000), [1.0, 2.0, 0.5, 1e-300, 1e300]])
+    assert np.max(np.abs(hc.flog(y) - np.log(y)) / np.maximum(np.abs(np.log(y)), 1.0)) < 5e-16
 
 
 def test_division_free_condition_has_the_sign_and_zeros_of_the_reference_condition(oracle):
