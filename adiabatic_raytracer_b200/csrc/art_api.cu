@@ -99,16 +99,21 @@ bool nccl_load(std::string& err) {
 // concurrently (host thread + CUDA stream each) so that the thin tail of one sub-chunk's wavefront loop
 // overlaps the sampler and the bulk steps of the others.
 struct Lane {
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr;  // stream2: root finder + tree, one iteration behind the stage kernel
+  cudaEvent_t ev_reset = nullptr, ev_side = nullptr;
   DBuf samples, tstate, stacks, q0, rout, rec, ctr;
-  DBuf wf_hot, wf_cold, wf_seg, wf_need, wf_neg, wf_pend, wf_sign, wf_act[4], wf_items, wf_roots, wf_fin, wf_ctr;
+  DBuf wf_hot, wf_cold, wf_seg, wf_need, wf_neg, wf_pend, wf_sign, wf_act[4], wf_items, wf_roots[2], wf_fin[2], wf_ctr;
   float ms_sampler = 0, ms_weights = 0, ms_tracer = 0;
   void release() {
     DBuf* all[] = {&samples, &tstate, &stacks, &q0, &rout, &rec, &ctr, &wf_hot, &wf_cold, &wf_seg, &wf_need, &wf_neg,
-                   &wf_pend, &wf_sign, &wf_act[0], &wf_act[1], &wf_act[2], &wf_act[3], &wf_items, &wf_roots, &wf_fin, &wf_ctr};
+                   &wf_pend, &wf_sign, &wf_act[0], &wf_act[1], &wf_act[2], &wf_act[3], &wf_items, &wf_roots[0], &wf_roots[1], &wf_fin[0], &wf_fin[1], &wf_ctr};
     for (DBuf* b : all) b->release();
     if (stream) cudaStreamDestroy(stream);
-    stream = nullptr;
+    if (stream2) cudaStreamDestroy(stream2);
+    if (ev_reset) cudaEventDestroy(ev_reset);
+    if (ev_side) cudaEventDestroy(ev_side);
+    stream = stream2 = nullptr;
+    ev_reset = ev_side = nullptr;
   }
 };
 
@@ -170,6 +175,9 @@ int ensure_lanes(art_handle* h, int n) {
   while ((int)h->lanes.size() < n) {
     h->lanes.emplace_back();
     CU(cudaStreamCreateWithFlags(&h->lanes.back().stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->lanes.back().stream2, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&h->lanes.back().ev_reset, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->lanes.back().ev_side, cudaEventDisableTiming));
   }
   return ART_OK;
 }
@@ -188,8 +196,10 @@ int launch_trace_wf(art_handle* h, Lane& L, const QueuedRay* q, long long n, Ray
   CU(L.wf_sign.ensure((size_t)n * 8));
   for (int k = 0; k < 4; ++k) CU(L.wf_act[k].ensure((size_t)n * 4));
   CU(L.wf_pend.ensure((size_t)n * 4));
-  CU(L.wf_roots.ensure((size_t)n * 4));
-  CU(L.wf_fin.ensure((size_t)n * 4));
+  for (int k = 0; k < 2; ++k) {
+    CU(L.wf_roots[k].ensure((size_t)n * 4));
+    CU(L.wf_fin[k].ensure((size_t)n * 4));
+  }
   CU(L.wf_ctr.ensure(WC_N * 8));
   WfPool W;
   W.hot = L.wf_hot.as<RayHot>(); W.cold = L.wf_cold.as<RayCold>(); W.seg = L.wf_seg.as<double>();
@@ -198,7 +208,7 @@ int launch_trace_wf(art_handle* h, Lane& L, const QueuedRay* q, long long n, Ray
   for (int par = 0; par < 2; ++par)
     for (int sp = 0; sp < 2; ++sp) W.act[par][sp] = L.wf_act[par * 2 + sp].as<int>();
   W.pend = L.wf_pend.as<int>();
-  W.roots = L.wf_roots.as<int>(); W.fin = L.wf_fin.as<int>();
+  for (int k = 0; k < 2; ++k) { W.roots[k] = L.wf_roots[k].as<int>(); W.fin[k] = L.wf_fin[k].as<int>(); }
   W.ctr = L.wf_ctr.as<unsigned long long>();
   const size_t ksmem = (size_t)(K_ROWS + K_PARK) * WF_THREADS * sizeof(double);
   CU(cudaMemsetAsync(W.ctr, 0, WC_N * 8, st));
@@ -207,33 +217,46 @@ int launch_trace_wf(art_handle* h, Lane& L, const QueuedRay* q, long long n, Ray
   k_wf_init<<<grid(n, WF_THREADS), WF_THREADS, 0, st>>>(h->dp, q, n, W, rec, rec_cap, stats);
   h->launches++;
   CU(cudaGetLastError());
-  long long n_act = n;  // upper bound of the active count, refreshed at every host check
+  long long n_act = n;  // upper bound of the rays in flight, refreshed at every host check
   int cur = 0;
   const bool trace = getenv("ART_WF_TRACE") != nullptr;
+  cudaStream_t s2 = L.stream2;
   for (long long iter = 0;;) {
     const int burst = n_act > 500000 ? 8 : (n_act > 65536 ? 16 : 32);  // steps between host checks (deep queue: host jitter must not idle the GPU)
     const bool tail = n_act < 8LL * h->n_sm * WF_THREADS;               // fewer rays than one resident wave
     for (int b = 0; b < burst; ++b, ++iter) {
       const int next = 1 - cur;
+      const int lpar = (int)(iter & 1), lin = 1 - lpar;  // lists this iteration fills / lists of the previous one
       const int g1 = grid(n_act, WF_THREADS);
-      k_wf_reset<<<1, 32, 0, st>>>(W, next);
-      k_wf_stages<<<2 * g1, WF_THREADS, ksmem, st>>>(h->dp, W, cur, tail ? h->tail_nstep : h->bulk_nstep, tail ? 1 : 16);
-      k_wf_scan<<<grid(n_act * 11, SCAN_THREADS), SCAN_THREADS, 0, st>>>(h->dp, W, stats);
-      k_wf_detect<<<g1, WF_THREADS, 0, st>>>(h->dp, W, next);
-      k_wf_root<<<grid(n_act / 2 + 1, WF_THREADS), WF_THREADS, 0, st>>>(h->dp, W, next, stats);
+      // main stream: the side stream's previous pass must be through before its lists are zeroed
+      CU(cudaStreamWaitEvent(st, L.ev_side, 0));
+      k_wf_reset<<<1, 32, 0, st>>>(W, next, lpar);
+      CU(cudaEventRecord(L.ev_reset, st));
+      // side stream: root finder and tree of the PREVIOUS iteration's lists, concurrent with this stage kernel
+      CU(cudaStreamWaitEvent(s2, L.ev_reset, 0));
+      k_wf_root<<<grid(n_act / 2 + 1, WF_THREADS), WF_THREADS, 0, s2>>>(h->dp, W, next, lin, lpar, stats);
       if (tree)
-        k_wf_tree<<<grid(n_act / 2 + 1, WF_THREADS), WF_THREADS, 0, st>>>(h->dp, W, *tree, next, rec, rec_cap, stats);
+        k_wf_tree<<<grid(n_act / 2 + 1, WF_THREADS), WF_THREADS, 0, s2>>>(h->dp, W, *tree, next, lin, rec, rec_cap, stats);
       else
-        k_wf_collect<<<grid(n_act / 4 + 1, WF_THREADS), WF_THREADS, 0, st>>>(h->dp, W, out, stats);
+        k_wf_collect<<<grid(n_act / 4 + 1, WF_THREADS), WF_THREADS, 0, s2>>>(h->dp, W, lin, out, stats);
+      CU(cudaEventRecord(L.ev_side, s2));
+      k_wf_stages<<<2 * g1, WF_THREADS, ksmem, st>>>(h->dp, W, cur, lpar, tail ? h->tail_nstep : h->bulk_nstep, tail ? 1 : 16);
+      k_wf_scan<<<grid(n_act * 11, SCAN_THREADS), SCAN_THREADS, 0, st>>>(h->dp, W, stats);
+      k_wf_detect<<<g1, WF_THREADS, 0, st>>>(h->dp, W, next, lpar);
       h->launches += 6;
       cur = next;
     }
     CU(cudaGetLastError());
-    unsigned long long na[2] = {0, 0};
-    CU(cudaMemcpyAsync(na, W.ctr + WC_ACT + cur * 2, 16, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamWaitEvent(st, L.ev_side, 0));
+    unsigned long long c[WC_N];
+    CU(cudaMemcpyAsync(c, W.ctr, sizeof(c), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    n_act = (long long)(na[0] + na[1]);
-    if (trace) fprintf(stderr, "[wf %p] iter %lld active %lld (ax %llu ph %llu)\n", (void*)&L, iter, n_act, na[0], na[1]);
+    const int lastpar = (int)((iter - 1) & 1);
+    const unsigned long long na0 = c[WC_ACT + cur * 2], na1 = c[WC_ACT + cur * 2 + 1];
+    n_act = (long long)(na0 + na1 + c[WC_ROOTS + lastpar] + c[WC_FIN + lastpar]);
+    if (trace)
+      fprintf(stderr, "[wf %p] iter %lld in flight %lld (ax %llu ph %llu roots %llu finished %llu)\n", (void*)&L, iter, n_act, na0, na1,
+              c[WC_ROOTS + lastpar], c[WC_FIN + lastpar]);
     if (n_act == 0) break;
     if (iter > 64LL * h->params.maxiters) return fail(h, ART_ERR_CUDA, "wavefront tracer did not terminate");
   }

@@ -27,8 +27,11 @@
 //                  step's active list — events of any tree depth share one loop, there are no
 //                  per-generation launches or host round trips
 //
-// Survivors are appended to the next step's active lists inside detect/root/tree (warp-aggregated
-// atomics); nothing waits on another kernel; the host reads one counter every few steps.
+// Survivors are appended to the next step's active lists inside stages/detect/root/tree (warp-aggregated
+// atomics); the host reads a few counters every 8–32 steps.  k_wf_root and k_wf_tree are latency-bound
+// (≈ 30–50 µs whatever the list length), so they run on a second stream, one iteration behind: the roots
+// and finished rays that iteration k produces are processed while iteration k+1's stage kernel runs, and
+// rejoin the active list of iteration k+2 (lists and counters are double-buffered by iteration parity).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -47,7 +50,7 @@ constexpr int WF_THREADS = 128;
 constexpr int SEG_PAD = 36;  // doubles per published segment (SEG_N = 35, padded)
 constexpr int SEG_NUDGE = 35;  // padding slot: 1.0 if the step follows an event (the scan then includes the nudge point)
 
-enum { WC_SPARE = 0, WC_ROOTS = 1, WC_FIN = 2, WC_PEND = 3, WC_ACT = 4 /* + parity*2 + species */, WC_N = 8 };
+enum { WC_PEND = 0, WC_ROOTS = 1 /* + list parity */, WC_FIN = 3 /* + list parity */, WC_ACT = 5 /* + parity*2 + species */, WC_N = 16 };
 
 struct WfPool {
   RayHot* hot;                // [cap] per-step ray state
@@ -58,8 +61,9 @@ struct WfPool {
   unsigned long long* mzero;  // [cap] … exactly zero
   int* act[2][2];             // [parity][species][cap] ray ids
   int* pend;                  // [cap] rays with a pending step
-  int* roots;                 // [cap]
-  int* fin;                   // [cap]
+  int* roots[2];              // [list parity][cap] rays with a bracketed sign change, produced in one iteration and
+                              // consumed (k_wf_root) during the next, concurrently with its stage kernel
+  int* fin[2];                // [list parity][cap] finished rays, consumed by k_wf_tree / k_wf_collect the same way
   unsigned long long* ctr;    // WC_*
 };
 
@@ -111,10 +115,10 @@ struct WfStat {
 // Stream compaction of survivors.  Every lane of the warp calls this: finished rays join the finished
 // list (their result is written by k_wf_tree / k_wf_collect), rays with a pending step the pending
 // list, live rays the next step's active list of their species — one atomic per warp and list.
-__device__ __forceinline__ void wf_route(const WfPool& W, int next, bool valid, int id, bool done, bool pending, bool axion) {
+__device__ __forceinline__ void wf_route(const WfPool& W, int next, int lpar, bool valid, int id, bool done, bool pending, bool axion) {
   const bool fin = valid && done;
-  const long long sf = warp_pop(W.ctr + WC_FIN, fin);
-  if (fin) W.fin[sf] = id;
+  const long long sf = warp_pop(W.ctr + WC_FIN + lpar, fin);
+  if (fin) (lpar ? W.fin[1] : W.fin[0])[sf] = id;
   const bool pd = valid && !done && pending;
   const long long sp_ = warp_pop(W.ctr + WC_PEND, pd);
   if (pd) W.pend[sp_] = id;
@@ -136,9 +140,9 @@ __device__ __forceinline__ int wf_spread(long long n) {
   return s;
 }
 
-__global__ void k_wf_reset(WfPool W, int next) {
+__global__ void k_wf_reset(WfPool W, int next, int lpar) {
   if (threadIdx.x == 0) {
-    W.ctr[WC_ROOTS] = 0; W.ctr[WC_FIN] = 0; W.ctr[WC_PEND] = 0;
+    W.ctr[WC_ROOTS + lpar] = 0; W.ctr[WC_FIN + lpar] = 0; W.ctr[WC_PEND] = 0;
     W.ctr[WC_ACT + next * 2] = 0; W.ctr[WC_ACT + next * 2 + 1] = 0;
   }
 }
@@ -162,7 +166,7 @@ k_wf_init(const __grid_constant__ DevParams P, const QueuedRay* __restrict__ q, 
       W.cold[i] = static_cast<const RayCold&>(R);
     }
     // rays that start past the end of the span stay `done`: the first k_wf_stages launch retires them
-    wf_route(W, 0, valid, (int)i, false, false, R.axion);
+    wf_route(W, 0, 0, valid, (int)i, false, false, R.axion);
   }
 }
 
@@ -178,7 +182,7 @@ k_wf_init(const __grid_constant__ DevParams P, const QueuedRay* __restrict__ q, 
 // far-field rays and rejected steps do not pay a state round trip per attempt (bulk: 4 attempts, half
 // the warp; thin tail of a batch: 16 attempts, any lane — there only latency counts).
 template <int SP>
-__device__ __forceinline__ void wf_stages_body(const DevParams& P, const WfPool& W, int cur, int nstep, int min_go,
+__device__ __forceinline__ void wf_stages_body(const DevParams& P, const WfPool& W, int cur, int lpar, int nstep, int min_go,
                                                unsigned bid, unsigned nblocks, double* ksm) {
   const KStoreT<WF_THREADS> K{ksm + threadIdx.x};
   const int next = 1 - cur;
@@ -246,7 +250,7 @@ __device__ __forceinline__ void wf_stages_body(const DevParams& P, const WfPool&
       if (it + 1 < nstep && __popc(__ballot_sync(FULL, go)) < min_go) break;
     }
     if (valid) W.hot[id] = static_cast<const RayHot&>(R);
-    wf_route(W, next, valid, id, done, pending, SP == SPECIES_AXION);
+    wf_route(W, next, lpar, valid, id, done, pending, SP == SPECIES_AXION);
   }
 }
 
@@ -254,11 +258,11 @@ __device__ __forceinline__ void wf_stages_body(const DevParams& P, const WfPool&
 // photon list (a warp never executes both right-hand sides; in the thin tail of a batch the two lists
 // are stepped concurrently instead of one launch after the other).
 __global__ void __launch_bounds__(WF_THREADS, ART_STAGE_MINBLOCKS)
-k_wf_stages(const __grid_constant__ DevParams P, WfPool W, int cur, int nstep, int min_go) {
+k_wf_stages(const __grid_constant__ DevParams P, WfPool W, int cur, int lpar, int nstep, int min_go) {
   extern __shared__ double ksm[];
   const unsigned half = gridDim.x >> 1;
-  if (blockIdx.x < half) wf_stages_body<SPECIES_AXION>(P, W, cur, nstep, min_go, blockIdx.x, half, ksm);
-  else wf_stages_body<SPECIES_PHOTON>(P, W, cur, nstep, min_go, blockIdx.x - half, half, ksm);
+  if (blockIdx.x < half) wf_stages_body<SPECIES_AXION>(P, W, cur, lpar, nstep, min_go, blockIdx.x, half, ksm);
+  else wf_stages_body<SPECIES_PHOTON>(P, W, cur, lpar, nstep, min_go, blockIdx.x - half, half, ksm);
 }
 
 // ---- crossing scan: one warp per group of pending steps -----------------------------------------------
@@ -385,7 +389,7 @@ __device__ __forceinline__ void wf_load_pending(Ray& R, const SegAoS D) {
 
 // ---- events: detection over the pending rays; no crossing ⇒ the optimistic advance stands ------------
 __global__ void __launch_bounds__(WF_THREADS)
-k_wf_detect(const __grid_constant__ DevParams P, WfPool W, int next) {
+k_wf_detect(const __grid_constant__ DevParams P, WfPool W, int next, int lpar) {
   const long long n = (long long)W.ctr[WC_PEND];
   const long long nthreads = (long long)gridDim.x * blockDim.x;
   const long long nround = ((n + nthreads - 1) / nthreads) * nthreads;
@@ -422,17 +426,18 @@ k_wf_detect(const __grid_constant__ DevParams P, WfPool W, int next) {
         H.event_last = false; H.done = R.done;
       }
     }
-    const long long sr = warp_pop(W.ctr + WC_ROOTS, to_root);
-    if (to_root) W.roots[sr] = id;
-    wf_route(W, next, valid && !to_root, id, done, false, axion);
+    const long long sr = warp_pop(W.ctr + WC_ROOTS + lpar, to_root);
+    if (to_root) (lpar ? W.roots[1] : W.roots[0])[sr] = id;
+    wf_route(W, next, lpar, valid && !to_root, id, done, false, axion);
   }
 }
 
 // ---- root finder (all lanes iterate together), crossing callback, state update ------------------------
 __global__ void __launch_bounds__(WF_THREADS)
-k_wf_root(const __grid_constant__ DevParams P, WfPool W, int next, DevStats* stats) {
+k_wf_root(const __grid_constant__ DevParams P, WfPool W, int next, int lin, int lpar, DevStats* stats) {
   unsigned long long n_full = 0;
-  const long long n = (long long)W.ctr[WC_ROOTS];
+  const long long n = (long long)W.ctr[WC_ROOTS + lin];
+  const int* __restrict__ roots = lin ? W.roots[1] : W.roots[0];
   const int spread = wf_spread(n);
   const long long nthreads = (long long)gridDim.x * blockDim.x / spread;
   const long long nround = ((n + nthreads - 1) / nthreads) * nthreads;
@@ -442,7 +447,7 @@ k_wf_root(const __grid_constant__ DevParams P, WfPool W, int next, DevStats* sta
     bool done = false, axion = false;
     int id = -1;
     if (valid) {
-      id = W.roots[t];
+      id = roots[t];
       Ray R;
       static_cast<RayHot&>(R) = W.hot[id];
       static_cast<RayCold&>(R) = W.cold[id];
@@ -463,7 +468,7 @@ k_wf_root(const __grid_constant__ DevParams P, WfPool W, int next, DevStats* sta
       done = R.done;
       axion = R.axion;
     }
-    wf_route(W, next, valid, id, done, false, axion);
+    wf_route(W, next, lpar, valid, id, done, false, axion);
   }
   n_full = warp_sum(n_full);
   if ((threadIdx.x & 31) == 0 && stats && n_full) atomicAdd(&stats->n_cond_eval, n_full);
@@ -481,11 +486,12 @@ __device__ __forceinline__ RayOut wf_result(const DevParams& P, const RayHot& H,
 
 // plain ray batches (art_propagate): results of the finished rays
 __global__ void __launch_bounds__(WF_THREADS)
-k_wf_collect(const __grid_constant__ DevParams P, WfPool W, RayOut* __restrict__ out, DevStats* stats) {
+k_wf_collect(const __grid_constant__ DevParams P, WfPool W, int lin, RayOut* __restrict__ out, DevStats* stats) {
   WfStat st;
-  const long long n = (long long)W.ctr[WC_FIN];
+  const long long n = (long long)W.ctr[WC_FIN + lin];
+  const int* __restrict__ fin = lin ? W.fin[1] : W.fin[0];
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
-    const int id = W.fin[t];
+    const int id = fin[t];
     out[id] = wf_result(P, W.hot[id], st);
   }
   st.flush(stats);
@@ -527,11 +533,12 @@ __device__ __forceinline__ bool wf_tree_step(const DevParams& P, const WfTree& T
 }
 
 __global__ void __launch_bounds__(WF_THREADS)
-k_wf_tree(const __grid_constant__ DevParams P, WfPool W, WfTree T, int next, double* __restrict__ rec, int rec_cap,
+k_wf_tree(const __grid_constant__ DevParams P, WfPool W, WfTree T, int next, int lin, double* __restrict__ rec, int rec_cap,
           DevStats* stats) {
   WfStat st;
   unsigned long long n_start = 0;
-  const long long n = (long long)W.ctr[WC_FIN];
+  const long long n = (long long)W.ctr[WC_FIN + lin];
+  const int* __restrict__ fin = lin ? W.fin[1] : W.fin[0];
   const int spread = wf_spread(n);
   const long long nthreads = (long long)gridDim.x * blockDim.x / spread;
   const long long nround = ((n + nthreads - 1) / nthreads) * nthreads;
@@ -543,7 +550,7 @@ k_wf_tree(const __grid_constant__ DevParams P, WfPool W, WfTree T, int next, dou
     bool spawn = false;
     int id = -1;
     if (t < n && (t0 % spread) == 0) {
-      id = W.fin[t];
+      id = fin[t];
       const RayOut o = wf_result(P, W.hot[id], st);
       spawn = wf_tree_step(P, T, id, o, rec, rec_cap, R);
       if (spawn) {
