@@ -743,6 +743,19 @@ int art_fetch_rows(art_handle* h, double* rows, int64_t rows_cap, int64_t* n_row
   return ART_OK;
 }
 
+int art_host_alloc(void** p, int64_t bytes) {
+  if (!p || bytes <= 0) return ART_ERR_ARG;
+  *p = nullptr;
+  const cudaError_t e = cudaMallocHost(p, (size_t)bytes);
+  if (e != cudaSuccess) return fail(nullptr, ART_ERR_CUDA, std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+  return ART_OK;
+}
+
+int art_host_free(void* p) {
+  if (!p) return ART_OK;
+  return cudaFreeHost(p) == cudaSuccess ? ART_OK : ART_ERR_CUDA;
+}
+
 int art_run(art_handle* h, uint64_t seed, int64_t first_event, int64_t n_events, double* rows, int64_t rows_cap,
             int64_t* n_rows, int64_t* f_inx, int64_t* tot_count, art_stats* stats) {
   int rc = art_run_device(h, seed, first_event, n_events, n_rows, f_inx, tot_count, stats);

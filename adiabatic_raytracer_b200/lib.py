@@ -38,6 +38,8 @@ SIGNATURES = {
                           C.POINTER(ArtStats)]),
     "art_run_device": (C.c_int, [_H, C.c_uint64, C.c_int64, C.c_int64, _i64p, _i64p, _i64p, C.POINTER(ArtStats)]),
     "art_fetch_rows": (C.c_int, [_H, C.c_void_p, C.c_int64, _i64p]),
+    "art_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
+    "art_host_free": (C.c_int, [C.c_void_p]),
     "art_normalize_rows": (C.c_int, [_dp, C.c_int64, C.c_int32, C.c_int64]),
     "art_write_npy": (C.c_int, [C.c_char_p, _dp, C.c_int64, C.c_int32]),
     "art_npy_name": (C.c_int, [_PP, C.c_int64, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int64]),
@@ -242,3 +244,29 @@ def normalize_rows(rows: np.ndarray, f_inx_total: int):
     rc = load().art_normalize_rows(rows, rows.shape[0], rows.shape[1], f_inx_total)
     if rc != 0:
         raise ArtError(rc, "art_normalize_rows")
+
+
+class PinnedRows:
+    """A (cap × ncols) float64 row buffer in page-locked host memory (art_host_alloc): `.array` is a numpy
+    view to pass as `rows_out`; free with `.close()` (or use as a context manager)."""
+
+    def __init__(self, cap: int, ncols: int):
+        L = load()
+        self._p = C.c_void_p()
+        rc = L.art_host_alloc(C.byref(self._p), int(cap) * int(ncols) * 8)
+        if rc != 0:
+            raise ArtError(rc, L.art_last_error(None).decode())
+        buf = (C.c_double * (int(cap) * int(ncols))).from_address(self._p.value)
+        self.array = np.frombuffer(buf, dtype=np.float64).reshape(int(cap), int(ncols))
+
+    def close(self):
+        if self._p:
+            self.array = None
+            load().art_host_free(self._p)
+            self._p = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()

@@ -207,6 +207,12 @@ int art_run_device(art_handle* h, uint64_t seed, int64_t first_event, int64_t n_
                    int64_t* n_rows, int64_t* f_inx, int64_t* tot_count, art_stats* stats);
 int art_fetch_rows(art_handle* h, double* rows, int64_t rows_cap, int64_t* n_rows);
 
+/* Page-locked host memory for the row buffers (optional: any host pointer works, a pinned one makes the
+ * device→host copy of the rows a single DMA transfer at PCIe speed instead of a staged pageable copy).
+ * A Julia host wraps the pointer with unsafe_wrap(Array, Ptr{Float64}(p), (ncols, cap)).              */
+int art_host_alloc(void** p, int64_t bytes);
+int art_host_free(void* p);
+
 /* rows[:,7] /= f_inx_total  (MainRunner.jl:749)                                              */
 int art_normalize_rows(double* rows, int64_t n_rows, int32_t ncols, int64_t f_inx_total);
 
