@@ -280,31 +280,15 @@ constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_PACK = ART_SCAN_PACK;  // steps per warp and trip (at most)
 constexpr int SCAN_ROUNDS = 5;  // ballot words kept per sign class
 
-__device__ __forceinline__ unsigned scan_pick(const unsigned (&b)[SCAN_ROUNDS], int k) {
-  unsigned v = 0;
-#pragma unroll
-  for (int q = 0; q < SCAN_ROUNDS; ++q) v = (q == k) ? b[q] : v;
-  return v;
-}
-// bits [off, off + M) of the ballot words, re-ordered to grid-point order: slot q < M−1 ↔ point q + 1,
-// slot M−1 ↔ the nudge point 0
-__device__ __forceinline__ unsigned long long scan_extract(const unsigned (&b)[SCAN_ROUNDS], int off, int M) {
-  const int w = off >> 5, sh = off & 31;
-  const unsigned long long lo = (unsigned long long)scan_pick(b, w) | ((unsigned long long)scan_pick(b, w + 1) << 32);
-  const unsigned long long hi = scan_pick(b, w + 2);
-  unsigned long long r = lo >> sh;
-  if (sh) r |= hi << (64 - sh);
-  if (M < 64) r &= (1ull << M) - 1ull;
-  const unsigned long long pts = r & ((1ull << (M - 1)) - 1ull);
-  return (pts << 1) | ((r >> (M - 1)) & 1ull);
-}
-
 #ifndef ART_SCAN_MINBLOCKS
 #define ART_SCAN_MINBLOCKS 3
 #endif
 __global__ void __launch_bounds__(SCAN_THREADS, ART_SCAN_MINBLOCKS)
 k_wf_scan(const __grid_constant__ DevParams P, WfPool W, DevStats* stats) {
   __shared__ double seg_sm[SCAN_THREADS / 32][SCAN_PACK][SEG_PAD];
+  __shared__ double th_sm[SCAN_ROUNDS][SCAN_THREADS];        // per lane and round: dense-output parameter of its slot
+  __shared__ short j_sm[SCAN_ROUNDS][SCAN_THREADS];          // … segment index, +8 for a nudge slot, −1 for no slot
+  __shared__ unsigned bal_sm[SCAN_THREADS / 32][3][SCAN_ROUNDS + 2];  // ballot words of the current trip
   const long long n = (long long)W.ctr[WC_PEND];
   const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const long long nwarps = (long long)gridDim.x * (SCAN_THREADS / 32);
@@ -312,19 +296,17 @@ k_wf_scan(const __grid_constant__ DevParams P, WfPool W, DevStats* stats) {
   const int pack = min(SCAN_PACK, (32 * SCAN_ROUNDS) / M);  // M ≤ 64 ⇒ pack ≥ 2
   const int rounds = (pack * M + 31) >> 5;
   // what this lane does in each round does not depend on the steps: which of the (up to three) staged
-  // segments it reads, at which dense-output parameter, and whether its slot is a nudge slot
-  const double* seg_rd[SCAN_ROUNDS];
-  double th_rd[SCAN_ROUNDS];
-  int j_rd[SCAN_ROUNDS];  // segment index, +8 for a nudge slot, −1 for no slot
-#pragma unroll
+  // segments it reads, at which dense-output parameter, and whether its slot is a nudge slot.  Kept in
+  // shared memory so that the round loop can stay ROLLED (one copy of the condition: unrolled five times the
+  // kernel spent 1.4 warps per issue waiting for instructions — profiles/r01_wf12_iteration10_keys.txt)
   for (int rd = 0; rd < SCAN_ROUNDS; ++rd) {
     const int slot = rd * 32 + (int)lane;
     const int j = slot / M, q = slot - j * M;
     const bool has = rd < rounds && j < pack;
-    j_rd[rd] = has ? (q < M - 1 ? j : j + 8) : -1;
-    th_rd[rd] = seg_theta(P, (q < M - 1) ? q + 1 : 0);
-    seg_rd[rd] = seg_sm[wib][has ? j : 0];
+    j_sm[rd][threadIdx.x] = (short)(has ? (q < M - 1 ? j : j + 8) : -1);
+    th_sm[rd][threadIdx.x] = seg_theta(P, (q < M - 1) ? q + 1 : 0);
   }
+  if (lane < 3 * (SCAN_ROUNDS + 2)) (&bal_sm[wib][0][0])[lane] = 0u;
   unsigned long long n_full = 0;
   for (long long p = (blockIdx.x * (long long)(SCAN_THREADS / 32) + wib) * pack; p < n; p += nwarps * pack) {
     const int cnt = (int)min((long long)pack, n - p);
@@ -338,36 +320,43 @@ k_wf_scan(const __grid_constant__ DevParams P, WfPool W, DevStats* stats) {
       if (lane < SEG_PAD - 32) seg_sm[wib][j][32 + lane] = src[32 + lane];
     }
     __syncwarp();
-    unsigned bp[SCAN_ROUNDS], bn[SCAN_ROUNDS], bz[SCAN_ROUNDS];
-#pragma unroll
-    for (int rd = 0; rd < SCAN_ROUNDS; ++rd) {
-      bp[rd] = bn[rd] = bz[rd] = 0u;
-      if (rd < rounds) {
-        int code = 0;  // 1 positive, 2 negative, 3 zero, 0 NaN / no point
-        const int j = j_rd[rd];
-        if (j >= 0 && (j & 7) < cnt) {
-          const SegAoS D{const_cast<double*>(seg_rd[rd])};
-          if (j < 8 || D(SEG_NUDGE) != 0.0) {
-            const double th = th_rd[rd];
-            const int qk = seg_quick(P, D, th);
-            if (qk == -1) code = 2;
-            else if (qk == 0) {
-              const double g = seg_cond_full<true>(P, D, th);
-              n_full++;
-              code = (g > 0.0) ? 1 : ((g < 0.0) ? 2 : ((g == 0.0) ? 3 : 0));
-            }
+#pragma unroll 1
+    for (int rd = 0; rd < rounds; ++rd) {
+      int code = 0;  // 1 positive, 2 negative, 3 zero, 0 NaN / no point
+      const int j = j_sm[rd][threadIdx.x];
+      if (j >= 0 && (j & 7) < cnt) {
+        const SegAoS D{seg_sm[wib][j & 7]};
+        if (j < 8 || D(SEG_NUDGE) != 0.0) {
+          const double th = th_sm[rd][threadIdx.x];
+          const int qk = seg_quick(P, D, th);
+          if (qk == -1) code = 2;
+          else if (qk == 0) {
+            const double g = seg_cond_full<true>(P, D, th);
+            n_full++;
+            code = (g > 0.0) ? 1 : ((g < 0.0) ? 2 : ((g == 0.0) ? 3 : 0));
           }
         }
-        bp[rd] = __ballot_sync(FULL, code == 1);
-        bn[rd] = __ballot_sync(FULL, code == 2);
-        bz[rd] = __ballot_sync(FULL, code == 3);
+      }
+      const unsigned bp = __ballot_sync(FULL, code == 1), bn = __ballot_sync(FULL, code == 2), bz = __ballot_sync(FULL, code == 3);
+      if (lane == 0) {
+        bal_sm[wib][0][rd] = bp; bal_sm[wib][1][rd] = bn; bal_sm[wib][2][rd] = bz;
       }
     }
+    __syncwarp();
     if ((int)lane < cnt) {
-      const int off = (int)lane * M;
-      W.mpos[my_id] = scan_extract(bp, off, M);
-      W.mneg[my_id] = scan_extract(bn, off, M);
-      W.mzero[my_id] = scan_extract(bz, off, M);
+      // bits [off, off + M) of each class, re-ordered to grid-point order: slot q < M−1 ↔ point q + 1,
+      // slot M−1 ↔ the nudge point 0
+      const int off = (int)lane * M, w = off >> 5, sh = off & 31;
+      unsigned long long m3[3];
+      for (int c = 0; c < 3; ++c) {
+        const unsigned* b = bal_sm[wib][c];
+        const unsigned long long lo = (unsigned long long)b[w] | ((unsigned long long)b[w + 1] << 32);
+        unsigned long long r = lo >> sh;
+        if (sh) r |= (unsigned long long)b[w + 2] << (64 - sh);
+        if (M < 64) r &= (1ull << M) - 1ull;
+        m3[c] = ((r & ((1ull << (M - 1)) - 1ull)) << 1) | ((r >> (M - 1)) & 1ull);
+      }
+      W.mpos[my_id] = m3[0]; W.mneg[my_id] = m3[1]; W.mzero[my_id] = m3[2];
     }
   }
   n_full = warp_sum(n_full);
