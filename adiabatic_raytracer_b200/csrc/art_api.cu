@@ -254,9 +254,16 @@ int launch_trace_wf(art_handle* h, Lane& L, const QueuedRay* q, long long n, Ray
     const int lastpar = (int)((iter - 1) & 1);
     const unsigned long long na0 = c[WC_ACT + cur * 2], na1 = c[WC_ACT + cur * 2 + 1];
     n_act = (long long)(na0 + na1 + c[WC_ROOTS + lastpar] + c[WC_FIN + lastpar]);
-    if (trace)
-      fprintf(stderr, "[wf %p] iter %lld in flight %lld (ax %llu ph %llu roots %llu finished %llu)\n", (void*)&L, iter, n_act, na0, na1,
-              c[WC_ROOTS + lastpar], c[WC_FIN + lastpar]);
+    if (trace) {
+      timespec ts;
+      clock_gettime(CLOCK_MONOTONIC, &ts);
+      const double now = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+      static thread_local double t_prev = 0.0;
+      fprintf(stderr, "[wf %p] iter %lld in flight %lld (ax %llu ph %llu roots %llu finished %llu) +%.2f ms = %.0f us/iteration\n", (void*)&L,
+              iter, n_act, na0, na1, c[WC_ROOTS + lastpar], c[WC_FIN + lastpar], t_prev > 0 ? now - t_prev : 0.0,
+              t_prev > 0 ? (now - t_prev) * 1e3 / burst : 0.0);
+      t_prev = now;
+    }
     if (n_act == 0) break;
     if (iter > 64LL * h->params.maxiters) return fail(h, ART_ERR_CUDA, "wavefront tracer did not terminate");
   }
