@@ -428,3 +428,20 @@ def test_rotation_phase_resolved_run_matches_oracle(lib, oracle, phase):
         s0.close()
         assert np.abs(x0 - sa["x"]).max() > 1e-3
     h.close()
+
+
+def test_pinned_row_buffer_and_evaluation_counters(lib):
+    """art_host_alloc / art_host_free: art_run into a page-locked buffer gives the same rows as a pageable one;
+    n_cond_eval counts the conditions actually evaluated (≤ the reference's count, the rest is the far-field
+    shortcut)."""
+    p = ArtParams.default(theta_m=0.2)
+    h = lib.Handle(p, 0)
+    n = 3000
+    a = h.run(11, 1, n)
+    with lib.PinnedRows(n * 3 + 1024, h.ncols) as pin:
+        b = h.run(11, 1, n, rows_out=pin.array)
+        assert np.array_equal(a["rows"], b["rows"])
+    st = a["stats"]
+    assert 0 < st["n_cond_eval"] < st["n_cond"]
+    assert st["n_cond_eval"] > 0.2 * st["n_cond"]
+    h.close()
