@@ -22,7 +22,6 @@ namespace art {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int SAMPLE_THREADS = 128;
-constexpr int SAMPLE_BURST = 8;
 
 struct DevStats {  // accumulated with atomics; mirrors the counters of art_stats
   unsigned long long n_attempts, n_sampler_cond, n_rays, n_rays_photon, n_acc, n_rej, n_rhs, n_cond;
@@ -95,11 +94,8 @@ k_sample_events(const __grid_constant__ DevParams P, unsigned long long seed, lo
       }
     }
     if (__ballot_sync(FULL, have) == 0) break;
-    // a burst of condition evaluations between refill checks (an attempt takes ~300 of them); lanes
-    // whose attempt ends inside the burst idle for at most SAMPLE_BURST − 1 evaluations
-#pragma unroll 1
-    for (int k = 0; k < SAMPLE_BURST; ++k)
-      if (have && !S.done) S.advance(P);
+    // one trip = M−1 condition evaluations for every lane (art_sampler.cuh)
+    S.trip(P, have);
     if (have) {
       if (S.done) {
         SampleResult R;

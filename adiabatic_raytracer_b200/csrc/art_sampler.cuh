@@ -5,10 +5,10 @@
 // ContinuousCallback (interp_points = 20) that root-finds every sign change of the thick-surface
 // condition; one of the kept crossings is selected with probability 1/n_max.
 //
-// B200 formulation: the attempt is a small state machine whose `advance()` performs exactly ONE
-// condition evaluation (scan point, repeat-nudge point or root-finder iterate), so that the 32
-// lanes of a warp — each on its own attempt, at its own march position — execute the same
-// instruction stream.  Two exact shortcuts relative to the literal march:
+// B200 formulation: the attempt is a small state machine advanced in TRIPS of M−1 condition evaluations
+// (Sampler::trip): the 32 lanes of a warp — each on its own attempt, at its own march position, scanning a
+// step or iterating on a root — evaluate the condition together at one call site.  Two exact shortcuts
+// relative to the literal march:
 //   * the condition is strictly negative wherever max_angles ωp(r) < m_a, i.e. outside the
 //     sphere r = Rcut = maxR/1.01 (θ = θm/2 maximises |B_z|, which is how the reference derives
 //     maxR, RT.jl:1250-1263): grid steps entirely outside that sphere cannot contain a sign
@@ -42,10 +42,14 @@ struct Sampler {
   double E2, vI[3];            // E∞², v∞ components [km/s]
   double mv;                   // m̂·v
   double tau, tau_new, h, tau_out;
-  double g_prev, th_a, g_a, a, fa, b, fb, f0, w1, w2;
+  double a, fa, b, fb, f0, w1, w2;  // root finder
   double* taus;    // crossing list, SAMP_KEEP entries `taus_stride` apart (device: shared memory column)
   int taus_stride;
-  int i, sgn_prev, side, it, phase;  // phase: 0 scan, 1 nudge, 2 root, 3 first point of the march
+  // mode: what the attempt evaluates next — SCAN: the M−1 grid points of one Euler step (a whole trip());
+  // ROOT: one root-finder iterate; NUDGE: the reference sign 1 % into the step after an event; INIT: the sign at
+  // the first point of the march
+  enum { SCAN = 0, ROOT = 1, NUDGE = 2, INIT = 3 };
+  int sgn_prev, side, it, mode, rinit;
   int n_cross, n_cond;
   bool event_last, done, pure;
 
@@ -133,6 +137,7 @@ struct Sampler {
     }
   }
 
+  // start of the next Euler step from tau (OrdinaryDiffEq Euler, dt = 0.5 km, last step clipped to the span)
   ART_HD void next_step(const DevParams& P) {
     if (!(tau < P.T_samp) || !(tau < tau_out)) {
       done = true;
@@ -144,15 +149,7 @@ struct Sampler {
       h = P.T_samp - tau;
       tau_new = P.T_samp;
     }
-    i = 1;
-    if (event_last) {
-      phase = 1;
-    } else {
-      phase = 0;
-      sgn_prev = (g_prev > 0.0) - (g_prev < 0.0);
-      th_a = 0.0;
-      g_a = g_prev;
-    }
+    mode = event_last ? NUDGE : SCAN;
   }
 
   // set up one attempt from its 10 uniforms (RT.jl:1486-1542)
@@ -188,9 +185,9 @@ struct Sampler {
     event_last = false;
     done = false;
     pure = false;
-    phase = 3;
-    i = 1; sgn_prev = 0; side = 0; it = 0;
-    tau_new = h = g_prev = th_a = g_a = a = fa = b = fb = f0 = w1 = w2 = 0.0;
+    mode = INIT;
+    sgn_prev = 0; side = 0; it = 0; rinit = 0;
+    tau_new = h = a = fa = b = fb = f0 = w1 = w2 = 0.0;
     // chord of the line inside the sphere r = Rcut
     const double bq = xs[0] * va[0] + xs[1] * va[1] + xs[2] * va[2];
     const double cq = xs[0] * xs[0] + xs[1] * xs[1] + xs[2] * xs[2] - P.Rcut * P.Rcut;
@@ -205,7 +202,7 @@ struct Sampler {
     const double tau_in = -bq - sd;
     tau_out = -bq + sd;
     const double n0 = floor(fmax(tau_in, 0.0) / P.samp_dt);
-    tau = n0 * P.samp_dt;  // the first advance() evaluates the condition here (phase 3)
+    tau = n0 * P.samp_dt;  // the first trip evaluates the condition here (mode INIT)
   }
 
   ART_HD void event(const DevParams& P, double th) {
@@ -216,83 +213,128 @@ struct Sampler {
     next_step(P);
   }
 
-  // Exactly one condition evaluation, at ONE call site: every lane of a warp — whatever the phase of
-  // its attempt — first picks its evaluation point, then all lanes evaluate together, then each
-  // finishes its phase's bookkeeping.
-  ART_HD void advance(const DevParams& P) {
+  // One trip = M−1 condition evaluations, at ONE call site, for every lane of a warp together.
+  //   * An attempt in SCAN mode spends the trip on the M−1 grid points of its Euler step and keeps nothing
+  //     but the signs (two bit masks); after the trip the first sign change — with the reference's rule for
+  //     the left end of the bracket: the last point that still had the old sign — starts the root finder,
+  //     otherwise the step is done.  Per evaluation that is the condition plus ≈ 10 instructions.
+  //   * The other modes do one evaluation per slot of the trip: the root finder's iterates (its two bracket
+  //     values are re-evaluated first — same numbers as the scan saw), the nudge point after an event, the
+  //     first point of the march; when they are through they wait for the next trip to scan.
+  // The earlier form — one evaluation per call with the whole state machine around it, predicated — executed
+  // ≈ 440 instructions per evaluation, two thirds of them bookkeeping (profiles/r01_sampler_v2_v3_hotlines.txt).
+  ART_HD void trip(const DevParams& P, bool active) {
     const int M = P.M_samp;
-    double tq, th = 0.0, c = 0.0;
-    bool end = false;
-    if (phase == 2) {
-      const double tol = ROOT_RTOL * fmax(fmax(fabs(a), fabs(b)), 0.01);
-      const double width = fabs(b - a);
-      if (width <= tol || it >= 200) {
-        event(P, fmin(a, b));
-        return;
-      }
-      if (it == 3 && fmin(fabs(fa), fabs(fb)) > 0.25 * f0) pure = true;
-      c = (a * fb - b * fa) * frcp(fb - fa);
-      const double lo = fmin(a, b), hi = fmax(a, b);
-      if (pure || (it >= 3 && width > 0.5 * w2) || !(c > lo && c < hi) || width <= 2.0 * tol) c = 0.5 * (a + b);
-      else if (fabs(c - b) < tol) c = b + copysign(tol, a - b);
-      w2 = w1;
-      w1 = width;
-      tq = tau + c * h;
-    } else if (phase == 0) {
-      end = (i == M - 1);
-      th = end ? 1.0 : (double)i * P.inv_Msm1;
-      tq = end ? tau_new : tau + th * h;
-    } else if (phase == 1) {  // repeat-nudge reference sign after an event (DiffEqBase repeat_nudge = 1/100)
-      tq = tau + 0.01 * h;
-    } else {
-      tq = tau;
-    }
-    const double g = cond(P, tq);
-    if (phase == 0) {
-      const int sg = (g > 0.0) - (g < 0.0);
-      if (sgn_prev != 0 && sgn_prev * sg < 0) {
-        a = th_a; fa = g_a; b = th; fb = g;
-        f0 = fmin(fabs(fa), fabs(fb)); w1 = w2 = 2.0; pure = false;
-        side = 0; it = 0; phase = 2;
-        return;
-      }
-      if (sg == sgn_prev) {
-        th_a = th;
-        g_a = g;
-      }
-      if (end) {
-        if (sgn_prev != 0 && g == 0.0) {
-          event(P, 1.0);
+    const bool scanning = active && !done && mode == SCAN;
+    unsigned mpos = 0u, mneg = 0u, mzero = 0u;
+    // what this lane evaluates in the current slot: SCAN for the whole trip, or ROOT / NUDGE / INIT until the
+    // attempt is ready to scan (then −1: idle until the next trip); re-derived only where the mode changes
+    int md = scanning ? SCAN : ((active && !done && mode != SCAN) ? mode : -1);
+    for (int k = 1; k <= M - 1; ++k) {
+      double tq = tau, th = 0.0;
+      bool ev = (md >= 0);
+      if (md == SCAN) {
+        tq = (k == M - 1) ? tau_new : tau + ((double)k * P.inv_Msm1) * h;
+      } else if (md == ROOT) {
+        if (rinit > 0) {  // bracket values first: fa, then fb
+          th = (rinit == 2) ? a : b;
         } else {
-          tau = tau_new;
-          g_prev = g;
-          event_last = false;
-          next_step(P);
+          const double tol = ROOT_RTOL * fmax(fmax(fabs(a), fabs(b)), 0.01);
+          const double width = fabs(b - a);
+          if (width <= tol || it >= 200) {
+            event(P, fmin(a, b));
+            ev = false;
+          } else {
+            if (it == 3 && fmin(fabs(fa), fabs(fb)) > 0.25 * f0) pure = true;
+            double c = (a * fb - b * fa) * frcp(fb - fa);
+            const double lo = fmin(a, b), hi = fmax(a, b);
+            if (pure || (it >= 3 && width > 0.5 * w2) || !(c > lo && c < hi) || width <= 2.0 * tol) c = 0.5 * (a + b);
+            else if (fabs(c - b) < tol) c = b + copysign(tol, a - b);
+            w2 = w1;
+            w1 = width;
+            th = c;
+          }
         }
+        tq = tau + th * h;
+      } else if (md == NUDGE) {  // DiffEqBase repeat_nudge = 1/100
+        tq = tau + 0.01 * h;
+      }
+      double g = 0.0;
+      if (ev) g = cond(P, tq);
+      if (md == SCAN) {
+        const unsigned bit = 1u << k;
+        mpos |= (g > 0.0) ? bit : 0u;
+        mneg |= (g < 0.0) ? bit : 0u;
+        mzero |= (g == 0.0) ? bit : 0u;
+      } else if (md == ROOT) {
+        if (ev) {
+          if (rinit == 2) {
+            fa = g;
+            rinit = 1;
+          } else if (rinit == 1) {
+            fb = g;
+            rinit = 0;
+            f0 = fmin(fabs(fa), fabs(fb));
+          } else {
+            it++;
+            if (g == 0.0) {
+              event(P, th);
+            } else {
+              if ((g < 0.0) != (fb < 0.0)) {
+                a = b; fa = fb; side = 0;
+              } else {
+                if (side == 1) fa *= 0.5;
+                side = 1;
+              }
+              b = th; fb = g;
+            }
+          }
+        }
+      } else if (md == NUDGE) {
+        sgn_prev = (g > 0.0) - (g < 0.0);
+        mode = SCAN;
+      } else if (md == INIT) {
+        sgn_prev = (g > 0.0) - (g < 0.0);
+        next_step(P);
+      }
+      if (md > SCAN) md = (done || mode == SCAN) ? -1 : mode;
+    }
+    if (scanning) {
+      // first point whose sign is opposite to the reference sign; the left end of the bracket is the last
+      // point before it that still had the reference sign (exact zeros and NaNs neither trigger nor move it)
+      const unsigned opp = sgn_prev > 0 ? mneg : (sgn_prev < 0 ? mpos : 0u);
+      if (opp) {
+#if defined(__CUDA_ARCH__)
+        const int ib = __ffs((int)opp) - 1;
+#else
+        const int ib = __builtin_ffs((int)opp) - 1;
+#endif
+        const unsigned same = (sgn_prev > 0 ? mpos : mneg) & ((1u << ib) - 1u);
+        int ia = 0;
+        if (same) {
+#if defined(__CUDA_ARCH__)
+          ia = 31 - __clz((int)same);
+#else
+          ia = 31 - __builtin_clz(same);
+#endif
+        }
+        a = (ia == 0) ? (event_last ? 0.01 : 0.0) : (double)ia * P.inv_Msm1;
+        b = (ib == M - 1) ? 1.0 : (double)ib * P.inv_Msm1;
+        w1 = w2 = 2.0;
+        pure = false;
+        side = 0;
+        it = 0;
+        rinit = 2;
+        mode = ROOT;
+      } else if (sgn_prev != 0 && ((mzero >> (M - 1)) & 1u)) {
+        event(P, 1.0);  // the end point lies exactly on the surface
       } else {
-        i++;
+        const unsigned endbit = 1u << (M - 1);
+        sgn_prev = (mpos & endbit) ? 1 : ((mneg & endbit) ? -1 : 0);
+        tau = tau_new;
+        event_last = false;
+        next_step(P);
       }
-    } else if (phase == 2) {
-      it++;
-      if (g == 0.0) {
-        event(P, c);
-        return;
-      }
-      if ((g < 0.0) != (fb < 0.0)) {
-        a = b; fa = fb; side = 0;
-      } else {
-        if (side == 1) fa *= 0.5;
-        side = 1;
-      }
-      b = c; fb = g;
-    } else if (phase == 1) {
-      sgn_prev = (g > 0.0) - (g < 0.0);
-      th_a = 0.01;
-      g_a = g;
-      phase = 0;
-    } else {
-      g_prev = g;
-      next_step(P);
     }
   }
 
@@ -325,7 +367,7 @@ ART_HD void sample_attempt(const DevParams& P, const double U[10], SampleResult&
   S.taus = taus;
   S.taus_stride = 1;
   S.begin(P, U);
-  while (!S.done) S.advance(P);
+  while (!S.done) S.trip(P, true);
   S.finish(P, U[9], R);
 }
 
