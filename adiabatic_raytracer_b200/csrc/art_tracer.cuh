@@ -197,11 +197,7 @@ ART_HD double seg_cond(const DevParams& P, const DS D, double th) {
   const int qk = seg_quick(P, D, th);
   if (qk == -1) return -1.0;
   if (qk == 2) return NAN;
-  double w[6];
-  seg_state(D, th, w);
-  const double E = D(SEG_U70) + D(SEG_FAC7) * (w[5] - D(SEG_U60));
-  const double t = fexp(D(SEG_S) + th * D(SEG_H));
-  return thick_condition(P, w[0], w[1], w[2] - P.Omega * t, w[3], w[4], w[5], E, P.rs_ray, true);
+  return seg_cond_full<true>(P, D, th);  // the scan keeps the sign only
 }
 
 // Ray state, split by access pattern: the HOT record is what an attempted step reads
@@ -216,7 +212,7 @@ struct alignas(16) RayHot {
   int sgn_end;    // sign of the condition at the end of the last accepted step (= start of the next)
   int n_acc, n_rej, n_rhs, n_cond;
   bool axion, starting, event_last, done;
-  int pad_;
+  int left_box;   // the ray has (possibly) left the ±0.01 % box around its start point: no more in-box shortcuts
 };
 struct alignas(16) RayCold {
   double x0[3];
@@ -224,9 +220,11 @@ struct alignas(16) RayCold {
   int rec_cap, max_cross;
   int br_a, br_b, br_sg;  // bracket found by detect(), waiting for the root kernel (wavefront path)
   int pad2_;
+  double s0[3];   // start point in spherical coordinates (r, θ, φ)
+  double box_m;   // min_c |x0_c| · (1 − 1/1.0001): the start box's half width in its narrowest component
 };
 static_assert(sizeof(RayHot) == 192, "RayHot layout");
-static_assert(sizeof(RayCold) == 64, "RayCold layout");
+static_assert(sizeof(RayCold) == 96, "RayCold layout");
 
 struct Ray : RayHot, RayCold {
   // transient: the attempted step between attempt() and apply()
@@ -245,6 +243,9 @@ struct Ray : RayHot, RayCold {
     for (int i = 0; i < 3; ++i) x0[i] = in.x0[i];
     ray_initial_state(P, in.x0, in.k0, erg, in.dOmega, u, u7_0);
     u6_0 = u[5];
+    for (int i = 0; i < 3; ++i) s0[i] = u[i];
+    box_m = fmin(fmin(fabs(x0[0]), fabs(x0[1])), fabs(x0[2])) * (1.0 - 1.0 / 1.0001) * (1.0 - 1e-6);
+    left_box = 0;
     fac7 = axion ? 0.0 : P.Omega * erg / C_KM;
     s = log(fmax(in.t_start, P.t_floor));  // MR.jl:166
     dt = 0.0;
@@ -254,7 +255,7 @@ struct Ray : RayHot, RayCold {
     sgn_end = 0;
     n_cross = iters = n_acc = n_rej = n_rhs = n_cond = 0;
     br_a = br_b = br_sg = 0;
-    pad_ = pad2_ = 0;
+    pad2_ = 0;
     status = RAY_END;
     event_last = false;
     starting = true;
@@ -520,6 +521,24 @@ struct Ray : RayHot, RayCold {
     const double de = fabs(fac7) * 0.25 * (fabs(r5[1]) + fabs(r5[2]) + 0.25 * fabs(r5[3]));
     const double emin = fmin(fabs(e0), fabs(e1)) - de;
     return emin > 0.0 && emin * emin >= P.ma2 * (1.0 + 1e-12);
+  }
+
+  // Does the whole accepted step lie inside the ±0.01 % box around the start point (RT.jl:307-311)?  Then every
+  // sign change on it is discarded by the start-box rule and only the sign at its end point survives (as the
+  // next step's reference sign): the scan can evaluate ONE point instead of M−1.  A ray spends its first
+  // 10–15 steps there while the step size grows from the initial 1e-6 — more than half of all condition
+  // evaluations of a run.  Rigorous bound: each spherical coordinate stays within its chord ± ¼(|r2|+|r3|+¼|r4|)
+  // (as in step_all_far), and a Cartesian component moves by at most δr + r_max(δθ + δφ).
+  template <class KS>
+  ART_HD bool step_in_start_box(const KS K, const double s0_[3], double box_m_) const {
+    double d[3];
+    for (int i = 0; i < 3; ++i) {
+      double r[4];
+      dense_comp(K, i, r);
+      const double dev = 0.25 * (fabs(r[1]) + fabs(r[2]) + 0.25 * fabs(r[3]));
+      d[i] = fmax(fabs(u[i] - s0_[i]), fabs(u[i] + r[0] - s0_[i])) + dev;
+    }
+    return d[0] + (s0_[0] + d[0]) * (d[1] + d[2]) < box_m_;
   }
 
   // stages(): sequential form of start-up / attempted step (host check).  Returns true if a step was

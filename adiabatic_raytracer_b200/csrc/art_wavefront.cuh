@@ -48,7 +48,8 @@ constexpr int WF_THREADS = 128;
 #define ART_STAGE_NSTEP 4      // attempted steps a ray may take inside one k_wf_stages launch
 #endif
 constexpr int SEG_PAD = 36;  // doubles per published segment (SEG_N = 35, padded)
-constexpr int SEG_NUDGE = 35;  // padding slot: 1.0 if the step follows an event (the scan then includes the nudge point)
+constexpr int SEG_NUDGE = 35;  // padding slot, flags: 1 = the step follows an event (the scan then includes the nudge point),
+                               // 2 = the whole step lies inside the start box (the scan evaluates its end point only)
 
 enum { WC_PEND = 0, WC_ROOTS = 1 /* + list parity */, WC_FIN = 3 /* + list parity */, WC_ACT = 5 /* + parity*2 + species */, WC_N = 16 };
 
@@ -234,7 +235,14 @@ __device__ __forceinline__ void wf_stages_body(const DevParams& P, const WfPool&
           } else {
             const SegAoS D{W.seg + (size_t)id * SEG_PAD};
             R.publish(K, D);
-            D(SEG_NUDGE) = R.event_last ? 1.0 : 0.0;
+            bool inbox = false;
+            if (R.n_cross == 0 && !R.event_last && !R.left_box) {
+              const RayCold& C = W.cold[id];
+              const double s0_[3] = {C.s0[0], C.s0[1], C.s0[2]};
+              inbox = R.step_in_start_box(K, s0_, C.box_m);
+              if (!inbox) R.left_box = 1;
+            }
+            D(SEG_NUDGE) = (R.event_last ? 1.0 : 0.0) + (inbox ? 2.0 : 0.0);
             // optimistic advance; k_wf_detect / k_wf_root complete or override it
             for (int i = 0; i < 6; ++i) {
               R.u[i] = R.un[i];
@@ -326,7 +334,10 @@ k_wf_scan(const __grid_constant__ DevParams P, WfPool W, DevStats* stats) {
       const int j = j_sm[rd][threadIdx.x];
       if (j >= 0 && (j & 7) < cnt) {
         const SegAoS D{seg_sm[wib][j & 7]};
-        if (j < 8 || D(SEG_NUDGE) != 0.0) {
+        const int flags = (int)D(SEG_NUDGE);
+        // in-box step: only the slot of the end point (grid point M−1) is evaluated
+        const bool wanted = (flags & 2) ? (j < 8 && th_sm[rd][threadIdx.x] >= 1.0) : (j < 8 || (flags & 1));
+        if (wanted) {
           const double th = th_sm[rd][threadIdx.x];
           const int qk = seg_quick(P, D, th);
           if (qk == -1) code = 2;
@@ -347,6 +358,7 @@ k_wf_scan(const __grid_constant__ DevParams P, WfPool W, DevStats* stats) {
       // bits [off, off + M) of each class, re-ordered to grid-point order: slot q < M−1 ↔ point q + 1,
       // slot M−1 ↔ the nudge point 0
       const int off = (int)lane * M, w = off >> 5, sh = off & 31;
+      const bool inbox = ((int)seg_sm[wib][lane][SEG_NUDGE] & 2) != 0;
       unsigned long long m3[3];
       for (int c = 0; c < 3; ++c) {
         const unsigned* b = bal_sm[wib][c];
@@ -355,6 +367,9 @@ k_wf_scan(const __grid_constant__ DevParams P, WfPool W, DevStats* stats) {
         if (sh) r |= (unsigned long long)b[w + 2] << (64 - sh);
         if (M < 64) r &= (1ull << M) - 1ull;
         m3[c] = ((r & ((1ull << (M - 1)) - 1ull)) << 1) | ((r >> (M - 1)) & 1ull);
+        // in-box step: every grid point takes the sign of the end point (all sign changes inside the box are
+        // discarded by k_wf_detect; what survives is the end sign — art_tracer.cuh: step_in_start_box)
+        if (inbox) m3[c] = ((m3[c] >> (M - 1)) & 1ull) ? (((M >= 64) ? ~0ull : ((1ull << M) - 1ull)) & ~1ull) : 0ull;
       }
       W.mpos[my_id] = m3[0]; W.mneg[my_id] = m3[1]; W.mzero[my_id] = m3[2];
     }
