@@ -217,7 +217,7 @@ __device__ __forceinline__ void wf_stages_body(const DevParams& P, const WfPool&
           go = false;
           done = true;
         } else if (R.template attempt<SP>(P, K)) {
-          if ((R.event_last || R.sgn_end <= 0) && R.step_all_far(P, K)) {
+          if ((R.event_last || R.sgn_end <= 0) && (R.step_all_far(P, K) || R.step_dark(P, K, K.park(5)))) {
             // no crossing possible: apply(th_ev < 0, sg_last = −1)
             for (int i = 0; i < 6; ++i) {
               R.u[i] = R.un[i];
