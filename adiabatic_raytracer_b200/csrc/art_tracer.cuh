@@ -523,14 +523,17 @@ struct Ray : RayHot, RayCold {
     return emin > 0.0 && emin * emin >= P.ma2 * (1.0 + 1e-12);
   }
 
-  // Direction-aware refinement of step_all_far: is the plasma frequency below the axion mass along the WHOLE
-  // accepted step, i.e. Q|b_z(θ,ψ)| < m_a² r³ for every point of it?  Then the condition is negative at every
-  // scan point whatever the momentum (thick_F: F ≤ base·(Q|b_z| − m_a² r³)) and no scan is needed.  Photons
-  // leave the conversion surface outwards: all their steps between the surface and Rcut are of this kind.
-  // Rigorous bound: r, θ, φ stay within chord ± ¼(|r2|+|r3|+¼|r4|) of the dense output; ψ = φ − Ωt with
-  // t ∈ [e^s, e^{s_new}]; |b_z| ≤ |b_z(centre)| + 3(|cosθm| + sinθm)·δθ + 1.5 sinθm·δψ (sup of its partials).
+  // Direction-aware refinement of step_all_far: the sign of the condition along the WHOLE accepted step, when
+  // it can be certified without the momentum:  F = base·(Q|b_z| − m_a² r³) − Q|b_z|·g^rr NrmSq·ww N'² with
+  // 0 ≤ g^rr k∥² ≤ E² − m_a² g^rr (Cauchy–Schwarz), so
+  //   Q|b_z| < m_a² r³            ⇒ F < 0   ("dark": the plasma frequency is below the axion mass), return −1
+  //   Q|b_z| g^rr > E² r³         ⇒ F > 0   ("lit": well inside the conversion surface),            return +1
+  // and only the thin shell in between (≈ 6 % in radius) needs the scan.  Photons leave the surface outwards
+  // (dark until Rcut), back-traced axions run inwards (lit).  Rigorous bounds: r, θ, φ stay within chord ±
+  // ¼(|r2|+|r3|+¼|r4|) of the dense output; ψ = φ − Ωt with t ∈ [e^s, e^{s_new}]; |b_z| within
+  // |b_z(centre)| ± [3(|cosθm| + sinθm)·δθ + 1.5 sinθm·δψ] (sup of its partials); E within its chord ± dev.
   template <class KS>
-  ART_HD bool step_dark(const DevParams& P, const KS K, double t_new) const {
+  ART_HD int step_sign(const DevParams& P, const KS K, double t_new) const {
     double lo[3], hi[3];
     for (int i = 0; i < 3; ++i) {
       double r[4];
@@ -539,15 +542,13 @@ struct Ray : RayHot, RayCold {
       lo[i] = fmin(u[i], u[i] + r[0]) - dev;
       hi[i] = fmax(u[i], u[i] + r[0]) + dev;
     }
-    if (!(lo[0] > P.r_int && lo[0] > P.rNS)) return false;
-    {  // E² ≥ m_a² over the step (NrmSq ≥ 0), as in step_all_far
-      double r5[4];
-      dense_comp(K, 5, r5);
-      const double e0 = u7_0 + fac7 * (u[5] - u6_0), e1 = e0 + fac7 * r5[0];
-      const double de = fabs(fac7) * 0.25 * (fabs(r5[1]) + fabs(r5[2]) + 0.25 * fabs(r5[3]));
-      const double emin = fmin(fabs(e0), fabs(e1)) - de;
-      if (!(emin > 0.0 && emin * emin >= P.ma2 * (1.0 + 1e-12))) return false;
-    }
+    if (!(lo[0] > P.r_int && lo[0] > P.rNS)) return 0;
+    double r5[4];
+    dense_comp(K, 5, r5);
+    const double e0 = u7_0 + fac7 * (u[5] - u6_0), e1 = e0 + fac7 * r5[0];
+    const double de = fabs(fac7) * 0.25 * (fabs(r5[1]) + fabs(r5[2]) + 0.25 * fabs(r5[3]));
+    const double emin = fmin(fabs(e0), fabs(e1)) - de, emax = fmax(fabs(e0), fabs(e1)) + de;
+    if (!(emin > 0.0 && emin * emin >= P.ma2 * (1.0 + 1e-12))) return 0;  // NrmSq ≥ 0 over the step
     const double t_old = fexp(s);
     const double p0 = lo[2] - P.Omega * t_new, p1 = hi[2] - P.Omega * t_old;
     const double thm = 0.5 * (lo[1] + hi[1]), dth = 0.5 * (hi[1] - lo[1]);
@@ -555,9 +556,13 @@ struct Ray : RayHot, RayCold {
     double sn, cs, sp, cp;
     fsincos(thm, &sn, &cs);
     fsincos(psm, &sp, &cp);
-    const double bzm = P.cm * (3.0 * cs * cs - 1.0) + 3.0 * P.sm * sn * cs * cp;
-    const double bzmax = fabs(bzm) + 3.0 * (fabs(P.cm) + fabs(P.sm)) * dth + 1.5 * fabs(P.sm) * dps;
-    return P.Q * bzmax < P.ma2 * (lo[0] * lo[0] * lo[0]) * (1.0 - 1e-9);
+    const double bzm = fabs(P.cm * (3.0 * cs * cs - 1.0) + 3.0 * P.sm * sn * cs * cp);
+    const double slack = 3.0 * (fabs(P.cm) + fabs(P.sm)) * dth + 1.5 * fabs(P.sm) * dps;
+    const double r3lo = lo[0] * lo[0] * lo[0], r3hi = hi[0] * hi[0] * hi[0];
+    if (P.Q * (bzm + slack) < P.ma2 * r3lo * (1.0 - 1e-9)) return -1;
+    const double grr_min = 1.0 - P.rs_ray / lo[0];
+    if (!P.isotropic && P.Q * (bzm - slack) * grr_min > emax * emax * r3hi * (1.0 + 1e-9)) return 1;
+    return 0;
   }
 
   // Does the whole accepted step lie inside the ±0.01 % box around the start point (RT.jl:307-311)?  Then every

@@ -217,14 +217,17 @@ __device__ __forceinline__ void wf_stages_body(const DevParams& P, const WfPool&
           go = false;
           done = true;
         } else if (R.template attempt<SP>(P, K)) {
-          if ((R.event_last || R.sgn_end <= 0) && (R.step_all_far(P, K) || R.step_dark(P, K, K.park(5)))) {
-            // no crossing possible: apply(th_ev < 0, sg_last = −1)
+          // certified sign of the condition along the whole step: −1 far field / dark, +1 lit, 0 unknown
+          int cs = R.step_all_far(P, K) ? -1 : R.step_sign(P, K, K.park(5));
+          if (cs != 0 && !R.event_last && R.sgn_end * cs < 0) cs = 0;  // a sign change against the reference sign: scan
+          if (cs != 0) {
+            // no crossing possible: apply(th_ev < 0, sg_last = cs)
             for (int i = 0; i < 6; ++i) {
               R.u[i] = R.un[i];
               R.k1[i] = K(6, i);
             }
             R.s = R.s_new;
-            R.sgn_end = -1;
+            R.sgn_end = cs;
             R.event_last = false;
             R.dt = R.dt_new;
             R.settle(P);
