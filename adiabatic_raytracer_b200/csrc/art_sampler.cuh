@@ -153,19 +153,21 @@ struct Sampler {
     mode = event_last ? NUDGE : SCAN;
   }
 
-  // Is the plasma frequency below the axion mass on the WHOLE segment [t0, t0 + L] of the line?  Then the
-  // condition is negative at every point of it, whatever the momentum (F ≤ base·(ωp² − m_a²), see cond()).
+  // Certified sign of the condition on the WHOLE segment [t0, t0 + L] of the line, when the momentum is not
+  // needed to know it (cond(): F = base·(ωp² − m_a²) − ωp²·g^rr NrmSq·ww N², 0 ≤ N² ≤ ww D):
+  //   ωp² < m_a² everywhere on the segment          ⇒ F < 0  ("dark"), return −1
+  //   ωp² (1 − rs/r) > E² everywhere, outside the star ⇒ F > 0  ("lit"),  return +1
   // Rigorous interval bound: on the segment |x − x_mid| ≤ L/2, so r ∈ [r_mid − L/2, r_mid + L/2] and, for a
-  // unit vector n, n·x ∈ [n·x_mid ± (L/2)|n·â|]; hence intervals for m̂·r̂ and ẑ·r̂, for their product, and
-  // |b_z| = |3(m̂·r̂)(ẑ·r̂) − cosθm| ≤ max over the product interval's ends.  A direction-aware refinement of the
-  // Rcut sphere: 58 % of the Euler steps inside that sphere are dark (reference parameters).
-  ART_HD bool dark(const DevParams& P, double t0, double L) const {
+  // unit vector n, n·x ∈ [n·x_mid ± (L/2)|n·â|]; hence intervals for m̂·r̂ and ẑ·r̂, for their product, and for
+  // b_z = 3(m̂·r̂)(ẑ·r̂) − cosθm.  A direction-aware refinement of the Rcut sphere: only the steps that straddle
+  // the conversion surface (and those inside the star) are left to evaluate.
+  ART_HD int seg_sign(const DevParams& P, double t0, double L) const {
     const double hm = 0.5 * L, tm = t0 + hm;
     const double x = xs[0] + tm * va[0], y = xs[1] + tm * va[1], z = xs[2] + tm * va[2];
     const double r2 = x * x + y * y + z * z;
     const double rm = r2 * frsqrt(r2);
     const double rlo = rm - hm;
-    if (!(rlo > 0.25 * rm)) return false;
+    if (!(rlo > 0.25 * rm)) return 0;
     const double ilo = frcp(rlo), ihi = frcp(rm + hm);  // 1/r ∈ [ihi, ilo]
     const double am = P.mh[0] * x + P.mh[1] * y + P.mh[2] * z, dm = hm * mva, dz = hm * zva;
     const double m0 = am - dm, m1 = am + dm, z0 = z - dz, z1 = z + dz;
@@ -173,18 +175,24 @@ struct Sampler {
     const double zlo = z0 * (z0 >= 0.0 ? ihi : ilo), zhi = z1 * (z1 >= 0.0 ? ilo : ihi);
     const double p1 = mlo * zlo, p2 = mlo * zhi, p3 = mhi * zlo, p4 = mhi * zhi;
     const double plo = fmin(fmin(p1, p2), fmin(p3, p4)), phi = fmax(fmax(p1, p2), fmax(p3, p4));
-    const double bzmax = fmax(fabs(3.0 * plo - P.cm), fabs(3.0 * phi - P.cm));
-    return P.Q * bzmax * ilo * ilo * ilo < P.ma2 * (1.0 - 1e-9);
+    const double b0 = 3.0 * plo - P.cm, b1 = 3.0 * phi - P.cm;  // b_z ∈ [b0, b1]
+    const double bzmax = fmax(fabs(b0), fabs(b1));
+    if (P.Q * bzmax * ilo * ilo * ilo < P.ma2 * (1.0 - 1e-9)) return -1;
+    const double bzmin = (b0 > 0.0) ? b0 : ((b1 < 0.0) ? -b1 : 0.0);
+    if (!P.isotropic && rlo > P.rNS && rlo > P.r_int &&
+        P.Q * bzmin * ihi * ihi * ihi * (1.0 - P.rs_real * ilo) > E2 * (1.0 + 1e-9))
+      return 1;
+    return 0;
   }
 
-  // Steps that are dark from a non-positive reference sign hold no event: all their grid points are negative.
-  // They are passed over in blocks (16, 4, 1 steps; at most 42 per call), with the reference's own
-  // accumulation of tau.  Called where a step ends without an event.
-  ART_HD void skip_dark_steps(const DevParams& P) {
+  // Steps whose sign is certified and agrees with the reference sign hold no event: all their grid points
+  // have that sign.  They are passed over in blocks (16, 4, 1 steps; at most 42 per call), with the
+  // reference's own accumulation of tau.  Called where a step ends without an event.
+  ART_HD void skip_certified_steps(const DevParams& P) {
 #if defined(ART_NO_DARK_SKIP)
     return;
 #endif
-    if (done || mode != SCAN || sgn_prev > 0) return;
+    if (done || mode != SCAN) return;
     const double lim = fmin(P.T_samp, tau_out);
     bool any = false;
 #if defined(__CUDA_ARCH__)
@@ -193,15 +201,16 @@ struct Sampler {
     for (int pass = 0; pass < 6; ++pass) {
       const int blk = pass < 2 ? 16 : (pass < 4 ? 4 : 1);
       const double L = (double)blk * P.samp_dt;
-      if (tau + L < lim && dark(P, tau, L)) {
-        for (int q = 0; q < blk; ++q) tau += P.samp_dt;
-        any = true;
+      if (tau + L < lim) {
+        const int sg = seg_sign(P, tau, L);
+        if (sg != 0 && sgn_prev * sg >= 0) {
+          for (int q = 0; q < blk; ++q) tau += P.samp_dt;
+          sgn_prev = sg;
+          any = true;
+        }
       }
     }
-    if (any) {
-      sgn_prev = -1;
-      next_step(P);
-    }
+    if (any) next_step(P);
   }
 
   // set up one attempt from its 10 uniforms (RT.jl:1486-1542)
@@ -350,7 +359,7 @@ struct Sampler {
       } else if (md == INIT) {
         sgn_prev = (g > 0.0) - (g < 0.0);
         next_step(P);
-        skip_dark_steps(P);
+        skip_certified_steps(P);
       }
       if (md > SCAN) md = (done || mode == SCAN) ? -1 : mode;
     }
@@ -389,7 +398,7 @@ struct Sampler {
         tau = tau_new;
         event_last = false;
         next_step(P);
-        skip_dark_steps(P);
+        skip_certified_steps(P);
       }
     }
   }
