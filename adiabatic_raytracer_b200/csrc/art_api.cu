@@ -240,7 +240,7 @@ int launch_trace_wf(art_handle* h, Lane& L, const QueuedRay* q, long long n, Ray
       else
         k_wf_collect<<<grid(n_act / 4 + 1, WF_THREADS), WF_THREADS, 0, s2>>>(h->dp, W, lin, out, stats);
       CU(cudaEventRecord(L.ev_side, s2));
-      k_wf_stages<<<2 * g1, WF_THREADS, ksmem, st>>>(h->dp, W, cur, lpar, tail ? h->tail_nstep : h->bulk_nstep, tail ? 1 : 16);
+      k_wf_stages<<<2 * g1, WF_THREADS, ksmem, st>>>(h->dp, W, cur, lpar, tail ? h->tail_nstep : h->bulk_nstep, tail ? 1 : 16, stats);
       k_wf_scan<<<grid(n_act * 11, SCAN_THREADS), SCAN_THREADS, 0, st>>>(h->dp, W, stats);
       k_wf_detect<<<g1, WF_THREADS, 0, st>>>(h->dp, W, next, lpar);
       h->launches += 6;

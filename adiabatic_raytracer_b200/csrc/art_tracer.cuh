@@ -567,7 +567,7 @@ struct Ray : RayHot, RayCold {
 
   // Does the whole accepted step lie inside the ±0.01 % box around the start point (RT.jl:307-311)?  Then every
   // sign change on it is discarded by the start-box rule and only the sign at its end point survives (as the
-  // next step's reference sign): the scan can evaluate ONE point instead of M−1.  A ray spends its first
+  // next step's reference sign): ONE evaluation instead of M−1, done by the stage kernel itself.  A ray spends its first
   // 10–15 steps there while the step size grows from the initial 1e-6 — more than half of all condition
   // evaluations of a run.  Rigorous bound: each spherical coordinate stays within its chord ± ¼(|r2|+|r3|+¼|r4|)
   // (as in step_all_far), and a Cartesian component moves by at most δr + r_max(δθ + δφ).

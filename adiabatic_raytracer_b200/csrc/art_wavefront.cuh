@@ -48,8 +48,7 @@ constexpr int WF_THREADS = 128;
 #define ART_STAGE_NSTEP 4      // attempted steps a ray may take inside one k_wf_stages launch
 #endif
 constexpr int SEG_PAD = 36;  // doubles per published segment (SEG_N = 35, padded)
-constexpr int SEG_NUDGE = 35;  // padding slot, flags: 1 = the step follows an event (the scan then includes the nudge point),
-                               // 2 = the whole step lies inside the start box (the scan evaluates its end point only)
+constexpr int SEG_NUDGE = 35;  // padding slot: 1.0 if the step follows an event (the scan then includes the nudge point)
 
 enum { WC_PEND = 0, WC_ROOTS = 1 /* + list parity */, WC_FIN = 3 /* + list parity */, WC_ACT = 5 /* + parity*2 + species */, WC_N = 16 };
 
@@ -184,7 +183,8 @@ k_wf_init(const __grid_constant__ DevParams P, const QueuedRay* __restrict__ q, 
 // the warp; thin tail of a batch: 16 attempts, any lane — there only latency counts).
 template <int SP>
 __device__ __forceinline__ void wf_stages_body(const DevParams& P, const WfPool& W, int cur, int lpar, int nstep, int min_go,
-                                               unsigned bid, unsigned nblocks, double* ksm) {
+                                               unsigned bid, unsigned nblocks, double* ksm, DevStats* stats) {
+  unsigned long long n_full = 0;  // condition evaluations done here (end points of in-box steps)
   const KStoreT<WF_THREADS> K{ksm + threadIdx.x};
   const int next = 1 - cur;
   const long long n = (long long)W.ctr[WC_ACT + cur * 2 + SP];
@@ -220,7 +220,26 @@ __device__ __forceinline__ void wf_stages_body(const DevParams& P, const WfPool&
           // certified sign of the condition along the whole step: −1 far field / dark, +1 lit, 0 unknown
           int cs = R.step_all_far(P, K) ? -1 : R.step_sign(P, K, K.park(5));
           if (cs != 0 && !R.event_last && R.sgn_end * cs < 0) cs = 0;  // a sign change against the reference sign: scan
-          if (cs != 0) {
+          bool settled = cs != 0;
+          if (!settled && R.n_cross == 0 && !R.event_last && !R.left_box) {
+            // a step inside the start box keeps nothing but the sign at its end point (step_in_start_box):
+            // evaluated here, the ray goes on without a round trip through the scan
+            const RayCold& C = W.cold[id];
+            const double s0_[3] = {C.s0[0], C.s0[1], C.s0[2]};
+            if (R.step_in_start_box(K, s0_, C.box_m)) {
+              const double E = R.u7_of(R.un[5]);
+              const double g = thick_F<true>(P, R.un[0], R.un[1], R.un[2] - P.Omega * K.park(5), R.un[3], R.un[4], R.un[5], E,
+                                             P.rs_ray, true);
+              n_full++;
+              if (g != 0.0) {  // (an exact zero at the end point is an event: left to the scan)
+                cs = (g > 0.0) - (g < 0.0);  // NaN: 0
+                settled = true;
+              }
+            } else {
+              R.left_box = 1;
+            }
+          }
+          if (settled) {
             // no crossing possible: apply(th_ev < 0, sg_last = cs)
             for (int i = 0; i < 6; ++i) {
               R.u[i] = R.un[i];
@@ -238,14 +257,7 @@ __device__ __forceinline__ void wf_stages_body(const DevParams& P, const WfPool&
           } else {
             const SegAoS D{W.seg + (size_t)id * SEG_PAD};
             R.publish(K, D);
-            bool inbox = false;
-            if (R.n_cross == 0 && !R.event_last && !R.left_box) {
-              const RayCold& C = W.cold[id];
-              const double s0_[3] = {C.s0[0], C.s0[1], C.s0[2]};
-              inbox = R.step_in_start_box(K, s0_, C.box_m);
-              if (!inbox) R.left_box = 1;
-            }
-            D(SEG_NUDGE) = (R.event_last ? 1.0 : 0.0) + (inbox ? 2.0 : 0.0);
+            D(SEG_NUDGE) = R.event_last ? 1.0 : 0.0;
             // optimistic advance; k_wf_detect / k_wf_root complete or override it
             for (int i = 0; i < 6; ++i) {
               R.u[i] = R.un[i];
@@ -263,17 +275,19 @@ __device__ __forceinline__ void wf_stages_body(const DevParams& P, const WfPool&
     if (valid) W.hot[id] = static_cast<const RayHot&>(R);
     wf_route(W, next, lpar, valid, id, done, pending, SP == SPECIES_AXION);
   }
+  n_full = warp_sum(n_full);
+  if ((threadIdx.x & 31) == 0 && stats && n_full) atomicAdd(&stats->n_cond_eval, n_full);
 }
 
 // One launch steps both species: the first half of the grid walks the axion list, the second half the
 // photon list (a warp never executes both right-hand sides; in the thin tail of a batch the two lists
 // are stepped concurrently instead of one launch after the other).
 __global__ void __launch_bounds__(WF_THREADS, ART_STAGE_MINBLOCKS)
-k_wf_stages(const __grid_constant__ DevParams P, WfPool W, int cur, int lpar, int nstep, int min_go) {
+k_wf_stages(const __grid_constant__ DevParams P, WfPool W, int cur, int lpar, int nstep, int min_go, DevStats* stats) {
   extern __shared__ double ksm[];
   const unsigned half = gridDim.x >> 1;
-  if (blockIdx.x < half) wf_stages_body<SPECIES_AXION>(P, W, cur, lpar, nstep, min_go, blockIdx.x, half, ksm);
-  else wf_stages_body<SPECIES_PHOTON>(P, W, cur, lpar, nstep, min_go, blockIdx.x - half, half, ksm);
+  if (blockIdx.x < half) wf_stages_body<SPECIES_AXION>(P, W, cur, lpar, nstep, min_go, blockIdx.x, half, ksm, stats);
+  else wf_stages_body<SPECIES_PHOTON>(P, W, cur, lpar, nstep, min_go, blockIdx.x - half, half, ksm, stats);
 }
 
 // ---- crossing scan: one warp per group of pending steps -----------------------------------------------
@@ -337,10 +351,7 @@ k_wf_scan(const __grid_constant__ DevParams P, WfPool W, DevStats* stats) {
       const int j = j_sm[rd][threadIdx.x];
       if (j >= 0 && (j & 7) < cnt) {
         const SegAoS D{seg_sm[wib][j & 7]};
-        const int flags = (int)D(SEG_NUDGE);
-        // in-box step: only the slot of the end point (grid point M−1) is evaluated
-        const bool wanted = (flags & 2) ? (j < 8 && th_sm[rd][threadIdx.x] >= 1.0) : (j < 8 || (flags & 1));
-        if (wanted) {
+        if (j < 8 || D(SEG_NUDGE) != 0.0) {
           const double th = th_sm[rd][threadIdx.x];
           const int qk = seg_quick(P, D, th);
           if (qk == -1) code = 2;
@@ -361,7 +372,6 @@ k_wf_scan(const __grid_constant__ DevParams P, WfPool W, DevStats* stats) {
       // bits [off, off + M) of each class, re-ordered to grid-point order: slot q < M−1 ↔ point q + 1,
       // slot M−1 ↔ the nudge point 0
       const int off = (int)lane * M, w = off >> 5, sh = off & 31;
-      const bool inbox = ((int)seg_sm[wib][lane][SEG_NUDGE] & 2) != 0;
       unsigned long long m3[3];
       for (int c = 0; c < 3; ++c) {
         const unsigned* b = bal_sm[wib][c];
@@ -370,9 +380,6 @@ k_wf_scan(const __grid_constant__ DevParams P, WfPool W, DevStats* stats) {
         if (sh) r |= (unsigned long long)b[w + 2] << (64 - sh);
         if (M < 64) r &= (1ull << M) - 1ull;
         m3[c] = ((r & ((1ull << (M - 1)) - 1ull)) << 1) | ((r >> (M - 1)) & 1ull);
-        // in-box step: every grid point takes the sign of the end point (all sign changes inside the box are
-        // discarded by k_wf_detect; what survives is the end sign — art_tracer.cuh: step_in_start_box)
-        if (inbox) m3[c] = ((m3[c] >> (M - 1)) & 1ull) ? (((M >= 64) ? ~0ull : ((1ull << M) - 1ull)) & ~1ull) : 0ull;
       }
       W.mpos[my_id] = m3[0]; W.mneg[my_id] = m3[1]; W.mzero[my_id] = m3[2];
     }
