@@ -133,7 +133,8 @@ struct art_handle {
   long long rows_cap = 0;         // rows held on device
   long long n_rows_dev = 0;
   int ncols = 13;
-  int n_ct = 16, n_ph = 16;
+  int n_ct = 16, n_ph = 16, n_dw = 1;
+  double dw_lo = 0.0, dw_hi = 0.0;
   double host_counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   void* comm = nullptr;
   int nranks = 1, rank = 0;
@@ -506,13 +507,22 @@ int art_propagate(art_handle* h, int64_t n, const int32_t* species, const double
 // ---- fused pipeline ----------------------------------------------------------------------------
 
 int art_hist_config(art_handle* h, int32_t n_costheta, int32_t n_phi) {
-  if (!h || n_costheta < 1 || n_phi < 1 || (long long)n_costheta * n_phi > (1 << 20)) return ART_ERR_ARG;
+  return art_hist_config_spectrum(h, n_costheta, n_phi, 1, 0.0, 0.0);
+}
+
+int art_hist_config_spectrum(art_handle* h, int32_t n_costheta, int32_t n_phi, int32_t n_domega, double domega_lo,
+                             double domega_hi) {
+  if (!h || n_costheta < 1 || n_phi < 1 || n_domega < 1 || (long long)n_costheta * n_phi * n_domega > (1 << 20)) return ART_ERR_ARG;
+  if (n_domega > 1 && !(domega_hi > domega_lo)) return ART_ERR_ARG;
   h->n_ct = n_costheta;
   h->n_ph = n_phi;
+  h->n_dw = n_domega;
+  h->dw_lo = domega_lo;
+  h->dw_hi = domega_hi;
   return art_hist_reset(h);
 }
 
-int64_t art_hist_len(const art_handle* h) { return h ? (int64_t)2 * h->n_ct * h->n_ph * 4 + 8 : 0; }
+int64_t art_hist_len(const art_handle* h) { return h ? (int64_t)2 * h->n_ct * h->n_ph * h->n_dw * 4 + 8 : 0; }
 
 int art_hist_reset(art_handle* h) {
   if (!h) return ART_ERR_ARG;
@@ -678,10 +688,11 @@ int art_run_device(art_handle* h, uint64_t seed, int64_t first_event, int64_t n_
     k_patch_rows<<<nblk(nr, 256), 256, 0, h->stream>>>(nr, h->rows.as<double>(), h->keys.as<long long>(), ncols, 0,
                                                        h->events.as<EventData>(), h->fin_count.as<int>(),
                                                        h->fin_info.as<int>(), 0);
-    const int nb = 2 * h->n_ct * h->n_ph * 4;
+    const int nb = 2 * h->n_ct * h->n_ph * h->n_dw * 4;
     const int use_smem = nb * (int)sizeof(double) <= 48 * 1024;
     const int blocks = (int)std::min<long long>(h->n_sm * 4, (nr + 255) / 256);
-    k_hist<<<blocks, 256, use_smem ? nb * sizeof(double) : 0, h->stream>>>(0, nr, h->rows.as<double>(), ncols, h->n_ct, h->n_ph,
+    k_hist<<<blocks, 256, use_smem ? nb * sizeof(double) : 0, h->stream>>>(0, nr, h->rows.as<double>(), ncols, h->n_ct, h->n_ph, h->n_dw, h->dw_lo,
+                                                                           h->n_dw > 1 ? (double)h->n_dw / (h->dw_hi - h->dw_lo) : 0.0,
                                                                            h->hist.as<double>(), use_smem);
     h->launches += 2;
     CU(cudaGetLastError());

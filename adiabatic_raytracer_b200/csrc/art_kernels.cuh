@@ -248,12 +248,12 @@ __global__ void k_gather_rows(const double* __restrict__ rows, const int* __rest
 }
 
 // ------------------------------------------------------------------------------------------
-// K5: binned flux.  bins: [species(2)][n_ct][n_ph][4] = Σ w·sln, Σ (w·sln)², Σ w, count
+// K5: binned flux / spectra.  bins: [species(2)][n_ct][n_ph][n_dw][4] = Σ w·sln, Σ (w·sln)², Σ w, count
 // ------------------------------------------------------------------------------------------
 __global__ void k_hist(long long row_begin, long long n_rows, const double* __restrict__ rows, int ncols, int n_ct,
-                       int n_ph, double* __restrict__ hist, int use_smem) {
+                       int n_ph, int n_dw, double dw_lo, double dw_scale, double* __restrict__ hist, int use_smem) {
   extern __shared__ double sh[];
-  const int nb = 2 * n_ct * n_ph * 4;
+  const int nb = 2 * n_ct * n_ph * n_dw * 4;
   if (use_smem) {
     for (int k = threadIdx.x; k < nb; k += blockDim.x) sh[k] = 0.0;
     __syncthreads();
@@ -269,7 +269,12 @@ __global__ void k_hist(long long row_begin, long long n_rows, const double* __re
     int ip = (int)floor((r[3] + PI) / (2.0 * PI) * n_ph);
     ip = ip < 0 ? 0 : (ip >= n_ph ? n_ph - 1 : ip);
     const double w = r[8] * r[7];
-    double* b = H + ((size_t)(id * n_ct + ic) * n_ph + ip) * 4;
+    int iw = 0;
+    if (n_dw > 1) {
+      iw = (int)floor((r[12] - dw_lo) * dw_scale);
+      iw = iw < 0 ? 0 : (iw >= n_dw ? n_dw - 1 : iw);
+    }
+    double* b = H + (((size_t)(id * n_ct + ic) * n_ph + ip) * n_dw + iw) * 4;
     atomicAdd(b + 0, w);
     atomicAdd(b + 1, w * w);
     atomicAdd(b + 2, r[8]);

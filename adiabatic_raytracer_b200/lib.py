@@ -44,6 +44,7 @@ SIGNATURES = {
     "art_write_npy": (C.c_int, [C.c_char_p, _dp, C.c_int64, C.c_int32]),
     "art_npy_name": (C.c_int, [_PP, C.c_int64, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int64]),
     "art_hist_config": (C.c_int, [_H, C.c_int32, C.c_int32]),
+    "art_hist_config_spectrum": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double]),
     "art_hist_len": (C.c_int64, [_H]),
     "art_hist_reset": (C.c_int, [_H]),
     "art_hist_get": (C.c_int, [_H, _dp, C.c_int64]),
@@ -186,8 +187,9 @@ class Handle:
         return rows[: nr.value]
 
     # ---- histogram / multi-GPU ------------------------------------------------------------
-    def hist_config(self, n_costheta, n_phi):
-        self._chk(self._L.art_hist_config(self._h, n_costheta, n_phi))
+    def hist_config(self, n_costheta, n_phi, n_domega=1, domega_lo=0.0, domega_hi=0.0):
+        """Bins [species][cosθf][ϕf][Δω][4]; n_domega > 1 adds the energy axis of the binned spectra."""
+        self._chk(self._L.art_hist_config_spectrum(self._h, n_costheta, n_phi, n_domega, domega_lo, domega_hi))
 
     def hist_reset(self):
         self._chk(self._L.art_hist_reset(self._h))

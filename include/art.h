@@ -229,6 +229,11 @@ int art_npy_name(const art_params* p, int64_t Ntajs, const char* dir_tag, const 
  * [f_inx, n_rows, n_events, n_acc, n_rej, n_rhs, n_cond, n_rays].  sln_prob is the
  * un-normalised value; divide the first two moments by f_inx (f_inx²) after the reduce.      */
 int art_hist_config(art_handle* h, int32_t n_costheta, int32_t n_phi);
+/* Binned spectra (BASELINE config 3): a third axis of n_domega equal bins of Δω (row column 12, MainRunner.jl:709)
+ * on [domega_lo, domega_hi); values outside fall in the end bins.  Layout [species(2)][n_costheta][n_phi][n_domega][4].
+ * art_hist_config(h, a, b) is art_hist_config_spectrum(h, a, b, 1, 0, 0).                                   */
+int art_hist_config_spectrum(art_handle* h, int32_t n_costheta, int32_t n_phi, int32_t n_domega, double domega_lo,
+                             double domega_hi);
 int64_t art_hist_len(const art_handle* h); /* doubles */
 int art_hist_reset(art_handle* h);
 int art_hist_get(art_handle* h, double* out, int64_t cap);

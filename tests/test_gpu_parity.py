@@ -447,3 +447,31 @@ def test_pinned_row_buffer_and_evaluation_counters(lib):
     assert 0 < st["n_cond_eval"] < st["n_cond"]
     assert st["n_cond_eval"] > 0.2 * st["n_cond"]
     h.close()
+
+
+def test_binned_spectra_histogram_matches_numpy(lib):
+    """BASELINE config 3 "binned radio spectra": 16 viewing-angle bins × energy bins in Δω (row column 12)."""
+    p = ArtParams.default(theta_m=0.2)
+    h = lib.Handle(p, 0)
+    n_ct, n_dw, lo, hi = 16, 12, -1.0 - 3e-6, -1.0 + 3e-6
+    h.hist_config(n_ct, 1, n_dw, lo, hi)
+    out = h.run(5, 1, 4000)
+    r = out["rows"]
+    H = h.hist_get()
+    assert H.size == 2 * n_ct * n_dw * 4 + 8
+    bins = H[:-8].reshape(2, n_ct, 1, n_dw, 4)
+    w = r[:, 8] * r[:, 7]
+    for sp in (0, 1):
+        m = r[:, 1] == sp
+        ic = np.clip(np.floor((np.cos(r[m, 2]) + 1) * 0.5 * n_ct).astype(int), 0, n_ct - 1)
+        iw = np.clip(np.floor((r[m, 12] - lo) * (n_dw / (hi - lo))).astype(int), 0, n_dw - 1)
+        ref = np.zeros((n_ct, n_dw))
+        np.add.at(ref, (ic, iw), w[m])
+        cnt = np.zeros((n_ct, n_dw))
+        np.add.at(cnt, (ic, iw), 1.0)
+        assert np.array_equal(bins[sp, :, 0, :, 3], cnt)
+        assert np.allclose(bins[sp, :, 0, :, 0], ref, rtol=1e-9, atol=0)
+    assert bins[1, :, 0, :, 3].sum() == (r[:, 1] == 1).sum()
+    ph = r[:, 1] == 1
+    assert (np.abs(r[ph, 12] + 1.0) < 3e-6).mean() > 0.5  # the chosen window holds most of the photon line
+    h.close()
