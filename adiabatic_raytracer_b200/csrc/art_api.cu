@@ -221,7 +221,9 @@ int launch_trace_wf(art_handle* h, Lane& L, const QueuedRay* q, long long n, Ray
   long long n_act = n;  // upper bound of the rays in flight, refreshed at every host check
   int cur = 0;
   const bool trace = getenv("ART_WF_TRACE") != nullptr;
-  cudaStream_t s2 = L.stream2;
+  // ART_SIDE_STREAM=0 keeps everything on one stream (profilers serialise kernels and make stream waits costly)
+  const bool side = !(getenv("ART_SIDE_STREAM") && atoi(getenv("ART_SIDE_STREAM")) == 0);
+  cudaStream_t s2 = side ? L.stream2 : st;
   for (long long iter = 0;;) {
     const int burst = n_act > 500000 ? 8 : (n_act > 65536 ? 16 : 32);  // steps between host checks (deep queue: host jitter must not idle the GPU)
     const bool tail = n_act < 8LL * h->n_sm * WF_THREADS;               // fewer rays than one resident wave
@@ -230,17 +232,17 @@ int launch_trace_wf(art_handle* h, Lane& L, const QueuedRay* q, long long n, Ray
       const int lpar = (int)(iter & 1), lin = 1 - lpar;  // lists this iteration fills / lists of the previous one
       const int g1 = grid(n_act, WF_THREADS);
       // main stream: the side stream's previous pass must be through before its lists are zeroed
-      CU(cudaStreamWaitEvent(st, L.ev_side, 0));
+      if (side) CU(cudaStreamWaitEvent(st, L.ev_side, 0));
       k_wf_reset<<<1, 32, 0, st>>>(W, next, lpar);
-      CU(cudaEventRecord(L.ev_reset, st));
+      if (side) CU(cudaEventRecord(L.ev_reset, st));
       // side stream: root finder and tree of the PREVIOUS iteration's lists, concurrent with this stage kernel
-      CU(cudaStreamWaitEvent(s2, L.ev_reset, 0));
+      if (side) CU(cudaStreamWaitEvent(s2, L.ev_reset, 0));
       k_wf_root<<<grid(n_act / 2 + 1, WF_THREADS), WF_THREADS, 0, s2>>>(h->dp, W, next, lin, lpar, stats);
       if (tree)
         k_wf_tree<<<grid(n_act / 2 + 1, WF_THREADS), WF_THREADS, 0, s2>>>(h->dp, W, *tree, next, lin, rec, rec_cap, stats);
       else
         k_wf_collect<<<grid(n_act / 4 + 1, WF_THREADS), WF_THREADS, 0, s2>>>(h->dp, W, lin, out, stats);
-      CU(cudaEventRecord(L.ev_side, s2));
+      if (side) CU(cudaEventRecord(L.ev_side, s2));
       k_wf_stages<<<2 * g1, WF_THREADS, ksmem, st>>>(h->dp, W, cur, lpar, tail ? h->tail_nstep : h->bulk_nstep, tail ? 1 : 16, stats);
       k_wf_scan<<<grid(n_act * 11, SCAN_THREADS), SCAN_THREADS, 0, st>>>(h->dp, W, stats);
       k_wf_detect<<<g1, WF_THREADS, 0, st>>>(h->dp, W, next, lpar);
@@ -248,7 +250,7 @@ int launch_trace_wf(art_handle* h, Lane& L, const QueuedRay* q, long long n, Ray
       cur = next;
     }
     CU(cudaGetLastError());
-    CU(cudaStreamWaitEvent(st, L.ev_side, 0));
+    if (side) CU(cudaStreamWaitEvent(st, L.ev_side, 0));
     unsigned long long c[WC_N];
     CU(cudaMemcpyAsync(c, W.ctr, sizeof(c), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
