@@ -17,7 +17,8 @@
 //     Hairer-style initial-step heuristic and its PI controller with the DP5 constants
 //     (β1 = 0.17, β2 = 0.04, γ = 0.9, qmin = 0.2, qmax = 10, steady band [1, 1.2]),
 //   * DiffEqBase's event semantics: sign scan at `interp_points` equally spaced points of the
-//     dense output per accepted step, first sign change is root-found to floating precision,
+//     dense output per accepted step, first sign change is located by the bracketing root finder
+//     below (find_root: Illinois + Brent's minimum step + bisection safeguards, 1e-13 of the step),
 //     the step is truncated there, the callback runs, integration resumes from the root with
 //     a repeat-nudge of dt/100 for the next step's reference sign.
 // Accuracy against the converged solution is pinned separately by tests/golden (scipy DOP853,
