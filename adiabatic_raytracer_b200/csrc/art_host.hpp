@@ -20,10 +20,6 @@ inline int make_dev_params(const art_params& p, DevParams& d, std::string& err) 
     err = "bndry_lyr > 0 (boundary-layer plasma term, RayTracer.jl:1156-1162) is not supported by this build";
     return ART_ERR_ARG;
   }
-  if (!p.melrose && !p.isotropic) {
-    err = "melrose=false (Ctheta_B_sphere branch, RayTracer.jl:546-548) is not supported by this build";
-    return ART_ERR_ARG;
-  }
   if (!p.thick_surface) {
     err = "thick_surface=false is not supported by this build";
     return ART_ERR_ARG;
@@ -67,6 +63,8 @@ inline int make_dev_params(const art_params& p, DevParams& d, std::string& err) 
   d.n_max = p.n_maxSample;
   d.isotropic = p.isotropic ? 1 : 0;
   d.flat = p.flat ? 1 : 0;
+  d.melrose = p.melrose ? 1 : 0;
+  d.thick = p.thick_surface ? 1 : 0;
   d.num_cutoff = p.num_cutoff;
   d.MC_nodes = p.MC_nodes;
   d.max_nodes = p.max_nodes;

@@ -218,6 +218,7 @@ struct DevParams {
   double rho_DM;
   int32_t maxiters, M_ray, M_samp, n_max;
   int32_t isotropic, flat;
+  int32_t melrose, thick;  // hamiltonian's melrose switch (RT.jl:546-551); sampler's thick_surface switch (RT.jl:1548)
   int32_t num_cutoff, MC_nodes, max_nodes;
   double prob_cutoff;
   double inv_Mrm1, inv_Msm1;  // 1/(M_ray − 1), 1/(M_samp − 1): dense-output grid spacing
@@ -371,14 +372,45 @@ ART_HD void rhs_photon(const DevParams& P, double r, double th, double ph, doubl
   const double N_r = (0.5 * m.dgrr * m.isq) * kr * f.br - (kt * n_t + kp * n_p) * rinv;
   const double N_t = kr * sq * f.br_t + kt * f.bt_t * rinv - kp * n_p * f.c * sinv;
   const double N_p = kr * sq * f.br_p + kt * f.bt_p * rinv + kp * f.bp_p * rinv * sinv;
+  const double fac = C_KM * t * m.grr * ominv;
+  const double face = fac * einv;
+  if (!P.melrose && !P.isotropic) {
+    // hamiltonian's "original form" (melrose = false, RT.jl:546-548) with cosθ_B from Ctheta_B_sphere
+    // (RT.jl:957-971):  H = ½[g^tt ω² + K² + G],  G = ωp² Wm (K² − κ)/(Wm K² − ωp² κ),
+    //   K² = g^ij k_i k_j,  κ = N²/D (= K² cos²θ_B),  Wm = ω²/g^rr.
+    // Chain rule through (ωp², κ, K², Wm) with the same ∂N/∂x, ∂D/∂x, ∂b_z/∂x as the Melrose form:
+    //   G_P = Wm² K² (K² − κ)/den²,  G_κ = ωp² Wm K² (ωp² − Wm)/den²,
+    //   G_K = ωp² Wm κ (Wm − ωp²)/den²,  G_W = −ωp⁴ κ (K² − κ)/den²,   den = Wm K² − ωp² κ.
+    const double K2 = m.grr * kr * kr + kt2 + kp2;
+    const double kap = N * N * Dinv;
+    const double gri = m.isq * m.isq;  // 1/g^rr
+    const double Wm = om * om * gri;
+    const double dinv = frcp(Wm * K2 - Pp * kap);
+    const double d2 = dinv * dinv;
+    const double cP = Wm * Wm * K2 * (K2 - kap) * d2;
+    const double ck = Pp * Wm * K2 * (Pp - Wm) * d2;
+    const double cK1 = 1.0 + Pp * Wm * kap * (Wm - Pp) * d2;
+    const double cW = -Pp * Pp * kap * (K2 - kap) * d2;
+    const double cN = ck * N * Dinv;  // ½ G_κ ∂κ/∂N
+    const double ckk = ck * kap * Dinv;
+    const double Hr = 0.5 * (m.dgtt * om * om + cK1 * (m.dgrr * kr * kr - 2.0 * (kt2 + kp2) * rinv) - 3.0 * Pp * rinv * cP -
+                             cW * om * om * m.dgrr * gri * gri) + cN * N_r;
+    const double Ht = 0.5 * (-2.0 * f.c * sinv * kp2 * cK1 + sg * f.bz_t * cP - ckk * f.D_t) + cN * N_t;
+    const double Hp = 0.5 * (sg * f.bz_p * cP - ckk * f.D_p) + cN * N_p;
+    du[0] = (cK1 * m.grr * kr + cN * n_r) * fac;
+    du[1] = (cK1 * kt * rinv2 + cN * n_t) * fac;
+    du[2] = (cK1 * kp * s2inv + cN * n_p) * fac;
+    du[3] = -Hr * face;
+    du[4] = -Ht * face;
+    du[5] = -Hp * face;
+    return;
+  }
   // ∂H/∂x
   const double H_r = 0.5 * (m.dgtt * om * om + m.dgrr * kr * kr - 2.0 * (kt2 + kp2) * rinv - 3.0 * Pp * rinv * X -
                             W * (m.dgrr * N * N + 2.0 * m.grr * N * N_r));
   const double H_t = 0.5 * (-2.0 * f.c * sinv * kp2 + sg * f.bz_t * X -
                             W * m.grr * (2.0 * N * N_t - N * N * f.D_t * Dinv));
   const double H_p = 0.5 * (sg * f.bz_p * X - W * m.grr * (2.0 * N * N_p - N * N * f.D_p * Dinv));
-  const double fac = C_KM * t * m.grr * ominv;
-  const double face = fac * einv;
   du[0] = Hk_r * fac;
   du[1] = Hk_t * fac;
   du[2] = Hk_p * fac;

@@ -28,7 +28,7 @@ static NSParams ns_of(const art_params& p) {
   NSParams n;
   n.thm = p.theta_m; n.w = p.omega_pul; n.B0 = p.B0; n.rNS = p.rNS; n.Mass_NS = p.Mass_NS;
   n.Mass_a = p.Mass_a; n.Ax_g = p.Ax_g; n.bndry_lyr = p.bndry_lyr;
-  n.flat = p.flat != 0; n.isotropic = p.isotropic != 0;
+  n.flat = p.flat != 0; n.isotropic = p.isotropic != 0; n.melrose = p.melrose != 0;
   n.t0 = p.t0_sample; n.r_int = p.metric_interior_radius;
   return n;
 }
@@ -422,7 +422,7 @@ int orc_pointwise(const art_params* p, int which, int64_t n, const double* in, d
       const double* a = in + 8 * i;  // r th ph kr kth kph t omega
       double k[3] = {a[3], a[4], a[5]};
       out[i] = hamiltonian<double>(a[0], a[1], a[2], k, a[6], a[7], N.thm, N.w, N.B0, N.rNS,
-                                   N.flat ? 0.0 : N.Mass_NS, N.Mass_a, N.isotropic, false, -1.0);
+                                   N.flat ? 0.0 : N.Mass_NS, N.Mass_a, N.isotropic, false, -1.0, N.melrose);
     } else if (which == 3) {
       const double* a = in + 8 * i;  // u[7], lnt
       RayParams rp = ray_of(*p, 1.0, p->B0, false);

@@ -58,13 +58,13 @@ inline void rhs(const RayParams& P, const double u[7], double lnt, double du[7])
     {  // RT.jl:84
       D3 k[3] = {D3(u[3] * erg), D3(u[4] * erg), D3(u[5] * erg)};
       D3 H = hamiltonian<D3>(D3::seed(u[0], 0), D3::seed(u[1], 1), D3::seed(u[2], 2), k, D3(time),
-                             D3(om), N.thm, N.w, P.B0, N.rNS, Mass_NS, N.Mass_a, N.isotropic, false, -1.0);
+                             D3(om), N.thm, N.w, P.B0, N.rNS, Mass_NS, N.Mass_a, N.isotropic, false, -1.0, N.melrose);
       for (int i = 0; i < 3; ++i) du[3 + i] = -H.d[i] * c_km * t * (g.grr / om) / erg;
     }
     {  // RT.jl:85
       D3 k[3] = {D3::seed(u[3] * erg, 0), D3::seed(u[4] * erg, 1), D3::seed(u[5] * erg, 2)};
       D3 H = hamiltonian<D3>(D3(u[0]), D3(u[1]), D3(u[2]), k, D3(time), D3(om), N.thm, N.w, P.B0,
-                             N.rNS, Mass_NS, N.Mass_a, N.isotropic, false, -1.0);
+                             N.rNS, Mass_NS, N.Mass_a, N.isotropic, false, -1.0, N.melrose);
       for (int i = 0; i < 3; ++i) du[i] = H.d[i] * c_km * t * (g.grr / om);
     }
     if (u[0] <= N.rNS * 1.01)  // RT.jl:86
@@ -72,7 +72,7 @@ inline void rhs(const RayParams& P, const double u[7], double lnt, double du[7])
     {  // RT.jl:88 (the only term that sees bndry_lyr)
       D1 k[3] = {D1(u[3] * erg), D1(u[4] * erg), D1(u[5] * erg)};
       D1 H = hamiltonian<D1>(D1(u[0]), D1(u[1]), D1(u[2]), k, D1::seed(time, 0), D1(om), N.thm, N.w,
-                             P.B0, N.rNS, Mass_NS, N.Mass_a, N.isotropic, false, N.bndry_lyr);
+                             P.B0, N.rNS, Mass_NS, N.Mass_a, N.isotropic, false, N.bndry_lyr, N.melrose);
       du[6] = H.d[0] * t * (g.grr / om);
     }
   } else {

@@ -90,6 +90,24 @@ def hamiltonian(g):
     return sp.Rational(1, 2) * (ksqr + wp**2 * (om**2 / g[1] - kp**2) / (om**2 / g[1]))
 
 
+def ctheta_B_sphere(time, g, k):
+    """Ctheta_B_sphere, RT.jl:957-971."""
+    Br, Bth, Bph = dipole(time)
+    Br, Bth, Bph = Br * sp.sqrt(g[1]), Bth * sp.sqrt(g[2]), Bph * sp.sqrt(g[3])
+    Bnorm = sp.sqrt(Br**2 / g[1] + Bth**2 / g[2] + Bph**2 / g[3])
+    knorm = sp.sqrt(g[1] * k[0] ** 2 + g[2] * k[1] ** 2 + g[3] * k[2] ** 2)
+    return (k[0] * Br + k[1] * Bth + k[2] * Bph) / knorm / Bnorm
+
+
+def hamiltonian_nonmelrose(g):
+    """hamiltonian with melrose=false ("original form"), RT.jl:537,546-548."""
+    k = (kr, kth, kph)
+    ksqr = g[0] * om**2 + g[1] * kr**2 + g[2] * kth**2 + g[3] * kph**2
+    ct = ctheta_B_sphere(t, g, k)
+    wp = omega_p(t)
+    return sp.Rational(1, 2) * (ksqr - wp**2 * (1 - ct**2) / (wp**2 * ct**2 - om**2 / g[1]) * om**2 / g[1])
+
+
 def hamiltonian_axion(g):
     """RT.jl:632-640."""
     return sp.Rational(1, 2) * (g[0] * om**2 + g[1] * kr**2 + g[2] * kth**2 + g[3] * kph**2)
@@ -188,6 +206,21 @@ def pointwise():
                 out["r_int_used"] = float(aa[0])
             out[k] = fnum(f(*aa))
         pts.append(dict(args=a, out=out))
+    return pts
+
+
+def pointwise_nonmelrose():
+    """H and its 7 partials for melrose=false at the argument points of pointwise.json."""
+    g = metric_ext()
+    H = hamiltonian_nonmelrose(g)
+    exprs = {"H": H, "dH_dr": sp.diff(H, r), "dH_dth": sp.diff(H, th), "dH_dph": sp.diff(H, ph),
+             "dH_dkr": sp.diff(H, kr), "dH_dkth": sp.diff(H, kth), "dH_dkph": sp.diff(H, kph),
+             "dH_dt": sp.diff(H, t), "grr": g[1]}
+    fns = {k: lam(v, "mpmath") for k, v in exprs.items()}
+    pts = []
+    for case in json.load(open(os.path.join(HERE, "pointwise.json"))):
+        a = case["args"]
+        pts.append(dict(args=a, out={k: fnum(f(*mpf_args(a))) for k, f in fns.items()}))
     return pts
 
 
@@ -444,6 +477,9 @@ def main():
     pw = pointwise()
     with open(os.path.join(HERE, "pointwise.json"), "w") as fjs:
         json.dump(pw, fjs, indent=1)
+    nm = pointwise_nonmelrose()
+    with open(os.path.join(HERE, "pointwise_nonmelrose.json"), "w") as fjs:
+        json.dump(nm, fjs, indent=1)
     cp = conversion_prob_cases()
     with open(os.path.join(HERE, "conv_prob.json"), "w") as fjs:
         json.dump(cp, fjs, indent=1)

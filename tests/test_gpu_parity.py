@@ -43,7 +43,8 @@ def rel(a, b):
 
 def test_rhs_matches_oracle(lib, oracle):
     rng = np.random.default_rng(3)
-    for kw in (dict(theta_m=0.2), dict(theta_m=0.9, omega_pul=2 * math.pi, flat=1), dict(theta_m=0.3, isotropic=1)):
+    for kw in (dict(theta_m=0.2), dict(theta_m=0.9, omega_pul=2 * math.pi, flat=1), dict(theta_m=0.3, isotropic=1),
+               dict(theta_m=0.2, melrose=0), dict(theta_m=0.9, omega_pul=2 * math.pi, flat=1, melrose=0)):
         p = ArtParams.default(**kw)
         h = lib.Handle(p, 0)
         n = 4096
@@ -64,7 +65,8 @@ def test_rhs_matches_oracle(lib, oracle):
             d_gpu = h.rhs(species, u, erg, lnt)
             d_ref = oracle.rhs(p, species, u, erg, lnt)
             scale = np.abs(d_ref).max(axis=1, keepdims=True) + 1e-300
-            assert (np.abs(d_gpu - d_ref) / scale).max() < 1e-11
+            # (the non-Melrose form divides by Wm K² − ωp² κ, which can get small: 3e-11 there)
+            assert (np.abs(d_gpu - d_ref) / scale).max() < (1e-11 if p.melrose or p.isotropic else 3e-11)
         h.close()
 
 
@@ -158,7 +160,8 @@ def _ray_inputs(oracle, p, n, seed=5):
     return s["x"], w["k_init"], w["erg_inf"]
 
 
-@pytest.mark.parametrize("kw", [dict(theta_m=0.2), dict(theta_m=0.2, flat=1), dict(theta_m=0.6, omega_pul=2 * math.pi)])
+@pytest.mark.parametrize("kw", [dict(theta_m=0.2), dict(theta_m=0.2, flat=1), dict(theta_m=0.6, omega_pul=2 * math.pi),
+                                dict(theta_m=0.2, melrose=0)])
 def test_propagate_matches_oracle(lib, oracle, kw):
     p = ArtParams.default(**kw)
     h = lib.Handle(p, 0)
@@ -215,7 +218,8 @@ def test_rays_against_dop853_golden(lib):
 
 
 @pytest.mark.parametrize("kw", [dict(theta_m=0.2, save_mode=1), dict(theta_m=0.2, save_mode=0, Ax_g=1e-10, MC_nodes=2, max_nodes=12),
-                                dict(theta_m=0.5, save_mode=1, omega_pul=2 * math.pi, Mass_a=2e-5)])
+                                dict(theta_m=0.5, save_mode=1, omega_pul=2 * math.pi, Mass_a=2e-5),
+                                dict(theta_m=0.2, save_mode=1, melrose=0)])
 def test_fused_pipeline_matches_oracle(lib, oracle, kw):
     p = ArtParams.default(**kw)
     h = lib.Handle(p, 0)

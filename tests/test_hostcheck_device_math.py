@@ -53,7 +53,34 @@ def test_division_free_condition_has_the_sign_and_zeros_of_the_reference_conditi
     assert np.all(f[big] / a[big] > 0)
 
 
-@pytest.mark.parametrize("kw", [dict(theta_m=0.2), dict(theta_m=0.2, flat=1)])
+def test_closed_form_rhs_matches_dual_number_gradients(oracle):
+    """rhs_photon / rhs_axion (hand-derived partials; Melrose, non-Melrose and isotropic forms of the
+    Hamiltonian, RT.jl:542-551) against the oracle's ForwardDiff-style dual numbers."""
+    rng = np.random.default_rng(3)
+    for kw in (dict(theta_m=0.2), dict(theta_m=0.3, isotropic=1), dict(theta_m=0.2, melrose=0),
+               dict(theta_m=0.9, omega_pul=2 * math.pi, flat=1, melrose=0)):
+        p = ArtParams.default(**kw)
+        n = 4096
+        u = np.zeros((n, 7))
+        u[:, 0] = 10.2 + 60 * rng.random(n)
+        u[:, 1] = 0.05 + 3.0 * rng.random(n)
+        u[:, 2] = -3 + 6 * rng.random(n)
+        u[:, 3] = rng.normal(size=n) * 0.5
+        u[:, 4] = rng.normal(size=n) * 0.5 * u[:, 0]
+        u[:, 5] = rng.normal(size=n) * 0.5 * u[:, 0] * np.sin(u[:, 1])
+        erg = np.full(n, 1.0000003e-5)
+        u[:, 6] = -erg * (1 + 1e-6 * rng.normal(size=n))
+        lnt = rng.uniform(-25, -4, n)
+        for sp in (1, 0):
+            species = np.full(n, sp, np.int32)
+            a = hc.rhs(p, species, u, erg, lnt)
+            b = oracle.rhs(p, species, u, erg, lnt)
+            scale = np.abs(b).max(axis=1, keepdims=True) + 1e-300
+            # the non-Melrose form divides by Wm K² − ωp² κ, which can get small: 3e-11 instead of 1e-11
+            assert (np.abs(a - b) / scale).max() < (1e-11 if p.melrose or p.isotropic else 3e-11)
+
+
+@pytest.mark.parametrize("kw", [dict(theta_m=0.2), dict(theta_m=0.2, flat=1), dict(theta_m=0.2, melrose=0)])
 def test_host_compiled_tracer_matches_oracle(oracle, kw):
     p = ArtParams.default(**kw)
     n = 400

@@ -90,6 +90,30 @@ def test_rhs_against_symbolic_gradients(oracle):
     assert n_checked >= 6
 
 
+def test_nonmelrose_hamiltonian_against_symbolic_gradients(oracle):
+    """melrose=false (`Ctheta_B_sphere` form, RT.jl:546-548): H and func!'s seven components vs sympy."""
+    n_checked = 0
+    for case in load("pointwise_nonmelrose.json"):
+        a, o = case["args"], case["out"]
+        p = params_of(a).copy(melrose=0)
+        H = oracle.pointwise(p, 2, [[a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]]])[0]
+        assert abs(H - o["H"]) < 1e-13 * max(a[7] ** 2, abs(o["H"]))
+        if a[6] <= 0:
+            continue
+        erg = 1.0e-5
+        t, om = a[6], a[7]
+        u = np.array([[a[0], a[1], a[2], a[3] / erg, a[4] / erg, a[5] / erg, -om]])
+        du = oracle.rhs(p, [1], u, [erg], [math.log(t)])[0]
+        f = c_km * t * o["grr"] / om
+        exp = [o["dH_dkr"] * f, o["dH_dkth"] * f, o["dH_dkph"] * f, -o["dH_dr"] * f / erg, -o["dH_dth"] * f / erg,
+               -o["dH_dph"] * f / erg, o["dH_dt"] * t * o["grr"] / om]
+        scale_x = max(abs(e) for e in exp[:3])
+        for i in range(7):
+            assert abs(du[i] - exp[i]) <= 1e-10 * max(abs(exp[i]), 1e-3 * scale_x if i < 3 else 0.0) + 1e-300, (i, du[i], exp[i])
+        n_checked += 1
+    assert n_checked >= 6
+
+
 def test_invariant_u7_tracks_u6(oracle):
     """∂H/∂t = -Ω ∂H/∂φ (the field depends on t only through ψ = φ - Ωt, RT.jl:1142), hence
     du7 = (Ω·erg/c_km)·du6 — the identity the CUDA kernel exploits."""
