@@ -20,10 +20,6 @@ inline int make_dev_params(const art_params& p, DevParams& d, std::string& err) 
     err = "bndry_lyr > 0 (boundary-layer plasma term, RayTracer.jl:1156-1162) is not supported by this build";
     return ART_ERR_ARG;
   }
-  if (!p.thick_surface) {
-    err = "thick_surface=false is not supported by this build";
-    return ART_ERR_ARG;
-  }
   if (p.n_maxSample < 1 || p.n_maxSample > SAMP_KEEP) {
     err = "n_maxSample must be in 1..8";
     return ART_ERR_ARG;

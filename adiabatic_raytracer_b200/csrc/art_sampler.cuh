@@ -83,6 +83,9 @@ struct Sampler {
     const double D = 3.0 * mx * mx + 1.0;
     const double bz = 3.0 * mx * cz - P.cm;
     const double Pq = P.Q * fabs(bz) * rinv * rinv * rinv;               // ωp²
+    // thick_surface = false (RT.jl:1548-1551): log ωp − log m_a, i.e. the sign and zeros of ωp² − m_a²
+    // (GJ_Model_ωp_vec: no zeroIn, the plasma frequency continues inside the star)
+    if (!P.thick) return Pq - P.ma2;
     const double vb = 3.0 * mx * vx - mv;                                // v·b
     double ww = 1.0, N = vb, gn = E2 - P.ma2 * (1.0 - P.rs_real * rinv);
     if (!(r >= P.rNS && r > P.r_int)) {
@@ -179,6 +182,7 @@ struct Sampler {
     const double bzmax = fmax(fabs(b0), fabs(b1));
     if (P.Q * bzmax * ilo * ilo * ilo < P.ma2 * (1.0 - 1e-9)) return -1;
     const double bzmin = (b0 > 0.0) ? b0 : ((b1 < 0.0) ? -b1 : 0.0);
+    if (!P.thick) return (P.Q * bzmin * ihi * ihi * ihi > P.ma2 * (1.0 + 1e-9)) ? 1 : 0;  // ωp > m_a on the whole segment
     if (!P.isotropic && rlo > P.rNS && rlo > P.r_int &&
         P.Q * bzmin * ihi * ihi * ihi * (1.0 - P.rs_real * ilo) > E2 * (1.0 + 1e-9))
       return 1;

@@ -76,9 +76,13 @@ static SampleOut find_sample(const double U[10], double maxR, const art_params& 
   auto point = [&](double tau, double u[3]) {
     for (int i = 0; i < 3; ++i) u[i] = xs[i] + tau * vall[i];
   };
-  auto cond = [&](double tau) {  // RT.jl:1554-1581
+  auto cond = [&](double tau) {  // RT.jl:1547-1581
     double u[3], s[3];
     point(tau, u);
+    if (!p.thick_surface) {  // RT.jl:1548-1551
+      S.n_cond++;
+      return std::log(omega_p_cart(u, N.t0, N.thm, N.w, N.B0, N.rNS, N.bndry_lyr, N.Mass_a)) - std::log(N.Mass_a);
+    }
     cart_to_sph(u, s);
     double AA = 1.0 - r_s0 / s[0];
     if (s[0] < N.rNS) AA = 1.0;

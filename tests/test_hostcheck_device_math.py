@@ -101,7 +101,8 @@ def test_host_compiled_tracer_matches_oracle(oracle, kw):
 
 
 def test_host_compiled_sampler_matches_oracle(oracle):
-    for kw in (dict(theta_m=0.2), dict(theta_m=0.2, rNS=12.0), dict(theta_m=0.2, rNS=8.0)):
+    for kw in (dict(theta_m=0.2), dict(theta_m=0.2, rNS=12.0), dict(theta_m=0.2, rNS=8.0), dict(theta_m=0.2, thick_surface=0),
+               dict(theta_m=1.1, Mass_a=2e-5, B0=2e14, omega_pul=3.0, thick_surface=0)):
         p = ArtParams.default(**kw)
         u = np.random.default_rng(1).random((6000, 10))
         a = hc.sample_from_uniforms(p, u)
