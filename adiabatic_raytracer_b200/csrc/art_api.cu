@@ -132,6 +132,7 @@ struct art_handle {
   DBuf q[2];                      // fine-grained art_propagate queue
   long long rows_cap = 0;         // rows held on device
   long long n_rows_dev = 0;
+  long long last_first_event = 0, last_n_events = 0;  // event range of the last pipeline call (art_fetch_events)
   int ncols = 13;
   int n_ct = 16, n_ph = 16, n_dw = 1;
   double dw_lo = 0.0, dw_hi = 0.0;
@@ -324,7 +325,7 @@ int art_create(const art_params* p, int device_id, art_handle** out) {
   h->params = *p;
   h->dp = d;
   h->device = device_id;
-  h->ncols = p->save_mode > 0 ? ART_ROW_COLS_LONG : ART_ROW_COLS_SHORT;
+  h->ncols = p->save_mode > 1 ? ART_ROW_COLS_FULL : (p->save_mode > 0 ? ART_ROW_COLS_LONG : ART_ROW_COLS_SHORT);
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, device_id);
   h->n_sm = prop.multiProcessorCount;
@@ -642,6 +643,8 @@ int art_run_device(art_handle* h, uint64_t seed, int64_t first_event, int64_t n_
   }
   h->n_rows_dev = 0;
   h->launches = 0;
+  h->last_first_event = first_event;
+  h->last_n_events = 0;
   unsigned long long* gctr = h->gctr.as<unsigned long long>();
   // gctr layout: [0] failed sampler attempts, [1] tot_count, [6] n_rows, [7,8] n_final (photon, axion)
   CU(cudaMemsetAsync(gctr, 0, 16 * sizeof(unsigned long long), h->stream));
@@ -709,6 +712,7 @@ int art_run_device(art_handle* h, uint64_t seed, int64_t first_event, int64_t n_
   DevStats ds;
   CU(cudaMemcpy(&ds, dstats, sizeof(ds), cudaMemcpyDeviceToHost));
   h->n_rows_dev = nr;
+  h->last_n_events = n_events;
   const long long f_inx = (long long)hc[0] + (long long)hc[7];
   if (n_rows_out) *n_rows_out = h->n_rows_dev;
   if (f_inx_out) *f_inx_out = f_inx;
@@ -760,6 +764,28 @@ int art_fetch_rows(art_handle* h, double* rows, int64_t rows_cap, int64_t* n_row
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(rows, s[3].p, (size_t)n * ncols * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
+  return ART_OK;
+}
+
+int art_fetch_events(art_handle* h, double* events, int64_t events_cap, int64_t* n_events) {
+  if (!h || !events || !n_events) return ART_ERR_ARG;
+  CU(cudaSetDevice(h->device));
+  const long long n = h->last_n_events;
+  *n_events = n;
+  if (n > events_cap) return fail(h, ART_ERR_CAPACITY, "event buffer too small");
+  if (n == 0) return ART_OK;
+  std::vector<EventData> ev((size_t)n);
+  std::vector<int> cnt((size_t)n);
+  CU(cudaMemcpy(ev.data(), h->events.p, (size_t)n * sizeof(EventData), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(cnt.data(), h->fin_count.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+  for (long long i = 0; i < n; ++i) {
+    const EventData& E = ev[(size_t)i];
+    double* o = events + i * ART_EVENT_COLS;
+    o[0] = (double)(h->last_first_event + i);
+    for (int c = 0; c < 3; ++c) { o[1 + c] = E.vinf[c]; o[5 + c] = E.x[c]; o[8 + c] = E.k_init[c]; }
+    o[4] = E.sln_prob;
+    o[11] = (double)cnt[(size_t)i];
+  }
   return ART_OK;
 }
 
@@ -838,6 +864,38 @@ int art_npy_name(const art_params* p, int64_t Ntajs, const char* dir_tag, const 
   s += std::string("_") + (file_tag ? file_tag : "") + ".npy";
   if ((int64_t)s.size() + 1 > out_cap) return ART_ERR_CAPACITY;
   memcpy(out, s.c_str(), s.size() + 1);
+  return ART_OK;
+}
+
+int art_write_event_files(const char* dir_tag, const char* file_tag, const double* rows, int64_t n_rows,
+                          const double* events, int64_t n_events) {
+  if ((!rows && n_rows > 0) || (!events && n_events > 0)) return ART_ERR_ARG;
+  const std::string dir = std::string(dir_tag ? dir_tag : "results") + "/event/", tag = file_tag ? file_tag : "";
+  auto jint = [](double v) { return std::to_string((long long)v); };
+  FILE* f = fopen((dir + "final_" + tag).c_str(), "w");
+  if (!f) return ART_ERR_IO;
+  for (int64_t i = 0; i < n_rows; ++i) {  // MR.jl:689-701
+    const double* r = rows + i * ART_ROW_COLS_FULL;
+    // the root node's time is the integer literal 0 of MR.jl:656 (prints "0"); every other node's is a Float64
+    const std::string t = r[30] == 0.0 ? std::string("0") : julia_float(r[30]);
+    fprintf(f, "%s %s %s %s %s %s %s %s %s %s\n", jint(r[0]).c_str(), julia_float(r[13]).c_str(), jint(r[1]).c_str(),
+            julia_float(r[2]).c_str(), julia_float(r[3]).c_str(), julia_float(r[29]).c_str(), julia_float(r[4]).c_str(),
+            julia_float(r[5]).c_str(), julia_float(r[6]).c_str(), t.c_str());
+  }
+  fclose(f);
+  f = fopen((dir + "event_" + tag).c_str(), "w");
+  if (!f) return ART_ERR_IO;
+  for (int64_t i = 0; i < n_events; ++i) {  // MR.jl:593-610 and 733-735
+    const double* e = events + i * ART_EVENT_COLS;
+    fprintf(f, "%s %s %s %s %s", jint(e[0]).c_str(), julia_float(e[1]).c_str(), julia_float(e[2]).c_str(),
+            julia_float(e[3]).c_str(), julia_float(e[4]).c_str());
+    for (int c = 0; c < 3; ++c) fprintf(f, " %s", julia_float(e[5 + c]).c_str());    // nb.x, nb.y, nb.z: the sample point
+    for (int c = 0; c < 3; ++c) fprintf(f, " %s", julia_float(-e[8 + c]).c_str());   // nb.kx …: −k_init (back-trace node)
+    for (int c = 0; c < 3; ++c) fprintf(f, " %s", julia_float(e[5 + c]).c_str());    // xpos_flat
+    for (int c = 0; c < 3; ++c) fprintf(f, " %s", julia_float(e[8 + c]).c_str());    // k_init
+    fprintf(f, " 0.0 %s\n", jint(e[11]).c_str());  // wall-clock seconds of the event (not reproduced), count
+  }
+  fclose(f);
   return ART_OK;
 }
 

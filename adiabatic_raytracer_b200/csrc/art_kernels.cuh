@@ -160,7 +160,7 @@ __global__ void k_weights_events(const __grid_constant__ DevParams P, long long 
   const EventSample e = s[i];
   const SampleWeights W = sample_weights(P, e.x, e.vloc, e.vinf);
   EventData E;
-  for (int c = 0; c < 3; ++c) { E.x[c] = e.x[c]; E.k_init[c] = W.k_init[c]; }
+  for (int c = 0; c < 3; ++c) { E.x[c] = e.x[c]; E.k_init[c] = W.k_init[c]; E.vinf[c] = e.vinf[c]; }
   E.erg_inf = W.erg_inf; E.vel_eng = W.vel_eng; E.sln_prob = W.sln_prob; E.cos_w = W.cos_w;
   E.back_weight = 0.0; E.prob0 = 0.0; E.c_bck = 0; E.n_failed = e.n_failed;
   ev[i] = E;

@@ -23,7 +23,7 @@ struct TreeNode {  // RT.node, RayTracer.jl:126-163 (fields that reach the outpu
 };
 
 struct EventData {  // per-event scalars of MainRunner.jl:498-557 and of the back-trace
-  double x[3], k_init[3];
+  double x[3], k_init[3], vinf[3];
   double erg_inf, vel_eng, sln_prob, cos_w;
   double back_weight, prob0;  // samp_back_weight (MR.jl:630), Prob_nonAD_0 (MR.jl:626)
   int c_bck, n_failed;
@@ -170,6 +170,10 @@ ART_HD void emit_row(const DevParams& P, const EventData& E, const TreeState& T,
     row[26] = absfX;
     row[27] = 0.0;  // c_bck            — patch_row
     row[28] = 0.0;  // Prob_nonAD_0     — patch_row
+  }
+  if (S.ncols > 29) {  // save_mode ≥ 2: the final_* text file's extra numbers, MR.jl:689-701
+    row[29] = absf;
+    row[30] = n.t;
   }
 }
 

@@ -38,6 +38,8 @@ SIGNATURES = {
                           C.POINTER(ArtStats)]),
     "art_run_device": (C.c_int, [_H, C.c_uint64, C.c_int64, C.c_int64, _i64p, _i64p, _i64p, C.POINTER(ArtStats)]),
     "art_fetch_rows": (C.c_int, [_H, C.c_void_p, C.c_int64, _i64p]),
+    "art_fetch_events": (C.c_int, [_H, _dp, C.c_int64, _i64p]),
+    "art_write_event_files": (C.c_int, [C.c_char_p, C.c_char_p, _dp, C.c_int64, _dp, C.c_int64]),
     "art_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
     "art_host_free": (C.c_int, [C.c_void_p]),
     "art_normalize_rows": (C.c_int, [_dp, C.c_int64, C.c_int32, C.c_int64]),
@@ -92,7 +94,7 @@ class Handle:
         rc = L.art_create(C.byref(params), device, C.byref(self._h))
         if rc != 0:
             raise ArtError(rc, L.art_last_error(None).decode())
-        self.ncols = 29 if params.save_mode > 0 else 13
+        self.ncols = 31 if params.save_mode > 1 else (29 if params.save_mode > 0 else 13)
 
     def close(self):
         if self._h:
@@ -186,6 +188,13 @@ class Handle:
         self._chk(self._L.art_fetch_rows(self._h, rows.ctypes.data, rows.shape[0], C.byref(nr)))
         return rows[: nr.value]
 
+    def fetch_events(self, n_events):
+        """Event table of the last run (n_events × 12: id, v_inf[3], sln_prob, x[3], k_init[3], count)."""
+        ev = np.zeros((max(n_events, 1), 12))
+        n = C.c_int64()
+        self._chk(self._L.art_fetch_events(self._h, ev, ev.shape[0], C.byref(n)))
+        return ev[: n.value]
+
     # ---- histogram / multi-GPU ------------------------------------------------------------
     def hist_config(self, n_costheta, n_phi, n_domega=1, domega_lo=0.0, domega_hi=0.0):
         """Bins [species][cosθf][ϕf][Δω][4]; n_domega > 1 adds the energy axis of the binned spectra."""
@@ -239,6 +248,16 @@ def write_npy(path: str, rows: np.ndarray):
     rc = load().art_write_npy(path.encode(), rows, rows.shape[0], rows.shape[1])
     if rc != 0:
         raise ArtError(rc, f"art_write_npy({path})")
+
+
+def write_event_files(dir_tag: str, file_tag: str, rows: np.ndarray, events: np.ndarray):
+    """<dir_tag>/event/final_<file_tag> and event_<file_tag> (saveMode > 1, MainRunner.jl:435-444)."""
+    rows = np.ascontiguousarray(rows, np.float64)
+    events = np.ascontiguousarray(events, np.float64)
+    assert rows.shape[1] == 31 and events.shape[1] == 12
+    rc = load().art_write_event_files(dir_tag.encode(), file_tag.encode(), rows, rows.shape[0], events, events.shape[0])
+    if rc != 0:
+        raise ArtError(rc, f"art_write_event_files({dir_tag}/event/*_{file_tag})")
 
 
 def normalize_rows(rows: np.ndarray, f_inx_total: int):

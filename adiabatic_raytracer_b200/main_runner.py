@@ -9,7 +9,12 @@ host.  All arithmetic happens in libart_b200.so on the GPU.
 Differences a user can observe:
   * random numbers come from per-event Philox streams, not Julia's global RNG;
   * ``iseed < 0`` draws a seed from os.urandom like the reference draws rand(0:1e8);
-  * saveMode ≥ 2 clear-text dumps (MainRunner.jl:435-444, 565-611, 689-701) are not written.
+  * saveMode = 2 writes <dir_tag>/event/final_<file_tag> and event_<file_tag> once, after the run (the
+    reference appends per event); the per-event wall-clock field of event_* is 0.0;
+  * saveMode = 3 (one tree_<file_tag><event> text file per event with the trajectories sampled at ``ntimes``
+    points, MainRunner.jl:17-65, 574-578) is not supported and raises;
+  * ``v_NS`` is accepted and, as in the reference (MainRunner.jl:418-422 computes two angles that nothing
+    reads; the velocity shift at :497 is commented out), has no effect.
 """
 import math
 import os
@@ -44,6 +49,8 @@ def main_runner_tree(Mass_a, Ax_g, theta_m, omega_pul, B0, rNS, Mass_NS, omega_p
                      return_rows=False):
     """Drop-in for ``main_runner_tree`` (MainRunner.jl:355).  Returns tot_count (or None when
     there is no conversion surface, MainRunner.jl:389-396)."""
+    if saveMode > 2:
+        raise NotImplementedError("saveMode=3 (per-event tree_* text files with sampled trajectories) is not supported")
     if iseed < 0:  # MainRunner.jl:365-372
         iseed = int.from_bytes(os.urandom(4), "little") % 100000001
     elif iseed == 0:
@@ -65,9 +72,14 @@ def main_runner_tree(Mass_a, Ax_g, theta_m, omega_pul, B0, rNS, Mass_NS, omega_p
         # numbered 1 … Ntajs−1 (MainRunner.jl:399,450)
         n_events = max(int(Ntajs) - 1, 0)
         out = h.run(iseed, 1, n_events)
+        events = h.fetch_events(n_events) if saveMode > 1 else None
     finally:
         pass
     rows = np.ascontiguousarray(out["rows"])
+    if saveMode > 1:  # MainRunner.jl:435-444, 593-610, 689-701 (the directory must exist, as in the reference)
+        os.makedirs(os.path.join(dir_tag, "event"), exist_ok=True)
+        _lib.write_event_files(dir_tag, file_tag, rows, events)
+        rows = np.ascontiguousarray(rows[:, :29])
     if rows.shape[0] == 0:
         h.close()
         raise RuntimeError("no final particles: the reference fails here too (saveAll is nothing, MainRunner.jl:749)")

@@ -50,6 +50,12 @@ extern "C" {
 /* row widths written by main_runner_tree (MainRunner.jl:715,720)                            */
 #define ART_ROW_COLS_SHORT 13
 #define ART_ROW_COLS_LONG 29
+/* save_mode >= 2: the 29 columns + |k_f| and the time of the node, the two numbers of the final_* text file
+ * (MainRunner.jl:689-701) that the .npy row does not hold; the .npy file still gets columns 0..28        */
+#define ART_ROW_COLS_FULL 31
+/* per-event numbers of the event_* text file (MainRunner.jl:593-610, 733-735):
+ * event id, v_inf[3] (units of c), sln_prob (not normalised), sample point x[3], k_init[3], count       */
+#define ART_EVENT_COLS 12
 
 /*
  * Every physics and numerics knob of main_runner_tree's signature and of the fixed block
@@ -90,7 +96,9 @@ typedef struct art_params {
   int32_t MC_nodes;      /* --MCNodes   default 5                                           */
   int32_t max_nodes;     /* --maxNodes  default 50                                          */
   int32_t ntimes;        /* Gen_Samples.jl:164 = 3 (only used in the file name)             */
-  int32_t save_mode;     /* 0 → 13-column rows, >=1 → 29-column rows (MR.jl:714-721)        */
+  int32_t save_mode;     /* 0 → 13-column rows, 1 → 29-column rows (MR.jl:714-721), 2 → 31 columns + event table
+                            (clear-text final_* / event_* files, MR.jl:435-444, 593-610, 689-701); 3 (one tree_* file
+                            per event with the sampled trajectories, MR.jl:17-65) is not supported */
   int32_t interp_points_ray;     /* ContinuousCallback interp_points, RT.jl:357 = 50        */
   int32_t interp_points_sampler; /* RT.jl:1599 = 20                                         */
   int32_t maxiters;      /* RT.jl:384 = 1e5                                                 */
@@ -206,6 +214,18 @@ int art_run(art_handle* h, uint64_t seed, int64_t first_event, int64_t n_events,
 int art_run_device(art_handle* h, uint64_t seed, int64_t first_event, int64_t n_events,
                    int64_t* n_rows, int64_t* f_inx, int64_t* tot_count, art_stats* stats);
 int art_fetch_rows(art_handle* h, double* rows, int64_t rows_cap, int64_t* n_rows);
+
+/* Event table of the last art_run / art_run_device call: n_events × ART_EVENT_COLS, row-major, in event order
+ * (what main_runner_tree writes per event into <dir_tag>/event/event_<file_tag> when saveMode > 1).          */
+int art_fetch_events(art_handle* h, double* events, int64_t events_cap, int64_t* n_events);
+
+/* saveMode > 1 clear-text files (MainRunner.jl:435-444): <dir_tag>/event/final_<file_tag> — one line per final
+ * particle: event, weight, species id, θf ϕf |k_f|, θfX ϕfX |x_f|, time of the node (MR.jl:689-701) — from
+ * ART_ROW_COLS_FULL-column rows in event order, and <dir_tag>/event/event_<file_tag> — one line per event
+ * (MR.jl:593-610, 733-735) from the event table.  Numbers are printed like Julia's string(); the per-event
+ * wall-clock field of the reference is written as 0.0.  The directory must exist (as in the reference).     */
+int art_write_event_files(const char* dir_tag, const char* file_tag, const double* rows, int64_t n_rows,
+                          const double* events, int64_t n_events);
 
 /* Page-locked host memory for the row buffers (optional: any host pointer works, a pinned one makes the
  * device→host copy of the rows a single DMA transfer at PCIe speed instead of a staged pageable copy).

@@ -65,7 +65,8 @@ function main_runner_tree(Mass_a, Ax_g, θm, ωPul, B0, rNS, Mass_NS, ωProp, Nt
     h = Ref{Ptr{Cvoid}}(C_NULL)
     art_check(ccall((:art_create, LIBART), Cint, (Ref{ArtParams}, Cint, Ref{Ptr{Cvoid}}), p, device, h))
     n_events = max(Ntajs - 1, 0)      # `while photon_trajs < desired_trajs`, photon_trajs starts at 1
-    ncols = saveMode > 0 ? 29 : 13
+    saveMode > 2 && error("saveMode=3 (per-event tree_* text files) is not supported by the GPU path")
+    ncols = saveMode > 1 ? 31 : (saveMode > 0 ? 29 : 13)
     cap = 3 * n_events + 1024
     rows = Matrix{Float64}(undef, ncols, cap)   # column-major ncols×cap == row-major cap×ncols for C
     n_rows = Ref{Int64}(0); f_inx = Ref{Int64}(0); tot_count = Ref{Int64}(0)
@@ -75,10 +76,19 @@ function main_runner_tree(Mass_a, Ax_g, θm, ωPul, B0, rNS, Mass_NS, ωProp, Nt
                         h[], UInt64(iseed), 1, n_events, rows, cap, n_rows, f_inx, tot_count, C_NULL), h[])
         art_check(ccall((:art_normalize_rows, LIBART), Cint, (Ptr{Cdouble}, Int64, Cint, Int64),
                         rows, n_rows[], ncols, f_inx[]))           # saveAll[:, 8] ./= f_inx, MainRunner.jl:749
+        if saveMode > 1   # clear-text final_* / event_* files, MainRunner.jl:435-444, 593-610, 689-701
+            events = Matrix{Float64}(undef, 12, max(n_events, 1)); n_ev = Ref{Int64}(0)
+            art_check(ccall((:art_fetch_events, LIBART), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Int64, Ref{Int64}),
+                            h[], events, size(events, 2), n_ev), h[])
+            # (the reference writes sln_prob before the division by f_inx; the table holds that raw value)
+            art_check(ccall((:art_write_event_files, LIBART), Cint,
+                            (Cstring, Cstring, Ptr{Cdouble}, Int64, Ptr{Cdouble}, Int64),
+                            dir_tag, file_tag, rows, n_rows[], events, n_ev[]))
+        end
     end
     ccall((:art_destroy, LIBART), Cvoid, (Ptr{Cvoid},), h[])
 
-    saveAll = permutedims(rows[:, 1:n_rows[]])                     # n_rows × ncols, as the reference builds it
+    saveAll = permutedims(rows[1:min(ncols, 29), 1:n_rows[]])                     # n_rows × ncols, as the reference builds it
     fileN = dir_tag*"/npy/tree_"                                    # MainRunner.jl:750-761 verbatim
     fileN *= "MassAx_"*string(Mass_a)*"_AxionG_"*string(Ax_g)
     fileN *="_ThetaM_"*string(θm)*"_rotPulsar_"*string(ωPul)*"_B0_"*string(B0)

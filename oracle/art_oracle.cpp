@@ -342,6 +342,7 @@ struct EventOut {
   std::vector<double> rows;  // row-major, ncols each
   int64_t n_failed = 0, n_final_photon = 0, n_final_axion = 0, tot_count = 0, n_cond_sampler = 0;
   Counters C;
+  double event_line[ART_EVENT_COLS];  // numbers of the event_* text file of saveMode > 1, MR.jl:593-610, 733-735
 };
 
 static void run_event(const art_params& p, double maxR, uint64_t seed, uint64_t e, int ncols, EventOut& E) {
@@ -381,13 +382,20 @@ static void run_event(const art_params& p, double maxR, uint64_t seed, uint64_t 
     double weight_tmp = n.weight;  // opticalDepth = 0, weightC = 1
     double dOm = n.u7e / p.Mass_a + W.vel_eng;  // MR.jl:709
     if (id == 1) E.n_final_photon++; else E.n_final_axion++;
-    double row[29] = {(double)e, (double)id, thf, phf, thfX, phfX, absfX, W.sln_prob, weight_tmp,
-                      S.x[0], S.x[1], S.x[2], dOm,
-                      n.weight, 0.0, 1.0, W.k_init[0], W.k_init[1], W.k_init[2], W.cos_w,
-                      (double)fw.count, (double)fw.info, n.prob, n.prob_conv, n.prob_conv0,
-                      samp_back_weight, absfX, (double)c_bck, Prob_nonAD_0};
+    // columns 29, 30 (save_mode > 1): |k_f| and the node's time, the two numbers of the final_* text
+    // file (MR.jl:689-701) that are not in the 29-column row
+    double row[ART_ROW_COLS_FULL] = {(double)e, (double)id, thf, phf, thfX, phfX, absfX, W.sln_prob, weight_tmp,
+                                     S.x[0], S.x[1], S.x[2], dOm,
+                                     n.weight, 0.0, 1.0, W.k_init[0], W.k_init[1], W.k_init[2], W.cos_w,
+                                     (double)fw.count, (double)fw.info, n.prob, n.prob_conv, n.prob_conv0,
+                                     samp_back_weight, absfX, (double)c_bck, Prob_nonAD_0, absf, n.t};
     E.rows.insert(E.rows.end(), row, row + ncols);
   }
+  // event_* line, MR.jl:593-610 (nb.x … nb.kz are the back-trace node's initial conditions: the sample
+  // point and −k_init) and 733-735 (count; the wall-clock field is not reproduced)
+  const double line[ART_EVENT_COLS] = {(double)e, S.vinf[0], S.vinf[1], S.vinf[2], W.sln_prob, S.x[0], S.x[1], S.x[2],
+                                       W.k_init[0], W.k_init[1], W.k_init[2], (double)fw.count};
+  std::memcpy(E.event_line, line, sizeof(line));
 }
 
 }  // namespace orc
@@ -553,12 +561,12 @@ int orc_propagate(const art_params* p, int64_t n, const int32_t* species, const 
 
 // main_runner_tree's event loop over e ∈ [first_event, first_event+n_events); OpenMP over
 // events (the moral equivalent of the reference's N-process replication, runner_example.sh).
-int orc_run(const art_params* p, uint64_t seed, int64_t first_event, int64_t n_events, double* rows,
-            int64_t rows_cap, int64_t* n_rows, int64_t* f_inx, int64_t* tot_count, art_stats* st) {
+int orc_run_events(const art_params* p, uint64_t seed, int64_t first_event, int64_t n_events, double* rows,
+                   int64_t rows_cap, int64_t* n_rows, int64_t* f_inx, int64_t* tot_count, art_stats* st, double* events) {
   double maxR;
   int rc = orc_max_radius(p, &maxR);
   if (rc) return rc;
-  const int ncols = p->save_mode > 0 ? ART_ROW_COLS_LONG : ART_ROW_COLS_SHORT;
+  const int ncols = p->save_mode > 1 ? ART_ROW_COLS_FULL : (p->save_mode > 0 ? ART_ROW_COLS_LONG : ART_ROW_COLS_SHORT);
   std::vector<EventOut> ev((size_t)n_events);
 #pragma omp parallel for schedule(dynamic, 1)
   for (int64_t i = 0; i < n_events; ++i) run_event(*p, maxR, seed, (uint64_t)(first_event + i), ncols, ev[(size_t)i]);
@@ -578,9 +586,17 @@ int orc_run(const art_params* p, uint64_t seed, int64_t first_event, int64_t n_e
     S.n_final_axion += E.n_final_axion;
     for (int k2 = 0; k2 < 5; ++k2) S.n_status[k2] += E.C.n_status[k2];
   }
+  if (events)
+    for (int64_t i = 0; i < n_events; ++i)
+      std::memcpy(events + i * ART_EVENT_COLS, ev[(size_t)i].event_line, sizeof(double) * ART_EVENT_COLS);
   *n_rows = nr; *f_inx = fi; *tot_count = tc;
   if (st) *st = S;
   return ART_OK;
+}
+
+int orc_run(const art_params* p, uint64_t seed, int64_t first_event, int64_t n_events, double* rows,
+            int64_t rows_cap, int64_t* n_rows, int64_t* f_inx, int64_t* tot_count, art_stats* st) {
+  return orc_run_events(p, seed, first_event, n_events, rows, rows_cap, n_rows, f_inx, tot_count, st, nullptr);
 }
 
 // step log of one ray: out[k*5 + (s, dt, EEst, accepted, event)], returns number of steps

@@ -45,6 +45,7 @@ def lib():
                                     _dp, _dp, _dp, _ip, _ip, _dp, C.c_int32, C.c_void_p]
         L.orc_run.argtypes = [PP, C.c_uint64, C.c_int64, C.c_int64, _dp, C.c_int64, C.POINTER(C.c_int64),
                               C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(ArtStats)]
+        L.orc_run_events.argtypes = L.orc_run.argtypes + [_dp]
         L.orc_philox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_sampler_uniforms.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, _dp]
         L.orc_num_threads.restype = C.c_int
@@ -129,13 +130,15 @@ def propagate(p, species, x0, k0, erg, t_start, dOmega, b_sign=1, max_crossings=
 
 
 def run(p, seed, first_event, n_events, rows_cap=None):
-    ncols = 29 if p.save_mode > 0 else 13
+    ncols = 31 if p.save_mode > 1 else (29 if p.save_mode > 0 else 13)
     cap = rows_cap or (n_events * 8 + 64)
     rows = np.zeros((cap, ncols))
+    events = np.zeros((max(n_events, 1), 12))  # ART_EVENT_COLS
     nr, fi, tc = C.c_int64(), C.c_int64(), C.c_int64()
     st = ArtStats()
-    _chk(lib().orc_run(C.byref(p), seed, first_event, n_events, rows, cap, C.byref(nr), C.byref(fi), C.byref(tc), C.byref(st)))
-    return dict(rows=rows[: nr.value].copy(), f_inx=fi.value, tot_count=tc.value, stats=st.as_dict())
+    _chk(lib().orc_run_events(C.byref(p), seed, first_event, n_events, rows, cap, C.byref(nr), C.byref(fi), C.byref(tc),
+                              C.byref(st), events))
+    return dict(rows=rows[: nr.value].copy(), f_inx=fi.value, tot_count=tc.value, stats=st.as_dict(), events=events[:n_events])
 
 
 def philox(ctr, key):

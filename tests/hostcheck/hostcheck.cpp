@@ -174,7 +174,7 @@ int hc_run(const art_params* p, uint64_t seed, int64_t first_event, int64_t n_ev
   DevParams P;
   int rc = dev(p, P);
   if (rc) return rc;
-  const int ncols = p->save_mode > 0 ? ART_ROW_COLS_LONG : ART_ROW_COLS_SHORT;
+  const int ncols = p->save_mode > 1 ? ART_ROW_COLS_FULL : (p->save_mode > 0 ? ART_ROW_COLS_LONG : ART_ROW_COLS_SHORT);
   std::vector<long long> keys((size_t)rows_cap);
   unsigned long long nr = 0, nfin[2] = {0, 0};
   RowSink S{rows, keys.data(), &nr, (unsigned long long)rows_cap, ncols, nfin};
@@ -193,7 +193,7 @@ int hc_run(const art_params* p, uint64_t seed, int64_t first_event, int64_t n_ev
     }
     SampleWeights W = sample_weights(P, R.x, R.vloc, R.vinf);
     EventData E;
-    for (int c = 0; c < 3; ++c) { E.x[c] = R.x[c]; E.k_init[c] = W.k_init[c]; }
+    for (int c = 0; c < 3; ++c) { E.x[c] = R.x[c]; E.k_init[c] = W.k_init[c]; E.vinf[c] = R.vinf[c]; }
     E.erg_inf = W.erg_inf; E.vel_eng = W.vel_eng; E.sln_prob = W.sln_prob; E.cos_w = W.cos_w;
     RayIn in;
     for (int c = 0; c < 3; ++c) { in.x0[c] = E.x[c]; in.k0[c] = -E.k_init[c]; }

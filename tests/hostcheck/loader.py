@@ -126,7 +126,7 @@ def propagate(p, species, x0, k0, erg, t_start, dOmega, b_sign=1, max_crossings=
 
 
 def run(p, seed, first_event, n_events):
-    ncols = 29 if p.save_mode > 0 else 13
+    ncols = 31 if p.save_mode > 1 else (29 if p.save_mode > 0 else 13)
     cap = n_events * 8 + 64
     rows = np.zeros((cap, ncols))
     nr, fi, tc = C.c_int64(), C.c_int64(), C.c_int64()

@@ -479,3 +479,43 @@ def test_binned_spectra_histogram_matches_numpy(lib):
     ph = r[:, 1] == 1
     assert (np.abs(r[ph, 12] + 1.0) < 3e-6).mean() > 0.5  # the chosen window holds most of the photon line
     h.close()
+
+
+def test_save_mode_2_rows_event_table_and_text_files(lib, oracle, tmp_path):
+    """saveMode 2: 31-column rows, event table and the clear-text final_* / event_* files
+    (MainRunner.jl:435-444, 593-610, 689-701) against the oracle."""
+    p = ArtParams.default(theta_m=0.2, save_mode=2, Ax_g=1e-10)
+    n = 600
+    h = lib.Handle(p, 0)
+    a = h.run(1769, 1, n)
+    ev = h.fetch_events(n)
+    h.close()
+    b = oracle.run(p, 1769, 1, n)
+    assert a["rows"].shape[1] == 31 and ev.shape == (n, 12)
+    assert np.array_equal(ev[:, 0], b["events"][:, 0])
+    assert rel(ev[:, 1:11], b["events"][:, 1:11]).max() < 1e-9          # v_inf, sln_prob, x, k_init
+    assert (ev[:, 11] == b["events"][:, 11]).mean() > 0.99              # count (tree shape, see module doc)
+    ca = np.bincount(a["rows"][:, 0].astype(int), minlength=n + 1)
+    cb = np.bincount(b["rows"][:, 0].astype(int), minlength=n + 1)
+    good = ca == cb
+    assert good[1:].mean() > 0.99
+    A = a["rows"][good[a["rows"][:, 0].astype(int)]]
+    B = b["rows"][good[b["rows"][:, 0].astype(int)]]
+    dk = rel(A[:, 29], B[:, 29])
+    assert np.median(dk) < 1e-9 and dk.max() < 2e-3
+    assert (A[:, 30] == 0).sum() == (B[:, 30] == 0).sum() and np.any(B[:, 30] > 0)
+    m = B[:, 30] > 0
+    assert np.median(rel(A[m, 30], B[m, 30])) < 1e-7
+    # the drop-in writes the files the reference writes
+    from adiabatic_raytracer_b200 import main_runner_tree
+    tot, rows, fname, out = main_runner_tree(1e-5, 1e-10, 0.2, 1.0, 1e14, 10.0, 1.0, "Simple", n + 1, [1.0, 1.0], flat=False,
+                                             melrose=True, file_tag="s2", saveMode=2, dir_tag=str(tmp_path / "res"),
+                                             iseed=1769, return_rows=True)
+    assert np.load(fname).shape == (a["rows"].shape[0], 29)
+    fin = open(tmp_path / "res" / "event" / "final_s2").read().splitlines()
+    evl = open(tmp_path / "res" / "event" / "event_s2").read().splitlines()
+    assert len(fin) == a["rows"].shape[0] and len(evl) == n
+    f0 = fin[0].split()
+    assert len(f0) == 10 and f0[0] == "1" and f0[2] in ("0", "1") and float(f0[1]) == a["rows"][0, 13]
+    e0 = evl[0].split()
+    assert len(e0) == 19 and e0[0] == "1" and float(e0[5]) == ev[0, 5] and float(e0[8]) == -ev[0, 8] and e0[-1] == str(int(ev[0, 11]))

@@ -94,3 +94,20 @@ def test_no_cpu_fallback(L):
     with pytest.raises(lib.ArtError) as e:
         lib.Handle(ArtParams.default(theta_m=0.2), 0)
     assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+
+
+def test_event_text_files_follow_the_reference_layout(L, tmp_path):
+    """saveMode > 1: <dir_tag>/event/final_<tag> and event_<tag>, MainRunner.jl:593-610, 689-701, 733-735
+    (numbers printed like Julia's string(): 1.0e-5, 0.25, integers without a decimal point)."""
+    from adiabatic_raytracer_b200 import lib
+    os.makedirs(tmp_path / "event")
+    rows = np.zeros((2, 31))
+    rows[0, [0, 1, 2, 3, 4, 5, 6, 13, 29, 30]] = [3, 1, 0.5, -1.25, 2.0, 1e-5, 299792.0, 2.5e-7, 1.0e-5, 0.0]
+    rows[1, [0, 1, 2, 3, 4, 5, 6, 13, 29, 30]] = [3, 0, 1.5, 0.125, 0.25, 3.0, 1.0e7, 0.75, 9.5e-6, 1.5e-4]
+    events = np.array([[3, 4.2e-4, 4.3e-4, 4.4e-4, 1.5e30, 10.0, -20.0, 30.5, 1e-6, -2e-6, 3e-6, 7]])
+    lib.write_event_files(str(tmp_path), "tagX", rows, events)
+    fin = open(tmp_path / "event" / "final_tagX").read().splitlines()
+    assert fin[0] == "3 2.5e-7 1 0.5 -1.25 1.0e-5 2.0 1.0e-5 299792.0 0"
+    assert fin[1] == "3 0.75 0 1.5 0.125 9.5e-6 0.25 3.0 1.0e7 0.00015"
+    ev = open(tmp_path / "event" / "event_tagX").read().splitlines()
+    assert ev == ["3 0.00042 0.00043 0.00044 1.5e30 10.0 -20.0 30.5 -1.0e-6 2.0e-6 -3.0e-6 10.0 -20.0 30.5 1.0e-6 -2.0e-6 3.0e-6 0.0 7"]
