@@ -219,7 +219,8 @@ def test_rays_against_dop853_golden(lib):
 
 @pytest.mark.parametrize("kw", [dict(theta_m=0.2, save_mode=1), dict(theta_m=0.2, save_mode=0, Ax_g=1e-10, MC_nodes=2, max_nodes=12),
                                 dict(theta_m=0.5, save_mode=1, omega_pul=2 * math.pi, Mass_a=2e-5),
-                                dict(theta_m=0.2, save_mode=1, melrose=0), dict(theta_m=0.2, thick_surface=0)])
+                                dict(theta_m=0.2, save_mode=1, melrose=0), dict(theta_m=0.2, thick_surface=0),
+                                dict(theta_m=0.2, flat=1, omega_pul=2 * math.pi)])  # last: BASELINE configs[0] (flat, P = 1 s)
 def test_fused_pipeline_matches_oracle(lib, oracle, kw):
     p = ArtParams.default(**kw)
     h = lib.Handle(p, 0)
@@ -519,3 +520,26 @@ def test_save_mode_2_rows_event_table_and_text_files(lib, oracle, tmp_path):
     assert len(f0) == 10 and f0[0] == "1" and f0[2] in ("0", "1") and float(f0[1]) == a["rows"][0, 13]
     e0 = evl[0].split()
     assert len(e0) == 19 and e0[0] == "1" and float(e0[5]) == ev[0, 5] and float(e0[8]) == -ev[0, 8] and e0[-1] == str(int(ev[0, 11]))
+
+
+def test_baseline_config0_flat_run_full_size_matches_oracle(lib, oracle):
+    """BASELINE configs[0] at full size: flat-space run, m_a=1e-5 eV, B0=1e14 G, P=1 s (rotW=2π), θm=0.2, M=1, R=10 km,
+    1e4 conversion-surface samples (Ntajs = 1e4 ⇒ 9999 events).  Per-event agreement of the tree shapes, and the
+    sky-binned photon flux (16 cosθf bins) within Monte-Carlo error."""
+    p = ArtParams.default(theta_m=0.2, flat=1, omega_pul=2 * math.pi)
+    n = 9999
+    h = lib.Handle(p, 0)
+    a = h.run(1769, 1, n)
+    h.close()
+    b = oracle.run(p, 1769, 1, n)
+    ca = np.bincount(a["rows"][:, 0].astype(int), minlength=n + 1)
+    cb = np.bincount(b["rows"][:, 0].astype(int), minlength=n + 1)
+    assert (ca == cb)[1:].mean() > 0.99
+    assert abs(a["f_inx"] - b["f_inx"]) <= 0.005 * b["f_inx"] and abs(a["tot_count"] - b["tot_count"]) <= 0.01 * b["tot_count"]
+    fa, fb = _binned(a["rows"]), _binned(b["rows"])
+    ph = b["rows"][:, 1] == 1
+    ic = np.clip(np.floor((np.cos(b["rows"][ph, 2]) + 1) * 0.5 * 16).astype(int), 0, 15)
+    var = np.zeros(16)
+    np.add.at(var, ic, (b["rows"][ph, 8] * b["rows"][ph, 7]) ** 2)
+    assert abs(fa.sum() - fb.sum()) <= 0.01 * fb.sum()
+    assert np.all(np.abs(fa - fb) <= 3.0 * np.sqrt(var) + 1e-3 * fb.sum())

@@ -113,8 +113,9 @@ def test_host_compiled_sampler_matches_oracle(oracle):
         assert np.abs(a["x"] - b["x"])[:, m].max() < 1e-10
 
 
-def test_host_compiled_pipeline_matches_oracle(oracle):
-    p = ArtParams.default(theta_m=0.2)
+@pytest.mark.parametrize("kw", [dict(theta_m=0.2), dict(theta_m=0.2, flat=1, omega_pul=2 * math.pi)])
+def test_host_compiled_pipeline_matches_oracle(oracle, kw):
+    p = ArtParams.default(**kw)
     a = hc.run(p, 1769, 1, 200)
     b = oracle.run(p, 1769, 1, 200)
     assert a["rows"].shape == b["rows"].shape
