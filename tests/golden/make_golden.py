@@ -354,11 +354,12 @@ def maxM(par):
 
 
 # ------------------------------------------------------------------------------------------
-def rays():
-    """DOP853 (rtol 1e-12) integration of func!/func_axion! from symbolic gradients."""
+def rays(ham=None, want_ph=6, want_ax=4, seed=99):
+    """DOP853 (rtol 1e-12) integration of func!/func_axion! from symbolic gradients.
+    ham: photon Hamiltonian builder (default: the Melrose form)."""
     g = metric_ext()
     gi = metric_int()
-    H = hamiltonian(g)
+    H = (ham or hamiltonian)(g)
     Hax = hamiltonian_axion(g)
     Haxi = hamiltonian_axion(gi)
     TC = thick_condition(g)
@@ -429,15 +430,15 @@ def rays():
         return np.array([rr, tt_, pp_, w0[0], w0[1], w0[2], erg * dOmega]), k0
 
     out = []
-    rng = np.random.default_rng(99)
+    rng = np.random.default_rng(seed)
     par = dict(thm=0.2, w=1.0, B0=1e14, rNS=10.0, MNS=1.0, ma=1e-5)
     erg = 1e-5 * math.sqrt(1 + (220.0 / C_KM) ** 2)
     ln0, ln1 = -30.0, math.log(1.0 / par["w"])
     n_ph, n_ax = 0, 0
     tries = 0
-    while (n_ph < 6 or n_ax < 4) and tries < 200:
+    while (n_ph < want_ph or n_ax < want_ax) and tries < 200:
         tries += 1
-        axion = n_ph >= 6
+        axion = n_ph >= want_ph
         # start on/near the conversion surface, direction roughly outward (photon) / any (axion)
         tt_ = float(0.2 + (math.pi - 0.4) * rng.random())
         pp_ = float(-math.pi + 2 * math.pi * rng.random())
@@ -486,6 +487,9 @@ def main():
     ry = rays()
     with open(os.path.join(HERE, "rays.json"), "w") as fjs:
         json.dump(ry, fjs, indent=1)
+    rn = rays(ham=hamiltonian_nonmelrose, want_ph=5, want_ax=0, seed=7)  # melrose = false photons
+    with open(os.path.join(HERE, "rays_nonmelrose.json"), "w") as fjs:
+        json.dump(rn, fjs, indent=1)
     print("pointwise", len(pw), "conv_prob", len(cp), "rays", len(ry))
 
 

@@ -163,15 +163,17 @@ def test_max_radius_matches_survey(oracle):
 
 
 @pytest.mark.parametrize("tight", [True, False])
-def test_rays_against_dop853(oracle, tight):
+@pytest.mark.parametrize("fixture", ["rays.json", "rays_nonmelrose.json"])
+def test_rays_against_dop853(oracle, tight, fixture):
     """Oracle DP5 vs scipy DOP853(rtol 1e-12) on the same ICs.  tight: oracle at reltol 1e-12 /
     abstol 1e-14 (agreement = accuracy of the restated RHS + integrator);  not tight: production
     tolerances reltol 1e-7 / abstol 1e-6 (agreement = the integrator's own truncation error,
     the level at which ANY two schemes — incl. the reference's Vern6 — differ)."""
     worst = 0.0
-    for ray in load("rays.json"):
+    for ray in load(fixture):
         par = ray["par"]
-        kw = dict(theta_m=par["thm"], omega_pul=par["w"], B0=par["B0"], rNS=par["rNS"], Mass_NS=par["MNS"], Mass_a=par["ma"])
+        kw = dict(theta_m=par["thm"], omega_pul=par["w"], B0=par["B0"], rNS=par["rNS"], Mass_NS=par["MNS"], Mass_a=par["ma"],
+                  melrose=0 if "nonmelrose" in fixture else 1)  # second fixture: photons of the melrose = false Hamiltonian
         if tight:
             kw.update(reltol=1e-12, ode_err=1e-14)
         p = ArtParams.default(**kw)
