@@ -320,10 +320,23 @@ ART_HD MetHot metric_hot(double r, double rinv, double rs, double R) {
     m.sq = A * y;
     m.isq = y;
   } else {
-    const Met g = metric(r, rs, R);
-    m.gtt = g.gtt; m.grr = g.grr; m.dgtt = g.dgtt; m.dgrr = g.dgrr;
-    m.sq = sqrt(g.grr);
-    m.isq = 1.0 / m.sq;
+    // interior branch of metric() with the branch-free reciprocal / rsqrt (axions crossing the star: a few
+    // lanes of a warp walk this path, and IEEE sqrt and division made it 12 % of the stage kernel's
+    // instructions — profiles/r01_final_lines.txt)
+    const double Rinv = frcp(R);
+    const double q = r * Rinv, q2 = q * q;
+    const double a = rs * Rinv * q2 * q;
+    const double b = a * q2;
+    const double ysa = frsqrt(1.0 - a), ysb = frsqrt(1.0 - b);
+    const double sb = (1.0 - b) * ysb;
+    const double dinv = frcp(3.0 * (1.0 - a) * ysa - sb);
+    const double dinv2 = dinv * dinv;
+    m.grr = 1.0 - b;
+    m.gtt = -4.0 * dinv2;
+    m.dgrr = -5.0 * b * rinv;
+    m.dgtt = 8.0 * (2.5 * b * ysb - 4.5 * a * ysa) * rinv * dinv2 * dinv;
+    m.sq = sb;
+    m.isq = ysb;
   }
   return m;
 }

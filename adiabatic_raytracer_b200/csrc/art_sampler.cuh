@@ -294,6 +294,9 @@ struct Sampler {
     const int M = P.M_samp;
     const bool scanning = active && !done && mode == SCAN;
     unsigned mpos = 0u, mneg = 0u, mzero = 0u;
+    bool skip = false;  // the next step starts without an event: pass over certified steps (ONE call site, at the end
+                        // of the trip — inlined at the INIT slot as well it ran for one lane at a time and made up
+                        // a tenth of the kernel's instructions, profiles/r01_final_lines.txt)
     // what this lane evaluates in the current slot: SCAN for the whole trip, or ROOT / NUDGE / INIT until the
     // attempt is ready to scan (then −1: idle until the next trip); re-derived only where the mode changes
     int md = scanning ? SCAN : ((active && !done && mode != SCAN) ? mode : -1);
@@ -363,7 +366,7 @@ struct Sampler {
       } else if (md == INIT) {
         sgn_prev = (g > 0.0) - (g < 0.0);
         next_step(P);
-        skip_certified_steps(P);
+        skip = true;  // (the lane idles for the rest of the trip: mode is SCAN now)
       }
       if (md > SCAN) md = (done || mode == SCAN) ? -1 : mode;
     }
@@ -402,9 +405,10 @@ struct Sampler {
         tau = tau_new;
         event_last = false;
         next_step(P);
-        skip_certified_steps(P);
+        skip = true;
       }
     }
+    if (skip) skip_certified_steps(P);
   }
 
   // selection of one crossing, RT.jl:1618-1640

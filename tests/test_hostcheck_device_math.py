@@ -72,6 +72,8 @@ def test_closed_form_rhs_matches_dual_number_gradients(oracle):
         u[:, 6] = -erg * (1 + 1e-6 * rng.normal(size=n))
         lnt = rng.uniform(-25, -4, n)
         for sp in (1, 0):
+            if sp == 0:
+                u[: n // 4, 0] = 1.0 + 8.9 * rng.random(n // 4)  # axions inside the star (interior metric)
             species = np.full(n, sp, np.int32)
             a = hc.rhs(p, species, u, erg, lnt)
             b = oracle.rhs(p, species, u, erg, lnt)
