@@ -41,8 +41,10 @@ namespace art {
 
 constexpr int WF_THREADS = 128;
 #ifndef ART_STAGE_MINBLOCKS
-#define ART_STAGE_MINBLOCKS 3  // resident CTAs per SM the stage kernel's register allocation is tuned for (measured per 1e6
-                               // events: 2 → 200 registers, 274 ms; 3 → 168 registers, 68 B of spills, 270 ms)
+#define ART_STAGE_MINBLOCKS 2  // resident CTAs per SM the stage kernel's register allocation is tuned for (measured per 1e6
+                               // events, tracer only — early build: 2 → 200 registers, 274 ms; 3 → 168 registers, 68 B of
+                               // spills, 270 ms; final build: 3 → 168 registers, 324 B of spills, 202.9 ms; 2 → 255
+                               // registers, no spills, 199.5 ms)
 #endif
 #ifndef ART_STAGE_NSTEP
 #define ART_STAGE_NSTEP 4      // attempted steps a ray may take inside one k_wf_stages launch
