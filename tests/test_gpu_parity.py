@@ -553,3 +553,27 @@ def test_baseline_config0_flat_run_full_size_matches_oracle(lib, oracle):
     np.add.at(var, ic, (b["rows"][ph, 8] * b["rows"][ph, 7]) ** 2)
     assert abs(fa.sum() - fb.sum()) <= 0.01 * fb.sum()
     assert np.all(np.abs(fa - fb) <= 3.0 * np.sqrt(var) + 1e-3 * fb.sum())
+
+
+def test_sub_chunked_and_multi_lane_runs_equal_the_single_chunk_run(lib, monkeypatch):
+    """A call larger than one sub-chunk (2^21 events by default — BASELINE configs 3-5 run 1e7+ events per GPU) walks
+    the events in sub-chunks, optionally on several streams; rows, counters and the event table must not depend
+    on how the call was cut."""
+    p = ArtParams.default(theta_m=0.2, save_mode=2)
+    n = 5000
+    h = lib.Handle(p, 0)
+    a = h.run(11, 1, n)
+    ea = h.fetch_events(n)
+    h.close()
+    for env in (dict(ART_SUBCHUNK="1024"), dict(ART_SUBCHUNK="1500", ART_LANES="2")):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        h = lib.Handle(p, 0)
+        b = h.run(11, 1, n)
+        eb = h.fetch_events(n)
+        h.close()
+        for k in env:
+            monkeypatch.delenv(k)
+        assert np.array_equal(a["rows"], b["rows"]) and np.array_equal(ea, eb)
+        assert a["f_inx"] == b["f_inx"] and a["tot_count"] == b["tot_count"]
+        assert b["stats"]["n_launches"] > a["stats"]["n_launches"]  # it was cut
