@@ -38,6 +38,18 @@ NS = dict(Mass_a=1e-5, Ax_g=1e-12, theta_m=0.2, omega_pul=1.0, B0=1e14, rNS=10.0
 SEED = 1769
 
 
+# from profiles/r01_final_keys.txt (ncu --set full, 1e6-event pass, final build of round 1); dram = dram__bytes_read.sum +
+# dram__bytes_write.sum of that launch; k_wf_detect is the compaction pass (hot records + sign masks in, survivor lists out)
+NCU_HARDWARE_VIEW = {
+    "source": "profiles/r01_final_keys.txt",
+    "k_sample_events": {"ms": 49.85, "fp64_pipe_pct": 43.1, "issue_pct": 56.3, "threads_per_inst": 13.2, "dram_MB": 29.3},
+    "k_wf_stages": {"ms": 1.315, "fp64_pipe_pct": 37.4, "issue_pct": 36.9, "threads_per_inst": 23.5, "dram_MB": 1015.8},
+    "k_wf_scan": {"ms": 0.778, "fp64_pipe_pct": 51.6, "issue_pct": 62.2, "threads_per_inst": 27.1, "dram_MB": 437.0},
+    "k_wf_detect": {"ms": 0.148, "fp64_pipe_pct": 3.8, "issue_pct": 11.7, "dram_MB": 527.3, "dram_GBps": 3563.0,
+                    "frac_of_measured_hbm_peak": 0.544},
+}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -287,6 +299,9 @@ def main():
         "sampler": {"achieved": agg["n_sampler_cond"] * F_SAMPLER_COND / (agg["ms_sampler"] * 1e-3) / 1e12,
                     "unit": "TFLOP/s", "cond_per_attempt": agg["n_sampler_cond"] / agg["n_attempts"]},
         "stage_ms_per_step": {k: agg[k] / args.steps for k in ("ms_sampler", "ms_weights", "ms_tracer", "ms_tree", "ms_total")},
+        # hardware view — NOT measured in this run: one `ncu --set full --clock-control none` capture of the same build
+        # and workload (sampler launch; iteration 10 of the wavefront loop), summarised in profiles/r01_final_keys.txt
+        "ncu": NCU_HARDWARE_VIEW,
     }
 
     cpu = None
