@@ -141,6 +141,8 @@ struct art_handle {
   int nranks = 1, rank = 0;
   std::atomic<long long> launches{0};  // kernels launched since the current pipeline call began
   int bulk_nstep = ART_STAGE_NSTEP;  // attempts per stage launch in the bulk (ART_BULK_NSTEP)
+  int wf_grid_per_sm = 8;         // grid cap of the wavefront kernels, CTAs per SM (ART_WF_GRID_PER_SM)
+  long long tail_below = 0;       // rays in flight below which the stage kernel switches to its tail policy (ART_TAIL_BELOW; default 256 per SM)
   int tail_nstep = 4;             // attempts per stage launch once fewer rays than one resident wave are left (ART_TAIL_NSTEP)
   int n_lanes = 1;                // concurrent sub-chunks (ART_LANES); measured: one big chunk beats overlapped small ones
   long long sub_chunk = 1 << 21;  // events per sub-chunk (ART_SUBCHUNK)
@@ -212,9 +214,9 @@ int launch_trace_wf(art_handle* h, Lane& L, const QueuedRay* q, long long n, Ray
   W.pend = L.wf_pend.as<int>();
   for (int k = 0; k < 2; ++k) { W.roots[k] = L.wf_roots[k].as<int>(); W.fin[k] = L.wf_fin[k].as<int>(); }
   W.ctr = L.wf_ctr.as<unsigned long long>();
-  const size_t ksmem = (size_t)(K_ROWS + K_PARK) * WF_THREADS * sizeof(double);
+  const size_t ksmem = (size_t)(K_ROWS + K_PARK) * STAGE_THREADS * sizeof(double);
   CU(cudaMemsetAsync(W.ctr, 0, WC_N * 8, st));
-  const int gmax = h->n_sm * 8;
+  const int gmax = h->n_sm * h->wf_grid_per_sm;
   auto grid = [&](long long work, int threads) { return (int)std::max<long long>(1, std::min<long long>(gmax, (work + threads - 1) / threads)); };
   k_wf_init<<<grid(n, WF_THREADS), WF_THREADS, 0, st>>>(h->dp, q, n, W, rec, rec_cap, stats);
   h->launches++;
@@ -227,7 +229,7 @@ int launch_trace_wf(art_handle* h, Lane& L, const QueuedRay* q, long long n, Ray
   cudaStream_t s2 = side ? L.stream2 : st;
   for (long long iter = 0;;) {
     const int burst = n_act > 500000 ? 8 : (n_act > 65536 ? 16 : 32);  // steps between host checks (deep queue: host jitter must not idle the GPU)
-    const bool tail = n_act < 8LL * h->n_sm * WF_THREADS;               // fewer rays than one resident wave
+    const bool tail = n_act < h->tail_below;                            // thin tail: any lane keeps its warp stepping
     for (int b = 0; b < burst; ++b, ++iter) {
       const int next = 1 - cur;
       const int lpar = (int)(iter & 1), lin = 1 - lpar;  // lists this iteration fills / lists of the previous one
@@ -244,8 +246,9 @@ int launch_trace_wf(art_handle* h, Lane& L, const QueuedRay* q, long long n, Ray
       else
         k_wf_collect<<<grid(n_act / 4 + 1, WF_THREADS), WF_THREADS, 0, s2>>>(h->dp, W, lin, out, stats);
       if (side) CU(cudaEventRecord(L.ev_side, s2));
-      k_wf_stages<<<2 * g1, WF_THREADS, ksmem, st>>>(h->dp, W, cur, lpar, tail ? h->tail_nstep : h->bulk_nstep, tail ? 1 : 16, stats);
-      k_wf_scan<<<grid(n_act * 11, SCAN_THREADS), SCAN_THREADS, 0, st>>>(h->dp, W, stats);
+      k_wf_stages<<<2 * grid(n_act, STAGE_THREADS), STAGE_THREADS, ksmem, st>>>(h->dp, W, cur, lpar, tail ? h->tail_nstep : h->bulk_nstep, tail ? 1 : 16, stats);
+      k_wf_scan<<<(int)std::max<long long>(1, std::min<long long>((long long)h->n_sm * (2048 / SCAN_THREADS), (n_act * 11 + SCAN_THREADS - 1) / SCAN_THREADS)),
+                  SCAN_THREADS, 0, st>>>(h->dp, W, stats);
       k_wf_detect<<<g1, WF_THREADS, 0, st>>>(h->dp, W, next, lpar);
       h->launches += 6;
       cur = next;
@@ -330,12 +333,15 @@ int art_create(const art_params* p, int device_id, art_handle** out) {
   cudaGetDeviceProperties(&prop, device_id);
   h->n_sm = prop.multiProcessorCount;
   int occ = 0;
-  cudaFuncSetAttribute(k_wf_stages, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((K_ROWS + K_PARK) * WF_THREADS * sizeof(double)));
+  cudaFuncSetAttribute(k_wf_stages, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((K_ROWS + K_PARK) * STAGE_THREADS * sizeof(double)));
   cudaFuncSetAttribute(k_wf_stages, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sample_events, SAMPLE_THREADS, 0);
   h->blocks_sample = h->n_sm * std::max(occ, 1);
   if (const char* t = getenv("ART_BULK_NSTEP")) h->bulk_nstep = std::max(1, atoi(t));
   if (const char* t = getenv("ART_TAIL_NSTEP")) h->tail_nstep = std::max(1, atoi(t));
+  if (const char* t = getenv("ART_WF_GRID_PER_SM")) h->wf_grid_per_sm = std::max(1, atoi(t));
+  h->tail_below = 256LL * h->n_sm;
+  if (const char* t = getenv("ART_TAIL_BELOW")) h->tail_below = std::max(0LL, atoll(t));
   if (const char* t = getenv("ART_LANES")) h->n_lanes = std::max(1, std::min(16, atoi(t)));
   if (const char* t = getenv("ART_SUBCHUNK")) h->sub_chunk = std::max(1024LL, atoll(t));
   ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);

@@ -39,12 +39,23 @@
 
 namespace art {
 
-constexpr int WF_THREADS = 128;
+#ifndef ART_WF_THREADS
+#define ART_WF_THREADS 32   // threads per CTA of the init / detect / root / tree kernels (tracer per 1e6 events with
+                            // one-warp stage CTAs: 256 threads 207.6 ms, 128 195.3, 64 188.2, 32 185.3)
+#endif
+constexpr int WF_THREADS = ART_WF_THREADS;
+// The stage kernel runs ONE WARP per CTA: a CTA retires as soon as its warp is through, so a warp whose rays take all
+// their attempts does not hold the slots of three finished ones.  Measured per 1e6 events (tracer, 255 registers, 8 warps
+// per SM in every case): 256 threads x 1 CTA 221 ms, 128 x 2 199 ms, 64 x 4 189 ms, 32 x 8 185 ms.
+#ifndef ART_STAGE_THREADS
+#define ART_STAGE_THREADS 32
+#endif
+constexpr int STAGE_THREADS = ART_STAGE_THREADS;
 #ifndef ART_STAGE_MINBLOCKS
-#define ART_STAGE_MINBLOCKS 2  // resident CTAs per SM the stage kernel's register allocation is tuned for (measured per 1e6
-                               // events, tracer only — early build: 2 → 200 registers, 274 ms; 3 → 168 registers, 68 B of
-                               // spills, 270 ms; final build: 3 → 168 registers, 324 B of spills, 202.9 ms; 2 → 255
-                               // registers, no spills, 199.5 ms)
+#define ART_STAGE_MINBLOCKS 8  // resident CTAs per SM the stage kernel's register allocation is tuned for: 8 warps per SM,
+                               // 255 registers, no spills (128-thread CTAs, tracer per 1e6 events — early build: 2 CTAs,
+                               // 200 registers, 274 ms; 3 CTAs, 168 registers, 68 B of spills, 270 ms; final build: 3 CTAs,
+                               // 168 registers, 324 B of spills, 202.9 ms; 2 CTAs, 255 registers, no spills, 199.5 ms)
 #endif
 #ifndef ART_STAGE_NSTEP
 #define ART_STAGE_NSTEP 4      // attempted steps a ray may take inside one k_wf_stages launch
@@ -187,7 +198,7 @@ template <int SP>
 __device__ __forceinline__ void wf_stages_body(const DevParams& P, const WfPool& W, int cur, int lpar, int nstep, int min_go,
                                                unsigned bid, unsigned nblocks, double* ksm, DevStats* stats) {
   unsigned long long n_full = 0;  // condition evaluations done here (end points of in-box steps)
-  const KStoreT<WF_THREADS> K{ksm + threadIdx.x};
+  const KStoreT<STAGE_THREADS> K{ksm + threadIdx.x};
   const int next = 1 - cur;
   const long long n = (long long)W.ctr[WC_ACT + cur * 2 + SP];
   const int* __restrict__ act = cur ? W.act[1][SP] : W.act[0][SP];  // (a dynamic index would copy the parameter struct to local memory)
@@ -284,7 +295,7 @@ __device__ __forceinline__ void wf_stages_body(const DevParams& P, const WfPool&
 // One launch steps both species: the first half of the grid walks the axion list, the second half the
 // photon list (a warp never executes both right-hand sides; in the thin tail of a batch the two lists
 // are stepped concurrently instead of one launch after the other).
-__global__ void __launch_bounds__(WF_THREADS, ART_STAGE_MINBLOCKS)
+__global__ void __launch_bounds__(STAGE_THREADS, ART_STAGE_MINBLOCKS)
 k_wf_stages(const __grid_constant__ DevParams P, WfPool W, int cur, int lpar, int nstep, int min_go, DevStats* stats) {
   extern __shared__ double ksm[];
   const unsigned half = gridDim.x >> 1;
@@ -300,7 +311,10 @@ k_wf_stages(const __grid_constant__ DevParams P, WfPool W, int cur, int lpar, in
 // evaluate the condition together; three ballots per round turn the signs into the bit masks k_wf_detect
 // works on.  No per-ray work list, no per-point sign bytes: each segment is read once (staged in shared
 // memory) and 24 bytes of masks are written per step.
-constexpr int SCAN_THREADS = 256;
+#ifndef ART_SCAN_THREADS
+#define ART_SCAN_THREADS 256
+#endif
+constexpr int SCAN_THREADS = ART_SCAN_THREADS;
 #ifndef ART_SCAN_PACK
 #define ART_SCAN_PACK 3
 #endif

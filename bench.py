@@ -160,12 +160,30 @@ def run_reference(args):
         "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's original stdout; everything else printed on fd 1 while the bench runs
+    (NCCL's version banner, library chatter) is diverted to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
     args = parse()
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -333,7 +351,7 @@ def main():
             "cpu_baseline": cpu,
             "clocks": clk,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     host_rows = None
