@@ -141,6 +141,7 @@ struct art_handle {
   int nranks = 1, rank = 0;
   std::atomic<long long> launches{0};  // kernels launched since the current pipeline call began
   int bulk_nstep = ART_STAGE_NSTEP;  // attempts per stage launch in the bulk (ART_BULK_NSTEP)
+  int stage_grid_per_sm = 8;      // … of each species half of the stage kernel's grid (ART_STAGE_GRID_PER_SM)
   int wf_grid_per_sm = 8;         // grid cap of the wavefront kernels, CTAs per SM (ART_WF_GRID_PER_SM)
   long long tail_below = 0;       // rays in flight below which the stage kernel switches to its tail policy (ART_TAIL_BELOW; default 256 per SM)
   int tail_nstep = 4;             // attempts per stage launch once fewer rays than one resident wave are left (ART_TAIL_NSTEP)
@@ -246,7 +247,8 @@ int launch_trace_wf(art_handle* h, Lane& L, const QueuedRay* q, long long n, Ray
       else
         k_wf_collect<<<grid(n_act / 4 + 1, WF_THREADS), WF_THREADS, 0, s2>>>(h->dp, W, lin, out, stats);
       if (side) CU(cudaEventRecord(L.ev_side, s2));
-      k_wf_stages<<<2 * grid(n_act, STAGE_THREADS), STAGE_THREADS, ksmem, st>>>(h->dp, W, cur, lpar, tail ? h->tail_nstep : h->bulk_nstep, tail ? 1 : 16, stats);
+      const int gs = (int)std::max<long long>(1, std::min<long long>((long long)h->n_sm * h->stage_grid_per_sm, (n_act + STAGE_THREADS - 1) / STAGE_THREADS));
+      k_wf_stages<<<2 * gs, STAGE_THREADS, ksmem, st>>>(h->dp, W, cur, lpar, tail ? h->tail_nstep : h->bulk_nstep, tail ? 1 : 16, stats);
       k_wf_scan<<<(int)std::max<long long>(1, std::min<long long>((long long)h->n_sm * (2048 / SCAN_THREADS), (n_act * 11 + SCAN_THREADS - 1) / SCAN_THREADS)),
                   SCAN_THREADS, 0, st>>>(h->dp, W, stats);
       k_wf_detect<<<g1, WF_THREADS, 0, st>>>(h->dp, W, next, lpar);
@@ -340,6 +342,7 @@ int art_create(const art_params* p, int device_id, art_handle** out) {
   if (const char* t = getenv("ART_BULK_NSTEP")) h->bulk_nstep = std::max(1, atoi(t));
   if (const char* t = getenv("ART_TAIL_NSTEP")) h->tail_nstep = std::max(1, atoi(t));
   if (const char* t = getenv("ART_WF_GRID_PER_SM")) h->wf_grid_per_sm = std::max(1, atoi(t));
+  if (const char* t = getenv("ART_STAGE_GRID_PER_SM")) h->stage_grid_per_sm = std::max(1, atoi(t));
   h->tail_below = 256LL * h->n_sm;
   if (const char* t = getenv("ART_TAIL_BELOW")) h->tail_below = std::max(0LL, atoll(t));
   if (const char* t = getenv("ART_LANES")) h->n_lanes = std::max(1, std::min(16, atoi(t)));

@@ -295,7 +295,12 @@ __device__ __forceinline__ void wf_stages_body(const DevParams& P, const WfPool&
 // One launch steps both species: the first half of the grid walks the axion list, the second half the
 // photon list (a warp never executes both right-hand sides; in the thin tail of a batch the two lists
 // are stepped concurrently instead of one launch after the other).
+#ifdef ART_STAGE_MAXNREG  // tuning: an explicit register cap instead of the cap implied by the resident-CTA count (tracer per
+                          // 1e6 events: 224 registers / 9 warps 187.9 ms, 200 / 10 190.2, 184 / 11 190.3; 255 / 8: 185.3)
+__global__ void __maxnreg__(ART_STAGE_MAXNREG)
+#else
 __global__ void __launch_bounds__(STAGE_THREADS, ART_STAGE_MINBLOCKS)
+#endif
 k_wf_stages(const __grid_constant__ DevParams P, WfPool W, int cur, int lpar, int nstep, int min_go, DevStats* stats) {
   extern __shared__ double ksm[];
   const unsigned half = gridDim.x >> 1;
