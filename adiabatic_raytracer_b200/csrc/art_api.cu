@@ -141,6 +141,11 @@ struct art_handle {
   int nranks = 1, rank = 0;
   std::atomic<long long> launches{0};  // kernels launched since the current pipeline call began
   int bulk_nstep = ART_STAGE_NSTEP;  // attempts per stage launch in the bulk (ART_BULK_NSTEP)
+  int scan_grid_per_sm = ART_SCAN_MINBLOCKS;  // grid of the scan kernel = one resident wave (ART_SCAN_GRID_PER_SM; tracer per 1e6
+                                  // events: 3 CTAs per SM 182.6 ms, 6 183.4, 8 185.3, 12 185.7, 24 189.0)
+  int detect_grid_per_sm = 24;    // grid cap of the detect kernel (HBM-latency bound, 80 registers: 24 one-warp CTAs per SM are
+                                  // one resident wave; ART_DETECT_GRID_PER_SM; tracer per 1e6 events: 4 → 189.5 ms, 8 → 183.2,
+                                  // 16 → 181.8, 24 → 181.8, 48 → 180.5)
   int stage_grid_per_sm = 8;      // … of each species half of the stage kernel's grid (ART_STAGE_GRID_PER_SM)
   int wf_grid_per_sm = 8;         // grid cap of the wavefront kernels, CTAs per SM (ART_WF_GRID_PER_SM)
   long long tail_below = 0;       // rays in flight below which the stage kernel switches to its tail policy (ART_TAIL_BELOW; default 256 per SM)
@@ -234,7 +239,6 @@ int launch_trace_wf(art_handle* h, Lane& L, const QueuedRay* q, long long n, Ray
     for (int b = 0; b < burst; ++b, ++iter) {
       const int next = 1 - cur;
       const int lpar = (int)(iter & 1), lin = 1 - lpar;  // lists this iteration fills / lists of the previous one
-      const int g1 = grid(n_act, WF_THREADS);
       // main stream: the side stream's previous pass must be through before its lists are zeroed
       if (side) CU(cudaStreamWaitEvent(st, L.ev_side, 0));
       k_wf_reset<<<1, 32, 0, st>>>(W, next, lpar);
@@ -249,9 +253,10 @@ int launch_trace_wf(art_handle* h, Lane& L, const QueuedRay* q, long long n, Ray
       if (side) CU(cudaEventRecord(L.ev_side, s2));
       const int gs = (int)std::max<long long>(1, std::min<long long>((long long)h->n_sm * h->stage_grid_per_sm, (n_act + STAGE_THREADS - 1) / STAGE_THREADS));
       k_wf_stages<<<2 * gs, STAGE_THREADS, ksmem, st>>>(h->dp, W, cur, lpar, tail ? h->tail_nstep : h->bulk_nstep, tail ? 1 : 16, stats);
-      k_wf_scan<<<(int)std::max<long long>(1, std::min<long long>((long long)h->n_sm * (2048 / SCAN_THREADS), (n_act * 11 + SCAN_THREADS - 1) / SCAN_THREADS)),
+      k_wf_scan<<<(int)std::max<long long>(1, std::min<long long>((long long)h->n_sm * h->scan_grid_per_sm, (n_act * 11 + SCAN_THREADS - 1) / SCAN_THREADS)),
                   SCAN_THREADS, 0, st>>>(h->dp, W, stats);
-      k_wf_detect<<<g1, WF_THREADS, 0, st>>>(h->dp, W, next, lpar);
+      k_wf_detect<<<(int)std::max<long long>(1, std::min<long long>((long long)h->n_sm * h->detect_grid_per_sm, (n_act + WF_THREADS - 1) / WF_THREADS)),
+                    WF_THREADS, 0, st>>>(h->dp, W, next, lpar);
       h->launches += 6;
       cur = next;
     }
@@ -342,6 +347,8 @@ int art_create(const art_params* p, int device_id, art_handle** out) {
   if (const char* t = getenv("ART_BULK_NSTEP")) h->bulk_nstep = std::max(1, atoi(t));
   if (const char* t = getenv("ART_TAIL_NSTEP")) h->tail_nstep = std::max(1, atoi(t));
   if (const char* t = getenv("ART_WF_GRID_PER_SM")) h->wf_grid_per_sm = std::max(1, atoi(t));
+  if (const char* t = getenv("ART_SCAN_GRID_PER_SM")) h->scan_grid_per_sm = std::max(1, atoi(t));
+  if (const char* t = getenv("ART_DETECT_GRID_PER_SM")) h->detect_grid_per_sm = std::max(1, atoi(t));
   if (const char* t = getenv("ART_STAGE_GRID_PER_SM")) h->stage_grid_per_sm = std::max(1, atoi(t));
   h->tail_below = 256LL * h->n_sm;
   if (const char* t = getenv("ART_TAIL_BELOW")) h->tail_below = std::max(0LL, atoll(t));
