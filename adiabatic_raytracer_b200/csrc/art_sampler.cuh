@@ -119,6 +119,7 @@ struct Sampler {
     // NrmSq < 0 (E below the local mass shell): the reference would throw; NaN = "no crossing"
     if (gn < 0.0) gn = NAN;
     const double base = ww * D * E2;
+    if (P.isotropic) N = 0.0;  // `if iso kpar = 0.0`, RT.jl:1573-1574 (gn stays in the product: its NaN must survive)
     return Pq * (base - gn * N * N) - P.ma2 * base;
   }
 

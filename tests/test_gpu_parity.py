@@ -72,7 +72,8 @@ def test_rhs_matches_oracle(lib, oracle):
 
 def test_sampler_from_uniforms_matches_oracle(lib, oracle):
     rng = np.random.default_rng(11)
-    for kw in (dict(theta_m=0.2), dict(theta_m=1.1, Mass_a=2e-5, B0=2e14, omega_pul=3.0), dict(theta_m=0.2, thick_surface=0)):
+    for kw in (dict(theta_m=0.2), dict(theta_m=1.1, Mass_a=2e-5, B0=2e14, omega_pul=3.0), dict(theta_m=0.2, thick_surface=0),
+               dict(theta_m=0.2, isotropic=1)):
         p = ArtParams.default(**kw)
         h = lib.Handle(p, 0)
         U = rng.random((6000, 10))
@@ -221,7 +222,8 @@ def test_rays_against_dop853_golden(lib, fixture):
 @pytest.mark.parametrize("kw", [dict(theta_m=0.2, save_mode=1), dict(theta_m=0.2, save_mode=0, Ax_g=1e-10, MC_nodes=2, max_nodes=12),
                                 dict(theta_m=0.5, save_mode=1, omega_pul=2 * math.pi, Mass_a=2e-5),
                                 dict(theta_m=0.2, save_mode=1, melrose=0), dict(theta_m=0.2, thick_surface=0),
-                                dict(theta_m=0.2, flat=1, omega_pul=2 * math.pi)])  # last: BASELINE configs[0] (flat, P = 1 s)
+                                dict(theta_m=0.2, flat=1, omega_pul=2 * math.pi),   # BASELINE configs[0] (flat, P = 1 s)
+                                dict(theta_m=0.2, isotropic=1), dict(theta_m=0.2, flat=1, isotropic=1, melrose=0, thick_surface=0)])
 def test_fused_pipeline_matches_oracle(lib, oracle, kw):
     p = ArtParams.default(**kw)
     h = lib.Handle(p, 0)

@@ -143,3 +143,33 @@ def test_save_mode_2_rows_match_oracle(oracle):
     first = {int(e): r for e, r in reversed(list(zip(b["rows"][:, 0], b["rows"])))}
     for e, r in first.items():
         assert np.array_equal(ev[e - 1, 5:8], r[9:12]) and np.array_equal(ev[e - 1, 8:11], r[16:19]) and ev[e - 1, 11] == r[20]
+
+
+_SWITCHES = [dict(theta_m=0.2, flat=f, isotropic=i, melrose=m, thick_surface=t)
+             for f in (0, 1) for i in (0, 1) for m in (0, 1) for t in (0, 1)]
+_OTHERS = [dict(theta_m=1.8), dict(theta_m=2.9, omega_pul=3.0), dict(theta_m=0.2, Mass_NS=1.4, rNS=12.0),
+           dict(theta_m=0.5, Mass_a=2e-6), dict(theta_m=0.2, Ax_g=3e-10, MC_nodes=1, max_nodes=8, num_cutoff=2),
+           dict(theta_m=0.2, Ax_g=1e-9, prob_cutoff=1e-3), dict(theta_m=0.0), dict(theta_m=0.2, n_maxSample=8),
+           dict(theta_m=0.2, n_maxSample=1), dict(theta_m=0.2, save_mode=1, B0=5e13, omega_pul=2 * math.pi),
+           dict(theta_m=0.2, fix_time=0.3, t0_sample=0.3), dict(theta_m=0.2, ode_err=1e-8, reltol=1e-9)]
+
+
+@pytest.mark.parametrize("kw", _SWITCHES + _OTHERS, ids=lambda kw: ",".join(f"{k}={v}" for k, v in kw.items() if k != "theta_m" or len(kw) == 1))
+def test_switch_matrix_pipeline_matches_oracle(oracle, kw):
+    """Every combination of main_runner_tree's physics switches (flat × isotropic × melrose × thick_surface) and a
+    spread of the other knobs: the host-compiled device pipeline against the oracle, event by event."""
+    p = ArtParams.default(**kw)
+    n = 120
+    a = hc.run(p, 1769, 1, n)
+    b = oracle.run(p, 1769, 1, n)
+    ca = np.bincount(a["rows"][:, 0].astype(int), minlength=n + 1)
+    cb = np.bincount(b["rows"][:, 0].astype(int), minlength=n + 1)
+    assert (ca == cb)[1:].mean() >= 0.98
+    assert abs(a["f_inx"] - b["f_inx"]) <= 0.02 * b["f_inx"] + 2
+    assert abs(a["tot_count"] - b["tot_count"]) <= 0.03 * b["tot_count"] + 2
+    good = ca == cb
+    A = a["rows"][good[a["rows"][:, 0].astype(int)]]
+    B = b["rows"][good[b["rows"][:, 0].astype(int)]]
+    assert np.array_equal(A[:, :2], B[:, :2])
+    assert np.max(np.abs(A[:, 7] - B[:, 7]) / B[:, 7]) < 1e-9      # sln_prob
+    assert np.max(np.abs(A[:, 9:12] - B[:, 9:12])) < 1e-9          # sample point
