@@ -25,6 +25,7 @@ inline int make_dev_params(const art_params& p, DevParams& d, std::string& err) 
     return ART_ERR_ARG;
   }
   if (p.max_nodes < 1 || p.max_nodes > 250 || p.interp_points_ray < 2 || p.interp_points_ray > 64 || p.interp_points_sampler < 2 ||
+      p.interp_points_sampler > 32 ||  // (sign masks of one scanned step: 64-bit words in the tracer, 32-bit in the sampler)
       p.cross_cap < 1 || p.cross_cap > 64 || !(p.reltol > 0) || !(p.ode_err > 0) || !(p.sampler_dt > 0)) {
     err = "numerics parameter out of range";
     return ART_ERR_ARG;

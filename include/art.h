@@ -99,8 +99,8 @@ typedef struct art_params {
   int32_t save_mode;     /* 0 → 13-column rows, 1 → 29-column rows (MR.jl:714-721), 2 → 31 columns + event table
                             (clear-text final_* / event_* files, MR.jl:435-444, 593-610, 689-701); 3 (one tree_* file
                             per event with the sampled trajectories, MR.jl:17-65) is not supported */
-  int32_t interp_points_ray;     /* ContinuousCallback interp_points, RT.jl:357 = 50        */
-  int32_t interp_points_sampler; /* RT.jl:1599 = 20                                         */
+  int32_t interp_points_ray;     /* ContinuousCallback interp_points, RT.jl:357 = 50; 2..64  */
+  int32_t interp_points_sampler; /* RT.jl:1599 = 20; 2..32                                  */
   int32_t maxiters;      /* RT.jl:384 = 1e5                                                 */
   int32_t cross_cap;     /* capacity of the per-ray crossing record list in the fused
                             pipeline (the reference's list is unbounded; overflow is
