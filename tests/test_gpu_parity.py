@@ -579,3 +579,31 @@ def test_sub_chunked_and_multi_lane_runs_equal_the_single_chunk_run(lib, monkeyp
         assert np.array_equal(a["rows"], b["rows"]) and np.array_equal(ea, eb)
         assert a["f_inx"] == b["f_inx"] and a["tot_count"] == b["tot_count"]
         assert b["stats"]["n_launches"] > a["stats"]["n_launches"]  # it was cut
+
+
+def _switch_cases():
+    from tests.test_hostcheck_device_math import _OTHERS, _SWITCHES
+    return _SWITCHES + _OTHERS
+
+
+@pytest.mark.parametrize("kw", _switch_cases(), ids=lambda kw: ",".join(f"{k}={v}" for k, v in kw.items() if k != "theta_m" or len(kw) == 1))
+def test_switch_matrix_gpu_pipeline_matches_oracle(lib, oracle, kw):
+    """flat × isotropic × melrose × thick_surface and a spread of the other knobs through art_run, event by event."""
+    p = ArtParams.default(**kw)
+    n = 300
+    h = lib.Handle(p, 0)
+    a = h.run(1769, 1, n)
+    h.close()
+    b = oracle.run(p, 1769, 1, n)
+    ca = np.bincount(a["rows"][:, 0].astype(int), minlength=n + 1)
+    cb = np.bincount(b["rows"][:, 0].astype(int), minlength=n + 1)
+    assert (ca == cb)[1:].mean() >= 0.98
+    assert abs(a["f_inx"] - b["f_inx"]) <= 0.02 * b["f_inx"] + 2
+    assert abs(a["tot_count"] - b["tot_count"]) <= 0.03 * b["tot_count"] + 2
+    good = ca == cb
+    A = a["rows"][good[a["rows"][:, 0].astype(int)]]
+    B = b["rows"][good[b["rows"][:, 0].astype(int)]]
+    assert np.array_equal(A[:, :2], B[:, :2])
+    assert rel(A[:, 7], B[:, 7]).max() < 1e-9 and np.abs(A[:, 9:12] - B[:, 9:12]).max() < 1e-9
+    ph = B[:, 1] == 1
+    assert np.median(np.abs(A[ph, 2] - B[ph, 2])) < 1e-7
