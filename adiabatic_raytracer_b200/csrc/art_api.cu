@@ -149,6 +149,7 @@ struct art_handle {
   int stage_grid_per_sm = 8;      // … of each species half of the stage kernel's grid (ART_STAGE_GRID_PER_SM)
   int wf_grid_per_sm = 8;         // grid cap of the wavefront kernels, CTAs per SM (ART_WF_GRID_PER_SM)
   long long tail_below = 0;       // rays in flight below which the stage kernel switches to its tail policy (ART_TAIL_BELOW; default 256 per SM)
+  int bulk_min_go = 16;           // a warp goes on to its next attempt while this many lanes can (ART_BULK_MIN_GO)
   int tail_nstep = 4;             // attempts per stage launch once fewer rays than one resident wave are left (ART_TAIL_NSTEP)
   int n_lanes = 1;                // concurrent sub-chunks (ART_LANES); measured: one big chunk beats overlapped small ones
   long long sub_chunk = 1 << 21;  // events per sub-chunk (ART_SUBCHUNK)
@@ -252,7 +253,7 @@ int launch_trace_wf(art_handle* h, Lane& L, const QueuedRay* q, long long n, Ray
         k_wf_collect<<<grid(n_act / 4 + 1, WF_THREADS), WF_THREADS, 0, s2>>>(h->dp, W, lin, out, stats);
       if (side) CU(cudaEventRecord(L.ev_side, s2));
       const int gs = (int)std::max<long long>(1, std::min<long long>((long long)h->n_sm * h->stage_grid_per_sm, (n_act + STAGE_THREADS - 1) / STAGE_THREADS));
-      k_wf_stages<<<2 * gs, STAGE_THREADS, ksmem, st>>>(h->dp, W, cur, lpar, tail ? h->tail_nstep : h->bulk_nstep, tail ? 1 : 16, stats);
+      k_wf_stages<<<2 * gs, STAGE_THREADS, ksmem, st>>>(h->dp, W, cur, lpar, tail ? h->tail_nstep : h->bulk_nstep, tail ? 1 : h->bulk_min_go, stats);
       k_wf_scan<<<(int)std::max<long long>(1, std::min<long long>((long long)h->n_sm * h->scan_grid_per_sm, (n_act * 11 + SCAN_THREADS - 1) / SCAN_THREADS)),
                   SCAN_THREADS, 0, st>>>(h->dp, W, stats);
       k_wf_detect<<<(int)std::max<long long>(1, std::min<long long>((long long)h->n_sm * h->detect_grid_per_sm, (n_act + WF_THREADS - 1) / WF_THREADS)),
@@ -346,6 +347,7 @@ int art_create(const art_params* p, int device_id, art_handle** out) {
   h->blocks_sample = h->n_sm * std::max(occ, 1);
   if (const char* t = getenv("ART_BULK_NSTEP")) h->bulk_nstep = std::max(1, atoi(t));
   if (const char* t = getenv("ART_TAIL_NSTEP")) h->tail_nstep = std::max(1, atoi(t));
+  if (const char* t = getenv("ART_BULK_MIN_GO")) h->bulk_min_go = std::max(1, std::min(32, atoi(t)));
   if (const char* t = getenv("ART_WF_GRID_PER_SM")) h->wf_grid_per_sm = std::max(1, atoi(t));
   if (const char* t = getenv("ART_SCAN_GRID_PER_SM")) h->scan_grid_per_sm = std::max(1, atoi(t));
   if (const char* t = getenv("ART_DETECT_GRID_PER_SM")) h->detect_grid_per_sm = std::max(1, atoi(t));
