@@ -106,9 +106,17 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def use_all_host_threads():
+    """The CPU arms run on every host core this process may use: torchrun exports OMP_NUM_THREADS=1 to its workers, which
+    would time the OpenMP oracle on ONE core.  Must run before the oracle library (libgomp) is first loaded."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = os.environ.get("ART_CPU_THREADS", str(n))
+
+
 def cpu_baseline(seconds, events_hint=None):
     """Oracle (CPU port of the reference path, OpenMP over events) on a bounded sample of the SAME
     workload; rays-to-observer per second on the host cores of this box."""
+    use_all_host_threads()
     from adiabatic_raytracer_b200.params import ArtParams
     from oracle import loader as oracle
     p = ArtParams.default(**NS)
@@ -135,6 +143,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    use_all_host_threads()
     from adiabatic_raytracer_b200.params import ArtParams
     from oracle import loader as oracle
     p = ArtParams.default(**NS)
