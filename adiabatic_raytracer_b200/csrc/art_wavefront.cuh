@@ -428,12 +428,23 @@ k_wf_detect(const __grid_constant__ DevParams P, WfPool W, int next, int lpar) {
   const long long n = (long long)W.ctr[WC_PEND];
   const long long nthreads = (long long)gridDim.x * blockDim.x;
   const long long nround = ((n + nthreads - 1) / nthreads) * nthreads;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nround; t += nthreads) {
+  // (the id of this thread's next trip is kept in flight and that ray's hot record and sign masks are pulled into L2
+  // while the current ray is being looked at: the kernel waits on HBM, long scoreboard 41 cycles per issue)
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  int id_next = t < n ? W.pend[t] : -1;
+  for (; t < nround; t += nthreads) {
     const bool valid = t < n;
     bool to_root = false, done = false, axion = false;
-    int id = -1;
+    int id = id_next;
+    id_next = t + nthreads < n ? W.pend[t + nthreads] : -1;
+    if (id_next >= 0) {
+      const char* nx = (const char*)(W.hot + id_next);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 128));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(W.mpos + id_next));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(W.mneg + id_next));
+    }
     if (valid) {
-      id = W.pend[t];
       Ray R;
       static_cast<RayHot&>(R) = W.hot[id];
       axion = R.axion;
