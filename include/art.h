@@ -198,8 +198,8 @@ int art_rhs(art_handle* h, int64_t n, const int32_t* species, const double* u,
 /* ---- fused pipeline: the body of main_runner_tree's event loop (MR.jl:450-747) --------- */
 
 /* Runs events e ∈ [first_event, first_event + n_events): sampling, weights, back-trace,
- * forward tree, row assembly.  rows: row-major n_rows × ncols (ncols = 13 or 29 by
- * save_mode) into caller memory of rows_cap rows; column 0 is the event id e (the
+ * forward tree, row assembly.  rows: row-major n_rows × ncols (ncols = 13, 29 or 31 by
+ * save_mode: ART_ROW_COLS_SHORT / _LONG / _FULL) into caller memory of rows_cap rows; column 0 is the event id e (the
  * reference numbers events photon_trajs = 1,2,…), column 7 (sln_prob) is NOT yet divided by
  * f_inx — that normalisation needs the global count (MR.jl:749): use art_normalize_rows.
  * f_inx = failed sampler attempts + final photon rows of these events (MR.jl:469,477,713).
