@@ -342,7 +342,14 @@ def conversion_prob_cases():
         vloc_ = mp.sqrt(wE**2 - maM**2) / wE
         pref = wE**4 * stB**2 / (ctB**2 * wp**2 * (wp**2 - 2 * wE**2) + wE**4)
         Prob = mp.pi / 2 * pref * (mp.mpf(par["Ax_g"]) * mp.mpf(10) ** -9 * Bmag) ** 2 / (abs(vhat) * vloc_ * cK * hB)
-        cases.append(dict(par=par, x=[float(v) for v in x], v_loc=[float(v) for v in vloc], v_inf=[float(v) for v in vinf],
+        # isotropic switch (MR.jl:82-85: cosθ_B := 0, sinθ_B := 1; RT.jl:1420-1422: ∇E = ∇ω with ω = √(kmag² + ωp²),
+        # omega_function's iso branch RT.jl:578-579)
+        om_iso = mp.sqrt(kmag**2 + wp**2)
+        dE_iso = [wp * dwp[j] / om_iso for j in range(3)]
+        vhat_iso = sdot([k / kmag for k in ks], dE_iso)
+        Prob_iso = mp.pi / 2 * (mp.mpf(par["Ax_g"]) * mp.mpf(10) ** -9 * Bmag) ** 2 / (abs(vhat_iso) * vloc_ * cK * hB)
+        cases.append(dict(P_nonAD_iso=float(Prob_iso),
+                          par=par, x=[float(v) for v in x], v_loc=[float(v) for v in vloc], v_inf=[float(v) for v in vinf],
                           k_init=[float(v) for v in k_init], erg_inf=float(erg_inf), vel_eng=float(vel_eng),
                           cos_w=float(cos_w), jac_gr=float(jac), sln_prob_over_maxR2=float(sln_over_maxR2),
                           P_nonAD=float(Prob)))

@@ -153,6 +153,10 @@ def test_golden_conversion_probability(lib):
         P = h.conv_prob(x, np.array(c["k_init"]).reshape(3, 1), [c["erg_inf"]], 1 if par["B0"] > 0 else -1)[0]
         assert rel(P, c["P_nonAD"]) < 1e-9
         h.close()
+        h = lib.Handle(p.copy(isotropic=1), 0)  # isotropic switch (MR.jl:82-85, RT.jl:1420-1422)
+        P = h.conv_prob(x, np.array(c["k_init"]).reshape(3, 1), [c["erg_inf"]], 1 if par["B0"] > 0 else -1)[0]
+        assert rel(P, c["P_nonAD_iso"]) < 1e-9
+        h.close()
 
 
 def _ray_inputs(oracle, p, n, seed=5):

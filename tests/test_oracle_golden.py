@@ -152,6 +152,9 @@ def test_weights_and_conversion_probability(oracle):
         assert rel(W["sln_prob"][0], c["sln_prob_over_maxR2"] * maxR**2) < 1e-10
         P = oracle.conv_prob(p, x, np.array(c["k_init"]).reshape(3, 1), [c["erg_inf"]], b_sign)[0]
         assert rel(P, c["P_nonAD"]) < 1e-9, (P, c["P_nonAD"])
+        # isotropic switch (MR.jl:82-85, RT.jl:1420-1422)
+        Pi = oracle.conv_prob(p.copy(isotropic=1), x, np.array(c["k_init"]).reshape(3, 1), [c["erg_inf"]], b_sign)[0]
+        assert rel(Pi, c["P_nonAD_iso"]) < 1e-9, (Pi, c["P_nonAD_iso"])
 
 
 def test_max_radius_matches_survey(oracle):
