@@ -240,6 +240,9 @@ def conversion_prob_cases():
     d_c = [[sp.diff(comps[i], v) for v in X] for i in range(3)]
     OM = omega_function(g)
     d_om = [sp.diff(OM, v) for v in X]
+    # omega_function's iso branch, RT.jl:578-579: ω = √(g^ij k_i k_j + ωp²)
+    OM_iso = sp.sqrt(g[1] * kr**2 + g[2] * kth**2 + g[3] * kph**2 + WP**2)
+    d_om_iso = [lam(sp.diff(OM_iso, v), "mpmath") for v in X]
     f = dict(
         g=[lam(x, "mpmath") for x in g], wp=lam(WP, "mpmath"), Bcov=[lam(x, "mpmath") for x in Bcov],
         d_wp=[lam(x, "mpmath") for x in d_wp], d_B=[lam(x, "mpmath") for x in d_B],
@@ -303,6 +306,8 @@ def conversion_prob_cases():
         go = [fn(*argsk) for fn in f["d_om"]]
         nrm = mp.sqrt(sdot(go, go))
         cos_w = abs(sdot([k / kmag for k in ks], [x_ / nrm for x_ in go]))
+        go_i = [fn(*argsk) for fn in d_om_iso]
+        cos_w_iso = abs(sdot([k / kmag for k in ks], [x_ / mp.sqrt(sdot(go_i, go_i)) for x_ in go_i]))
         # g_det, RT.jl:743-753
         dwp = [fn(*args) for fn in f["d_wp"]]
         dr_th, dr_p = dwp[1] / dwp[0], dwp[2] / dwp[0]
@@ -348,7 +353,7 @@ def conversion_prob_cases():
         dE_iso = [wp * dwp[j] / om_iso for j in range(3)]
         vhat_iso = sdot([k / kmag for k in ks], dE_iso)
         Prob_iso = mp.pi / 2 * (mp.mpf(par["Ax_g"]) * mp.mpf(10) ** -9 * Bmag) ** 2 / (abs(vhat_iso) * vloc_ * cK * hB)
-        cases.append(dict(P_nonAD_iso=float(Prob_iso),
+        cases.append(dict(P_nonAD_iso=float(Prob_iso), cos_w_iso=float(cos_w_iso),
                           par=par, x=[float(v) for v in x], v_loc=[float(v) for v in vloc], v_inf=[float(v) for v in vinf],
                           k_init=[float(v) for v in k_init], erg_inf=float(erg_inf), vel_eng=float(vel_eng),
                           cos_w=float(cos_w), jac_gr=float(jac), sln_prob_over_maxR2=float(sln_over_maxR2),

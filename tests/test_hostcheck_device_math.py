@@ -145,6 +145,21 @@ def test_save_mode_2_rows_match_oracle(oracle):
         assert np.array_equal(ev[e - 1, 5:8], r[9:12]) and np.array_equal(ev[e - 1, 8:11], r[16:19]) and ev[e - 1, 11] == r[20]
 
 
+def test_isotropic_weights_and_conversion_probability_against_golden():
+    """Host-compiled device code in isotropic mode against the sympy/mpmath fixture (MR.jl:82-85, RT.jl:578-579, 1420-1422)."""
+    import json
+    import os
+    for c in json.load(open(os.path.join(os.path.dirname(__file__), "golden", "conv_prob.json"))):
+        par = c["par"]
+        p = ArtParams.default(theta_m=par["thm"], omega_pul=par["w"], B0=abs(par["B0"]), rNS=par["rNS"], Mass_NS=par["MNS"],
+                              Mass_a=par["ma"], Ax_g=par["Ax_g"], rho_DM=par["rho_DM"], n_maxSample=par["n_max"], isotropic=1)
+        x, vl, vi = (np.array(c[k]).reshape(3, 1) for k in ("x", "v_loc", "v_inf"))
+        W = hc.weights(p, x, vl, vi)
+        assert abs(W["cos_w"][0] - c["cos_w_iso"]) < 1e-10 * c["cos_w_iso"]
+        P = hc.conv_prob(p, x, np.array(c["k_init"]).reshape(3, 1), [c["erg_inf"]], 1 if par["B0"] > 0 else -1)[0]
+        assert abs(P - c["P_nonAD_iso"]) < 1e-9 * c["P_nonAD_iso"]
+
+
 _SWITCHES = [dict(theta_m=0.2, flat=f, isotropic=i, melrose=m, thick_surface=t)
              for f in (0, 1) for i in (0, 1) for m in (0, 1) for t in (0, 1)]
 _OTHERS = [dict(theta_m=1.8), dict(theta_m=2.9, omega_pul=3.0), dict(theta_m=0.2, Mass_NS=1.4, rNS=12.0),

@@ -155,6 +155,8 @@ def test_weights_and_conversion_probability(oracle):
         # isotropic switch (MR.jl:82-85, RT.jl:1420-1422)
         Pi = oracle.conv_prob(p.copy(isotropic=1), x, np.array(c["k_init"]).reshape(3, 1), [c["erg_inf"]], b_sign)[0]
         assert rel(Pi, c["P_nonAD_iso"]) < 1e-9, (Pi, c["P_nonAD_iso"])
+        Wi = oracle.weights(p.copy(isotropic=1), x, vl, vi)  # cos_w from omega_function's iso branch, RT.jl:578-579
+        assert rel(Wi["cos_w"][0], c["cos_w_iso"]) < 1e-10
 
 
 def test_max_radius_matches_survey(oracle):
