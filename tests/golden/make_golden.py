@@ -224,6 +224,23 @@ def pointwise_nonmelrose():
     return pts
 
 
+def pointwise_flat():
+    """func!'s Hamiltonian in "flat" mode (RT.jl:77-79: Mass_NS = 0 inside the right-hand side): H and its 7 partials,
+    Melrose and non-Melrose forms, at the argument points of pointwise.json with M_NS = 0."""
+    g = metric_ext()
+    out = []
+    forms = {"melrose": hamiltonian(g), "nonmelrose": hamiltonian_nonmelrose(g)}
+    fns = {name: {k: lam(v, "mpmath") for k, v in
+                  {"H": H, "dH_dr": sp.diff(H, r), "dH_dth": sp.diff(H, th), "dH_dph": sp.diff(H, ph), "dH_dkr": sp.diff(H, kr),
+                   "dH_dkth": sp.diff(H, kth), "dH_dkph": sp.diff(H, kph), "dH_dt": sp.diff(H, t)}.items()}
+           for name, H in forms.items()}
+    for case in json.load(open(os.path.join(HERE, "pointwise.json"))):
+        a = list(case["args"])
+        a[12] = 0.0  # M_NS
+        out.append(dict(args=a, **{name: {k: fnum(f(*mpf_args(a))) for k, f in fd.items()} for name, fd in fns.items()}))
+    return out
+
+
 # ------------------------------------------------------------------------------------------
 def conversion_prob_cases():
     """get_Prob_nonAD + conversion_prob (MR.jl:67-124, RT.jl:1405-1473) and the per-sample
@@ -493,6 +510,9 @@ def main():
     nm = pointwise_nonmelrose()
     with open(os.path.join(HERE, "pointwise_nonmelrose.json"), "w") as fjs:
         json.dump(nm, fjs, indent=1)
+    pf = pointwise_flat()
+    with open(os.path.join(HERE, "pointwise_flat.json"), "w") as fjs:
+        json.dump(pf, fjs, indent=1)
     cp = conversion_prob_cases()
     with open(os.path.join(HERE, "conv_prob.json"), "w") as fjs:
         json.dump(cp, fjs, indent=1)

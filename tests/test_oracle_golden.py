@@ -114,6 +114,32 @@ def test_nonmelrose_hamiltonian_against_symbolic_gradients(oracle):
     assert n_checked >= 6
 
 
+@pytest.mark.parametrize("form", ["melrose", "nonmelrose"])
+def test_flat_mode_rhs_against_symbolic_gradients(oracle, form):
+    """flat = true: func! evaluates the Hamiltonian with Mass_NS = 0 (RT.jl:77-79) — BASELINE configs[0]'s ray equations."""
+    from tests.hostcheck import loader as hc
+    n_checked = 0
+    for case in load("pointwise_flat.json"):
+        a, o = case["args"], case[form]
+        if a[6] <= 0:
+            continue
+        p = ArtParams.default(theta_m=a[8], omega_pul=a[9], B0=a[10], rNS=a[11], Mass_NS=1.0, Mass_a=a[13], flat=1,
+                              melrose=1 if form == "melrose" else 0)
+        erg = 1.0e-5
+        t, om = a[6], a[7]
+        u = np.array([[a[0], a[1], a[2], a[3] / erg, a[4] / erg, a[5] / erg, -om]])
+        f = c_km * t / om  # g^rr = 1
+        exp = [o["dH_dkr"] * f, o["dH_dkth"] * f, o["dH_dkph"] * f, -o["dH_dr"] * f / erg, -o["dH_dth"] * f / erg,
+               -o["dH_dph"] * f / erg, o["dH_dt"] * t / om]
+        scale_x = max(abs(e) for e in exp[:3])
+        for which, du in (("oracle", oracle.rhs(p, [1], u, [erg], [math.log(t)])[0]),
+                          ("device code on the host", hc.rhs(p, np.array([1], np.int32), u, [erg], [math.log(t)])[0])):
+            for i in range(7):
+                assert abs(du[i] - exp[i]) <= 1e-10 * max(abs(exp[i]), 1e-3 * scale_x if i < 3 else 0.0) + 1e-300, (which, i, du[i], exp[i])
+        n_checked += 1
+    assert n_checked >= 6
+
+
 def test_invariant_u7_tracks_u6(oracle):
     """∂H/∂t = -Ω ∂H/∂φ (the field depends on t only through ψ = φ - Ωt, RT.jl:1142), hence
     du7 = (Ω·erg/c_km)·du6 — the identity the CUDA kernel exploits."""
