@@ -383,9 +383,12 @@ def maxM(par):
 
 
 # ------------------------------------------------------------------------------------------
-def rays(ham=None, want_ph=6, want_ax=4, seed=99):
+def rays(ham=None, want_ph=6, want_ax=4, seed=99, flat=False):
     """DOP853 (rtol 1e-12) integration of func!/func_axion! from symbolic gradients.
-    ham: photon Hamiltonian builder (default: the Melrose form)."""
+    ham: photon Hamiltonian builder (default: the Melrose form).
+    flat: propagate's mixed "flat" mode — k_norm_Cart keeps the star's mass (RT.jl:181,185 are called before
+    `if flat Mass_NS = 0`, RT.jl:187-189), the initial celerity, the right-hand side (RT.jl:77-79) and the crossing
+    condition (closure over the zeroed Mass_NS) use M = 0."""
     g = metric_ext()
     gi = metric_int()
     H = (ham or hamiltonian)(g)
@@ -401,7 +404,7 @@ def rays(ham=None, want_ph=6, want_ax=4, seed=99):
     tc = num(TC)
 
     def make_rhs(par, erg, axion):
-        P = (par["thm"], par["w"], par["B0"], par["rNS"], par["MNS"], par["ma"])
+        P = (par["thm"], par["w"], par["B0"], par["rNS"], 0.0 if flat else par["MNS"], par["ma"])
 
         def f(lnt, u):
             tt = math.exp(lnt)
@@ -444,7 +447,7 @@ def rays(ham=None, want_ph=6, want_ax=4, seed=99):
         rs = 2 * par["MNS"] * GNEW / C_KM**2
         AA = 1 - rs / rr
 
-        def cel(kv):
+        def cel(kv, AA=AA):
             dr = float(np.dot(x0, kv)) / rr
             st = math.sin(tt_)
             v1 = (x0[2] * dr - rr * kv[2]) / (rr * st)
@@ -455,7 +458,7 @@ def rays(ham=None, want_ph=6, want_ax=4, seed=99):
         wv = cel(khat)
         NrmSq = (-erg**2 * gtt - par["ma"] ** 2) / (wv[0] ** 2 * grr + wv[1] ** 2 / rr**2 + wv[2] ** 2 / (rr * math.sin(tt_)) ** 2)
         k0 = math.sqrt(NrmSq) * np.asarray(khat)
-        w0 = cel(k0) / erg
+        w0 = (cel(k0, 1.0) if flat else cel(k0)) / erg
         return np.array([rr, tt_, pp_, w0[0], w0[1], w0[2], erg * dOmega]), k0
 
     out = []
@@ -477,7 +480,7 @@ def rays(ham=None, want_ph=6, want_ax=4, seed=99):
         d /= np.linalg.norm(d)
         if not axion and np.dot(d, x0) < 0:
             d = -d
-        u0, k0 = initial_state(par, x0, d * 0.3, erg, -1.0)
+        u0, k0 = initial_state(par, x0, d * 0.3, erg, -1.0, flat)
         f, cond = make_rhs(par, erg, axion)
         ev = lambda s, u: cond(s, u)
         sol = solve_ivp(f, (ln0, ln1), u0, method="DOP853", rtol=1e-12, atol=1e-16, events=ev, dense_output=False)
@@ -519,6 +522,9 @@ def main():
     ry = rays()
     with open(os.path.join(HERE, "rays.json"), "w") as fjs:
         json.dump(ry, fjs, indent=1)
+    rf = rays(want_ph=5, want_ax=0, seed=11, flat=True)  # flat = true photons (BASELINE configs[0])
+    with open(os.path.join(HERE, "rays_flat.json"), "w") as fjs:
+        json.dump(rf, fjs, indent=1)
     rn = rays(ham=hamiltonian_nonmelrose, want_ph=5, want_ax=0, seed=7)  # melrose = false photons
     with open(os.path.join(HERE, "rays_nonmelrose.json"), "w") as fjs:
         json.dump(rn, fjs, indent=1)

@@ -200,14 +200,16 @@ def test_propagate_matches_oracle(lib, oracle, kw):
     h.close()
 
 
-@pytest.mark.parametrize("fixture", ["rays.json", "rays_nonmelrose.json"])
+@pytest.mark.parametrize("fixture", ["rays.json", "rays_nonmelrose.json", "rays_flat.json"])
 def test_rays_against_dop853_golden(lib, fixture):
-    """GPU integrator at tight tolerance vs scipy DOP853(rtol 1e-12) fixtures (second fixture: melrose = false)."""
+    """GPU integrator at tight tolerance vs scipy DOP853(rtol 1e-12) fixtures (second fixture: melrose = false; third:
+    flat = true)."""
     worst = 0.0
     for ray in json.load(open(os.path.join(G, fixture))):
         par = ray["par"]
         p = ArtParams.default(theta_m=par["thm"], omega_pul=par["w"], B0=par["B0"], rNS=par["rNS"], Mass_NS=par["MNS"],
-                              Mass_a=par["ma"], reltol=1e-12, ode_err=1e-14, melrose=0 if "nonmelrose" in fixture else 1)
+                              Mass_a=par["ma"], reltol=1e-12, ode_err=1e-14, melrose=0 if "nonmelrose" in fixture else 1,
+                              flat=1 if "flat" in fixture else 0)
         h = lib.Handle(p, 0)
         R = h.propagate([ray["species"]], np.array(ray["x0"]).reshape(3, 1), np.array(ray["khat"]).reshape(3, 1),
                         [ray["erg"]], [0.0], [ray["dOmega"]], 1, 100000, 16)

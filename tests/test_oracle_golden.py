@@ -194,7 +194,7 @@ def test_max_radius_matches_survey(oracle):
 
 
 @pytest.mark.parametrize("tight", [True, False])
-@pytest.mark.parametrize("fixture", ["rays.json", "rays_nonmelrose.json"])
+@pytest.mark.parametrize("fixture", ["rays.json", "rays_nonmelrose.json", "rays_flat.json"])
 def test_rays_against_dop853(oracle, tight, fixture):
     """Oracle DP5 vs scipy DOP853(rtol 1e-12) on the same ICs.  tight: oracle at reltol 1e-12 /
     abstol 1e-14 (agreement = accuracy of the restated RHS + integrator);  not tight: production
@@ -204,7 +204,8 @@ def test_rays_against_dop853(oracle, tight, fixture):
     for ray in load(fixture):
         par = ray["par"]
         kw = dict(theta_m=par["thm"], omega_pul=par["w"], B0=par["B0"], rNS=par["rNS"], Mass_NS=par["MNS"], Mass_a=par["ma"],
-                  melrose=0 if "nonmelrose" in fixture else 1)  # second fixture: photons of the melrose = false Hamiltonian
+                  melrose=0 if "nonmelrose" in fixture else 1,  # second fixture: photons of the melrose = false Hamiltonian
+                  flat=1 if "flat" in fixture else 0)           # third: propagate's mixed "flat" mode (BASELINE configs[0])
         if tight:
             kw.update(reltol=1e-12, ode_err=1e-14)
         p = ArtParams.default(**kw)
