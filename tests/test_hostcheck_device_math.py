@@ -188,3 +188,24 @@ def test_switch_matrix_pipeline_matches_oracle(oracle, kw):
     assert np.array_equal(A[:, :2], B[:, :2])
     assert np.max(np.abs(A[:, 7] - B[:, 7]) / B[:, 7]) < 1e-9      # sln_prob
     assert np.max(np.abs(A[:, 9:12] - B[:, 9:12])) < 1e-9          # sample point
+
+
+@pytest.mark.parametrize("fixture", ["rays.json", "rays_nonmelrose.json", "rays_flat.json"])
+def test_host_compiled_tracer_against_dop853_fixtures(fixture):
+    """The product's stepper, dense output and right-hand sides (compiled for the host) at tight tolerance against scipy
+    DOP853 at rtol 1e-12 on the symbolic ray equations — no oracle in between."""
+    import json
+    import os
+    worst = 0.0
+    for ray in json.load(open(os.path.join(os.path.dirname(__file__), "golden", fixture))):
+        par = ray["par"]
+        p = ArtParams.default(theta_m=par["thm"], omega_pul=par["w"], B0=par["B0"], rNS=par["rNS"], Mass_NS=par["MNS"],
+                              Mass_a=par["ma"], reltol=1e-12, ode_err=1e-14, melrose=0 if "nonmelrose" in fixture else 1,
+                              flat=1 if "flat" in fixture else 0)
+        R = hc.propagate(p, np.array([ray["species"]], np.int32), np.array(ray["x0"]).reshape(3, 1),
+                         np.array(ray["khat"]).reshape(3, 1), [ray["erg"]], [0.0], [ray["dOmega"]], 1, 100000)
+        uf = np.array(ray["uf"])
+        xg = uf[0] * np.array([math.sin(uf[1]) * math.cos(uf[2]), math.sin(uf[1]) * math.sin(uf[2]), math.cos(uf[1])])
+        worst = max(worst, np.linalg.norm(R["x_f"][:, 0] - xg) / np.linalg.norm(xg))
+        assert abs(R["u7_f"][0] - uf[6]) <= 1e-9 * abs(uf[6])
+    assert worst < 1e-8
