@@ -506,7 +506,64 @@ def rays(ham=None, want_ph=6, want_ax=4, seed=99, flat=False):
     return out
 
 
+def sampler_thin_cases(n_lines=14, seed=2024):
+    """find_samples_new with thick_surface = false (RT.jl:1480-1653), restated independently of oracle/: the line of an
+    attempt from its uniforms (1486-1497, 1521-1529, 1542), Find_Conversion_Surface's radius (1250-1263), the thin
+    condition log ωp − log m_a (1548-1551) solved for ALL its roots on τ ∈ (0, 2.2 maxR) by a dense scan + brentq at
+    1e-15, and affect!'s filter (1585-1597).  Lines whose roots are closer than 0.1 km to each other or to the end
+    points are skipped: there the 20-point sampling of the 0.5-km Euler steps decides which roots are seen."""
+    from scipy.optimize import brentq
+    K2 = 4.0 * math.pi / 137.0 / 5.0e5 * (1.95e-2 * HBAR / math.sqrt(4.0 * math.pi / 137.0))  # RT.jl:1153-1154
+
+    def omega_p_cart(x, par):  # GJ_Model_ωp_vec, RT.jl:1066-1103 at t = 0
+        rr = math.sqrt(x[0] ** 2 + x[1] ** 2 + x[2] ** 2)
+        phi_, th_ = math.atan2(x[1], x[0]), math.acos(x[2] / rr)
+        Bn = par["B0"] * (par["rNS"] / rr) ** 3 / 2
+        Br = 2 * Bn * (math.cos(par["thm"]) * math.cos(th_) + math.sin(par["thm"]) * math.sin(th_) * math.cos(phi_))
+        Bt = Bn * (math.cos(par["thm"]) * math.sin(th_) - math.sin(par["thm"]) * math.cos(th_) * math.cos(phi_))
+        Bz = Br * math.cos(th_) - Bt * math.sin(th_)
+        return math.sqrt(K2 * abs(2.0 * par["w"] * Bz))  # nelec = |2ΩB_z|·…, ωp = √(4π nelec/137/5e5), RT.jl:1089-1090
+
+    rng = np.random.default_rng(seed)
+    out = []
+    par = dict(thm=0.2, w=1.0, B0=1e14, rNS=10.0, MNS=1.0, ma=1e-5, n_max=6)
+    ths = par["thm"] / 2.0  # Find_Conversion_Surface, RT.jl:1250-1263
+    maxR = 1.01 * par["rNS"] * (omega_p_cart([par["rNS"] * math.sin(ths), 0.0, par["rNS"] * math.cos(ths)], par) / par["ma"]) ** (2.0 / 3.0)
+    while len(out) < n_lines:
+        U = rng.random(10)
+        thi, phi = math.acos(1 - 2 * U[0]), 2 * math.pi * U[1]
+        phR, rR = 2 * math.pi * U[4], math.sqrt(U[5]) * maxR
+        va = np.array([math.sin(thi) * math.cos(phi), math.sin(thi) * math.sin(phi), math.cos(thi)])
+        x1, x2 = rR * math.cos(phR), rR * math.sin(phR)
+        x0 = np.array([x1 * math.cos(-phi) * math.cos(-thi) + x2 * math.sin(-phi), x2 * math.cos(-phi) - x1 * math.sin(-phi) * math.cos(-thi),
+                       x1 * math.sin(-thi)]) - 1.1 * maxR * va
+        vI = (220.0 + U[6:9] * 1e-5) / math.sqrt(3.0)
+        vmag = float(np.linalg.norm(vI))
+        erg_inf = par["ma"] * math.sqrt(1 + (vmag / C_KM / math.sqrt(1 - (vmag / C_KM) ** 2)) ** 2)
+        f = lambda tau: math.log(omega_p_cart(x0 + tau * va, par)) - math.log(par["ma"])
+        T = 2.2 * maxR
+        taus = np.arange(0.0, T, 0.004)
+        vals = np.array([f(tq) for tq in taus])
+        roots = [brentq(f, taus[i], taus[i + 1], xtol=1e-15, rtol=8.9e-16) for i in range(len(taus) - 1) if vals[i] * vals[i + 1] < 0]
+        if len(roots) == 0 or min(np.diff([0.0] + roots + [T])) < 0.1:
+            continue
+        kept = []
+        for tq in roots:  # affect!, RT.jl:1585-1597
+            xq = x0 + tq * va
+            rq = float(np.linalg.norm(xq))
+            grr = 1.0 - 2.0 * GNEW * par["MNS"] / C_KM**2 / rq
+            if rq > par["rNS"] and erg_inf / math.sqrt(grr) > omega_p_cart(xq, par):
+                kept.append([float(v) for v in xq])
+        if not kept:
+            continue
+        out.append(dict(par=par, maxR=maxR, U=[float(u) for u in U], crossings=kept))
+    return out
+
+
 def main():
+    st = sampler_thin_cases()
+    with open(os.path.join(HERE, "sampler_thin.json"), "w") as fjs:
+        json.dump(st, fjs, indent=1)
     pw = pointwise()
     with open(os.path.join(HERE, "pointwise.json"), "w") as fjs:
         json.dump(pw, fjs, indent=1)

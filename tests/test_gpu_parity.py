@@ -613,3 +613,19 @@ def test_switch_matrix_gpu_pipeline_matches_oracle(lib, oracle, kw):
     assert rel(A[:, 7], B[:, 7]).max() < 1e-9 and np.abs(A[:, 9:12] - B[:, 9:12]).max() < 1e-9
     ph = B[:, 1] == 1
     assert np.median(np.abs(A[ph, 2] - B[ph, 2])) < 1e-7
+
+
+def test_thin_surface_sampler_against_independent_root_solve(lib):
+    """art_sample_from_uniforms with thick_surface = false against the numpy/scipy fixture (tests/golden/sampler_thin.json)."""
+    from tests.test_oracle_golden import _thin_sampler_check
+    handles = {}
+
+    def sampler(p, U):
+        key = bytes(p)
+        if key not in handles:
+            handles[key] = lib.Handle(p, 0)
+        return handles[key].sample_from_uniforms(U)
+
+    _thin_sampler_check(sampler)
+    for h in handles.values():
+        h.close()

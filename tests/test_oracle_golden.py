@@ -229,3 +229,37 @@ def test_rays_against_dop853(oracle, tight, fixture):
             for gc, c in zip(got, gold):
                 assert abs(math.log(gc[6]) - c["lnt"]) < 1e-7
     assert worst < (1e-8 if tight else 1e-3), worst  # measured: 2e-4 (radial), 7e-5 (angles)
+
+
+def _thin_sampler_check(sampler):
+    """Every crossing of every fixture line, selected through the tenth uniform (randInx = 1 + floor(u·n_max), RT.jl:1623)."""
+    cases = load("sampler_thin.json")
+    par = cases[0]["par"]
+    p = ArtParams.default(theta_m=par["thm"], omega_pul=par["w"], B0=par["B0"], rNS=par["rNS"], Mass_NS=par["MNS"],
+                          Mass_a=par["ma"], n_maxSample=par["n_max"], thick_surface=0)
+    n_checked = 0
+    for c in cases:
+        nc = len(c["crossings"])
+        for j in range(par["n_max"]):
+            U = np.array(c["U"])
+            U[9] = (j + 0.5) / par["n_max"]
+            o = sampler(p, U.reshape(1, 10))
+            assert o["n_cross"][0] == nc
+            assert o["accepted"][0] == (1 if j < nc else 0)     # RT.jl:1628-1632
+            if j < nc:
+                assert np.abs(o["x"][:, 0] - np.array(c["crossings"][j])).max() < 1e-11
+                n_checked += 1
+    assert n_checked >= 28
+    return p, cases
+
+
+def test_thin_surface_sampler_against_independent_root_solve(oracle):
+    """find_samples_new with thick_surface = false: line construction, crossing roots, affect!'s filter and the index draw
+    against a numpy/scipy restatement that shares no code with oracle/ (tests/golden/make_golden.py: sampler_thin_cases)."""
+    p, cases = _thin_sampler_check(oracle.sample_from_uniforms)
+    assert rel(oracle.max_radius(p)[1], cases[0]["maxR"]) < 1e-14
+
+
+def test_thin_surface_sampler_device_code_against_independent_root_solve():
+    from tests.hostcheck import loader as hc
+    _thin_sampler_check(hc.sample_from_uniforms)
