@@ -506,7 +506,14 @@ def rays(ham=None, want_ph=6, want_ax=4, seed=99, flat=False):
     return out
 
 
-def sampler_thin_cases(n_lines=14, seed=2024):
+def sampler_cases(thick, n_lines=14, seed=2024):
+    """The same for the default thick_surface = true condition (RT.jl:1552-1581: celerity of the local velocity direction,
+    axion mass shell, K_par with the covariant dipole field, the AA = 1 quirk inside the star, g_schwartz's interior
+    branch below 10 km)."""
+    return sampler_thin_cases(n_lines, seed, thick)
+
+
+def sampler_thin_cases(n_lines=14, seed=2024, thick_mode=False):
     """find_samples_new with thick_surface = false (RT.jl:1480-1653), restated independently of oracle/: the line of an
     attempt from its uniforms (1486-1497, 1521-1529, 1542), Find_Conversion_Surface's radius (1250-1263), the thin
     condition log ωp − log m_a (1548-1551) solved for ALL its roots on τ ∈ (0, 2.2 maxR) by a dense scan + brentq at
@@ -540,7 +547,42 @@ def sampler_thin_cases(n_lines=14, seed=2024):
         vI = (220.0 + U[6:9] * 1e-5) / math.sqrt(3.0)
         vmag = float(np.linalg.norm(vI))
         erg_inf = par["ma"] * math.sqrt(1 + (vmag / C_KM / math.sqrt(1 - (vmag / C_KM) ** 2)) ** 2)
-        f = lambda tau: math.log(omega_p_cart(x0 + tau * va, par)) - math.log(par["ma"])
+        thl, phl = math.acos(1 - 2 * U[2]), 2 * math.pi * U[3]
+        vl = np.array([math.sin(thl) * math.cos(phl), math.sin(thl) * math.sin(phl), math.cos(thl)])  # vvec_loc, RT.jl:1524
+
+        def g_schwartz(rq, thq, R=10.0):  # RT.jl:455-501 (interior branch below the hard-wired 10 km)
+            rs = 2 * GNEW * par["MNS"] / C_KM**2
+            if rq <= R:
+                rs *= (rq / R) ** 3
+                return (-4 / (3 * math.sqrt(1 - rs / R) - math.sqrt(1 - rq**2 * rs / R**3)) ** 2, 1 - rq**2 * rs / R**3,
+                        1 / rq**2, 1 / (rq * math.sin(thq)) ** 2)
+            return -1 / (1 - rs / rq), 1 - rs / rq, 1 / rq**2, 1 / (rq * math.sin(thq)) ** 2
+
+        def thick(tau):  # condition, RT.jl:1552-1581
+            u = x0 + tau * va
+            rq = float(np.linalg.norm(u))
+            thq, phq = math.acos(u[2] / rq), math.atan2(u[1], u[0])
+            AA = 1.0 - 2 * GNEW * par["MNS"] / C_KM**2 / rq
+            if rq < par["rNS"]:
+                AA = 1.0
+            dr = float(np.dot(u, vl)) / rq
+            st = math.sin(thq)
+            v0 = [dr, (u[2] * dr - rq * vl[2]) / (rq * st), (-u[1] * vl[0] + u[0] * vl[1]) / (rq * st)]
+            w = np.array([v0[0] / math.sqrt(AA), v0[1] / rq * rq**2, v0[2] / (rq * st) * (rq * st) ** 2]) / AA
+            gtt, grr, gth, gpp = g_schwartz(rq, thq)
+            NrmSq = (-erg_inf**2 * gtt - par["ma"] ** 2) / (w[0] ** 2 * grr + w[1] ** 2 * gth + w[2] ** 2 * gpp)
+            w = w * math.sqrt(NrmSq)
+            omP = omega_p_cart(u, par)
+            Bn = par["B0"] * (par["rNS"] / rq) ** 3 / 2  # K_par, RT.jl:1044-1058 with GJ_Model_Sphereical's covariant B (1298)
+            Bs = [2 * Bn * (math.cos(par["thm"]) * math.cos(thq) + math.sin(par["thm"]) * st * math.cos(phq)) / math.sqrt(grr),
+                  Bn * (math.cos(par["thm"]) * st - math.sin(par["thm"]) * math.cos(thq) * math.cos(phq)) / math.sqrt(gth),
+                  Bn * math.sin(par["thm"]) * math.sin(phq) / math.sqrt(gpp)]
+            Bmag = math.sqrt(grr * Bs[0] ** 2 + gth * Bs[1] ** 2 + gpp * Bs[2] ** 2)
+            kpar = (grr * w[0] * Bs[0] + gth * w[1] * Bs[1] + gpp * w[2] * Bs[2]) / Bmag
+            ksqr = gtt * erg_inf**2 + grr * w[0] ** 2 + gth * w[1] ** 2 + gpp * w[2] ** 2
+            return 0.5 * (ksqr + omP**2 * (erg_inf**2 / grr - kpar**2) / (erg_inf**2 / grr)) / erg_inf**2
+
+        f = thick if thick_mode else (lambda tau: math.log(omega_p_cart(x0 + tau * va, par)) - math.log(par["ma"]))
         T = 2.2 * maxR
         taus = np.arange(0.0, T, 0.004)
         vals = np.array([f(tq) for tq in taus])
@@ -564,6 +606,9 @@ def main():
     st = sampler_thin_cases()
     with open(os.path.join(HERE, "sampler_thin.json"), "w") as fjs:
         json.dump(st, fjs, indent=1)
+    sk = sampler_cases(True, seed=2025)
+    with open(os.path.join(HERE, "sampler_thick.json"), "w") as fjs:
+        json.dump(sk, fjs, indent=1)
     pw = pointwise()
     with open(os.path.join(HERE, "pointwise.json"), "w") as fjs:
         json.dump(pw, fjs, indent=1)

@@ -615,9 +615,10 @@ def test_switch_matrix_gpu_pipeline_matches_oracle(lib, oracle, kw):
     assert np.median(np.abs(A[ph, 2] - B[ph, 2])) < 1e-7
 
 
-def test_thin_surface_sampler_against_independent_root_solve(lib):
-    """art_sample_from_uniforms with thick_surface = false against the numpy/scipy fixture (tests/golden/sampler_thin.json)."""
-    from tests.test_oracle_golden import _thin_sampler_check
+@pytest.mark.parametrize("thick", [False, True], ids=["thin", "thick"])
+def test_sampler_against_independent_root_solve(lib, thick):
+    """art_sample_from_uniforms, both surface conditions, against the numpy/scipy fixtures (tests/golden/sampler_*.json)."""
+    from tests.test_oracle_golden import _sampler_check
     handles = {}
 
     def sampler(p, U):
@@ -626,6 +627,6 @@ def test_thin_surface_sampler_against_independent_root_solve(lib):
             handles[key] = lib.Handle(p, 0)
         return handles[key].sample_from_uniforms(U)
 
-    _thin_sampler_check(sampler)
+    _sampler_check(sampler, thick)
     for h in handles.values():
         h.close()

@@ -231,12 +231,12 @@ def test_rays_against_dop853(oracle, tight, fixture):
     assert worst < (1e-8 if tight else 1e-3), worst  # measured: 2e-4 (radial), 7e-5 (angles)
 
 
-def _thin_sampler_check(sampler):
+def _sampler_check(sampler, thick):
     """Every crossing of every fixture line, selected through the tenth uniform (randInx = 1 + floor(u·n_max), RT.jl:1623)."""
-    cases = load("sampler_thin.json")
+    cases = load("sampler_thick.json" if thick else "sampler_thin.json")
     par = cases[0]["par"]
     p = ArtParams.default(theta_m=par["thm"], omega_pul=par["w"], B0=par["B0"], rNS=par["rNS"], Mass_NS=par["MNS"],
-                          Mass_a=par["ma"], n_maxSample=par["n_max"], thick_surface=0)
+                          Mass_a=par["ma"], n_maxSample=par["n_max"], thick_surface=1 if thick else 0)
     n_checked = 0
     for c in cases:
         nc = len(c["crossings"])
@@ -253,13 +253,15 @@ def _thin_sampler_check(sampler):
     return p, cases
 
 
-def test_thin_surface_sampler_against_independent_root_solve(oracle):
-    """find_samples_new with thick_surface = false: line construction, crossing roots, affect!'s filter and the index draw
-    against a numpy/scipy restatement that shares no code with oracle/ (tests/golden/make_golden.py: sampler_thin_cases)."""
-    p, cases = _thin_sampler_check(oracle.sample_from_uniforms)
+@pytest.mark.parametrize("thick", [False, True], ids=["thin", "thick"])
+def test_sampler_against_independent_root_solve(oracle, thick):
+    """find_samples_new, both surface conditions: line construction, crossing roots, affect!'s filter and the index draw
+    against a numpy/scipy restatement that shares no code with oracle/ (tests/golden/make_golden.py: sampler_*_cases)."""
+    p, cases = _sampler_check(oracle.sample_from_uniforms, thick)
     assert rel(oracle.max_radius(p)[1], cases[0]["maxR"]) < 1e-14
 
 
-def test_thin_surface_sampler_device_code_against_independent_root_solve():
+@pytest.mark.parametrize("thick", [False, True], ids=["thin", "thick"])
+def test_sampler_device_code_against_independent_root_solve(thick):
     from tests.hostcheck import loader as hc
-    _thin_sampler_check(hc.sample_from_uniforms)
+    _sampler_check(hc.sample_from_uniforms, thick)
