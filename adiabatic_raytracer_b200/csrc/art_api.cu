@@ -195,13 +195,14 @@ int ensure_lanes(art_handle* h, int n) {
 
 // step-batched tracer over a device queue (art_wavefront.cuh).  With a tree context the loop also
 // walks every event's tree: finished rays spawn the next node of their event in place.
-int launch_trace_wf(art_handle* h, Lane& L, const QueuedRay* q, long long n, RayOut* out, double* rec, int rec_cap,
-                    DevStats* stats, const WfTree* tree) {
+template <int IG>
+int launch_trace_wf_t(art_handle* h, Lane& L, const QueuedRay* q, long long n, RayOut* out, double* rec, int rec_cap,
+                      DevStats* stats, const WfTree* tree) {
   if (n <= 0) return ART_OK;
   cudaStream_t st = L.stream;
   CU(L.wf_hot.ensure((size_t)n * sizeof(RayHot)));
   CU(L.wf_cold.ensure((size_t)n * sizeof(RayCold)));
-  CU(L.wf_seg.ensure((size_t)n * SEG_PAD * sizeof(double)));
+  CU(L.wf_seg.ensure((size_t)n * Seg<IG>::N * sizeof(double)));
   CU(L.wf_need.ensure((size_t)n * 8));
   CU(L.wf_neg.ensure((size_t)n * 8));
   CU(L.wf_sign.ensure((size_t)n * 8));
@@ -225,7 +226,7 @@ int launch_trace_wf(art_handle* h, Lane& L, const QueuedRay* q, long long n, Ray
   CU(cudaMemsetAsync(W.ctr, 0, WC_N * 8, st));
   const int gmax = h->n_sm * h->wf_grid_per_sm;
   auto grid = [&](long long work, int threads) { return (int)std::max<long long>(1, std::min<long long>(gmax, (work + threads - 1) / threads)); };
-  k_wf_init<<<grid(n, WF_THREADS), WF_THREADS, 0, st>>>(h->dp, q, n, W, rec, rec_cap, stats);
+  k_wf_init<IG><<<grid(n, WF_THREADS), WF_THREADS, 0, st>>>(h->dp, q, n, W, rec, rec_cap, stats);
   h->launches++;
   CU(cudaGetLastError());
   long long n_act = n;  // upper bound of the rays in flight, refreshed at every host check
@@ -246,17 +247,17 @@ int launch_trace_wf(art_handle* h, Lane& L, const QueuedRay* q, long long n, Ray
       if (side) CU(cudaEventRecord(L.ev_reset, st));
       // side stream: root finder and tree of the PREVIOUS iteration's lists, concurrent with this stage kernel
       if (side) CU(cudaStreamWaitEvent(s2, L.ev_reset, 0));
-      k_wf_root<<<grid(n_act / 2 + 1, WF_THREADS), WF_THREADS, 0, s2>>>(h->dp, W, next, lin, lpar, stats);
+      k_wf_root<IG><<<grid(n_act / 2 + 1, WF_THREADS), WF_THREADS, 0, s2>>>(h->dp, W, next, lin, lpar, stats);
       if (tree)
-        k_wf_tree<<<grid(n_act / 2 + 1, WF_THREADS), WF_THREADS, 0, s2>>>(h->dp, W, *tree, next, lin, rec, rec_cap, stats);
+        k_wf_tree<IG><<<grid(n_act / 2 + 1, WF_THREADS), WF_THREADS, 0, s2>>>(h->dp, W, *tree, next, lin, rec, rec_cap, stats);
       else
         k_wf_collect<<<grid(n_act / 4 + 1, WF_THREADS), WF_THREADS, 0, s2>>>(h->dp, W, lin, out, stats);
       if (side) CU(cudaEventRecord(L.ev_side, s2));
       const int gs = (int)std::max<long long>(1, std::min<long long>((long long)h->n_sm * h->stage_grid_per_sm, (n_act + STAGE_THREADS - 1) / STAGE_THREADS));
-      k_wf_stages<<<2 * gs, STAGE_THREADS, ksmem, st>>>(h->dp, W, cur, lpar, tail ? h->tail_nstep : h->bulk_nstep, tail ? 1 : h->bulk_min_go, stats);
-      k_wf_scan<<<(int)std::max<long long>(1, std::min<long long>((long long)h->n_sm * h->scan_grid_per_sm, (n_act * 11 + SCAN_THREADS - 1) / SCAN_THREADS)),
+      k_wf_stages<IG><<<2 * gs, STAGE_THREADS, ksmem, st>>>(h->dp, W, cur, lpar, tail ? h->tail_nstep : h->bulk_nstep, tail ? 1 : h->bulk_min_go, stats);
+      k_wf_scan<IG><<<(int)std::max<long long>(1, std::min<long long>((long long)h->n_sm * h->scan_grid_per_sm, (n_act * 11 + SCAN_THREADS - 1) / SCAN_THREADS)),
                   SCAN_THREADS, 0, st>>>(h->dp, W, stats);
-      k_wf_detect<<<(int)std::max<long long>(1, std::min<long long>((long long)h->n_sm * h->detect_grid_per_sm, (n_act + WF_THREADS - 1) / WF_THREADS)),
+      k_wf_detect<IG><<<(int)std::max<long long>(1, std::min<long long>((long long)h->n_sm * h->detect_grid_per_sm, (n_act + WF_THREADS - 1) / WF_THREADS)),
                     WF_THREADS, 0, st>>>(h->dp, W, next, lpar);
       h->launches += 6;
       cur = next;
@@ -285,11 +286,17 @@ int launch_trace_wf(art_handle* h, Lane& L, const QueuedRay* q, long long n, Ray
   return ART_OK;
 }
 
+int launch_trace_wf(art_handle* h, Lane& L, const QueuedRay* q, long long n, RayOut* out, double* rec, int rec_cap,
+                    DevStats* stats, const WfTree* tree) {
+  return h->dp.integrator == IG_DP5 ? launch_trace_wf_t<IG_DP5>(h, L, q, n, out, rec, rec_cap, stats, tree)
+                                    : launch_trace_wf_t<IG_VERN6>(h, L, q, n, out, rec, rec_cap, stats, tree);
+}
+
 }  // namespace
 
 extern "C" {
 
-const char* art_version(void) { return "adiabatic_raytracer_b200 0.1 (sm_100a, DP5 integrator spec v1)"; }
+const char* art_version(void) { return "adiabatic_raytracer_b200 0.2 (sm_100a; integrators: Vern6 [default], DP5)"; }
 
 int art_params_default(art_params* p) {
   if (!p) return ART_ERR_ARG;
@@ -300,7 +307,7 @@ int art_params_default(art_params* p) {
   p->sampler_dt = 0.5; p->dtmin = 1e-13;
   p->flat = 0; p->isotropic = 0; p->melrose = 1; p->thick_surface = 1; p->n_maxSample = 6; p->num_cutoff = 5;
   p->MC_nodes = 5; p->max_nodes = 50; p->ntimes = 3; p->save_mode = 0; p->interp_points_ray = 50;
-  p->interp_points_sampler = 20; p->maxiters = 100000; p->cross_cap = 16;
+  p->interp_points_sampler = 20; p->maxiters = 100000; p->cross_cap = 16; p->integrator = ART_INTEGRATOR_VERN6;
   return ART_OK;
 }
 
@@ -341,8 +348,10 @@ int art_create(const art_params* p, int device_id, art_handle** out) {
   cudaGetDeviceProperties(&prop, device_id);
   h->n_sm = prop.multiProcessorCount;
   int occ = 0;
-  cudaFuncSetAttribute(k_wf_stages, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((K_ROWS + K_PARK) * STAGE_THREADS * sizeof(double)));
-  cudaFuncSetAttribute(k_wf_stages, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(k_wf_stages<IG_VERN6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((K_ROWS + K_PARK) * STAGE_THREADS * sizeof(double)));
+  cudaFuncSetAttribute(k_wf_stages<IG_VERN6>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(k_wf_stages<IG_DP5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((K_ROWS + K_PARK) * STAGE_THREADS * sizeof(double)));
+  cudaFuncSetAttribute(k_wf_stages<IG_DP5>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sample_events, SAMPLE_THREADS, 0);
   h->blocks_sample = h->n_sm * std::max(occ, 1);
   if (const char* t = getenv("ART_BULK_NSTEP")) h->bulk_nstep = std::max(1, atoi(t));

@@ -20,6 +20,10 @@ inline int make_dev_params(const art_params& p, DevParams& d, std::string& err) 
     err = "bndry_lyr > 0 (boundary-layer plasma term, RayTracer.jl:1156-1162) is not supported by this build";
     return ART_ERR_ARG;
   }
+  if (p.integrator != ART_INTEGRATOR_VERN6 && p.integrator != ART_INTEGRATOR_DP5) {
+    err = "integrator must be ART_INTEGRATOR_VERN6 (0) or ART_INTEGRATOR_DP5 (1)";
+    return ART_ERR_ARG;
+  }
   if (p.n_maxSample < 1 || p.n_maxSample > SAMP_KEEP) {
     err = "n_maxSample must be in 1..8";
     return ART_ERR_ARG;
@@ -65,6 +69,7 @@ inline int make_dev_params(const art_params& p, DevParams& d, std::string& err) 
   d.num_cutoff = p.num_cutoff;
   d.MC_nodes = p.MC_nodes;
   d.max_nodes = p.max_nodes;
+  d.integrator = p.integrator;
   d.prob_cutoff = p.prob_cutoff;
   d.inv_Mrm1 = 1.0 / (double)(p.interp_points_ray - 1);
   d.inv_Msm1 = 1.0 / (double)(p.interp_points_sampler - 1);

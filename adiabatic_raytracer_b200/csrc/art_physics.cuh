@@ -220,6 +220,7 @@ struct DevParams {
   int32_t isotropic, flat;
   int32_t melrose, thick;  // hamiltonian's melrose switch (RT.jl:546-551); sampler's thick_surface switch (RT.jl:1548)
   int32_t num_cutoff, MC_nodes, max_nodes;
+  int32_t integrator;  // IG_VERN6 / IG_DP5 (art_tracer.cuh)
   double prob_cutoff;
   double inv_Mrm1, inv_Msm1;  // 1/(M_ray − 1), 1/(M_samp − 1): dense-output grid spacing
   double cpsi0, spsi0, mh[3];  // cos/sin Ω t0 and the magnetic axis m̂ at the field time t0 (sampler)

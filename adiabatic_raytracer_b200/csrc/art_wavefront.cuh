@@ -60,15 +60,13 @@ constexpr int STAGE_THREADS = ART_STAGE_THREADS;
 #ifndef ART_STAGE_NSTEP
 #define ART_STAGE_NSTEP 4      // attempted steps a ray may take inside one k_wf_stages launch
 #endif
-constexpr int SEG_PAD = 36;  // doubles per published segment (SEG_N = 35, padded)
-constexpr int SEG_NUDGE = 35;  // padding slot: 1.0 if the step follows an event (the scan then includes the nudge point)
 
 enum { WC_PEND = 0, WC_ROOTS = 1 /* + list parity */, WC_FIN = 3 /* + list parity */, WC_ACT = 5 /* + parity*2 + species */, WC_N = 16 };
 
 struct WfPool {
   RayHot* hot;                // [cap] per-step ray state
   RayCold* cold;              // [cap] callback-only ray state
-  double* seg;                // [cap][36] dense-output segment of a pending (accepted, unscanned) step
+  double* seg;                // [cap][Seg<IG>::N] dense-output segment of a pending (accepted, unscanned) step
   unsigned long long* mpos;   // [cap] scan points with a positive condition (bit i = grid point i)
   unsigned long long* mneg;   // [cap] … negative (far-field points included)
   unsigned long long* mzero;  // [cap] … exactly zero
@@ -161,6 +159,7 @@ __global__ void k_wf_reset(WfPool W, int next, int lpar) {
 }
 
 // ---- start-up of a batch: IC transform, first RHS, initial step size, starting sign ----------------
+template <int IG>
 __global__ void __launch_bounds__(WF_THREADS)
 k_wf_init(const __grid_constant__ DevParams P, const QueuedRay* __restrict__ q, long long n, WfPool W,
           double* __restrict__ rec, int rec_cap, DevStats* stats) {
@@ -174,7 +173,7 @@ k_wf_init(const __grid_constant__ DevParams P, const QueuedRay* __restrict__ q, 
     const bool valid = i < n;
     if (valid) {
       R.init(P, q[i].in, rec + (size_t)i * rec_cap * 8, rec_cap);
-      if (!R.done && R.iter_guard(P)) R.startup<-1>(P);
+      if (!R.done && R.iter_guard(P)) R.template startup<IG, -1>(P);
       W.hot[i] = static_cast<const RayHot&>(R);
       W.cold[i] = static_cast<const RayCold&>(R);
     }
@@ -194,9 +193,10 @@ k_wf_init(const __grid_constant__ DevParams P, const QueuedRay* __restrict__ q, 
 // A warp keeps stepping (at most `nstep` attempts) while at least `min_go` of its lanes can go on, so
 // far-field rays and rejected steps do not pay a state round trip per attempt (bulk: 4 attempts, half
 // the warp; thin tail of a batch: 16 attempts, any lane — there only latency counts).
-template <int SP>
+template <int IG, int SP>
 __device__ __forceinline__ void wf_stages_body(const DevParams& P, const WfPool& W, int cur, int lpar, int nstep, int min_go,
                                                unsigned bid, unsigned nblocks, double* ksm, DevStats* stats) {
+  constexpr int LAST = Scheme<IG>::LAST, NEXTRA = Scheme<IG>::NEXTRA, TNEW = IG == IG_DP5 ? 5 : 6;  // park slot of e^{s_new}
   unsigned long long n_full = 0;  // condition evaluations done here (end points of in-box steps)
   const KStoreT<STAGE_THREADS> K{ksm + threadIdx.x};
   const int next = 1 - cur;
@@ -205,7 +205,7 @@ __device__ __forceinline__ void wf_stages_body(const DevParams& P, const WfPool&
   const long long nthreads = (long long)nblocks * blockDim.x;
   const long long nround = ((n + nthreads - 1) / nthreads) * nthreads;
   // the ids of this thread's next two trips are kept in flight and the hot record of the next trip is
-  // pulled into L2 while the current ray is being stepped (12 resident warps cannot hide an HBM miss)
+  // pulled into L2 while the current ray is being stepped (8 resident warps cannot hide an HBM miss)
   long long t = bid * (long long)blockDim.x + threadIdx.x;
   int id_a = t < n ? act[t] : -1;
   int id_b = t + nthreads < n ? act[t + nthreads] : -1;
@@ -224,66 +224,86 @@ __device__ __forceinline__ void wf_stages_body(const DevParams& P, const WfPool&
     if (valid) static_cast<RayHot&>(R) = W.hot[id];
     bool go = valid && !R.done;
     done = valid && R.done;
-    for (int it = 0; it < nstep; ++it) {
-      if (go) {
-        if (!R.iter_guard(P)) {
+    // Rounds.  A step round runs the LAST stages of one attempted step for every lane that can go on, at ONE call
+    // site of the right-hand side (the stage loop is rolled), then error control and the certified-sign tests.  A lane
+    // whose accepted step has to be scanned stops there with its stage store intact (pending).  The final round —
+    // after nstep step rounds, or as soon as fewer than min_go lanes can go on — runs the lazy dense-output stages of
+    // Vern6 for all pending lanes of the warp together (one round per launch at ≈ half the lanes, instead of one per
+    // attempt at a sixth), through the same call site; then the segments are published.
+    for (int it = 0;; ++it) {
+      const bool final_round = it >= nstep || __popc(__ballot_sync(FULL, go)) < (it == 0 ? 1 : min_go);
+      bool work = pending;
+      int st0 = LAST + 1, st1 = LAST + NEXTRA;
+      if (!final_round) {
+        if (go && !R.iter_guard(P)) {
           go = false;
           done = true;
-        } else if (R.template attempt<SP>(P, K)) {
-          // certified sign of the condition along the whole step: −1 far field / dark, +1 lit, 0 unknown
-          int cs = R.step_all_far(P, K) ? -1 : R.step_sign(P, K, K.park(5));
-          if (cs != 0 && !R.event_last && R.sgn_end * cs < 0) cs = 0;  // a sign change against the reference sign: scan
-          bool settled = cs != 0;
-          if (!settled && R.n_cross == 0 && !R.event_last && !R.left_box) {
-            // a step inside the start box keeps nothing but the sign at its end point (step_in_start_box):
-            // evaluated here, the ray goes on without a round trip through the scan
-            const RayCold& C = W.cold[id];
-            const double s0_[3] = {C.s0[0], C.s0[1], C.s0[2]};
-            if (R.step_in_start_box(K, s0_, C.box_m)) {
-              const double E = R.u7_of(R.un[5]);
-              const double g = thick_F<true>(P, R.un[0], R.un[1], R.un[2] - P.Omega * K.park(5), R.un[3], R.un[4], R.un[5], E,
-                                             P.rs_ray, true);
-              n_full++;
-              if (g != 0.0) {  // (an exact zero at the end point is an event: left to the scan)
-                cs = (g > 0.0) - (g < 0.0);  // NaN: 0
-                settled = true;
-              }
-            } else {
-              R.left_box = 1;
-            }
-          }
-          if (settled) {
-            // no crossing possible: apply(th_ev < 0, sg_last = cs)
-            for (int i = 0; i < 6; ++i) {
-              R.u[i] = R.un[i];
-              R.k1[i] = K(6, i);
-            }
-            R.s = R.s_new;
-            R.sgn_end = cs;
-            R.event_last = false;
-            R.dt = R.dt_new;
-            R.settle(P);
-            if (R.done) {
-              go = false;
-              done = true;
+        }
+        if (go) R.template begin_attempt<IG>(P, K);
+        work = go;
+        st0 = 1;
+        st1 = LAST;
+      }
+#pragma unroll 1
+      for (int st = st0; st <= st1; ++st)
+        if (work) R.template stage<IG, SP>(P, K, st);
+      if (final_round) break;
+      if (go && R.template control<IG>(P, K)) {
+        // certified sign of the condition along the whole step: −1 far field / dark, +1 lit, 0 unknown
+        int cs = R.template step_all_far<IG>(P, K) ? -1 : R.template step_sign<IG>(P, K, K.park(TNEW));
+        if (cs != 0 && !R.event_last && R.sgn_end * cs < 0) cs = 0;  // a sign change against the reference sign: scan
+        bool settled = cs != 0;
+        if (!settled && R.n_cross == 0 && !R.event_last && !R.left_box) {
+          // a step inside the start box keeps nothing but the sign at its end point (step_in_start_box):
+          // evaluated here, the ray goes on without a round trip through the scan
+          const RayCold& C = W.cold[id];
+          const double s0_[3] = {C.s0[0], C.s0[1], C.s0[2]};
+          if (R.template step_in_start_box<IG>(K, s0_, C.box_m)) {
+            const double E = R.u7_of(R.un[5]);
+            const double g = thick_F<true>(P, R.un[0], R.un[1], R.un[2] - P.Omega * K.park(TNEW), R.un[3], R.un[4], R.un[5], E,
+                                           P.rs_ray, true);
+            n_full++;
+            if (g != 0.0) {  // (an exact zero at the end point is an event: left to the scan)
+              cs = (g > 0.0) - (g < 0.0);  // NaN: 0
+              settled = true;
             }
           } else {
-            const SegAoS D{W.seg + (size_t)id * SEG_PAD};
-            R.publish(K, D);
-            D(SEG_NUDGE) = R.event_last ? 1.0 : 0.0;
-            // optimistic advance; k_wf_detect / k_wf_root complete or override it
-            for (int i = 0; i < 6; ++i) {
-              R.u[i] = R.un[i];
-              R.k1[i] = K(6, i);
-            }
-            R.s = R.s_new;
-            R.dt = R.dt_new;
-            go = false;
-            pending = true;
+            R.left_box = 1;
           }
         }
+        if (settled) {
+          // no crossing possible: apply(th_ev < 0, sg_last = cs)
+          for (int i = 0; i < 6; ++i) {
+            R.u[i] = R.un[i];
+            R.k1[i] = K(LAST, i);
+          }
+          R.s = R.s_new;
+          R.sgn_end = cs;
+          R.event_last = false;
+          R.dt = R.dt_new;
+          R.settle(P);
+          if (R.done) {
+            go = false;
+            done = true;
+          }
+        } else {
+          go = false;
+          pending = true;
+        }
       }
-      if (it + 1 < nstep && __popc(__ballot_sync(FULL, go)) < min_go) break;
+    }
+    if (pending) {
+      R.n_rhs += NEXTRA;
+      const SegAoS D{W.seg + (size_t)id * Seg<IG>::N};
+      R.template publish<IG>(K, D);
+      D(Seg<IG>::NUDGE) = R.event_last ? 1.0 : 0.0;
+      // optimistic advance; k_wf_detect / k_wf_root complete or override it
+      for (int i = 0; i < 6; ++i) {
+        R.u[i] = R.un[i];
+        R.k1[i] = K(LAST, i);
+      }
+      R.s = R.s_new;
+      R.dt = R.dt_new;
     }
     if (valid) W.hot[id] = static_cast<const RayHot&>(R);
     wf_route(W, next, lpar, valid, id, done, pending, SP == SPECIES_AXION);
@@ -295,6 +315,7 @@ __device__ __forceinline__ void wf_stages_body(const DevParams& P, const WfPool&
 // One launch steps both species: the first half of the grid walks the axion list, the second half the
 // photon list (a warp never executes both right-hand sides; in the thin tail of a batch the two lists
 // are stepped concurrently instead of one launch after the other).
+template <int IG>
 #ifdef ART_STAGE_MAXNREG  // tuning: an explicit register cap instead of the cap implied by the resident-CTA count (tracer per
                           // 1e6 events: 224 registers / 9 warps 187.9 ms, 200 / 10 190.2, 184 / 11 190.3; 255 / 8: 185.3)
 __global__ void __maxnreg__(ART_STAGE_MAXNREG)
@@ -304,8 +325,8 @@ __global__ void __launch_bounds__(STAGE_THREADS, ART_STAGE_MINBLOCKS)
 k_wf_stages(const __grid_constant__ DevParams P, WfPool W, int cur, int lpar, int nstep, int min_go, DevStats* stats) {
   extern __shared__ double ksm[];
   const unsigned half = gridDim.x >> 1;
-  if (blockIdx.x < half) wf_stages_body<SPECIES_AXION>(P, W, cur, lpar, nstep, min_go, blockIdx.x, half, ksm, stats);
-  else wf_stages_body<SPECIES_PHOTON>(P, W, cur, lpar, nstep, min_go, blockIdx.x - half, half, ksm, stats);
+  if (blockIdx.x < half) wf_stages_body<IG, SPECIES_AXION>(P, W, cur, lpar, nstep, min_go, blockIdx.x, half, ksm, stats);
+  else wf_stages_body<IG, SPECIES_PHOTON>(P, W, cur, lpar, nstep, min_go, blockIdx.x - half, half, ksm, stats);
 }
 
 // ---- crossing scan: one warp per group of pending steps -----------------------------------------------
@@ -329,8 +350,10 @@ constexpr int SCAN_ROUNDS = 5;  // ballot words kept per sign class
 #ifndef ART_SCAN_MINBLOCKS
 #define ART_SCAN_MINBLOCKS 3
 #endif
+template <int IG>
 __global__ void __launch_bounds__(SCAN_THREADS, ART_SCAN_MINBLOCKS)
 k_wf_scan(const __grid_constant__ DevParams P, WfPool W, DevStats* stats) {
+  constexpr int SEG_PAD = Seg<IG>::N;
   __shared__ double seg_sm[SCAN_THREADS / 32][SCAN_PACK][SEG_PAD];
   __shared__ double th_sm[SCAN_ROUNDS][SCAN_THREADS];        // per lane and round: dense-output parameter of its slot
   __shared__ short j_sm[SCAN_ROUNDS][SCAN_THREADS];          // … segment index, +8 for a nudge slot, −1 for no slot
@@ -372,12 +395,12 @@ k_wf_scan(const __grid_constant__ DevParams P, WfPool W, DevStats* stats) {
       const int j = j_sm[rd][threadIdx.x];
       if (j >= 0 && (j & 7) < cnt) {
         const SegAoS D{seg_sm[wib][j & 7]};
-        if (j < 8 || D(SEG_NUDGE) != 0.0) {
+        if (j < 8 || D(Seg<IG>::NUDGE) != 0.0) {
           const double th = th_sm[rd][threadIdx.x];
-          const int qk = seg_quick(P, D, th);
+          const int qk = seg_quick<IG>(P, D, th);
           if (qk == -1) code = 2;
           else if (qk == 0) {
-            const double g = seg_cond_full<true>(P, D, th);
+            const double g = seg_cond_full<IG, true>(P, D, th);
             n_full++;
             code = (g > 0.0) ? 1 : ((g < 0.0) ? 2 : ((g == 0.0) ? 3 : 0));
           }
@@ -411,18 +434,20 @@ k_wf_scan(const __grid_constant__ DevParams P, WfPool W, DevStats* stats) {
 
 // Rebuilds the transient view of a pending step from the hot record (optimistically advanced) and the
 // published segment (state at the start of the step).
+template <int IG>
 __device__ __forceinline__ void wf_load_pending(Ray& R, const SegAoS D) {
   for (int i = 0; i < 6; ++i) {
     R.un[i] = R.u[i];
-    R.u[i] = D(SEG_U + i);
+    R.u[i] = D(Seg<IG>::U + i);
   }
   R.s_new = R.s;
-  R.s = D(SEG_S);
-  R.h = D(SEG_H);
+  R.s = D(Seg<IG>::S);
+  R.h = D(Seg<IG>::H);
   R.dt_new = R.dt;
 }
 
 // ---- events: detection over the pending rays; no crossing ⇒ the optimistic advance stands ------------
+template <int IG>
 __global__ void __launch_bounds__(WF_THREADS)
 k_wf_detect(const __grid_constant__ DevParams P, WfPool W, int next, int lpar) {
   const long long n = (long long)W.ctr[WC_PEND];
@@ -449,14 +474,14 @@ k_wf_detect(const __grid_constant__ DevParams P, WfPool W, int next, int lpar) {
       static_cast<RayHot&>(R) = W.hot[id];
       axion = R.axion;
       const ScanMasks m{W.mpos[id], W.mneg[id], W.mzero[id]};
-      const SegAoS D{W.seg + (size_t)id * SEG_PAD};
+      const SegAoS D{W.seg + (size_t)id * Seg<IG>::N};
       // detect() only reads the start-box reference point from the cold record (first crossing only)
       if (R.n_cross == 0) {
         const RayCold& C = W.cold[id];
         R.x0[0] = C.x0[0]; R.x0[1] = C.x0[1]; R.x0[2] = C.x0[2];
       }
       int ia, ib, sgl;
-      const int ev = R.detect(P, D, m, ia, ib, sgl);
+      const int ev = R.template detect<IG>(P, D, m, ia, ib, sgl);
       if (ev != 0) {
         RayCold& C = W.cold[id];
         C.br_a = ia; C.br_b = (ev == 2) ? -2 : ib; C.br_sg = sgl;
@@ -479,6 +504,7 @@ k_wf_detect(const __grid_constant__ DevParams P, WfPool W, int next, int lpar) {
 }
 
 // ---- root finder (all lanes iterate together), crossing callback, state update ------------------------
+template <int IG>
 __global__ void __launch_bounds__(WF_THREADS)
 k_wf_root(const __grid_constant__ DevParams P, WfPool W, int next, int lin, int lpar, DevStats* stats) {
   unsigned long long n_full = 0;
@@ -497,6 +523,7 @@ k_wf_root(const __grid_constant__ DevParams P, WfPool W, int next, int lin, int 
       Ray R;
       static_cast<RayHot&>(R) = W.hot[id];
       static_cast<RayCold&>(R) = W.cold[id];
+      constexpr int SEG_PAD = Seg<IG>::N;
       double segl[SEG_PAD];  // the root finder evaluates the segment ~12 times: keep it on chip
       {
         const double* sgp = W.seg + (size_t)id * SEG_PAD;
@@ -504,12 +531,12 @@ k_wf_root(const __grid_constant__ DevParams P, WfPool W, int next, int lin, int 
         for (int k = 0; k < SEG_PAD; ++k) segl[k] = sgp[k];
       }
       const SegAoS D{segl};
-      wf_load_pending(R, D);
+      wf_load_pending<IG>(R, D);
       const K7View K{R.k1};
       const int c0 = R.n_cond;
-      const double th = (R.br_b == -2) ? 1.0 : R.locate(P, D, R.br_a, R.br_b);
+      const double th = (R.br_b == -2) ? 1.0 : R.template locate<IG>(P, D, R.br_a, R.br_b);
       n_full += (unsigned long long)(R.n_cond - c0);
-      R.apply(P, K, D, th, R.br_sg);
+      R.template apply<IG>(P, K, D, th, R.br_sg);
       W.hot[id] = static_cast<const RayHot&>(R);
       done = R.done;
       axion = R.axion;
@@ -578,6 +605,7 @@ __device__ __forceinline__ bool wf_tree_step(const DevParams& P, const WfTree& T
   return spawn;
 }
 
+template <int IG>
 __global__ void __launch_bounds__(WF_THREADS)
 k_wf_tree(const __grid_constant__ DevParams P, WfPool W, WfTree T, int next, int lin, double* __restrict__ rec, int rec_cap,
           DevStats* stats) {
@@ -603,7 +631,7 @@ k_wf_tree(const __grid_constant__ DevParams P, WfPool W, WfTree T, int next, int
         // a re-initialised ray that is already past the end of the span stays `done`: the next
         // k_wf_stages launch routes it back here (never happens for t < 1/Ω)
         if (!R.done && R.iter_guard(P)) {
-          R.startup<-1>(P);
+          R.template startup<IG, -1>(P);
           n_start++;
         }
         W.hot[id] = static_cast<const RayHot&>(R);

@@ -42,6 +42,8 @@ class ArtParams(C.Structure):
         ("interp_points_sampler", C.c_int32),
         ("maxiters", C.c_int32),
         ("cross_cap", C.c_int32),
+        ("integrator", C.c_int32),
+        ("reserved_", C.c_int32),
     ]
 
     @classmethod
@@ -54,7 +56,7 @@ class ArtParams(C.Structure):
             sampler_dt=0.5, dtmin=1e-13,
             flat=0, isotropic=0, melrose=1, thick_surface=1, n_maxSample=6, num_cutoff=5,
             MC_nodes=5, max_nodes=50, ntimes=3, save_mode=0, interp_points_ray=50,
-            interp_points_sampler=20, maxiters=100000, cross_cap=16,
+            interp_points_sampler=20, maxiters=100000, cross_cap=16, integrator=0, reserved_=0,
         )
         for k, v in overrides.items():
             if not hasattr(p, k):

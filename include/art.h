@@ -42,6 +42,9 @@ extern "C" {
 #define ART_RAY_MAXITERS 3  /* maxiters exhausted (RT.jl:383-384)                           */
 #define ART_RAY_CROSS_OVERFLOW 4 /* more crossings than the record capacity                 */
 
+#define ART_INTEGRATOR_VERN6 0
+#define ART_INTEGRATOR_DP5 1
+
 #define ART_SPECIES_AXION 0
 #define ART_SPECIES_PHOTON 1
 
@@ -89,8 +92,8 @@ typedef struct art_params {
   double dtmin;       /* RT.jl:384 = 1e-13 (forced)                                         */
   int32_t flat;          /* Gen_Samples.jl:165 = false ("mixed" flat mode)       */
   int32_t isotropic;     /* Gen_Samples.jl:166 = false                                      */
-  int32_t melrose;       /* Gen_Samples.jl:167 = true; only true is supported               */
-  int32_t thick_surface; /* Gen_Samples.jl:173 = true; only true is supported               */
+  int32_t melrose;       /* Gen_Samples.jl:167 = true; false = hamiltonian's "original form" (RT.jl:546-548) */
+  int32_t thick_surface; /* Gen_Samples.jl:173 = true; false = sampler condition log ωp − log m_a (RT.jl:1548) */
   int32_t n_maxSample;   /* Gen_Samples.jl:174 = 6                                          */
   int32_t num_cutoff;    /* --numCutoff default 5                                           */
   int32_t MC_nodes;      /* --MCNodes   default 5                                           */
@@ -105,6 +108,10 @@ typedef struct art_params {
   int32_t cross_cap;     /* capacity of the per-ray crossing record list in the fused
                             pipeline (the reference's list is unbounded; overflow is
                             reported as ART_RAY_CROSS_OVERFLOW)                            */
+  int32_t integrator;    /* ART_INTEGRATOR_VERN6 (0, default): Verner's 9-stage 6(5) pair, the
+                            reference's solve(prob, Vern6(), …) (RT.jl:383); ART_INTEGRATOR_DP5 (1):
+                            Dormand–Prince 5(4), round 1's scheme, kept for comparison              */
+  int32_t reserved_;     /* keeps sizeof(art_params) a multiple of 8; must be 0                    */
 } art_params;
 
 /* counters accumulated by the tracer / sampler kernels; they feed the roofline (SURVEY §8 d) */

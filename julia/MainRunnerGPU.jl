@@ -18,7 +18,7 @@ mutable struct ArtParams
     sampler_dt::Cdouble; dtmin::Cdouble
     flat::Cint; isotropic::Cint; melrose::Cint; thick_surface::Cint; n_maxSample::Cint; num_cutoff::Cint
     MC_nodes::Cint; max_nodes::Cint; ntimes::Cint; save_mode::Cint; interp_points_ray::Cint
-    interp_points_sampler::Cint; maxiters::Cint; cross_cap::Cint
+    interp_points_sampler::Cint; maxiters::Cint; cross_cap::Cint; integrator::Cint; reserved_::Cint
     ArtParams() = new()
 end
 

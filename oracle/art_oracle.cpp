@@ -39,6 +39,7 @@ static RayParams ray_of(const art_params& p, double erg, double B0, bool is_axio
   r.erg = erg; r.B0 = B0;
   r.reltol = p.reltol; r.abstol = p.ode_err; r.dtmin = p.dtmin;
   r.maxiters = p.maxiters; r.interp_points = p.interp_points_ray;
+  r.integrator = p.integrator;
   r.is_axion = is_axion;
   return r;
 }

@@ -21,7 +21,7 @@ _ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, f) for f in ("art_oracle.cpp", "physics.hpp", "tracer.hpp", "dual.hpp", "philox.hpp")]
+    srcs = [os.path.join(_HERE, f) for f in ("art_oracle.cpp", "physics.hpp", "tracer.hpp", "dual.hpp", "philox.hpp", "vern6.hpp")]
     srcs.append(os.path.join(_HERE, "..", "include", "art.h"))
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
         subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)

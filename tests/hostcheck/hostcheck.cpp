@@ -21,7 +21,7 @@ static int dev(const art_params* p, DevParams& d) {
 
 static void trace_one(const DevParams& P, const RayIn& in, double* rec, int cap, RayOut& o) {
   Ray R;
-  double kbuf[42], sbuf[SEG_N];
+  double kbuf[K_ROWS], sbuf[SEG_MAX];
   KStore K{kbuf, 1};
   SegStore D{sbuf, 1};
   R.init(P, in, rec, cap);
@@ -238,7 +238,7 @@ extern "C" int hc_trace_ray(const art_params* p, int32_t species, const double* 
   std::vector<double> rec((size_t)p->cross_cap * 8);
   int n = 0;
   Ray R;
-  double kbuf[42], sbuf[SEG_N];
+  double kbuf[K_ROWS], sbuf[SEG_MAX];
   KStore K{kbuf, 1};
   SegStore D{sbuf, 1};
   R.init(P, in, rec.data(), p->cross_cap);

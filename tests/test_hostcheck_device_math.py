@@ -82,9 +82,16 @@ def test_closed_form_rhs_matches_dual_number_gradients(oracle):
             assert (np.abs(a - b) / scale).max() < (1e-11 if p.melrose or p.isotropic else 3e-11)
 
 
+@pytest.mark.parametrize("integrator", [0, 1], ids=["vern6", "dp5"])
 @pytest.mark.parametrize("kw", [dict(theta_m=0.2), dict(theta_m=0.2, flat=1), dict(theta_m=0.2, melrose=0)])
-def test_host_compiled_tracer_matches_oracle(oracle, kw):
-    p = ArtParams.default(**kw)
+def test_host_compiled_tracer_matches_oracle(oracle, kw, integrator):
+    """Same scheme on both sides.  DP5: the accept/reject sequence is identical for ≥ 98 % of the rays and those agree to
+    round-off.  Vern6: its error estimator has a round-off floor (b̃7 = −176.5 and b̃8 = +173.0 act on the nearly equal
+    k7, k8, so EEst carries ≈ 1e-9 of absolute noise); two implementations that differ in FMA contraction or summation
+    order therefore choose step sizes that differ at the 1e-10 level, and the rejection bursts at the |B_z| kink of the
+    GJ model amplify that into different reject counts for a third of the rays.  Final states still agree to round-off
+    in the median and to the scheme's truncation error (≈ 5e-5 at reltol 1e-7) in the tail."""
+    p = ArtParams.default(integrator=integrator, **kw)
     n = 400
     s = oracle.sample(p, 5, 1, n)
     w = oracle.weights(p, s["x"], s["v_loc"], s["v_inf"])
@@ -95,11 +102,18 @@ def test_host_compiled_tracer_matches_oracle(oracle, kw):
         b = oracle.propagate(p, np.full(n, sp, np.int32), x, k0, erg, np.zeros(n), -np.ones(n), bs, mc)
         same = (a["status"] == b["status"]) & (a["n_cross"] == b["n_cross"])
         assert same.mean() > 0.99
-        steps = same & (a["counters"][:, 0] == b["counters"][:, 0]) & (a["counters"][:, 1] == b["counters"][:, 1])
-        assert steps.mean() > 0.98
         dx = np.linalg.norm(a["x_f"] - b["x_f"], axis=0) / np.linalg.norm(b["x_f"], axis=0)
-        assert np.median(dx[steps]) < 1e-10
-        assert dx[steps].max() < 2e-3  # round-off amplified at the |B_z| kink, bounded by the scheme's truncation error
+        if integrator == 1:
+            steps = same & (a["counters"][:, 0] == b["counters"][:, 0]) & (a["counters"][:, 1] == b["counters"][:, 1])
+            assert steps.mean() > 0.98
+            assert np.median(dx[steps]) < 1e-10
+            assert dx[steps].max() < 2e-3  # round-off amplified at the |B_z| kink, bounded by the scheme's truncation error
+        else:
+            assert np.median(dx[same]) < 1e-9
+            if sp == 1:  # measured: 80-86 % below 1e-6, 99 % below 2e-5
+                assert (dx[same] < 1e-6).mean() > 0.7 and np.percentile(dx[same], 98) < 2e-4
+            # oracle: literal Vern6 with the three dense-output stages on every accepted step
+            assert b["counters"][:, 2].mean() == pytest.approx(a["counters"][:, 2].mean(), rel=0.02)
 
 
 def test_host_compiled_sampler_matches_oracle(oracle):
@@ -115,14 +129,29 @@ def test_host_compiled_sampler_matches_oracle(oracle):
         assert np.abs(a["x"] - b["x"])[:, m].max() < 1e-10
 
 
+def _same_shape_rows(ra, rb, n):
+    """Rows of the events whose trees have the same sequence of final species on both sides."""
+    def sig(rows):
+        d = {}
+        for e, sp in zip(rows[:, 0].astype(int), rows[:, 1].astype(int)):
+            d.setdefault(e, []).append(sp)
+        return d
+    sa, sb = sig(ra), sig(rb)
+    good = np.zeros(n + 2, bool)
+    for e in range(1, n + 1):
+        good[e] = sa.get(e) == sb.get(e)
+    return ra[good[ra[:, 0].astype(int)]], rb[good[rb[:, 0].astype(int)]], good[1:n + 1]
+
+
 @pytest.mark.parametrize("kw", [dict(theta_m=0.2), dict(theta_m=0.2, flat=1, omega_pul=2 * math.pi)])
 def test_host_compiled_pipeline_matches_oracle(oracle, kw):
     p = ArtParams.default(**kw)
     a = hc.run(p, 1769, 1, 200)
     b = oracle.run(p, 1769, 1, 200)
-    assert a["rows"].shape == b["rows"].shape
-    assert np.array_equal(a["rows"][:, :2], b["rows"][:, :2])
-    assert abs(a["f_inx"] - b["f_inx"]) <= 2
+    A, B, good = _same_shape_rows(a["rows"], b["rows"], 200)
+    assert good.mean() >= 0.97  # (a ray whose step sequence differs at round-off level can gain or lose a crossing)
+    assert np.array_equal(A[:, :2], B[:, :2])
+    assert abs(a["f_inx"] - b["f_inx"]) <= 3
 
 
 def test_save_mode_2_rows_match_oracle(oracle):
@@ -130,14 +159,18 @@ def test_save_mode_2_rows_match_oracle(oracle):
     p = ArtParams.default(theta_m=0.2, save_mode=2, Ax_g=1e-10)
     a = hc.run(p, 1769, 1, 150)
     b = oracle.run(p, 1769, 1, 150)
-    assert a["rows"].shape == b["rows"].shape and a["rows"].shape[1] == 31
-    assert np.array_equal(a["rows"][:, :2], b["rows"][:, :2])
-    dk = np.abs(a["rows"][:, 29] - b["rows"][:, 29]) / b["rows"][:, 29]
-    assert np.median(dk) < 1e-9 and dk.max() < 2e-3  # (round-off amplified at the |B_z| kink, see test_gpu_parity.py)
+    assert a["rows"].shape[1] == 31 and b["rows"].shape[1] == 31
+    A, B, good = _same_shape_rows(a["rows"], b["rows"], 150)
+    assert good.mean() >= 0.98
+    assert np.array_equal(A[:, :2], B[:, :2])
+    dk = np.abs(A[:, 29] - B[:, 29]) / B[:, 29]
+    # Vern6: most rays differ in their step sequence (round-off floor of the error estimator), so |k_f| agrees to the
+    # difference of two truncation errors (≈ reltol) instead of round-off; tail: amplified at the |B_z| kink
+    assert np.median(dk) < 1e-6 and dk.max() < 2e-3
     # node times: 0 for the first node, crossing times (located to 1e-13 of a step) otherwise
-    assert np.array_equal(a["rows"][:, 30] == 0, b["rows"][:, 30] == 0) and np.any(b["rows"][:, 30] > 0)
-    dt = np.abs(a["rows"][:, 30] - b["rows"][:, 30]) / np.maximum(b["rows"][:, 30], 1e-300)
-    assert np.median(dt) < 1e-9 and dt.max() < 2e-3
+    assert np.array_equal(A[:, 30] == 0, B[:, 30] == 0) and np.any(B[:, 30] > 0)
+    dt = np.abs(A[:, 30] - B[:, 30]) / np.maximum(B[:, 30], 1e-300)
+    assert np.median(dt) < 1e-6 and dt.max() < 2e-3
     ev = b["events"]
     assert ev.shape == (150, 12) and np.array_equal(ev[:, 0], np.arange(1, 151))
     first = {int(e): r for e, r in reversed(list(zip(b["rows"][:, 0], b["rows"])))}
@@ -182,9 +215,8 @@ def test_switch_matrix_pipeline_matches_oracle(oracle, kw):
     assert (ca == cb)[1:].mean() >= 0.98
     assert abs(a["f_inx"] - b["f_inx"]) <= 0.02 * b["f_inx"] + 2
     assert abs(a["tot_count"] - b["tot_count"]) <= 0.03 * b["tot_count"] + 2
-    good = ca == cb
-    A = a["rows"][good[a["rows"][:, 0].astype(int)]]
-    B = b["rows"][good[b["rows"][:, 0].astype(int)]]
+    A, B, good = _same_shape_rows(a["rows"], b["rows"], n)
+    assert good.mean() >= 0.97
     assert np.array_equal(A[:, :2], B[:, :2])
     assert np.max(np.abs(A[:, 7] - B[:, 7]) / B[:, 7]) < 1e-9      # sln_prob
     assert np.max(np.abs(A[:, 9:12] - B[:, 9:12])) < 1e-9          # sample point
