@@ -34,7 +34,7 @@ F_RHS = 250.0
 F_COND = 150.0
 F_SAMPLER_COND = 150.0
 
-NS = dict(Mass_a=1e-5, Ax_g=1e-12, theta_m=0.2, omega_pul=1.0, B0=1e14, rNS=10.0, Mass_NS=1.0, flat=0)
+NS = dict(Mass_a=1e-5, Ax_g=1e-12, theta_m=0.2, omega_pul=1.0, B0=1e14, rNS=10.0, Mass_NS=1.0, flat=0, integrator=0)
 SEED = 1769
 
 
@@ -59,6 +59,8 @@ def parse():
     ap.add_argument("--events", type=int, default=1_000_000, help="events per rank per step")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--integrator", default="vern6", choices=["vern6", "dp5"],
+                    help="vern6 = the reference's scheme (default); dp5 = round 1's scheme, for comparison")
     return ap.parse_args()
 
 
@@ -190,6 +192,7 @@ def emit(line):
 def main():
     global _JSON_FD
     args = parse()
+    NS["integrator"] = 0 if args.integrator == "vern6" else 1
     sys.stdout.flush()
     _JSON_FD = os.dup(1)
     os.dup2(2, 1)
@@ -345,7 +348,8 @@ def main():
                             "M=1 Msun, R=10 km; 1e6 events per GPU per step (sampler + back-trace + forward tree)",
                 "events_per_gpu_per_step": E, "seed": SEED, "reltol": p.reltol, "abstol": p.ode_err,
                 "interp_points_ray": p.interp_points_ray, "interp_points_sampler": p.interp_points_sampler,
-                "integrator": "DP5(4) FSAL, OrdinaryDiffEq PI controller (Vern6 tableau unavailable offline)",
+                "integrator": ("Vern6 (Verner 9-stage 6(5), the reference's solve(prob, Vern6()) RT.jl:383), lazy 6th-order dense output"
+                               if p.integrator == 0 else "DP5(4) FSAL (round 1's scheme)") + ", OrdinaryDiffEq PI controller",
                 "l2": "working set ~8 GB per step >> 126 MB L2, no flush needed",
                 "events_per_s": agg["n_events"] * world / (ms_dev * 1e-3),
                 "ray_propagations_per_s": agg["n_rays"] * world / (ms_dev * 1e-3),

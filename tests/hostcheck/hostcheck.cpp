@@ -251,3 +251,59 @@ extern "C" int hc_trace_ray(const art_params* p, int32_t species, const double* 
   }
   return n;
 }
+
+// Certified-sign shortcuts of the wavefront stage kernel (Ray::step_all_far / step_sign / step_in_start_box) against the
+// literal scan of the same accepted step: counts[0] accepted steps, [1] steps with a certified sign, [2] certified steps
+// whose literal scan holds a point of another sign, [3] steps certified "inside the start box", [4] of those, steps with
+// a scan point outside the box.
+template <int IG>
+static void certify_ray(const DevParams& P, const RayIn& in, double* rec, int cap, long long counts[5]) {
+  Ray R;
+  double kbuf[K_ROWS], sbuf[SEG_MAX];
+  KStore K{kbuf, 1};
+  SegStore D{sbuf, 1};
+  R.init(P, in, rec, cap);
+  double s0[3] = {R.s0[0], R.s0[1], R.s0[2]};
+  while (!R.done) {
+    if (!R.template stages<IG>(P, K, D)) continue;
+    ScanMasks m = {0ull, 0ull, 0ull};
+    const int M = P.M_ray;
+    for (int i = R.event_last ? 0 : 1; i < M; ++i) {
+      const double g = seg_cond<IG>(P, D, seg_theta(P, i));
+      if (g > 0.0) m.pos |= 1ull << i;
+      else if (g < 0.0) m.neg |= 1ull << i;
+      else if (g == 0.0) m.zero |= 1ull << i;
+    }
+    counts[0]++;
+    const int cs = R.template step_all_far<IG>(P, K) ? -1 : R.template step_sign<IG>(P, K, exp(R.s_new));
+    if (cs != 0) {
+      counts[1]++;
+      const unsigned long long other = cs < 0 ? (m.pos | m.zero) : (m.neg | m.zero);
+      if (other) counts[2]++;
+    }
+    if (R.n_cross == 0 && R.template step_in_start_box<IG>(K, s0, R.box_m)) {
+      counts[3]++;
+      bool all_in = true;
+      for (int i = 1; i < M; ++i) all_in = all_in && R.template in_start_box<IG>(P, D, seg_theta(P, i));
+      if (!all_in) counts[4]++;
+    }
+    R.template finish_step<IG>(P, K, D, m);
+  }
+}
+
+extern "C" int hc_certificates(const art_params* p, int64_t n, const int32_t* species, const double* x0, const double* k0,
+                               const double* erg, int32_t max_crossings, long long* counts) {
+  DevParams P;
+  int rc = dev(p, P);
+  if (rc) return rc;
+  for (int k = 0; k < 5; ++k) counts[k] = 0;
+  std::vector<double> rec((size_t)p->cross_cap * 8);
+  for (int64_t i = 0; i < n; ++i) {
+    RayIn in;
+    for (int c = 0; c < 3; ++c) { in.x0[c] = x0[c * n + i]; in.k0[c] = k0[c * n + i]; }
+    in.erg = erg[i]; in.t_start = 0.0; in.dOmega = -1.0; in.max_cross = max_crossings; in.species = species[i];
+    if (P.integrator == IG_DP5) certify_ray<IG_DP5>(P, in, rec.data(), p->cross_cap, counts);
+    else certify_ray<IG_VERN6>(P, in, rec.data(), p->cross_cap, counts);
+  }
+  return 0;
+}

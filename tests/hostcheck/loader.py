@@ -132,3 +132,15 @@ def run(p, seed, first_event, n_events):
     nr, fi, tc = C.c_int64(), C.c_int64(), C.c_int64()
     _chk(lib().hc_run(C.byref(p), seed, first_event, n_events, rows, cap, C.byref(nr), C.byref(fi), C.byref(tc)))
     return dict(rows=rows[: nr.value].copy(), f_inx=fi.value, tot_count=tc.value)
+
+
+def certificates(p, species, x0, k0, erg, max_crossings=-1):
+    """Certified-sign shortcuts vs the literal scan: [accepted steps, certified, contradicted, in-box, in-box contradicted]."""
+    x0 = np.ascontiguousarray(x0, np.float64)
+    n = x0.shape[1]
+    counts = np.zeros(5, np.int64)
+    _chk(lib().hc_certificates(C.byref(p), n, np.ascontiguousarray(species, np.int32).ctypes.data_as(C.c_void_p),
+                               x0.ctypes.data_as(C.c_void_p), np.ascontiguousarray(k0, np.float64).ctypes.data_as(C.c_void_p),
+                               np.ascontiguousarray(erg, np.float64).ctypes.data_as(C.c_void_p), max_crossings,
+                               counts.ctypes.data_as(C.c_void_p)))
+    return counts

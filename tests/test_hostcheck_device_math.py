@@ -116,6 +116,24 @@ def test_host_compiled_tracer_matches_oracle(oracle, kw, integrator):
             assert b["counters"][:, 2].mean() == pytest.approx(a["counters"][:, 2].mean(), rel=0.02)
 
 
+@pytest.mark.parametrize("integrator", [0, 1], ids=["vern6", "dp5"])
+@pytest.mark.parametrize("kw", [dict(theta_m=0.2), dict(theta_m=0.2, flat=1, omega_pul=2 * math.pi), dict(theta_m=0.9, Mass_a=3e-6)])
+def test_certified_step_signs_never_contradict_the_literal_scan(oracle, kw, integrator):
+    """The wavefront stage kernel skips the crossing scan (and Vern6's three dense-output stages) of steps whose sign it can
+    certify from the stage store alone (Ray::step_all_far / step_sign / step_in_start_box).  For DP5 the enclosure of the
+    dense output is rigorous; for Vern6 it is the Hermite-cubic hull widened by half (art_tracer.cuh, chord_dev).  Here every
+    accepted step of host-compiled rays is certified AND scanned literally on its real 6th-order dense output: no certified
+    step may hold a scan point of another sign, no "inside the start box" step a scan point outside the box."""
+    p = ArtParams.default(integrator=integrator, **kw)
+    n = 250
+    s = oracle.sample(p, 5, 1, n)
+    w = oracle.weights(p, s["x"], s["v_loc"], s["v_inf"])
+    for sp, mc, bs in ((1, -1, 1), (0, 100000, -1)):
+        c = hc.certificates(p, np.full(n, sp, np.int32), s["x"], w["k_init"] * bs, w["erg_inf"], mc)
+        assert c[0] > 30 * n and c[1] > 0.25 * c[0] and c[3] > 0.03 * c[0]  # the shortcuts are actually taken
+        assert c[2] == 0 and c[4] == 0
+
+
 def test_host_compiled_sampler_matches_oracle(oracle):
     for kw in (dict(theta_m=0.2), dict(theta_m=0.2, rNS=12.0), dict(theta_m=0.2, rNS=8.0), dict(theta_m=0.2, thick_surface=0),
                dict(theta_m=1.1, Mass_a=2e-5, B0=2e14, omega_pul=3.0, thick_surface=0)):
