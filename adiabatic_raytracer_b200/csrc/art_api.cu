@@ -95,25 +95,38 @@ bool nccl_load(std::string& err) {
 
 }  // namespace
 
-// Per-stream working set: one "lane" traces one sub-chunk of events at a time.  Several lanes run
-// concurrently (host thread + CUDA stream each) so that the thin tail of one sub-chunk's wavefront loop
-// overlaps the sampler and the bulk steps of the others.
+// RAII for the CUDA events of one call (error paths return early: nothing may leak)
+struct EvGuard {
+  std::vector<cudaEvent_t> ev;
+  cudaEvent_t make(unsigned flags = cudaEventDefault) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreateWithFlags(&e, flags) != cudaSuccess) return nullptr;
+    ev.push_back(e);
+    return e;
+  }
+  ~EvGuard() {
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+  }
+};
+
+// Working set of the wavefront loop: three streams (main: stages → scan → detect; side: root finder, tree and injection,
+// one iteration behind; sampler: the next block of events, concurrently with the loop) and the ray / event-slot pools.
 struct Lane {
-  cudaStream_t stream = nullptr, stream2 = nullptr;  // stream2: root finder + tree, one iteration behind the stage kernel
-  cudaEvent_t ev_reset = nullptr, ev_side = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr;
+  cudaEvent_t ev_main = nullptr, ev_side = nullptr, ev_samp = nullptr;
   DBuf samples, tstate, stacks, q0, rout, rec, ctr;
-  DBuf wf_hot, wf_cold, wf_seg, wf_need, wf_neg, wf_pend, wf_sign, wf_act[4], wf_items, wf_roots[2], wf_fin[2], wf_ctr;
+  DBuf slot_event, slot_parts, ring;
+  DBuf wf_hot, wf_cold, wf_seg, wf_need, wf_neg, wf_pend, wf_sign, wf_act[4], wf_roots[2], wf_fin[2], wf_ctr;
   float ms_sampler = 0, ms_weights = 0, ms_tracer = 0;
   void release() {
-    DBuf* all[] = {&samples, &tstate, &stacks, &q0, &rout, &rec, &ctr, &wf_hot, &wf_cold, &wf_seg, &wf_need, &wf_neg,
-                   &wf_pend, &wf_sign, &wf_act[0], &wf_act[1], &wf_act[2], &wf_act[3], &wf_items, &wf_roots[0], &wf_roots[1], &wf_fin[0], &wf_fin[1], &wf_ctr};
+    DBuf* all[] = {&samples, &tstate, &stacks, &q0, &rout, &rec, &ctr, &slot_event, &slot_parts, &ring, &wf_hot, &wf_cold, &wf_seg,
+                   &wf_need, &wf_neg, &wf_pend, &wf_sign, &wf_act[0], &wf_act[1], &wf_act[2], &wf_act[3], &wf_roots[0], &wf_roots[1],
+                   &wf_fin[0], &wf_fin[1], &wf_ctr};
     for (DBuf* b : all) b->release();
-    if (stream) cudaStreamDestroy(stream);
-    if (stream2) cudaStreamDestroy(stream2);
-    if (ev_reset) cudaEventDestroy(ev_reset);
-    if (ev_side) cudaEventDestroy(ev_side);
-    stream = stream2 = nullptr;
-    ev_reset = ev_side = nullptr;
+    for (cudaStream_t* st : {&stream, &stream2, &stream3})
+      if (*st) { cudaStreamDestroy(*st); *st = nullptr; }
+    for (cudaEvent_t* e : {&ev_main, &ev_side, &ev_samp})
+      if (*e) { cudaEventDestroy(*e); *e = nullptr; }
   }
 };
 
@@ -128,11 +141,13 @@ struct art_handle {
   std::vector<Lane> lanes;
   // shared by all lanes of a pipeline call
   DBuf events, fin_count, fin_info, gctr, stats;
-  DBuf rows, keys, hist, scratch[12];
+  DBuf rows, keys, hist, hist_global, scratch[12];
+  bool have_global = false;       // hist_global holds the result of an all-reduce of the CURRENT local block
   DBuf q[2];                      // fine-grained art_propagate queue
   long long rows_cap = 0;         // rows held on device
   long long n_rows_dev = 0;
-  long long last_first_event = 0, last_n_events = 0;  // event range of the last pipeline call (art_fetch_events)
+  long long last_first_event = 0, last_n_events = 0;  // events of the last pipeline call (art_fetch_events)
+  long long last_batch_events = 1, last_batch_stride = 1;
   int ncols = 13;
   int n_ct = 16, n_ph = 16, n_dw = 1;
   double dw_lo = 0.0, dw_hi = 0.0;
@@ -151,8 +166,8 @@ struct art_handle {
   long long tail_below = 0;       // rays in flight below which the stage kernel switches to its tail policy (ART_TAIL_BELOW; default 256 per SM)
   int bulk_min_go = 16;           // a warp goes on to its next attempt while this many lanes can (ART_BULK_MIN_GO)
   int tail_nstep = 4;             // attempts per stage launch once fewer rays than one resident wave are left (ART_TAIL_NSTEP)
-  int n_lanes = 1;                // concurrent sub-chunks (ART_LANES); measured: one big chunk beats overlapped small ones
-  long long sub_chunk = 1 << 21;  // events per sub-chunk (ART_SUBCHUNK)
+  long long pool_slots = 1 << 20;  // event slots of the pool = events in flight at a time (ART_POOL_SLOTS); 2 rays per slot
+  long long refill_min = 0;        // free slots at which the next block of events is sampled (ART_REFILL_MIN; default pool / 8)
 };
 
 namespace {
@@ -187,33 +202,43 @@ int ensure_lanes(art_handle* h, int n) {
     h->lanes.emplace_back();
     CU(cudaStreamCreateWithFlags(&h->lanes.back().stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&h->lanes.back().stream2, cudaStreamNonBlocking));
-    CU(cudaEventCreateWithFlags(&h->lanes.back().ev_reset, cudaEventDisableTiming));
+    CU(cudaStreamCreateWithFlags(&h->lanes.back().stream3, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&h->lanes.back().ev_main, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->lanes.back().ev_side, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->lanes.back().ev_samp, cudaEventDisableTiming));
   }
   return ART_OK;
 }
 
-// step-batched tracer over a device queue (art_wavefront.cuh).  With a tree context the loop also
-// walks every event's tree: finished rays spawn the next node of their event in place.
-template <int IG>
-int launch_trace_wf_t(art_handle* h, Lane& L, const QueuedRay* q, long long n, RayOut* out, double* rec, int rec_cap,
-                      DevStats* stats, const WfTree* tree) {
-  if (n <= 0) return ART_OK;
-  cudaStream_t st = L.stream;
-  CU(L.wf_hot.ensure((size_t)n * sizeof(RayHot)));
-  CU(L.wf_cold.ensure((size_t)n * sizeof(RayCold)));
-  CU(L.wf_seg.ensure((size_t)n * Seg<IG>::N * sizeof(double)));
-  CU(L.wf_need.ensure((size_t)n * 8));
-  CU(L.wf_neg.ensure((size_t)n * 8));
-  CU(L.wf_sign.ensure((size_t)n * 8));
-  for (int k = 0; k < 4; ++k) CU(L.wf_act[k].ensure((size_t)n * 4));
-  CU(L.wf_pend.ensure((size_t)n * 4));
+// Events the loop still has to start (fused pipeline): sampled block by block on the sampler stream while the
+// loop runs, injected into free slots by the side pass.
+struct PoolJob {
+  uint64_t seed = 0;
+  long long first_event = 0, n_events = 0, next_e = 0;
+  long long batch_size = 1, batch_stride = 1;  // event (index e) has id first_event + (e / batch_size) batch_stride + e % batch_size
+  long long S = 0;                // event slots
+  unsigned long long head = 0;    // free-slot ring: slots [head, tail) are free; tail lives on the device
+  int state = 0;                  // 0 idle, 1 sampling, 2 sampled: inject in the next side pass
+  int m = 0, e0 = 0;              // block being sampled / injected
+  unsigned long long* gctr = nullptr;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> samp_ev;  // timing of the sampler launches
+  long long n_blocks = 0;
+};
+
+int wf_alloc(art_handle* h, Lane& L, long long n_rays, int seg_doubles, WfPool& W) {
+  CU(L.wf_hot.ensure((size_t)n_rays * sizeof(RayHot)));
+  CU(L.wf_cold.ensure((size_t)n_rays * sizeof(RayCold)));
+  CU(L.wf_seg.ensure((size_t)n_rays * seg_doubles * sizeof(double)));
+  CU(L.wf_need.ensure((size_t)n_rays * 8));
+  CU(L.wf_neg.ensure((size_t)n_rays * 8));
+  CU(L.wf_sign.ensure((size_t)n_rays * 8));
+  for (int k = 0; k < 4; ++k) CU(L.wf_act[k].ensure((size_t)n_rays * 4));
+  CU(L.wf_pend.ensure((size_t)n_rays * 4));
   for (int k = 0; k < 2; ++k) {
-    CU(L.wf_roots[k].ensure((size_t)n * 4));
-    CU(L.wf_fin[k].ensure((size_t)n * 4));
+    CU(L.wf_roots[k].ensure((size_t)n_rays * 4));
+    CU(L.wf_fin[k].ensure((size_t)n_rays * 4));
   }
   CU(L.wf_ctr.ensure(WC_N * 8));
-  WfPool W;
   W.hot = L.wf_hot.as<RayHot>(); W.cold = L.wf_cold.as<RayCold>(); W.seg = L.wf_seg.as<double>();
   W.mpos = L.wf_need.as<unsigned long long>(); W.mneg = L.wf_neg.as<unsigned long long>();
   W.mzero = L.wf_sign.as<unsigned long long>();
@@ -222,74 +247,151 @@ int launch_trace_wf_t(art_handle* h, Lane& L, const QueuedRay* q, long long n, R
   W.pend = L.wf_pend.as<int>();
   for (int k = 0; k < 2; ++k) { W.roots[k] = L.wf_roots[k].as<int>(); W.fin[k] = L.wf_fin[k].as<int>(); }
   W.ctr = L.wf_ctr.as<unsigned long long>();
+  return ART_OK;
+}
+
+// The wavefront loop (art_wavefront.cuh).  n_act0 rays are already on the active lists of iteration 0 (plain batches,
+// art_propagate); with a tree context every finished ray walks its event's tree, and with a job the loop keeps
+// starting new events in the slots that finished ones hand back.
+template <int IG>
+int wf_loop(art_handle* h, Lane& L, WfPool W, long long n_act0, RayOut* out, double* rec, int rec_cap, DevStats* stats,
+            const WfTree* tree, PoolJob* job, EvGuard& evg) {
+  cudaStream_t st = L.stream;
   const size_t ksmem = (size_t)(K_ROWS + K_PARK) * STAGE_THREADS * sizeof(double);
-  CU(cudaMemsetAsync(W.ctr, 0, WC_N * 8, st));
   const int gmax = h->n_sm * h->wf_grid_per_sm;
   auto grid = [&](long long work, int threads) { return (int)std::max<long long>(1, std::min<long long>(gmax, (work + threads - 1) / threads)); };
-  k_wf_init<IG><<<grid(n, WF_THREADS), WF_THREADS, 0, st>>>(h->dp, q, n, W, rec, rec_cap, stats);
-  h->launches++;
-  CU(cudaGetLastError());
-  long long n_act = n;  // upper bound of the rays in flight, refreshed at every host check
-  int cur = 0;
+  long long n_act = n_act0;  // upper bound of the rays in flight, refreshed at every host check
   const bool trace = getenv("ART_WF_TRACE") != nullptr;
   // ART_SIDE_STREAM=0 keeps everything on one stream (profilers serialise kernels and make stream waits costly)
   const bool side = !(getenv("ART_SIDE_STREAM") && atoi(getenv("ART_SIDE_STREAM")) == 0);
   cudaStream_t s2 = side ? L.stream2 : st;
+  cudaStream_t s3 = side ? L.stream3 : st;
+  const long long refill_min = job ? (h->refill_min > 0 ? h->refill_min : std::max<long long>(job->S / 8, 1)) : 0;
+  long long iter_cap = 64LL * h->params.maxiters;
+  if (job) iter_cap *= (job->n_events / std::max<long long>(job->S, 1) + 2);
+  unsigned long long ring_tail = job ? (unsigned long long)job->S : 0ull;  // as of the last counter read (k_ring_init: all slots free)
   for (long long iter = 0;;) {
-    const int burst = n_act > 500000 ? 8 : (n_act > 65536 ? 16 : 32);  // steps between host checks (deep queue: host jitter must not idle the GPU)
-    const bool tail = n_act < h->tail_below;                            // thin tail: any lane keeps its warp stepping
+    // ---- host check: start sampling the next block of events when enough slots are free ------------------------------
+    if (job) {
+      const long long n_free = (long long)(ring_tail - job->head);
+      const long long remaining = job->n_events - job->next_e;
+      // a block never straddles two batches of the call (the sampler numbers its events from one first id)
+      const long long batch_left = job->batch_size - job->next_e % job->batch_size;
+      if (job->state == 0 && remaining > 0 && n_free >= std::min(std::min(remaining, batch_left), refill_min)) {
+        job->m = (int)std::min(std::min(remaining, batch_left), n_free);
+        job->e0 = (int)job->next_e;
+        job->next_e += job->m;
+        cudaEvent_t ea = evg.make(), eb = evg.make();
+        if (!ea || !eb) return fail(h, ART_ERR_CUDA, "cudaEventCreate");
+        if (side) CU(cudaStreamWaitEvent(s3, L.ev_side, 0));  // (the sample buffer of the previous block has been consumed)
+        CU(cudaMemsetAsync(L.ctr.p, 0, 64, s3));
+        CU(cudaEventRecord(ea, s3));
+        const int blocks = (int)std::min<long long>(h->blocks_sample, (job->m + SAMPLE_THREADS - 1) / SAMPLE_THREADS);
+        const long long id0 = job->first_event + (job->e0 / job->batch_size) * job->batch_stride + job->e0 % job->batch_size;
+        k_sample_events<<<blocks, SAMPLE_THREADS, 0, s3>>>(h->dp, job->seed, id0, job->m,
+                                                           L.samples.as<EventSample>(), L.ctr.as<unsigned long long>(), stats, job->gctr);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(eb, s3));
+        CU(cudaEventRecord(L.ev_samp, s3));
+        job->samp_ev.emplace_back(ea, eb);
+        job->n_blocks++;
+        h->launches++;
+        job->state = 1;
+      }
+      if (job->state == 1) {
+        // nothing in flight: wait for the block; otherwise pick it up as soon as it is there
+        const cudaError_t q = n_act == 0 ? cudaEventSynchronize(L.ev_samp) : cudaEventQuery(L.ev_samp);
+        if (q == cudaSuccess) job->state = 2;
+        else if (q != cudaErrorNotReady) return fail(h, ART_ERR_CUDA, std::string("sampler: ") + cudaGetErrorString(q));
+      }
+      if (n_act == 0 && job->state == 0 && job->n_events - job->next_e == 0) break;
+    } else if (n_act == 0) {
+      break;
+    }
+    const long long n_plan = n_act + (job && job->state == 2 ? 2LL * job->m : 0);  // … with the block about to be injected
+    const int burst = n_plan > 500000 ? 8 : (n_plan > 65536 ? 16 : 32);  // steps between host checks (deep queue: host jitter must not idle the GPU)
+    const bool tail_mode = n_plan < h->tail_below;                        // thin tail: any lane keeps its warp stepping
     for (int b = 0; b < burst; ++b, ++iter) {
-      const int next = 1 - cur;
-      const int lpar = (int)(iter & 1), lin = 1 - lpar;  // lists this iteration fills / lists of the previous one
-      // main stream: the side stream's previous pass must be through before its lists are zeroed
-      if (side) CU(cudaStreamWaitEvent(st, L.ev_side, 0));
-      k_wf_reset<<<1, 32, 0, st>>>(W, next, lpar);
-      if (side) CU(cudaEventRecord(L.ev_reset, st));
-      // side stream: root finder and tree of the PREVIOUS iteration's lists, concurrent with this stage kernel
-      if (side) CU(cudaStreamWaitEvent(s2, L.ev_reset, 0));
-      k_wf_root<IG><<<grid(n_act / 2 + 1, WF_THREADS), WF_THREADS, 0, s2>>>(h->dp, W, next, lin, lpar, stats);
+      const int k = (int)(iter & 0x3fffffff);
+      // main stream: the side pass of iteration k − 1 has filled the active lists of iteration k
+      if (side) {
+        CU(cudaStreamWaitEvent(st, L.ev_side, 0));
+        CU(cudaEventRecord(L.ev_main, st));   // detect(k − 1) is through: its roots / finished lists are complete
+        CU(cudaStreamWaitEvent(s2, L.ev_main, 0));
+      }
+      // side stream: root finder, tree and injection on the lists iteration k − 1 produced, concurrent with stages(k)
+      k_wf_root<IG><<<grid(n_act / 2 + 1, WF_THREADS), WF_THREADS, 0, s2>>>(h->dp, W, k, stats);
       if (tree)
-        k_wf_tree<IG><<<grid(n_act / 2 + 1, WF_THREADS), WF_THREADS, 0, s2>>>(h->dp, W, *tree, next, lin, rec, rec_cap, stats);
+        k_wf_tree<IG><<<grid(n_act / 2 + 1, WF_THREADS), WF_THREADS, 0, s2>>>(h->dp, W, *tree, k, rec, rec_cap, stats);
       else
-        k_wf_collect<<<grid(n_act / 4 + 1, WF_THREADS), WF_THREADS, 0, s2>>>(h->dp, W, lin, out, stats);
+        k_wf_collect<<<grid(n_act / 4 + 1, WF_THREADS), WF_THREADS, 0, s2>>>(h->dp, W, k, out, stats);
+      h->launches += 2;
+      if (job && job->state == 2) {
+        if (side) CU(cudaStreamWaitEvent(s2, L.ev_samp, 0));
+        k_wf_inject<IG><<<grid(2LL * job->m, WF_THREADS), WF_THREADS, 0, s2>>>(h->dp, W, *tree, k, L.samples.as<EventSample>(), job->m,
+                                                                               job->e0, job->head, rec, rec_cap, stats);
+        h->launches++;
+        job->head += (unsigned long long)job->m;
+        n_act += 2LL * job->m;
+        job->state = 0;
+      }
       if (side) CU(cudaEventRecord(L.ev_side, s2));
       const int gs = (int)std::max<long long>(1, std::min<long long>((long long)h->n_sm * h->stage_grid_per_sm, (n_act + STAGE_THREADS - 1) / STAGE_THREADS));
-      k_wf_stages<IG><<<2 * gs, STAGE_THREADS, ksmem, st>>>(h->dp, W, cur, lpar, tail ? h->tail_nstep : h->bulk_nstep, tail ? 1 : h->bulk_min_go, stats);
+      k_wf_stages<IG><<<2 * gs, STAGE_THREADS, ksmem, st>>>(h->dp, W, k, tail_mode ? h->tail_nstep : h->bulk_nstep, tail_mode ? 1 : h->bulk_min_go, stats);
       k_wf_scan<IG><<<(int)std::max<long long>(1, std::min<long long>((long long)h->n_sm * h->scan_grid_per_sm, (n_act * 11 + SCAN_THREADS - 1) / SCAN_THREADS)),
-                  SCAN_THREADS, 0, st>>>(h->dp, W, stats);
+                      SCAN_THREADS, 0, st>>>(h->dp, W, k, stats);
       k_wf_detect<IG><<<(int)std::max<long long>(1, std::min<long long>((long long)h->n_sm * h->detect_grid_per_sm, (n_act + WF_THREADS - 1) / WF_THREADS)),
-                    WF_THREADS, 0, st>>>(h->dp, W, next, lpar);
-      h->launches += 6;
-      cur = next;
+                        WF_THREADS, 0, st>>>(h->dp, W, k);
+      h->launches += 3;
     }
     CU(cudaGetLastError());
     if (side) CU(cudaStreamWaitEvent(st, L.ev_side, 0));
     unsigned long long c[WC_N];
     CU(cudaMemcpyAsync(c, W.ctr, sizeof(c), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    const int lastpar = (int)((iter - 1) & 1);
-    const unsigned long long na0 = c[WC_ACT + cur * 2], na1 = c[WC_ACT + cur * 2 + 1];
-    n_act = (long long)(na0 + na1 + c[WC_ROOTS + lastpar] + c[WC_FIN + lastpar]);
+    // next iteration: its active lists, plus the roots / finished lists of the last one (the side pass picks them up)
+    const int kn = (int)(iter & 3), kl = (int)((iter - 1) & 3);
+    const unsigned long long na0 = c[kn * WC_SET + WC_ACT], na1 = c[kn * WC_SET + WC_ACT + 1];
+    n_act = (long long)(na0 + na1 + c[kl * WC_SET + WC_ROOTS] + c[kl * WC_SET + WC_FIN]);
+    ring_tail = c[WC_RING_TAIL];
     if (trace) {
       timespec ts;
       clock_gettime(CLOCK_MONOTONIC, &ts);
       const double now = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
       static thread_local double t_prev = 0.0;
-      fprintf(stderr, "[wf %p] iter %lld in flight %lld (ax %llu ph %llu roots %llu finished %llu) +%.2f ms = %.0f us/iteration\n", (void*)&L,
-              iter, n_act, na0, na1, c[WC_ROOTS + lastpar], c[WC_FIN + lastpar], t_prev > 0 ? now - t_prev : 0.0,
-              t_prev > 0 ? (now - t_prev) * 1e3 / burst : 0.0);
+      fprintf(stderr, "[wf] iter %lld in flight %lld (ax %llu ph %llu roots %llu finished %llu) started %lld free %lld +%.2f ms = %.0f us/iteration\n",
+              iter, n_act, na0, na1, c[kl * WC_SET + WC_ROOTS], c[kl * WC_SET + WC_FIN], job ? job->next_e : 0,
+              job ? (long long)(c[WC_RING_TAIL] - job->head) : 0, t_prev > 0 ? now - t_prev : 0.0, t_prev > 0 ? (now - t_prev) * 1e3 / burst : 0.0);
       t_prev = now;
     }
-    if (n_act == 0) break;
-    if (iter > 64LL * h->params.maxiters) return fail(h, ART_ERR_CUDA, "wavefront tracer did not terminate");
+    if (iter > iter_cap) return fail(h, ART_ERR_CUDA, "wavefront tracer did not terminate");
   }
   return ART_OK;
 }
 
+// step-batched tracer over a device queue of plain rays (art_propagate)
+template <int IG>
+int launch_trace_wf_t(art_handle* h, Lane& L, const QueuedRay* q, long long n, RayOut* out, double* rec, int rec_cap,
+                      DevStats* stats) {
+  if (n <= 0) return ART_OK;
+  cudaStream_t st = L.stream;
+  WfPool W;
+  if (int rc = wf_alloc(h, L, n, Seg<IG>::N, W)) return rc;
+  CU(cudaMemsetAsync(W.ctr, 0, WC_N * 8, st));
+  const int gmax = h->n_sm * h->wf_grid_per_sm;
+  k_wf_init<IG><<<(int)std::max<long long>(1, std::min<long long>(gmax, (n + WF_THREADS - 1) / WF_THREADS)), WF_THREADS, 0, st>>>(
+      h->dp, q, n, W, rec, rec_cap, stats);
+  h->launches++;
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(L.ev_side, st));  // (the first iteration waits for "the previous side pass")
+  EvGuard evg;
+  return wf_loop<IG>(h, L, W, n, out, rec, rec_cap, stats, nullptr, nullptr, evg);
+}
+
 int launch_trace_wf(art_handle* h, Lane& L, const QueuedRay* q, long long n, RayOut* out, double* rec, int rec_cap,
-                    DevStats* stats, const WfTree* tree) {
-  return h->dp.integrator == IG_DP5 ? launch_trace_wf_t<IG_DP5>(h, L, q, n, out, rec, rec_cap, stats, tree)
-                                    : launch_trace_wf_t<IG_VERN6>(h, L, q, n, out, rec, rec_cap, stats, tree);
+                    DevStats* stats) {
+  return h->dp.integrator == IG_DP5 ? launch_trace_wf_t<IG_DP5>(h, L, q, n, out, rec, rec_cap, stats)
+                                    : launch_trace_wf_t<IG_VERN6>(h, L, q, n, out, rec, rec_cap, stats);
 }
 
 }  // namespace
@@ -363,8 +465,8 @@ int art_create(const art_params* p, int device_id, art_handle** out) {
   if (const char* t = getenv("ART_STAGE_GRID_PER_SM")) h->stage_grid_per_sm = std::max(1, atoi(t));
   h->tail_below = 256LL * h->n_sm;
   if (const char* t = getenv("ART_TAIL_BELOW")) h->tail_below = std::max(0LL, atoll(t));
-  if (const char* t = getenv("ART_LANES")) h->n_lanes = std::max(1, std::min(16, atoi(t)));
-  if (const char* t = getenv("ART_SUBCHUNK")) h->sub_chunk = std::max(1024LL, atoll(t));
+  if (const char* t = getenv("ART_POOL_SLOTS")) h->pool_slots = std::max(32LL, atoll(t));
+  if (const char* t = getenv("ART_REFILL_MIN")) h->refill_min = std::max(1LL, atoll(t));
   ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (ce != cudaSuccess) {
     std::string m = cudaGetErrorString(ce);
@@ -380,7 +482,7 @@ void art_destroy(art_handle* h) {
   cudaSetDevice(h->device);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   for (Lane& L : h->lanes) L.release();
-  DBuf* all[] = {&h->events, &h->fin_count, &h->fin_info, &h->gctr, &h->stats, &h->rows, &h->keys, &h->hist, &h->q[0], &h->q[1]};
+  DBuf* all[] = {&h->events, &h->fin_count, &h->fin_info, &h->gctr, &h->stats, &h->rows, &h->keys, &h->hist, &h->hist_global, &h->q[0], &h->q[1]};
   for (DBuf* b : all) b->release();
   for (DBuf& b : h->scratch) b.release();
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -517,7 +619,7 @@ int art_propagate(art_handle* h, int64_t n, const int32_t* species, const double
   CU(L.rec.ensure((size_t)n * cross_cap * 8 * sizeof(double)));
   CU(cudaMemsetAsync(L.rec.p, 0, (size_t)n * cross_cap * 8 * sizeof(double), h->stream));
   CU(cudaStreamSynchronize(h->stream));
-  if (int rc = launch_trace_wf(h, L, h->q[0].as<QueuedRay>(), n, L.rout.as<RayOut>(), L.rec.as<double>(), cross_cap, nullptr, nullptr))
+  if (int rc = launch_trace_wf(h, L, h->q[0].as<QueuedRay>(), n, L.rout.as<RayOut>(), L.rec.as<double>(), cross_cap, nullptr))
     return rc;
   std::vector<RayOut> ro((size_t)n);
   CU(cudaMemcpyAsync(ro.data(), L.rout.p, n * sizeof(RayOut), cudaMemcpyDeviceToHost, h->stream));
@@ -561,6 +663,7 @@ int art_hist_reset(art_handle* h) {
   CU(h->hist.ensure(bytes));
   CU(cudaMemsetAsync(h->hist.p, 0, bytes, h->stream));
   for (double& c : h->host_counters) c = 0.0;
+  h->have_global = false;
   CU(cudaStreamSynchronize(h->stream));
   return ART_OK;
 }
@@ -571,6 +674,7 @@ static int hist_push_counters(art_handle* h) {
   return ART_OK;
 }
 
+// This GPU's block: bins accumulated by every pipeline call since the last reset + this GPU's trailing counters.
 int art_hist_get(art_handle* h, double* out, int64_t cap) {
   if (!h || !out || cap < art_hist_len(h)) return ART_ERR_ARG;
   CU(cudaSetDevice(h->device));
@@ -578,71 +682,85 @@ int art_hist_get(art_handle* h, double* out, int64_t cap) {
     int rc = art_hist_reset(h);
     if (rc) return rc;
   }
-  if (!h->comm || h->nranks == 1) {
-    int rc = hist_push_counters(h);
-    if (rc) return rc;
-  }
+  int rc = hist_push_counters(h);
+  if (rc) return rc;
   CU(cudaMemcpyAsync(out, h->hist.p, (size_t)art_hist_len(h) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return ART_OK;
 }
 
-// One sub-chunk of events on one lane: sampler → weights → fused wavefront loop (back-traces + trees).
-static int run_subchunk(art_handle* h, Lane& L, uint64_t seed, int64_t first_event, long long base, long long n,
-                        const RowSink& sink, unsigned long long* gctr, DevStats* dstats) {
+// The all-reduced block of the last art_comm_allreduce_hist (sum over the ranks of what art_hist_get returns on each).
+int art_hist_get_global(art_handle* h, double* out, int64_t cap) {
+  if (!h || !out || cap < art_hist_len(h)) return ART_ERR_ARG;
   CU(cudaSetDevice(h->device));
-  const DevParams& P = h->dp;
-  const int cap = h->params.cross_cap;
-  const int stack_stride = h->params.max_nodes + 4;
-  cudaStream_t st = L.stream;
-  CU(L.samples.ensure(n * sizeof(EventSample)));
-  CU(L.tstate.ensure(n * sizeof(TreeState)));
-  CU(L.stacks.ensure((size_t)n * stack_stride * sizeof(TreeNode)));
-  CU(L.q0.ensure(2 * n * sizeof(QueuedRay)));
-  CU(L.rout.ensure(2 * n * sizeof(RayOut)));
-  CU(L.rec.ensure((size_t)2 * n * cap * 8 * sizeof(double)));
-  CU(L.ctr.ensure(64));
-  cudaEvent_t ev[4];
-  for (auto& e : ev) CU(cudaEventCreate(&e));
-  EventData* events = h->events.as<EventData>() + base;
-  // K1 sampler
-  CU(cudaEventRecord(ev[0], st));
-  CU(cudaMemsetAsync(L.ctr.p, 0, 64, st));
-  {
-    const int blocks = (int)std::min<long long>(h->blocks_sample, (n + SAMPLE_THREADS - 1) / SAMPLE_THREADS);
-    k_sample_events<<<blocks, SAMPLE_THREADS, 0, st>>>(P, seed, first_event + base, n, L.samples.as<EventSample>(),
-                                                       L.ctr.as<unsigned long long>(), dstats, gctr + 0);
-    h->launches++;
-    CU(cudaGetLastError());
-  }
-  CU(cudaEventRecord(ev[1], st));
-  // K2 weights: EventData, first tree node, and the 2n rays of the loop (n back-traces + n forward photons)
-  k_weights_events<<<nblk(n, 128), 128, 0, st>>>(P, n, L.samples.as<EventSample>(), events, L.tstate.as<TreeState>(),
-                                                 L.q0.as<QueuedRay>());
-  h->launches++;
-  CU(cudaGetLastError());
-  CU(cudaEventRecord(ev[2], st));
-  // K3+K4 fused wavefront loop
-  WfTree T;
-  T.ev = events; T.ts = L.tstate.as<TreeState>(); T.stacks = L.stacks.as<TreeNode>();
-  T.stack_stride = stack_stride; T.seed = seed; T.first_event = first_event; T.chunk_base = base; T.n_events = n;
-  T.sink = sink; T.tot_count = gctr + 1; T.fin_count = h->fin_count.as<int>() + base; T.fin_info = h->fin_info.as<int>() + base;
-  if (int rc = launch_trace_wf(h, L, L.q0.as<QueuedRay>(), 2 * n, L.rout.as<RayOut>(), L.rec.as<double>(), cap, dstats, &T))
-    return rc;
-  CU(cudaEventRecord(ev[3], st));
-  CU(cudaStreamSynchronize(st));
-  float t01 = 0, t12 = 0, t23 = 0;
-  cudaEventElapsedTime(&t01, ev[0], ev[1]);
-  cudaEventElapsedTime(&t12, ev[1], ev[2]);
-  cudaEventElapsedTime(&t23, ev[2], ev[3]);
-  L.ms_sampler += t01; L.ms_weights += t12; L.ms_tracer += t23;
-  for (auto& e : ev) cudaEventDestroy(e);
+  if (!h->have_global) return fail(h, ART_ERR_ARG, "art_hist_get_global: no all-reduce since the last pipeline call / reset");
+  CU(cudaMemcpyAsync(out, h->hist_global.p, (size_t)art_hist_len(h) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
   return ART_OK;
 }
 
-int art_run_device(art_handle* h, uint64_t seed, int64_t first_event, int64_t n_events, int64_t* n_rows_out,
-                   int64_t* f_inx_out, int64_t* tot_count_out, art_stats* st_out) {
-  if (!h || n_events < 0) return ART_ERR_ARG;
+}  // extern "C"
+
+// The fused pipeline over the events of one call: one continuously refilled pool (art_wavefront.cuh).
+template <int IG>
+static int run_pool(art_handle* h, Lane& L, uint64_t seed, int64_t first_event, long long n_events, long long batch_size,
+                    long long batch_stride, const RowSink& sink, unsigned long long* gctr, DevStats* dstats, EvGuard& evg) {
+  const int cap = h->params.cross_cap;
+  const int stack_stride = h->params.max_nodes + 4;
+  const long long S = std::max<long long>(32, std::min<long long>(h->pool_slots, n_events));
+  cudaStream_t st = L.stream;
+  CU(L.samples.ensure(S * sizeof(EventSample)));
+  CU(L.tstate.ensure(S * sizeof(TreeState)));
+  CU(L.stacks.ensure((size_t)S * stack_stride * sizeof(TreeNode)));
+  CU(L.rec.ensure((size_t)2 * S * cap * 8 * sizeof(double)));
+  CU(L.ctr.ensure(64));
+  CU(L.slot_event.ensure(S * sizeof(int)));
+  CU(L.slot_parts.ensure(S * sizeof(int)));
+  CU(L.ring.ensure(S * sizeof(int)));
+  WfPool W;
+  if (int rc = wf_alloc(h, L, 2 * S, Seg<IG>::N, W)) return rc;
+  CU(cudaMemsetAsync(W.ctr, 0, WC_N * 8, st));
+  k_ring_init<<<nblk(S, 256), 256, 0, st>>>(L.ring.as<int>(), L.slot_parts.as<int>(), (int)S, W.ctr);
+  h->launches++;
+  CU(cudaGetLastError());
+  WfTree T;
+  T.ev = h->events.as<EventData>(); T.fin_count = h->fin_count.as<int>(); T.fin_info = h->fin_info.as<int>();
+  T.ts = L.tstate.as<TreeState>(); T.stacks = L.stacks.as<TreeNode>(); T.slot_event = L.slot_event.as<int>();
+  T.slot_parts = L.slot_parts.as<int>(); T.ring = L.ring.as<int>(); T.stack_stride = stack_stride; T.n_slots = (int)S;
+  T.seed = seed; T.first_event = first_event; T.batch_size = batch_size; T.batch_stride = batch_stride; T.sink = sink;
+  T.tot_count = gctr + 1;
+  PoolJob job;
+  job.seed = seed; job.first_event = first_event; job.n_events = n_events; job.S = S; job.gctr = gctr + 0;
+  job.batch_size = batch_size; job.batch_stride = batch_stride;
+  cudaEvent_t t0 = evg.make(), t1 = evg.make();
+  if (!t0 || !t1) return fail(h, ART_ERR_CUDA, "cudaEventCreate");
+  CU(cudaEventRecord(t0, st));
+  const int rc = wf_loop<IG>(h, L, W, 0, nullptr, L.rec.as<double>(), cap, dstats, &T, &job, evg);
+  CU(cudaEventRecord(t1, st));
+  // every stream is drained before anything is reported or freed, also on the error path
+  cudaStreamSynchronize(L.stream3);
+  cudaStreamSynchronize(L.stream2);
+  CU(cudaStreamSynchronize(st));
+  if (rc) return rc;
+  float ms = 0;
+  cudaEventElapsedTime(&ms, t0, t1);
+  L.ms_tracer += ms;
+  for (auto& pr : job.samp_ev) {
+    float m2 = 0;
+    cudaEventElapsedTime(&m2, pr.first, pr.second);
+    L.ms_sampler += m2;
+  }
+  return ART_OK;
+}
+
+extern "C" {
+
+int art_run_device_batches(art_handle* h, uint64_t seed, int64_t first_event, int64_t batch_events, int64_t n_batches,
+                           int64_t batch_stride, int64_t* n_rows_out, int64_t* f_inx_out, int64_t* tot_count_out,
+                           art_stats* st_out) {
+  if (!h || batch_events < 0 || n_batches < 1 || batch_stride < batch_events) return ART_ERR_ARG;
+  const long long n_events = batch_events * n_batches;
+  if (n_events >= (1LL << 31) - 1024) return fail(h, ART_ERR_ARG, "more than 2^31 events in one call");
   CU(cudaSetDevice(h->device));
   const int ncols = h->ncols;
   if (!h->hist.p) {
@@ -650,71 +768,59 @@ int art_run_device(art_handle* h, uint64_t seed, int64_t first_event, int64_t n_
     if (rc) return rc;
   }
   const long long ne = std::max<long long>(n_events, 1);
-  // sub-chunks: at most n_lanes in flight; small runs use a single one
-  long long sub = std::min<long long>(h->sub_chunk, ne);
-  if (ne > sub && ne < sub * h->n_lanes) sub = (ne + h->n_lanes - 1) / h->n_lanes;
-  const long long n_sub = (ne + sub - 1) / sub;
-  const int n_workers = (int)std::min<long long>(h->n_lanes, n_sub);
-  if (int rc = ensure_lanes(h, n_workers)) return rc;
+  if (int rc = ensure_lanes(h, 1)) return rc;
+  Lane& L = h->lanes[0];
   CU(h->events.ensure(ne * sizeof(EventData)));
   CU(h->fin_count.ensure(ne * sizeof(int)));
   CU(h->fin_info.ensure(ne * sizeof(int)));
   CU(h->gctr.ensure(16 * sizeof(unsigned long long)));
   CU(h->stats.ensure(sizeof(DevStats)));
-  // rows: the reference appends without bound; start with 3 rows/event and report overflow
-  const long long want_rows = n_events * 3 + 1024;
-  if (want_rows > h->rows_cap) {
-    CU(h->rows.ensure((size_t)want_rows * ncols * sizeof(double)));
-    CU(h->keys.ensure((size_t)want_rows * sizeof(long long)));
-    h->rows_cap = want_rows;
-  }
+  // Rows: the reference appends without bound.  A forward tree emits at most min(num_cutoff, max_nodes + 1) rows
+  // (every row counts towards num_cutoff, every node towards max_nodes); the buffer starts at min(that, 3) rows per event
+  // and, should a run need more, is re-allocated at the exact size and the call re-run (per-event Philox streams make
+  // the re-run identical).
+  const long long bound = std::max(1, std::min(h->params.num_cutoff, h->params.max_nodes + 1));
+  long long want_rows = n_events * std::min<long long>(bound, 3) + 1024;
+  if (const char* t = getenv("ART_ROWS_INIT_FRAC"))  // test hook: start with rows = frac · events, so that the re-run path is taken
+    want_rows = std::max<long long>(1, (long long)(atof(t) * (double)n_events));
   h->n_rows_dev = 0;
-  h->launches = 0;
+  h->have_global = false;
   h->last_first_event = first_event;
+  h->last_batch_events = std::max<long long>(batch_events, 1);
+  h->last_batch_stride = batch_stride;
   h->last_n_events = 0;
   unsigned long long* gctr = h->gctr.as<unsigned long long>();
-  // gctr layout: [0] failed sampler attempts, [1] tot_count, [6] n_rows, [7,8] n_final (photon, axion)
-  CU(cudaMemsetAsync(gctr, 0, 16 * sizeof(unsigned long long), h->stream));
-  CU(cudaMemsetAsync(h->stats.p, 0, sizeof(DevStats), h->stream));
   DevStats* dstats = h->stats.as<DevStats>();
-  RowSink sink{h->rows.as<double>(), h->keys.as<long long>(), gctr + 6, (unsigned long long)h->rows_cap, ncols, gctr + 7};
-  cudaEvent_t e0, e1;
-  CU(cudaEventCreate(&e0));
-  CU(cudaEventCreate(&e1));
-  CU(cudaEventRecord(e0, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
-  for (Lane& L : h->lanes) L.ms_sampler = L.ms_weights = L.ms_tracer = 0;
-
-  if (n_events > 0) {
-    std::atomic<long long> next_sub{0};
-    std::vector<int> rcs((size_t)n_workers, ART_OK);
-    auto worker = [&](int w) {
-      for (;;) {
-        const long long k = next_sub.fetch_add(1);
-        if (k >= n_sub) break;
-        const long long base = k * sub, n = std::min(sub, n_events - base);
-        const int rc = run_subchunk(h, h->lanes[(size_t)w], seed, first_event, base, n, sink, gctr, dstats);
-        if (rc) {
-          rcs[(size_t)w] = rc;
-          break;
-        }
-      }
-    };
-    if (n_workers == 1) {
-      worker(0);
-    } else {
-      std::vector<std::thread> th;
-      for (int w = 0; w < n_workers; ++w) th.emplace_back(worker, w);
-      for (auto& t : th) t.join();
-    }
-    for (int rc : rcs)
-      if (rc) return rc;
-  }
-  // all lanes are synchronised (run_subchunk ends with a stream sync): finish on the main stream
+  EvGuard evg;
+  cudaEvent_t e0 = evg.make(), e1 = evg.make();
+  if (!e0 || !e1) return fail(h, ART_ERR_CUDA, "cudaEventCreate");
   unsigned long long hc[16];
-  CU(cudaMemcpy(hc, gctr, sizeof(hc), cudaMemcpyDeviceToHost));
-  if ((long long)hc[6] > h->rows_cap)
-    return fail(h, ART_ERR_CAPACITY, "device row buffer overflow (more than 3 rows per event on average)");
+  float ms_tot = 0;
+  for (int attempt = 0;; ++attempt) {
+    if (want_rows > h->rows_cap) {
+      CU(h->rows.ensure((size_t)want_rows * ncols * sizeof(double)));
+      CU(h->keys.ensure((size_t)want_rows * sizeof(long long)));
+      h->rows_cap = want_rows;
+    }
+    h->launches = 0;
+    // gctr layout: [0] failed sampler attempts, [1] tot_count, [6] n_rows, [7,8] n_final (photon, axion)
+    CU(cudaMemsetAsync(gctr, 0, 16 * sizeof(unsigned long long), h->stream));
+    CU(cudaMemsetAsync(h->stats.p, 0, sizeof(DevStats), h->stream));
+    RowSink sink{h->rows.as<double>(), h->keys.as<long long>(), gctr + 6, (unsigned long long)h->rows_cap, ncols, gctr + 7};
+    CU(cudaEventRecord(e0, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    L.ms_sampler = L.ms_weights = L.ms_tracer = 0;
+    if (n_events > 0) {
+      const int rc = h->dp.integrator == IG_DP5
+                         ? run_pool<IG_DP5>(h, L, seed, first_event, n_events, h->last_batch_events, batch_stride, sink, gctr, dstats, evg)
+                         : run_pool<IG_VERN6>(h, L, seed, first_event, n_events, h->last_batch_events, batch_stride, sink, gctr, dstats, evg);
+      if (rc) return rc;
+    }
+    CU(cudaMemcpy(hc, gctr, sizeof(hc), cudaMemcpyDeviceToHost));
+    if ((long long)hc[6] <= h->rows_cap) break;
+    if (attempt >= 1) return fail(h, ART_ERR_CAPACITY, "device row buffer overflow after re-allocation");
+    want_rows = (long long)hc[6] + 1024;  // exact: the counter counts every row, stored or not
+  }
   const long long nr = (long long)hc[6];
   if (nr > 0) {
     k_patch_rows<<<nblk(nr, 256), 256, 0, h->stream>>>(nr, h->rows.as<double>(), h->keys.as<long long>(), ncols, 0,
@@ -731,10 +837,7 @@ int art_run_device(art_handle* h, uint64_t seed, int64_t first_event, int64_t n_
   }
   CU(cudaEventRecord(e1, h->stream));
   CU(cudaStreamSynchronize(h->stream));
-  float ms_tot = 0;
   cudaEventElapsedTime(&ms_tot, e0, e1);
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
 
   DevStats ds;
   CU(cudaMemcpy(&ds, dstats, sizeof(ds), cudaMemcpyDeviceToHost));
@@ -751,8 +854,8 @@ int art_run_device(art_handle* h, uint64_t seed, int64_t first_event, int64_t n_
   S.n_rej = (long long)ds.n_rej; S.n_rhs = (long long)ds.n_rhs; S.n_cond = (long long)ds.n_cond;
   S.n_final_photon = (long long)hc[7]; S.n_final_axion = (long long)hc[8];
   for (int k = 0; k < 5; ++k) S.n_status[k] = (long long)ds.n_status[k];
-  // stage times are summed over lanes (lanes overlap, so they can add up to more than ms_total)
-  for (Lane& L : h->lanes) { S.ms_sampler += L.ms_sampler; S.ms_weights += L.ms_weights; S.ms_tracer += L.ms_tracer; }
+  // ms_sampler: sum of the sampler launches (they overlap the loop on their own stream); ms_tracer: the loop, start to drain
+  S.ms_sampler = L.ms_sampler; S.ms_weights = 0.0; S.ms_tracer = L.ms_tracer;
   S.ms_tree = 0.0;
   S.ms_total = ms_tot;
   S.n_launches = h->launches.load();
@@ -765,12 +868,18 @@ int art_run_device(art_handle* h, uint64_t seed, int64_t first_event, int64_t n_
   return ART_OK;
 }
 
+int art_run_device(art_handle* h, uint64_t seed, int64_t first_event, int64_t n_events, int64_t* n_rows_out,
+                   int64_t* f_inx_out, int64_t* tot_count_out, art_stats* st_out) {
+  if (!h || n_events < 0) return ART_ERR_ARG;
+  return art_run_device_batches(h, seed, first_event, n_events, 1, n_events, n_rows_out, f_inx_out, tot_count_out, st_out);
+}
+
 int art_fetch_rows(art_handle* h, double* rows, int64_t rows_cap, int64_t* n_rows) {
   if (!h || !rows) return ART_ERR_ARG;
   CU(cudaSetDevice(h->device));
   const long long n = h->n_rows_dev;
   if (n_rows) *n_rows = n;
-  if (n > rows_cap) return fail(h, ART_ERR_CAPACITY, "rows_cap too small");
+  if (n > rows_cap) return fail(h, ART_ERR_CAPACITY, "rows_cap too small (n_rows holds the number of rows: enlarge the buffer and call art_fetch_rows again)");
   if (n == 0) return ART_OK;
   const int ncols = h->ncols;
   // order rows as the reference writes them — by event, then by position in the tree — on the device:
@@ -808,7 +917,7 @@ int art_fetch_events(art_handle* h, double* events, int64_t events_cap, int64_t*
   for (long long i = 0; i < n; ++i) {
     const EventData& E = ev[(size_t)i];
     double* o = events + i * ART_EVENT_COLS;
-    o[0] = (double)(h->last_first_event + i);
+    o[0] = (double)(h->last_first_event + (i / h->last_batch_events) * h->last_batch_stride + i % h->last_batch_events);
     for (int c = 0; c < 3; ++c) { o[1 + c] = E.vinf[c]; o[5 + c] = E.x[c]; o[8 + c] = E.k_init[c]; }
     o[4] = E.sln_prob;
     o[11] = (double)cnt[(size_t)i];
@@ -983,15 +1092,19 @@ int art_comm_allreduce_hist(art_handle* h) {
   }
   int rc = hist_push_counters(h);
   if (rc) return rc;
+  const size_t bytes = (size_t)art_hist_len(h) * sizeof(double);
+  CU(h->hist_global.ensure(bytes));
   if (h->comm && h->nranks > 1) {
-    // ncclAllReduce(sum, f64) over [bins | counters] in place — the only collective of the path
-    rc = g_nccl.AllReduce(h->hist.p, h->hist.p, (size_t)art_hist_len(h), /*ncclFloat64*/ 8, /*ncclSum*/ 0, h->comm, h->stream);
+    // ncclAllReduce(sum, f64) over [bins | counters], OUT OF PLACE — the only collective of the path.  The local
+    // block keeps accumulating untouched, so the call can be repeated (after every pipeline call, or once at the
+    // end): each time the global block is the sum over ranks of the local blocks as they stand.
+    rc = g_nccl.AllReduce(h->hist.p, h->hist_global.p, (size_t)art_hist_len(h), /*ncclFloat64*/ 8, /*ncclSum*/ 0, h->comm, h->stream);
     if (rc != 0) return fail(h, ART_ERR_NCCL, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+  } else {
+    CU(cudaMemcpyAsync(h->hist_global.p, h->hist.p, bytes, cudaMemcpyDeviceToDevice, h->stream));
   }
   CU(cudaStreamSynchronize(h->stream));
-  // after the reduce the device copy holds global counters; keep the host mirror in sync
-  const size_t off = (size_t)(art_hist_len(h) - 8) * sizeof(double);
-  CU(cudaMemcpy(h->host_counters, (char*)h->hist.p + off, 8 * sizeof(double), cudaMemcpyDeviceToHost));
+  h->have_global = true;
   return ART_OK;
 }
 

@@ -151,38 +151,8 @@ __global__ void k_sample_uniforms(const __grid_constant__ DevParams P, long long
 }
 
 // ------------------------------------------------------------------------------------------
-// K2: weights (fused: EventSample → EventData + back-trace ray) and fine-grained variants
+// K2: weights — fine-grained entry points (the fused pipeline computes them in k_wf_inject, art_wavefront.cuh)
 // ------------------------------------------------------------------------------------------
-__global__ void k_weights_events(const __grid_constant__ DevParams P, long long n, const EventSample* __restrict__ s,
-                                 EventData* __restrict__ ev, TreeState* __restrict__ ts, QueuedRay* __restrict__ q0) {
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const EventSample e = s[i];
-  const SampleWeights W = sample_weights(P, e.x, e.vloc, e.vinf);
-  EventData E;
-  for (int c = 0; c < 3; ++c) { E.x[c] = e.x[c]; E.k_init[c] = W.k_init[c]; E.vinf[c] = e.vinf[c]; }
-  E.erg_inf = W.erg_inf; E.vel_eng = W.vel_eng; E.sln_prob = W.sln_prob; E.cos_w = W.cos_w;
-  E.back_weight = 0.0; E.prob0 = 0.0; E.c_bck = 0; E.n_failed = e.n_failed;
-  ev[i] = E;
-  // slot i: back-trace parent — axion, −k, t = 0, Δω = −1, collect all crossings (MR.jl:581-589)
-  QueuedRay r;
-  for (int c = 0; c < 3; ++c) { r.in.x0[c] = e.x[c]; r.in.k0[c] = -W.k_init[c]; }
-  r.in.erg = W.erg_inf; r.in.t_start = 0.0; r.in.dOmega = -1.0; r.in.max_cross = 100000;
-  r.in.species = SPECIES_AXION;
-  r.owner = (int)i; r.pad_ = 0;
-  q0[i] = r;
-  // slot n+i: first node of the forward tree — photon, +k (MR.jl:653-657); independent of the
-  // back-trace, so both are propagated by the same launch
-  TreeState T;
-  tree_forward_start(P, E, T);
-  T.back_status = 0;
-  ts[i] = T;
-  for (int c = 0; c < 3; ++c) r.in.k0[c] = W.k_init[c];
-  r.in.max_cross = -1;
-  r.in.species = SPECIES_PHOTON;
-  q0[n + i] = r;
-}
-
 __global__ void k_weights_api(const __grid_constant__ DevParams P, long long n, const double* x, const double* vloc,
                               const double* vinf, double* k_init, double* cos_w, double* jac, double* sln,
                               double* erg, double* vel) {

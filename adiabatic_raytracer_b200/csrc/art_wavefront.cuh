@@ -31,7 +31,16 @@
 // atomics); the host reads a few counters every 8–32 steps.  k_wf_root and k_wf_tree are latency-bound
 // (≈ 30–50 µs whatever the list length), so they run on a second stream, one iteration behind: the roots
 // and finished rays that iteration k produces are processed while iteration k+1's stage kernel runs, and
-// rejoin the active list of iteration k+2 (lists and counters are double-buffered by iteration parity).
+// rejoin the active list of iteration k+2.  Lists are double-buffered by iteration parity; the list COUNTERS
+// come in four sets indexed by iteration mod 4: while iteration k runs, sets k−1 (roots / finished lists the
+// side pass consumes), k and k+1 (active lists being filled) are live and set k+2 is dead, so the stage kernel
+// of iteration k zeroes it — no reset launch.
+//
+// The fused pipeline keeps the loop FULL (art_api.cu, run_pool): events live in a pool of slots (slot s: ray s =
+// back-traced axion, ray S+s = forward tree); when both halves of an event are through, its slot goes onto a
+// device-side ring of free slots, and k_wf_inject — part of the side pass — starts freshly sampled events in
+// them.  The thin tail of late tree nodes (which used to be half the tracer time of a batch) then rides on the
+// bulk of the following events and only the very last block of a call drains alone.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -61,7 +70,9 @@ constexpr int STAGE_THREADS = ART_STAGE_THREADS;
 #define ART_STAGE_NSTEP 4      // attempted steps a ray may take inside one k_wf_stages launch
 #endif
 
-enum { WC_PEND = 0, WC_ROOTS = 1 /* + list parity */, WC_FIN = 3 /* + list parity */, WC_ACT = 5 /* + parity*2 + species */, WC_N = 16 };
+// counters: 4 sets of WC_SET (indexed by iteration & 3), then the free-slot ring's tail
+enum { WC_ACT = 0 /* + species */, WC_PEND = 2, WC_ROOTS = 3, WC_FIN = 4, WC_SET = 8, WC_RING_TAIL = 32, WC_N = 40 };
+__device__ __forceinline__ unsigned long long* wc(unsigned long long* ctr, int k, int which) { return ctr + (k & 3) * WC_SET + which; }
 
 struct WfPool {
   RayHot* hot;                // [cap] per-step ray state
@@ -78,17 +89,22 @@ struct WfPool {
   unsigned long long* ctr;    // WC_*
 };
 
-struct WfTree {  // per-event tree context (null ev ⇒ plain ray batch, art_propagate)
-  EventData* ev;
-  TreeState* ts;
-  TreeNode* stacks;
+struct WfTree {  // per-event tree context of the fused pipeline
+  EventData* ev;          // [events of the call] per-event scalars, indexed by the event's index in the call
+  int* fin_count;         // [events of the call] tree count / info of the finished forward tree
+  int* fin_info;
+  TreeState* ts;          // [slots]
+  TreeNode* stacks;       // [slots][stack_stride]
+  int* slot_event;        // [slots] event (index in the call) that occupies the slot
+  int* slot_parts;        // [slots] halves of the event that are through (back-trace, forward tree): 2 ⇒ the slot is free
+  int* ring;              // [slots] ring of free slots; tail = ctr[WC_RING_TAIL] (pushes), head kept by the host (pops)
   int stack_stride;
+  int n_slots;            // S: ray id < S = back-trace of slot id, otherwise forward tree of slot id − S
   unsigned long long seed;
-  long long first_event, chunk_base, n_events;
+  long long first_event;  // event id of the call's event 0; event e has id first_event + (e / batch_size) batch_stride + e % batch_size
+  long long batch_size, batch_stride;
   RowSink sink;
   unsigned long long* tot_count;
-  int* fin_count;
-  int* fin_info;
 };
 
 // apply()'s FSAL copy k1 ← K(6): on the device k7 is already in the hot record
@@ -126,18 +142,19 @@ struct WfStat {
 // Stream compaction of survivors.  Every lane of the warp calls this: finished rays join the finished
 // list (their result is written by k_wf_tree / k_wf_collect), rays with a pending step the pending
 // list, live rays the next step's active list of their species — one atomic per warp and list.
-__device__ __forceinline__ void wf_route(const WfPool& W, int next, int lpar, bool valid, int id, bool done, bool pending, bool axion) {
+// k = the iteration whose kernels call this: finished / pending lists of iteration k, active lists of iteration k + 1
+__device__ __forceinline__ void wf_route(const WfPool& W, int k, bool valid, int id, bool done, bool pending, bool axion) {
   const bool fin = valid && done;
-  const long long sf = warp_pop(W.ctr + WC_FIN + lpar, fin);
-  if (fin) (lpar ? W.fin[1] : W.fin[0])[sf] = id;
+  const long long sf = warp_pop(wc(W.ctr, k, WC_FIN), fin);
+  if (fin) ((k & 1) ? W.fin[1] : W.fin[0])[sf] = id;
   const bool pd = valid && !done && pending;
-  const long long sp_ = warp_pop(W.ctr + WC_PEND, pd);
+  const long long sp_ = warp_pop(wc(W.ctr, k, WC_PEND), pd);
   if (pd) W.pend[sp_] = id;
 #pragma unroll
   for (int sp = 0; sp < 2; ++sp) {
     const bool mine = valid && !done && !pending && ((axion ? SPECIES_AXION : SPECIES_PHOTON) == sp);
-    const long long s = warp_pop(W.ctr + WC_ACT + next * 2 + sp, mine);
-    if (mine) (next ? W.act[1][sp] : W.act[0][sp])[s] = id;
+    const long long s = warp_pop(wc(W.ctr, k + 1, WC_ACT + sp), mine);
+    if (mine) (((k + 1) & 1) ? W.act[1][sp] : W.act[0][sp])[s] = id;
   }
 }
 
@@ -149,13 +166,6 @@ __device__ __forceinline__ int wf_spread(long long n) {
   int s = 1;
   while (s < 32 && n * (2LL * s) <= nthreads) s <<= 1;
   return s;
-}
-
-__global__ void k_wf_reset(WfPool W, int next, int lpar) {
-  if (threadIdx.x == 0) {
-    W.ctr[WC_ROOTS + lpar] = 0; W.ctr[WC_FIN + lpar] = 0; W.ctr[WC_PEND] = 0;
-    W.ctr[WC_ACT + next * 2] = 0; W.ctr[WC_ACT + next * 2 + 1] = 0;
-  }
 }
 
 // ---- start-up of a batch: IC transform, first RHS, initial step size, starting sign ----------------
@@ -178,7 +188,7 @@ k_wf_init(const __grid_constant__ DevParams P, const QueuedRay* __restrict__ q, 
       W.cold[i] = static_cast<const RayCold&>(R);
     }
     // rays that start past the end of the span stay `done`: the first k_wf_stages launch retires them
-    wf_route(W, 0, 0, valid, (int)i, false, false, R.axion);
+    wf_route(W, -1, valid, (int)i, false, false, R.axion);  // active lists of iteration 0
   }
 }
 
@@ -194,14 +204,13 @@ k_wf_init(const __grid_constant__ DevParams P, const QueuedRay* __restrict__ q, 
 // far-field rays and rejected steps do not pay a state round trip per attempt (bulk: 4 attempts, half
 // the warp; thin tail of a batch: 16 attempts, any lane — there only latency counts).
 template <int IG, int SP>
-__device__ __forceinline__ void wf_stages_body(const DevParams& P, const WfPool& W, int cur, int lpar, int nstep, int min_go,
+__device__ __forceinline__ void wf_stages_body(const DevParams& P, const WfPool& W, int k, int nstep, int min_go,
                                                unsigned bid, unsigned nblocks, double* ksm, DevStats* stats) {
   constexpr int LAST = Scheme<IG>::LAST, NEXTRA = Scheme<IG>::NEXTRA, TNEW = IG == IG_DP5 ? 5 : 6;  // park slot of e^{s_new}
   unsigned long long n_full = 0;  // condition evaluations done here (end points of in-box steps)
   const KStoreT<STAGE_THREADS> K{ksm + threadIdx.x};
-  const int next = 1 - cur;
-  const long long n = (long long)W.ctr[WC_ACT + cur * 2 + SP];
-  const int* __restrict__ act = cur ? W.act[1][SP] : W.act[0][SP];  // (a dynamic index would copy the parameter struct to local memory)
+  const long long n = (long long)*wc(W.ctr, k, WC_ACT + SP);
+  const int* __restrict__ act = (k & 1) ? W.act[1][SP] : W.act[0][SP];  // (a dynamic index would copy the parameter struct to local memory)
   const long long nthreads = (long long)nblocks * blockDim.x;
   const long long nround = ((n + nthreads - 1) / nthreads) * nthreads;
   // the ids of this thread's next two trips are kept in flight and the hot record of the next trip is
@@ -306,7 +315,7 @@ __device__ __forceinline__ void wf_stages_body(const DevParams& P, const WfPool&
       R.dt = R.dt_new;
     }
     if (valid) W.hot[id] = static_cast<const RayHot&>(R);
-    wf_route(W, next, lpar, valid, id, done, pending, SP == SPECIES_AXION);
+    wf_route(W, k, valid, id, done, pending, SP == SPECIES_AXION);
   }
   n_full = warp_sum(n_full);
   if ((threadIdx.x & 31) == 0 && stats && n_full) atomicAdd(&stats->n_cond_eval, n_full);
@@ -322,11 +331,13 @@ __global__ void __maxnreg__(ART_STAGE_MAXNREG)
 #else
 __global__ void __launch_bounds__(STAGE_THREADS, ART_STAGE_MINBLOCKS)
 #endif
-k_wf_stages(const __grid_constant__ DevParams P, WfPool W, int cur, int lpar, int nstep, int min_go, DevStats* stats) {
+k_wf_stages(const __grid_constant__ DevParams P, WfPool W, int k, int nstep, int min_go, DevStats* stats) {
   extern __shared__ double ksm[];
+  // counter set k + 2 is dead while iteration k runs (see the header): zero it for its next use
+  if (blockIdx.x == 0 && threadIdx.x < WC_SET) wc(W.ctr, k + 2, 0)[threadIdx.x] = 0ull;
   const unsigned half = gridDim.x >> 1;
-  if (blockIdx.x < half) wf_stages_body<IG, SPECIES_AXION>(P, W, cur, lpar, nstep, min_go, blockIdx.x, half, ksm, stats);
-  else wf_stages_body<IG, SPECIES_PHOTON>(P, W, cur, lpar, nstep, min_go, blockIdx.x - half, half, ksm, stats);
+  if (blockIdx.x < half) wf_stages_body<IG, SPECIES_AXION>(P, W, k, nstep, min_go, blockIdx.x, half, ksm, stats);
+  else wf_stages_body<IG, SPECIES_PHOTON>(P, W, k, nstep, min_go, blockIdx.x - half, half, ksm, stats);
 }
 
 // ---- crossing scan: one warp per group of pending steps -----------------------------------------------
@@ -352,13 +363,13 @@ constexpr int SCAN_ROUNDS = 5;  // ballot words kept per sign class
 #endif
 template <int IG>
 __global__ void __launch_bounds__(SCAN_THREADS, ART_SCAN_MINBLOCKS)
-k_wf_scan(const __grid_constant__ DevParams P, WfPool W, DevStats* stats) {
+k_wf_scan(const __grid_constant__ DevParams P, WfPool W, int k, DevStats* stats) {
   constexpr int SEG_PAD = Seg<IG>::N;
   __shared__ double seg_sm[SCAN_THREADS / 32][SCAN_PACK][SEG_PAD];
   __shared__ double th_sm[SCAN_ROUNDS][SCAN_THREADS];        // per lane and round: dense-output parameter of its slot
   __shared__ short j_sm[SCAN_ROUNDS][SCAN_THREADS];          // … segment index, +8 for a nudge slot, −1 for no slot
   __shared__ unsigned bal_sm[SCAN_THREADS / 32][3][SCAN_ROUNDS + 2];  // ballot words of the current trip
-  const long long n = (long long)W.ctr[WC_PEND];
+  const long long n = (long long)*wc(W.ctr, k, WC_PEND);
   const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const long long nwarps = (long long)gridDim.x * (SCAN_THREADS / 32);
   const int M = P.M_ray;
@@ -449,8 +460,8 @@ __device__ __forceinline__ void wf_load_pending(Ray& R, const SegAoS D) {
 // ---- events: detection over the pending rays; no crossing ⇒ the optimistic advance stands ------------
 template <int IG>
 __global__ void __launch_bounds__(WF_THREADS)
-k_wf_detect(const __grid_constant__ DevParams P, WfPool W, int next, int lpar) {
-  const long long n = (long long)W.ctr[WC_PEND];
+k_wf_detect(const __grid_constant__ DevParams P, WfPool W, int k) {
+  const long long n = (long long)*wc(W.ctr, k, WC_PEND);
   const long long nthreads = (long long)gridDim.x * blockDim.x;
   const long long nround = ((n + nthreads - 1) / nthreads) * nthreads;
   // (the id of this thread's next trip is kept in flight and that ray's hot record and sign masks are pulled into L2
@@ -497,19 +508,20 @@ k_wf_detect(const __grid_constant__ DevParams P, WfPool W, int next, int lpar) {
         H.event_last = false; H.done = R.done;
       }
     }
-    const long long sr = warp_pop(W.ctr + WC_ROOTS + lpar, to_root);
-    if (to_root) (lpar ? W.roots[1] : W.roots[0])[sr] = id;
-    wf_route(W, next, lpar, valid && !to_root, id, done, false, axion);
+    const long long sr = warp_pop(wc(W.ctr, k, WC_ROOTS), to_root);
+    if (to_root) ((k & 1) ? W.roots[1] : W.roots[0])[sr] = id;
+    wf_route(W, k, valid && !to_root, id, done, false, axion);
   }
 }
 
 // ---- root finder (all lanes iterate together), crossing callback, state update ------------------------
 template <int IG>
 __global__ void __launch_bounds__(WF_THREADS)
-k_wf_root(const __grid_constant__ DevParams P, WfPool W, int next, int lin, int lpar, DevStats* stats) {
+k_wf_root(const __grid_constant__ DevParams P, WfPool W, int k, DevStats* stats) {
+  // side pass of iteration k: the roots list iteration k − 1 produced; survivors join iteration k + 1
   unsigned long long n_full = 0;
-  const long long n = (long long)W.ctr[WC_ROOTS + lin];
-  const int* __restrict__ roots = lin ? W.roots[1] : W.roots[0];
+  const long long n = (long long)*wc(W.ctr, k - 1, WC_ROOTS);
+  const int* __restrict__ roots = ((k - 1) & 1) ? W.roots[1] : W.roots[0];
   const int spread = wf_spread(n);
   const long long nthreads = (long long)gridDim.x * blockDim.x / spread;
   const long long nround = ((n + nthreads - 1) / nthreads) * nthreads;
@@ -541,7 +553,7 @@ k_wf_root(const __grid_constant__ DevParams P, WfPool W, int next, int lin, int 
       done = R.done;
       axion = R.axion;
     }
-    wf_route(W, next, lpar, valid, id, done, false, axion);
+    wf_route(W, k, valid, id, done, false, axion);
   }
   n_full = warp_sum(n_full);
   if ((threadIdx.x & 31) == 0 && stats && n_full) atomicAdd(&stats->n_cond_eval, n_full);
@@ -559,10 +571,10 @@ __device__ __forceinline__ RayOut wf_result(const DevParams& P, const RayHot& H,
 
 // plain ray batches (art_propagate): results of the finished rays
 __global__ void __launch_bounds__(WF_THREADS)
-k_wf_collect(const __grid_constant__ DevParams P, WfPool W, int lin, RayOut* __restrict__ out, DevStats* stats) {
+k_wf_collect(const __grid_constant__ DevParams P, WfPool W, int k, RayOut* __restrict__ out, DevStats* stats) {
   WfStat st;
-  const long long n = (long long)W.ctr[WC_FIN + lin];
-  const int* __restrict__ fin = lin ? W.fin[1] : W.fin[0];
+  const long long n = (long long)*wc(W.ctr, k - 1, WC_FIN);
+  const int* __restrict__ fin = ((k - 1) & 1) ? W.fin[1] : W.fin[0];
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
     const int id = fin[t];
     out[id] = wf_result(P, W.hot[id], st);
@@ -571,22 +583,33 @@ k_wf_collect(const __grid_constant__ DevParams P, WfPool W, int lin, RayOut* __r
 }
 
 // ---- tree: finished rays → get_tree loop body → next node re-initialised in the same slot ------------
+// One half of an event (its back-trace, or its forward tree) is through: the second one to arrive hands the slot back.
+__device__ __forceinline__ void wf_release_half(const WfTree& T, WfPool& W, int slot) {
+  if (atomicAdd(T.slot_parts + slot, 1) == 1) {
+    T.slot_parts[slot] = 0;
+    const unsigned long long at = atomicAdd(W.ctr + WC_RING_TAIL, 1ull);
+    T.ring[at % (unsigned long long)T.n_slots] = slot;
+  }
+}
+
 // Returns true when the event continues: R then holds the freshly initialised ray of the next node.
-__device__ __forceinline__ bool wf_tree_step(const DevParams& P, const WfTree& T, int id, const RayOut& ro,
+__device__ __forceinline__ bool wf_tree_step(const DevParams& P, const WfTree& T, WfPool& W, int id, const RayOut& ro,
                                              double* __restrict__ rec, int rec_cap, Ray& R) {
   const double* rc = rec + (size_t)id * rec_cap * 8;
-  if (id < T.n_events) {  // back-traced axion of event id: samp_back_weight
-    EventData E = T.ev[id];
+  if (id < T.n_slots) {  // back-traced axion of the event in slot id: samp_back_weight
+    const int e = T.slot_event[id];
+    EventData E = T.ev[e];
     tree_backward(P, E, ro, rc, rec_cap);
-    T.ev[id] = E;
-    T.ts[id].back_status = ro.status;
+    T.ev[e] = E;
+    wf_release_half(T, W, id);
     return false;
   }
-  const int e = id - (int)T.n_events;
-  const EventData E = T.ev[e];
-  TreeState S = T.ts[e];
-  tree_forward_update(P, E, S, T.stacks + (size_t)e * T.stack_stride, ro, rc, T.seed,
-                      (unsigned long long)(T.first_event + T.chunk_base + e), T.chunk_base + e, T.sink);
+  const int slot = id - T.n_slots;
+  const int e = T.slot_event[slot];
+  const EventData E = T.ev[e];  // (the back-trace only writes back_weight / prob0 / c_bck, which the forward tree does not read)
+  TreeState S = T.ts[slot];
+  tree_forward_update(P, E, S, T.stacks + (size_t)slot * T.stack_stride, ro, rc, T.seed,
+                      (unsigned long long)(T.first_event + (e / T.batch_size) * T.batch_stride + e % T.batch_size), (long long)e, T.sink);
   bool spawn = false;
   if (S.active) {
     RayIn in;
@@ -601,18 +624,19 @@ __device__ __forceinline__ bool wf_tree_step(const DevParams& P, const WfTree& T
     T.fin_count[e] = S.count;
     T.fin_info[e] = S.info;
   }
-  T.ts[e] = S;
+  T.ts[slot] = S;
+  if (!spawn) wf_release_half(T, W, slot);
   return spawn;
 }
 
 template <int IG>
 __global__ void __launch_bounds__(WF_THREADS)
-k_wf_tree(const __grid_constant__ DevParams P, WfPool W, WfTree T, int next, int lin, double* __restrict__ rec, int rec_cap,
-          DevStats* stats) {
+k_wf_tree(const __grid_constant__ DevParams P, WfPool W, WfTree T, int k, double* __restrict__ rec, int rec_cap, DevStats* stats) {
+  // side pass of iteration k: the finished list iteration k − 1 produced; spawned nodes join iteration k + 1
   WfStat st;
   unsigned long long n_start = 0;
-  const long long n = (long long)W.ctr[WC_FIN + lin];
-  const int* __restrict__ fin = lin ? W.fin[1] : W.fin[0];
+  const long long n = (long long)*wc(W.ctr, k - 1, WC_FIN);
+  const int* __restrict__ fin = ((k - 1) & 1) ? W.fin[1] : W.fin[0];
   const int spread = wf_spread(n);
   const long long nthreads = (long long)gridDim.x * blockDim.x / spread;
   const long long nround = ((n + nthreads - 1) / nthreads) * nthreads;
@@ -626,7 +650,7 @@ k_wf_tree(const __grid_constant__ DevParams P, WfPool W, WfTree T, int next, int
     if (t < n && (t0 % spread) == 0) {
       id = fin[t];
       const RayOut o = wf_result(P, W.hot[id], st);
-      spawn = wf_tree_step(P, T, id, o, rec, rec_cap, R);
+      spawn = wf_tree_step(P, T, W, id, o, rec, rec_cap, R);
       if (spawn) {
         // a re-initialised ray that is already past the end of the span stays `done`: the next
         // k_wf_stages launch routes it back here (never happens for t < 1/Ω)
@@ -639,17 +663,85 @@ k_wf_tree(const __grid_constant__ DevParams P, WfPool W, WfTree T, int next, int
       }
     }
     // spawned rays join the next step's active list even when already done (see above)
-    const bool ax = R.axion;
-#pragma unroll
-    for (int sp = 0; sp < 2; ++sp) {
-      const bool mine = spawn && ((ax ? SPECIES_AXION : SPECIES_PHOTON) == sp);
-      const long long s = warp_pop(W.ctr + WC_ACT + next * 2 + sp, mine);
-      if (mine) (next ? W.act[1][sp] : W.act[0][sp])[s] = id;
-    }
+    wf_route(W, k, spawn, id, false, false, R.axion);
   }
   st.flush(stats);
   n_start = warp_sum(n_start);
   if ((threadIdx.x & 31) == 0 && stats && n_start) atomicAdd(&stats->n_cond_eval, n_start);
+}
+
+// ---- injection of freshly sampled events into free slots (side pass of iteration k) -------------------
+// Event j of the block (index e0 + j in the call) takes the slot ring[(head + j) % S]: per-sample weights
+// (MainRunner.jl:498-557), first tree node, and the IC transform / first right-hand side / initial step size /
+// starting sign of its two rays — the back-traced axion in ray slot s (MR.jl:581-589: −k, t = 0, Δω = −1, all
+// crossings) and the forward photon in ray slot S + s (MR.jl:653-657).  Both join iteration k + 1.
+template <int IG>
+__global__ void __launch_bounds__(WF_THREADS)
+k_wf_inject(const __grid_constant__ DevParams P, WfPool W, WfTree T, int k, const EventSample* __restrict__ samples, int m, int e0,
+            unsigned long long head, double* __restrict__ rec, int rec_cap, DevStats* stats) {
+  unsigned long long n_start = 0;
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  const long long n2 = 2LL * m;
+  const long long nround = ((n2 + nthreads - 1) / nthreads) * nthreads;
+  // thread t < m: event t's weights + back-trace ray; thread m + t: its forward ray (reads the weights again: cheap
+  // next to two right-hand sides, and it keeps the two rays of an event on different threads)
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nround; t += nthreads) {
+    Ray R;
+    R.done = true;
+    R.axion = false;
+    const bool valid = t < n2;
+    int id = -1;
+    if (valid) {
+      const bool fwd = t >= m;
+      const int j = (int)(fwd ? t - m : t);
+      const int slot = T.ring[(head + (unsigned long long)j) % (unsigned long long)T.n_slots];
+      const int e = e0 + j;
+      const EventSample smp = samples[j];
+      const SampleWeights Wt = sample_weights(P, smp.x, smp.vloc, smp.vinf);
+      RayIn in;
+      for (int c = 0; c < 3; ++c) { in.x0[c] = smp.x[c]; in.k0[c] = fwd ? Wt.k_init[c] : -Wt.k_init[c]; }
+      in.erg = Wt.erg_inf; in.t_start = 0.0; in.dOmega = -1.0;
+      in.max_cross = fwd ? -1 : 100000;
+      in.species = fwd ? SPECIES_PHOTON : SPECIES_AXION;
+      if (!fwd) {
+        EventData E;
+        for (int c = 0; c < 3; ++c) { E.x[c] = smp.x[c]; E.k_init[c] = Wt.k_init[c]; E.vinf[c] = smp.vinf[c]; }
+        E.erg_inf = Wt.erg_inf; E.vel_eng = Wt.vel_eng; E.sln_prob = Wt.sln_prob; E.cos_w = Wt.cos_w;
+        E.back_weight = 0.0; E.prob0 = 0.0; E.c_bck = 0; E.n_failed = smp.n_failed;
+        T.ev[e] = E;
+        T.slot_event[slot] = e;
+        T.slot_parts[slot] = 0;
+      } else {
+        EventData E;  // what tree_forward_start reads
+        for (int c = 0; c < 3; ++c) { E.x[c] = smp.x[c]; E.k_init[c] = Wt.k_init[c]; }
+        E.erg_inf = Wt.erg_inf;
+        TreeState S;
+        tree_forward_start(P, E, S);
+        S.back_status = 0;
+        T.ts[slot] = S;
+      }
+      id = fwd ? T.n_slots + slot : slot;
+      R.init(P, in, rec + (size_t)id * rec_cap * 8, rec_cap);
+      if (!R.done && R.iter_guard(P)) {
+        R.template startup<IG, -1>(P);
+        n_start++;
+      }
+      W.hot[id] = static_cast<const RayHot&>(R);
+      W.cold[id] = static_cast<const RayCold&>(R);
+    }
+    wf_route(W, k, valid, id, false, false, R.axion);
+  }
+  n_start = warp_sum(n_start);
+  if ((threadIdx.x & 31) == 0 && stats && n_start) atomicAdd(&stats->n_cond_eval, n_start);
+}
+
+__global__ void k_ring_init(int* ring, int* parts, int n, unsigned long long* ctr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    ring[i] = i;
+    parts[i] = 0;
+  }
+  if (i == 0) ctr[WC_RING_TAIL] = (unsigned long long)n;
 }
 
 }  // namespace art

@@ -8,7 +8,7 @@ import os
 
 import numpy as np
 
-from .params import ArtParams, ArtStats, CROSS_REC
+from .params import ART_ERR_CAPACITY, ArtParams, ArtStats, CROSS_REC
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("ART_SO", os.path.join(_HERE, "libart_b200.so"))  # ART_SO: tuning variants only
@@ -37,6 +37,8 @@ SIGNATURES = {
     "art_run": (C.c_int, [_H, C.c_uint64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, _i64p, _i64p, _i64p,
                           C.POINTER(ArtStats)]),
     "art_run_device": (C.c_int, [_H, C.c_uint64, C.c_int64, C.c_int64, _i64p, _i64p, _i64p, C.POINTER(ArtStats)]),
+    "art_run_device_batches": (C.c_int, [_H, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _i64p, _i64p, _i64p,
+                                         C.POINTER(ArtStats)]),
     "art_fetch_rows": (C.c_int, [_H, C.c_void_p, C.c_int64, _i64p]),
     "art_fetch_events": (C.c_int, [_H, _dp, C.c_int64, _i64p]),
     "art_write_event_files": (C.c_int, [C.c_char_p, C.c_char_p, _dp, C.c_int64, _dp, C.c_int64]),
@@ -50,6 +52,7 @@ SIGNATURES = {
     "art_hist_len": (C.c_int64, [_H]),
     "art_hist_reset": (C.c_int, [_H]),
     "art_hist_get": (C.c_int, [_H, _dp, C.c_int64]),
+    "art_hist_get_global": (C.c_int, [_H, _dp, C.c_int64]),
     "art_comm_unique_id": (C.c_int, [C.c_char_p]),
     "art_comm_init": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_char_p]),
     "art_comm_allreduce_hist": (C.c_int, [_H]),
@@ -165,15 +168,30 @@ class Handle:
 
     # ---- fused pipeline -------------------------------------------------------------------
     def run(self, seed, first_event, n_events, rows_out=None):
-        """art_run: host rows out (row-major n_rows × ncols, column 7 not yet divided by f_inx)."""
+        """art_run: host rows out (row-major n_rows × ncols, column 7 not yet divided by f_inx).  The reference appends rows
+        without bound; a buffer that turns out too small is re-allocated and the rows fetched again (no recomputation)."""
         cap = n_events * 3 + 1024
         if rows_out is None:
             rows_out = np.empty((cap, self.ncols))
         nr, fi, tc = C.c_int64(), C.c_int64(), C.c_int64()
         st = ArtStats()
-        self._chk(self._L.art_run(self._h, seed, first_event, n_events, rows_out.ctypes.data, rows_out.shape[0],
-                                  C.byref(nr), C.byref(fi), C.byref(tc), C.byref(st)))
+        rc = self._L.art_run(self._h, seed, first_event, n_events, rows_out.ctypes.data, rows_out.shape[0],
+                             C.byref(nr), C.byref(fi), C.byref(tc), C.byref(st))
+        if rc == ART_ERR_CAPACITY and nr.value > rows_out.shape[0]:
+            rows_out = np.empty((nr.value, self.ncols))
+            rc = self._L.art_fetch_rows(self._h, rows_out.ctypes.data, rows_out.shape[0], C.byref(nr))
+        self._chk(rc)
         return dict(rows=rows_out[: nr.value], f_inx=fi.value, tot_count=tc.value, stats=st.as_dict())
+
+    def run_device_batches(self, seed, first_event, batch_events, n_batches, batch_stride=None):
+        """art_run_device_batches: n_batches batches of batch_events events (ids first_event + b·batch_stride + [0, batch_events))
+        as one pipelined job; rows stay on the device (fetch_rows)."""
+        nr, fi, tc = C.c_int64(), C.c_int64(), C.c_int64()
+        st = ArtStats()
+        self._chk(self._L.art_run_device_batches(self._h, seed, first_event, batch_events, n_batches,
+                                                 batch_events if batch_stride is None else batch_stride,
+                                                 C.byref(nr), C.byref(fi), C.byref(tc), C.byref(st)))
+        return dict(n_rows=nr.value, f_inx=fi.value, tot_count=tc.value, stats=st.as_dict())
 
     def run_device(self, seed, first_event, n_events):
         nr, fi, tc = C.c_int64(), C.c_int64(), C.c_int64()
@@ -182,8 +200,8 @@ class Handle:
                                          C.byref(st)))
         return dict(n_rows=nr.value, f_inx=fi.value, tot_count=tc.value, stats=st.as_dict())
 
-    def fetch_rows(self, n_rows):
-        rows = np.empty((max(n_rows, 1), self.ncols))
+    def fetch_rows(self, n_rows, rows_out=None):
+        rows = np.empty((max(n_rows, 1), self.ncols)) if rows_out is None else rows_out
         nr = C.c_int64()
         self._chk(self._L.art_fetch_rows(self._h, rows.ctypes.data, rows.shape[0], C.byref(nr)))
         return rows[: nr.value]
@@ -207,6 +225,13 @@ class Handle:
         n = self._L.art_hist_len(self._h)
         out = np.zeros(n)
         self._chk(self._L.art_hist_get(self._h, out, n))
+        return out
+
+    def hist_get_global(self):
+        """The all-reduced block of the last comm_allreduce_hist()."""
+        n = self._L.art_hist_len(self._h)
+        out = np.zeros(n)
+        self._chk(self._L.art_hist_get_global(self._h, out, n))
         return out
 
     def comm_init(self, nranks, rank, uid: bytes):

@@ -128,11 +128,12 @@ typedef struct art_stats {
   int64_t n_final_photon; /* rows with id = 1 (photons that reached the observer sphere)   */
   int64_t n_final_axion;  /* rows with id = 0                                              */
   int64_t n_status[5];    /* ray termination statuses, index = ART_RAY_*                   */
-  double ms_sampler;      /* device time per pipeline stage (CUDA events), ms              */
-  double ms_weights;
-  double ms_tracer;
-  double ms_tree;
-  double ms_total;
+  double ms_sampler;      /* device time (CUDA events), ms: sum of the sampler launches — they run on
+                             their own stream, concurrently with the tracer loop            */
+  double ms_weights;      /* 0 (weights are computed where events are injected into the loop) */
+  double ms_tracer;       /* the wavefront loop from its first launch to the last drain      */
+  double ms_tree;         /* 0 (the tree is walked inside the loop)                          */
+  double ms_total;        /* the whole pipeline call                                         */
   int64_t n_launches;     /* kernels launched by the pipeline call                          */
   int64_t n_cond_eval;    /* … of n_cond, evaluations actually performed (the rest were decided by the
                              exact far-field shortcut r > Rcut)                             */
@@ -220,6 +221,17 @@ int art_run(art_handle* h, uint64_t seed, int64_t first_event, int64_t n_events,
  * HBM (fetch later with art_fetch_rows).                                                     */
 int art_run_device(art_handle* h, uint64_t seed, int64_t first_event, int64_t n_events,
                    int64_t* n_rows, int64_t* f_inx, int64_t* tot_count, art_stats* stats);
+/* Several batches of events as ONE pipelined job: batch b = events first_event + b·batch_stride + [0, batch_events),
+ * b = 0 … n_batches−1 (batch_stride ≥ batch_events; art_run_device is the case n_batches = 1).  The engine keeps its
+ * pool of ray slots full across batch boundaries — slots freed by the late tree nodes of one batch are refilled with
+ * events of the next — so only the last batch drains alone.  Results are those of n_batches separate calls (per-event
+ * random streams); rows come out in batch order.  This is what config 3–5 style production runs and bench.py's
+ * back-to-back steps call.                                                                                     */
+int art_run_device_batches(art_handle* h, uint64_t seed, int64_t first_event, int64_t batch_events, int64_t n_batches,
+                           int64_t batch_stride, int64_t* n_rows, int64_t* f_inx, int64_t* tot_count, art_stats* stats);
+/* Rows of the last pipeline call, ordered as the reference writes them (by event, then by position in the tree).  If
+ * rows_cap is too small: ART_ERR_CAPACITY with *n_rows = rows needed — enlarge the buffer and call again (nothing is
+ * recomputed).  On the device the row buffer grows by itself (the call is re-run once at the exact size).        */
 int art_fetch_rows(art_handle* h, double* rows, int64_t rows_cap, int64_t* n_rows);
 
 /* Event table of the last art_run / art_run_device call: n_events × ART_EVENT_COLS, row-major, in event order
@@ -263,12 +275,18 @@ int art_hist_config_spectrum(art_handle* h, int32_t n_costheta, int32_t n_phi, i
                              double domega_hi);
 int64_t art_hist_len(const art_handle* h); /* doubles */
 int art_hist_reset(art_handle* h);
-int art_hist_get(art_handle* h, double* out, int64_t cap);
+int art_hist_get(art_handle* h, double* out, int64_t cap);        /* THIS GPU's block (local bins + local counters)   */
+/* the all-reduced block of the last art_comm_allreduce_hist: Σ over ranks of what art_hist_get returns on each;
+ * ART_ERR_ARG if no all-reduce has run since the last pipeline call or reset                                  */
+int art_hist_get_global(art_handle* h, double* out, int64_t cap);
 
 /* ---- multi-GPU: one process (or thread) per GPU; only collective = all-reduce of hist --- */
 int art_comm_unique_id(char* id128);                       /* ncclGetUniqueId, 128 bytes      */
 int art_comm_init(art_handle* h, int32_t nranks, int32_t rank, const char* id128);
-int art_comm_allreduce_hist(art_handle* h);                /* ncclAllReduce(sum, f64) in place */
+/* ncclAllReduce(sum, f64) of [bins | counters], out of place: the local block is left untouched (so the call may be
+ * repeated, e.g. after every pipeline call), the result is read with art_hist_get_global.  Without a communicator
+ * (single GPU) the global block is a copy of the local one.                                                    */
+int art_comm_allreduce_hist(art_handle* h);
 int art_comm_destroy(art_handle* h);
 
 /* FP64 DFMA peak probe used as the roofline denominator (MEASURED_PEAKS.json has no FP64

@@ -575,17 +575,17 @@ def test_baseline_config0_flat_run_full_size_matches_oracle(lib, oracle):
     assert np.all(np.abs(fa - fb) <= 3.0 * np.sqrt(var) + 1e-3 * fb.sum())
 
 
-def test_sub_chunked_and_multi_lane_runs_equal_the_single_chunk_run(lib, monkeypatch):
-    """A call larger than one sub-chunk (2^21 events by default — BASELINE configs 3-5 run 1e7+ events per GPU) walks
-    the events in sub-chunks, optionally on several streams; rows, counters and the event table must not depend
-    on how the call was cut."""
+def test_refilled_pool_runs_equal_the_single_block_run(lib, monkeypatch):
+    """The pipeline keeps a pool of event slots full: slots handed back by finished events are refilled with freshly
+    sampled ones while the loop runs (BASELINE configs 3-5 run 1e7+ events per GPU through a 2^20-slot pool).  Rows,
+    counters and the event table must not depend on the pool size or on when blocks were injected."""
     p = ArtParams.default(theta_m=0.2, save_mode=2)
     n = 5000
     h = lib.Handle(p, 0)
     a = h.run(11, 1, n)
     ea = h.fetch_events(n)
     h.close()
-    for env in (dict(ART_SUBCHUNK="1024"), dict(ART_SUBCHUNK="1500", ART_LANES="2")):
+    for env in (dict(ART_POOL_SLOTS="256"), dict(ART_POOL_SLOTS="1000", ART_REFILL_MIN="10"), dict(ART_POOL_SLOTS="4096", ART_SIDE_STREAM="0")):
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         h = lib.Handle(p, 0)
@@ -594,9 +594,58 @@ def test_sub_chunked_and_multi_lane_runs_equal_the_single_chunk_run(lib, monkeyp
         h.close()
         for k in env:
             monkeypatch.delenv(k)
-        assert np.array_equal(a["rows"], b["rows"]) and np.array_equal(ea, eb)
+        assert np.array_equal(a["rows"], b["rows"]) and np.array_equal(ea, eb), env
         assert a["f_inx"] == b["f_inx"] and a["tot_count"] == b["tot_count"]
-        assert b["stats"]["n_launches"] > a["stats"]["n_launches"]  # it was cut
+        for k in ("n_rays", "n_attempts", "n_final_photon", "n_final_axion", "n_acc", "n_rej", "n_rhs"):
+            assert a["stats"][k] == b["stats"][k], k
+        if "ART_POOL_SLOTS" in env and int(env["ART_POOL_SLOTS"]) < n:
+            assert b["stats"]["n_launches"] > a["stats"]["n_launches"]  # it was refilled
+
+
+def test_batches_as_one_pipelined_job_equal_separate_calls(lib):
+    """art_run_device_batches: contiguous and strided batches (the multi-GPU bench gives rank r the event ids
+    1 + (step·world + r)·E + [0, E)) against one art_run per batch."""
+    p = ArtParams.default(theta_m=0.2)
+    h = lib.Handle(p, 0)
+    E, nb = 700, 4
+    for stride in (E, 3 * E):
+        out = h.run_device_batches(21, 1 + E, E, nb, stride)
+        rows = h.fetch_rows(out["n_rows"])
+        parts = [h.run(21, 1 + E + b * stride, E) for b in range(nb)]
+        ref = np.vstack([q["rows"] for q in parts])
+        assert np.array_equal(rows, ref), stride
+        assert out["f_inx"] == sum(q["f_inx"] for q in parts) and out["tot_count"] == sum(q["tot_count"] for q in parts)
+        assert out["stats"]["n_events"] == E * nb
+    h.close()
+
+
+def test_row_buffers_grow_instead_of_failing(lib, oracle, monkeypatch):
+    """The reference appends rows without bound (MainRunner.jl:729).  Device side: a row buffer that turns out too small is
+    re-allocated at the exact size and the call re-run (identical, per-event random streams); host side: ART_ERR_CAPACITY
+    reports the number of rows and art_fetch_rows is called again with a larger buffer.  Parameters of the reference's own
+    convergence sweep (jonas_test_analyses/runner_convergence.sh: MassA 2e-5, Axg 5e-10, MCNodes 50, maxNodes 100,
+    numCutoff 1000, probCutoff 1e-10, ThetaM 0); with them an event still ends in about one row, so the device buffer is
+    made to overflow by starting it at a fifth of an event per row (ART_ROWS_INIT_FRAC, a test hook)."""
+    p = ArtParams.default(theta_m=0.0, Mass_a=2e-5, Ax_g=5e-10, MC_nodes=50, max_nodes=100, num_cutoff=1000, prob_cutoff=1e-10,
+                          save_mode=1)
+    n = 400
+    h = lib.Handle(p, 0)
+    a = h.run(1769, 1, n)
+    small = np.empty((10, h.ncols))
+    c = h.run(1769, 1, n, rows_out=small)   # host buffer too small: re-fetched into a new one
+    h.close()
+    assert np.array_equal(a["rows"], c["rows"]) and a["rows"].shape[0] > 10
+    monkeypatch.setenv("ART_ROWS_INIT_FRAC", "0.2")
+    h = lib.Handle(p, 0)
+    b = h.run(1769, 1, n)
+    h.close()
+    monkeypatch.delenv("ART_ROWS_INIT_FRAC")
+    assert b["rows"].shape[0] > 0.2 * n and np.array_equal(a["rows"], b["rows"])
+    assert a["f_inx"] == b["f_inx"] and a["tot_count"] == b["tot_count"]
+    assert b["stats"]["n_launches"] > 0
+    o = oracle.run(p, 1769, 1, n, rows_cap=200 * n)
+    assert abs(a["rows"].shape[0] - o["rows"].shape[0]) <= 0.03 * o["rows"].shape[0] + 2
+    assert abs(a["tot_count"] - o["tot_count"]) <= 0.03 * o["tot_count"] + 2
 
 
 def _switch_cases():
