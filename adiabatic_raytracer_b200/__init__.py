@@ -6,13 +6,16 @@ Importing the package does not load the library; the first use does, and raises 
 """
 from .params import ArtParams, ArtStats  # noqa: F401
 
-__all__ = ["ArtParams", "ArtStats", "main_runner_tree", "Handle"]
+__all__ = ["ArtParams", "ArtStats", "main_runner_tree", "main_runner_tree_multi", "Handle"]
 
 
 def __getattr__(name):
     if name == "main_runner_tree":
         from .main_runner import main_runner_tree
         return main_runner_tree
+    if name == "main_runner_tree_multi":
+        from .main_runner import main_runner_tree_multi
+        return main_runner_tree_multi
     if name == "Handle":
         from .lib import Handle
         return Handle

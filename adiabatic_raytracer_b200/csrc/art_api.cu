@@ -118,6 +118,8 @@ struct Lane {
   DBuf slot_event, slot_parts, ring;
   DBuf wf_hot, wf_cold, wf_seg, wf_need, wf_neg, wf_pend, wf_sign, wf_act[4], wf_roots[2], wf_fin[2], wf_ctr;
   float ms_sampler = 0, ms_weights = 0, ms_tracer = 0;
+  float ms_k[3] = {0, 0, 0};  // ART_TIME_KERNELS: stage kernel, scan, detect
+  long long n_blocks = 0;
   void release() {
     DBuf* all[] = {&samples, &tstate, &stacks, &q0, &rout, &rec, &ctr, &slot_event, &slot_parts, &ring, &wf_hot, &wf_cold, &wf_seg,
                    &wf_need, &wf_neg, &wf_pend, &wf_sign, &wf_act[0], &wf_act[1], &wf_act[2], &wf_act[3], &wf_roots[0], &wf_roots[1],
@@ -266,6 +268,8 @@ int wf_loop(art_handle* h, Lane& L, WfPool W, long long n_act0, RayOut* out, dou
   const bool side = !(getenv("ART_SIDE_STREAM") && atoi(getenv("ART_SIDE_STREAM")) == 0);
   cudaStream_t s2 = side ? L.stream2 : st;
   cudaStream_t s3 = side ? L.stream3 : st;
+  const bool timek = getenv("ART_TIME_KERNELS") != nullptr;  // CUDA events around every launch of the main stream
+  std::vector<cudaEvent_t> tk;
   const long long refill_min = job ? (h->refill_min > 0 ? h->refill_min : std::max<long long>(job->S / 8, 1)) : 0;
   long long iter_cap = 64LL * h->params.maxiters;
   if (job) iter_cap *= (job->n_events / std::max<long long>(job->S, 1) + 2);
@@ -337,11 +341,22 @@ int wf_loop(art_handle* h, Lane& L, WfPool W, long long n_act0, RayOut* out, dou
       }
       if (side) CU(cudaEventRecord(L.ev_side, s2));
       const int gs = (int)std::max<long long>(1, std::min<long long>((long long)h->n_sm * h->stage_grid_per_sm, (n_act + STAGE_THREADS - 1) / STAGE_THREADS));
+      auto mark = [&]() {
+        if (timek) {
+          cudaEvent_t e = evg.make();
+          if (e) cudaEventRecord(e, st);
+          tk.push_back(e);
+        }
+      };
+      mark();
       k_wf_stages<IG><<<2 * gs, STAGE_THREADS, ksmem, st>>>(h->dp, W, k, tail_mode ? h->tail_nstep : h->bulk_nstep, tail_mode ? 1 : h->bulk_min_go, stats);
+      mark();
       k_wf_scan<IG><<<(int)std::max<long long>(1, std::min<long long>((long long)h->n_sm * h->scan_grid_per_sm, (n_act * 11 + SCAN_THREADS - 1) / SCAN_THREADS)),
                       SCAN_THREADS, 0, st>>>(h->dp, W, k, stats);
+      mark();
       k_wf_detect<IG><<<(int)std::max<long long>(1, std::min<long long>((long long)h->n_sm * h->detect_grid_per_sm, (n_act + WF_THREADS - 1) / WF_THREADS)),
                         WF_THREADS, 0, st>>>(h->dp, W, k);
+      mark();
       h->launches += 3;
     }
     CU(cudaGetLastError());
@@ -366,6 +381,12 @@ int wf_loop(art_handle* h, Lane& L, WfPool W, long long n_act0, RayOut* out, dou
     }
     if (iter > iter_cap) return fail(h, ART_ERR_CUDA, "wavefront tracer did not terminate");
   }
+  if (job) L.n_blocks += job->n_blocks;
+  for (size_t i = 0; i + 3 < tk.size(); i += 4)  // (the loop ends with a synchronised stream: every event has completed)
+    for (int j = 0; j < 3; ++j) {
+      float ms = 0;
+      if (tk[i + j] && tk[i + j + 1] && cudaEventElapsedTime(&ms, tk[i + j], tk[i + j + 1]) == cudaSuccess) L.ms_k[j] += ms;
+    }
   return ART_OK;
 }
 
@@ -810,6 +831,8 @@ int art_run_device_batches(art_handle* h, uint64_t seed, int64_t first_event, in
     CU(cudaEventRecord(e0, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     L.ms_sampler = L.ms_weights = L.ms_tracer = 0;
+    L.ms_k[0] = L.ms_k[1] = L.ms_k[2] = 0;
+    L.n_blocks = 0;
     if (n_events > 0) {
       const int rc = h->dp.integrator == IG_DP5
                          ? run_pool<IG_DP5>(h, L, seed, first_event, n_events, h->last_batch_events, batch_stride, sink, gctr, dstats, evg)
@@ -860,6 +883,9 @@ int art_run_device_batches(art_handle* h, uint64_t seed, int64_t first_event, in
   S.ms_total = ms_tot;
   S.n_launches = h->launches.load();
   S.n_cond_eval = (long long)ds.n_cond_eval;
+  S.n_scanned_steps = (long long)ds.n_scanned;
+  S.n_pool_blocks = L.n_blocks;
+  S.ms_k_stages = L.ms_k[0]; S.ms_k_scan = L.ms_k[1]; S.ms_k_detect = L.ms_k[2];
   if (st_out) *st_out = S;
   // trailing histogram counters: [f_inx, n_rows, n_events, n_acc, n_rej, n_rhs, n_cond, n_rays]
   h->host_counters[0] += (double)f_inx; h->host_counters[1] += (double)h->n_rows_dev; h->host_counters[2] += (double)n_events;

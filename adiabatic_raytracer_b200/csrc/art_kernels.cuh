@@ -27,6 +27,7 @@ struct DevStats {  // accumulated with atomics; mirrors the counters of art_stat
   unsigned long long n_attempts, n_sampler_cond, n_rays, n_rays_photon, n_acc, n_rej, n_rhs, n_cond;
   unsigned long long n_status[5];
   unsigned long long n_cond_eval;  // full evaluations of the crossing condition (scan + root finder + start-up)
+  unsigned long long n_scanned;    // accepted steps handed to the crossing scan
 };
 
 struct QueuedRay {  // one node to propagate

@@ -208,6 +208,7 @@ __device__ __forceinline__ void wf_stages_body(const DevParams& P, const WfPool&
                                                unsigned bid, unsigned nblocks, double* ksm, DevStats* stats) {
   constexpr int LAST = Scheme<IG>::LAST, NEXTRA = Scheme<IG>::NEXTRA, TNEW = IG == IG_DP5 ? 5 : 6;  // park slot of e^{s_new}
   unsigned long long n_full = 0;  // condition evaluations done here (end points of in-box steps)
+  unsigned long long n_scan = 0;  // steps handed to the crossing scan
   const KStoreT<STAGE_THREADS> K{ksm + threadIdx.x};
   const long long n = (long long)*wc(W.ctr, k, WC_ACT + SP);
   const int* __restrict__ act = (k & 1) ? W.act[1][SP] : W.act[0][SP];  // (a dynamic index would copy the parameter struct to local memory)
@@ -303,6 +304,7 @@ __device__ __forceinline__ void wf_stages_body(const DevParams& P, const WfPool&
     }
     if (pending) {
       R.n_rhs += NEXTRA;
+      n_scan++;
       const SegAoS D{W.seg + (size_t)id * Seg<IG>::N};
       R.template publish<IG>(K, D);
       D(Seg<IG>::NUDGE) = R.event_last ? 1.0 : 0.0;
@@ -318,7 +320,11 @@ __device__ __forceinline__ void wf_stages_body(const DevParams& P, const WfPool&
     wf_route(W, k, valid, id, done, pending, SP == SPECIES_AXION);
   }
   n_full = warp_sum(n_full);
-  if ((threadIdx.x & 31) == 0 && stats && n_full) atomicAdd(&stats->n_cond_eval, n_full);
+  n_scan = warp_sum(n_scan);
+  if ((threadIdx.x & 31) == 0 && stats) {
+    if (n_full) atomicAdd(&stats->n_cond_eval, n_full);
+    if (n_scan) atomicAdd(&stats->n_scanned, n_scan);
+  }
 }
 
 // One launch steps both species: the first half of the grid walks the axion list, the second half the

@@ -18,10 +18,12 @@ Differences a user can observe:
 """
 import math
 import os
+import time
 
 import numpy as np
 
 from . import lib as _lib
+from . import sharding as _sharding
 from .params import ArtParams, ART_ERR_NO_SURFACE
 
 
@@ -91,3 +93,88 @@ def main_runner_tree(Mass_a, Ax_g, theta_m, omega_pul, B0, rNS, Mass_NS, omega_p
     if return_rows:
         return out["tot_count"], rows, fname, out
     return out["tot_count"]
+
+
+def _exchange_comm_id(path: str, rank: int, timeout_s: float = 120.0) -> bytes:
+    """NCCL unique id from rank 0 to the other ranks through a file (the reference's own multi-process runs share nothing
+    but the file system, runner_GR_tasks.sh:22-28); any other channel (MPI, sockets, torch.distributed) works as well."""
+    if rank == 0:
+        uid = _lib.comm_unique_id()
+        tmp = path + ".tmp"
+        with open(tmp, "wb") as f:
+            f.write(uid)
+        os.replace(tmp, path)
+        return uid
+    t0 = time.time()
+    while not (os.path.exists(path) and os.path.getsize(path) == 128):
+        if time.time() - t0 > timeout_s:
+            raise TimeoutError(f"no NCCL id at {path}")
+        time.sleep(0.05)
+    return open(path, "rb").read()
+
+
+def main_runner_tree_multi(Mass_a, Ax_g, theta_m, omega_pul, B0, rNS, Mass_NS, omega_prop, Ntajs, gammaF, *, rank, world,
+                           comm_id=None, device=None, normalisation="global", write_files=True, fetch_rows=True,
+                           hist_bins=(16, 32), file_tag="", dir_tag="results", iseed=1769, **kwargs):
+    """One job of ``Ntajs − 1`` events over ``world`` GPUs, one process per GPU (rank = this process).
+
+    The reference's "multi-device" path is N independent single-process runs plus Combine_Files.py
+    (runner_GR_tasks.sh:22-28, Gen_Samples.jl:195-239).  Here the events 1 … Ntajs−1 of ONE seeded job are split in
+    contiguous ranges over the ranks (per-event random streams: the rows do not depend on ``world``), every rank writes its
+    own ``tree_…_<file_tag><rank>.npy``, and the only collective is the all-reduce of the binned flux whose trailing
+    counters carry the global ``f_inx`` (MainRunner.jl:749).
+
+    normalisation = "global":   column 8 (sln_prob) is divided by the all-reduced f_inx — concatenating the files gives
+                                exactly the single-GPU file of the same job;
+                  = "per_rank": divided by this rank's own f_inx, i.e. every file is a self-contained run as the
+                                reference's processes write them, to be combined by Combine_Files.py / combine_files
+                                (which divide by the number of files).
+    comm_id: the 128-byte NCCL id from ``lib.comm_unique_id()`` of rank 0, or None to exchange it through
+    ``<dir_tag>/.nccl_id_<file_tag>``.  Returns a dict (tot_count of this rank, global counters, reduced histogram,
+    file name); None when there is no conversion surface.
+    """
+    for k in ("saveMode", "cutT", "CLen_Scale", "v_NS", "ntimes_ax"):
+        kwargs.setdefault(k, {"saveMode": 0, "cutT": 100000, "CLen_Scale": True, "v_NS": (0, 0, 0), "ntimes_ax": 1000}[k])
+    saveMode = kwargs.pop("saveMode")
+    for k in ("cutT", "CLen_Scale", "v_NS", "ntimes_ax"):
+        kwargs.pop(k)
+    if saveMode > 1:
+        raise NotImplementedError("main_runner_tree_multi writes the .npy rows (saveMode 0 / 1)")
+    p = params_from_call(Mass_a, Ax_g, theta_m, omega_pul, B0, rNS, Mass_NS, saveMode=saveMode, **kwargs)
+    rc, maxR = _lib.max_radius(p)
+    if rc == ART_ERR_NO_SURFACE:
+        if rank == 0:
+            print("Too small Max R.... quitting.... ")
+        return None
+    n_total = max(int(Ntajs) - 1, 0)
+    first, count = _sharding.split_events(n_total, world)[rank]
+    h = _lib.Handle(p, rank if device is None else device)
+    h.hist_config(*hist_bins)
+    if world > 1:
+        if comm_id is None:
+            os.makedirs(dir_tag, exist_ok=True)
+            comm_id = _exchange_comm_id(os.path.join(dir_tag, f".nccl_id_{file_tag}"), rank)
+        h.comm_init(world, rank, comm_id)
+    t0 = time.perf_counter()
+    out = h.run_device(iseed, first, count)
+    h.comm_allreduce_hist()            # the only collective: [bins | f_inx, n_rows, n_events, …]
+    G = h.hist_get_global()
+    wall = time.perf_counter() - t0
+    f_inx_total = int(G[-_sharding.N_TRAILING])
+    rows = None
+    fname = None
+    if fetch_rows or write_files:
+        rows = np.ascontiguousarray(h.fetch_rows(out["n_rows"]))
+        f_norm = f_inx_total if normalisation == "global" else out["f_inx"]
+        if rows.shape[0] and f_norm > 0:
+            _lib.normalize_rows(rows, f_norm)  # MainRunner.jl:749
+        if write_files:
+            fname = _lib.npy_name(p, int(Ntajs), dir_tag, f"{file_tag}{rank}")
+            os.makedirs(os.path.dirname(fname), exist_ok=True)
+            _lib.write_npy(fname, rows)
+    res = dict(rank=rank, world=world, first_event=first, n_events=count, n_rows=out["n_rows"], f_inx=out["f_inx"],
+               tot_count=out["tot_count"], f_inx_total=f_inx_total, n_rows_total=int(G[-_sharding.N_TRAILING + 1]),
+               n_events_total=int(G[-_sharding.N_TRAILING + 2]), hist=G, hist_local=h.hist_get(), stats=out["stats"],
+               wall_s=wall, file=fname, rows=rows)
+    h.close()
+    return res

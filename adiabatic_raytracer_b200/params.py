@@ -97,6 +97,11 @@ class ArtStats(C.Structure):
         ("ms_total", C.c_double),
         ("n_launches", C.c_int64),
         ("n_cond_eval", C.c_int64),
+        ("n_scanned_steps", C.c_int64),
+        ("n_pool_blocks", C.c_int64),
+        ("ms_k_stages", C.c_double),
+        ("ms_k_scan", C.c_double),
+        ("ms_k_detect", C.c_double),
     ]
 
     def as_dict(self):

@@ -38,16 +38,20 @@ NS = dict(Mass_a=1e-5, Ax_g=1e-12, theta_m=0.2, omega_pul=1.0, B0=1e14, rNS=10.0
 SEED = 1769
 
 
-# from profiles/r01_final_keys.txt (ncu --set full, 1e6-event pass, final build of round 1); dram = dram__bytes_read.sum +
-# dram__bytes_write.sum of that launch; k_wf_detect is the compaction pass (hot records + sign masks in, survivor lists out)
-NCU_HARDWARE_VIEW = {
-    "source": "profiles/r01_final_keys.txt",
-    "k_sample_events": {"ms": 49.85, "fp64_pipe_pct": 43.1, "issue_pct": 56.3, "threads_per_inst": 13.2, "dram_MB": 29.3},
-    "k_wf_stages": {"ms": 1.315, "fp64_pipe_pct": 37.4, "issue_pct": 36.9, "threads_per_inst": 23.5, "dram_MB": 1015.8},
-    "k_wf_scan": {"ms": 0.778, "fp64_pipe_pct": 51.6, "issue_pct": 62.2, "threads_per_inst": 27.1, "dram_MB": 437.0},
-    "k_wf_detect": {"ms": 0.148, "fp64_pipe_pct": 3.8, "issue_pct": 11.7, "dram_MB": 527.3, "dram_GBps": 3563.0,
-                    "frac_of_measured_hbm_peak": 0.544},
-}
+# hardware view of the kernels (ncu --set full / launch list of THIS build, written by tools/ncu_summary.py): loaded, never
+# hard-coded; absent file ⇒ the keys are null
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "r02_ncu_summary.json")
+# algorithmic bytes the compaction pass (k_wf_detect) moves per scanned step: hot record 192 B + sign masks 24 B + list id
+# 4 B in, start-box reference point (one 32-byte sector) in, 16 B of the record (one sector) + survivor-list id 4 B out
+DETECT_BYTES_PER_STEP = 192 + 24 + 4 + 32 + 32 + 4
+HBM_FALLBACK_GBS = 6650.0  # B200_PROFILING.md, only if MEASURED_PEAKS.json is absent
+
+
+def hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
 
 
 def parse():
@@ -133,8 +137,9 @@ def cpu_baseline(seconds, events_hint=None):
     dt = time.perf_counter() - t0
     st = out["stats"]
     return {"value": st["n_final_photon"] / dt, "unit": "rays/s", "cores": cores, "kind": "port",
-            "sample": f"{n} events of the same workload (GR, seed {SEED}), oracle/ (C++ -O2 -fopenmp, literal "
-                      f"restatement incl. dual-number gradients), {dt:.1f} s; the Julia reference itself cannot run "
+            "sample": f"{n} events of the same workload (GR, seed {SEED}, Vern6), oracle/ (C++ -O2 -fopenmp port of the "
+                      f"reference's algorithm incl. dual-number gradients), {dt:.1f} s.  A FASTER-than-reference baseline: the "
+                      f"Julia code allocates per right-hand side and runs GC.gc() per event (MainRunner.jl:745); it cannot run "
                       f"here (no Julia in the image)",
             "events_per_s": n / dt}, out, dt, n
 
@@ -167,7 +172,8 @@ def run_reference(args):
         "config": {"workload": "BASELINE configs[1]: GR, m_a=1e-5 eV, B0=1e14 G, rotW=1, theta_m=0.2, M=1, R=10 km; "
                                f"bounded sample of {n} events per step on the host CPU"},
         "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
-                         "sample": f"{n} events/step x {args.steps} steps, oracle/ OpenMP on {cores} threads"},
+                         "sample": f"{n} events/step x {args.steps} steps, oracle/ OpenMP on {cores} threads (Vern6; a faster-than-"
+                                   "reference port: no per-call allocation, no GC per event)"},
         "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -224,8 +230,6 @@ def main():
 
     E = args.events
     ncols = h.ncols
-    pinned = lib.PinnedRows(E * 3 + 1024, ncols)  # e2e result buffer: page-locked host memory (art_host_alloc)
-    host_rows = pinned.array
 
     def first_event(step):  # disjoint event-id ranges per (step, rank): per-event Philox streams
         return 1 + (step * world + rank) * E
@@ -295,50 +299,110 @@ def main():
     # one step as a single call (its tail drains alone), for comparison with the pipelined figure
     single = h.run_device(SEED, first_event(2000), E)["stats"]["ms_total"]
 
-    # ---- timed: end to end through the C ABI with host buffers (e2e) ------------------------------
-    h.run(SEED, first_event(0), E, rows_out=host_rows)  # untimed: first use allocates the ordering scratch buffers
+    # ---- timed: end to end through the C ABI with HOST buffers (e2e) ---------------------------------------------
+    # the call a user makes for a production run: batches as one job, rows ordered on the device and copied into a
+    # page-locked host buffer, all-reduced histogram read back.  Chunks of at most 8 steps bound the host buffer (≈ 2 GB).
+    chunk = min(args.steps, 8)
+    pinned = lib.PinnedRows(int(chunk * E * 2.3) + 1024, ncols)  # e2e result buffer: page-locked host memory (art_host_alloc)
+    host_rows = pinned.array
+    h.run(SEED, first_event(3000), min(E, 20000), rows_out=host_rows)  # untimed: first use allocates the ordering scratch buffers
     barrier()
     t0 = time.perf_counter()
     e2e_rays = 0
     d2h = 0
-    for s in range(args.steps):
-        out = h.run(SEED, first_event(s), E, rows_out=host_rows)
+    done = 0
+    while done < args.steps:
+        nb_ = min(chunk, args.steps - done)
+        o = h.run_device_batches(SEED, first_event(done), E, nb_, world * E)
+        rows = h.fetch_rows(o["n_rows"], rows_out=host_rows)
         h.comm_allreduce_hist()
         hist = h.hist_get_global()
-        e2e_rays += out["stats"]["n_final_photon"]
-        d2h += out["rows"].shape[0] * ncols * 8 + hist.nbytes + 16 * 8
+        e2e_rays += o["stats"]["n_final_photon"]
+        d2h += rows.shape[0] * ncols * 8 + hist.nbytes + 16 * 8
+        done += nb_
     barrier()
     wall_e2e = max_over_ranks(time.perf_counter() - t0)
     e2e_total = sum_over_ranks(e2e_rays)
     e2e_value = e2e_total / wall_e2e
 
-    # ---- roofline of the tracer (k_wf_stages + k_wf_scan + k_wf_root …): algorithmic FP64 flop / its
-    # CUDA-event time.  Only crossing conditions that were actually EVALUATED count (n_cond_eval); the
-    # reference's remaining per-step evaluations are decided by the exact far-field shortcut (r > Rcut) and
-    # are reported separately, not credited as work.
+    # ---- comparison figures (untimed region, rank-local; only at N = 1 to keep the scaling runs short) ---------------
+    extra = {}
+    if world == 1:
+        ks = min(args.steps, 3)
+        # BASELINE configs' literal "P = 1 s" (rotW = 2π) GR workload
+        hp = lib.Handle(p.copy(omega_pul=2 * np.pi), local)
+        hp.run_device(SEED, 1, E)
+        op = hp.run_device_batches(SEED, 1 + E, E, ks)
+        hp.close()
+        extra["workload_p1s"] = "same as workload but P = 1 s (rotW = 2π)"
+        extra["value_p1s"] = op["stats"]["n_final_photon"] / (op["stats"]["ms_total"] * 1e-3)
+        extra["ms_per_step_p1s"] = op["stats"]["ms_total"] / ks
+        # the other integrator
+        other = 1 - p.integrator
+        ho = lib.Handle(p.copy(integrator=other), local)
+        ho.run_device(SEED, 1, E)
+        oo = ho.run_device_batches(SEED, 1 + E, E, ks)
+        ho.close()
+        extra["value_other_integrator"] = {"integrator": "DP5" if other == 1 else "Vern6",
+                                           "value": oo["stats"]["n_final_photon"] / (oo["stats"]["ms_total"] * 1e-3),
+                                           "ms_per_step": oo["stats"]["ms_total"] / ks,
+                                           "n_rhs_per_ray": oo["stats"]["n_rhs"] / oo["stats"]["n_rays"]}
+
+    # ---- per-kernel device times of one job (CUDA events around every launch of the main stream; a separate, untimed run) --
+    os.environ["ART_TIME_KERNELS"] = "1"
+    tk = h.run_device_batches(SEED, first_event(4000), E, min(args.steps, 2), world * E)["stats"]
+    del os.environ["ART_TIME_KERNELS"]
+    hbm, hbm_src = hbm_peak()
+    det_bytes = tk["n_scanned_steps"] * DETECT_BYTES_PER_STEP
+    det_gbs = det_bytes / (tk["ms_k_detect"] * 1e-3) / 1e9 if tk["ms_k_detect"] > 0 else None
+    kernels = {
+        "run": f"{min(args.steps, 2)} steps with ART_TIME_KERNELS=1 (events around every main-stream launch), untimed region",
+        "ms_total": tk["ms_total"], "ms_k_stages": tk["ms_k_stages"], "ms_k_scan": tk["ms_k_scan"], "ms_k_detect": tk["ms_k_detect"],
+        "ms_sampler_overlapped": tk["ms_sampler"],
+        "share_of_step": {k: tk[k] / tk["ms_total"] for k in ("ms_k_stages", "ms_k_scan", "ms_k_detect")},
+        "compaction": {"kernel": "k_wf_detect (ballot/popc compaction of the scanned rays into next-step / root / finished lists)",
+                       "scanned_steps": tk["n_scanned_steps"], "algorithmic_bytes": det_bytes,
+                       "bytes_per_step": DETECT_BYTES_PER_STEP, "ms": tk["ms_k_detect"], "GBps": det_gbs,
+                       "frac_of_hbm_peak": det_gbs / hbm if det_gbs else None, "hbm_peak_GBps": hbm, "hbm_peak_source": hbm_src},
+    }
+
+    # ---- roofline: algorithmic FP64 flop of the path's FP64-bound kernels over the device time of the job ------------------
+    # tracer: k_wf_stages (8 RHS per attempted Vern6 step + 3 dense-output RHS per scanned step) + k_wf_scan / k_wf_root
+    # (crossing conditions actually EVALUATED: n_cond_eval; the reference's remaining per-step evaluations are decided by
+    # the certified-sign shortcuts and are NOT credited); sampler: k_sample_events, which now overlaps the tracer on its
+    # own stream, so the two cannot be timed apart: flop of both over the job's total device time.
     n_cond_eval = agg.get("n_cond_eval", 0) or agg["n_cond"]
     flop_trace = agg["n_rhs"] * F_RHS + n_cond_eval * F_COND
-    t_trace = agg["ms_tracer"] * 1e-3
-    achieved = flop_trace / t_trace / 1e12
+    flop_samp = agg["n_sampler_cond"] * F_SAMPLER_COND
+    t_job = agg["ms_total"] * 1e-3
+    achieved = (flop_trace + flop_samp) / t_job / 1e12
+    ncu = None
+    if os.path.exists(NCU_SUMMARY):
+        try:
+            ncu = json.load(open(NCU_SUMMARY))
+        except Exception:
+            ncu = None
     roofline = {
         "bound": "fp64_alu", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-        "traffic": None,
-        "kernel": "wavefront tracer: k_wf_stages (6 RHS per attempted step) + k_wf_scan (crossing condition) + k_wf_root, "
-                  "sum over the launches of one step",
+        "traffic": (ncu or {}).get("dram_bytes_per_step"),
+        "kernel": "the FP64-bound kernels of the job: wavefront tracer (k_wf_stages + k_wf_scan + k_wf_root) and surface sampler "
+                  "(k_sample_events), which overlap on separate streams; sum of their algorithmic flop over the job's device time",
         "peak_source": "measured in this run by art_fp64_peak (register-resident DFMA chain, all SMs); "
                        "MEASURED_PEAKS.json has no FP64 entry (hbm_gbs / bf16 only)",
-        "algorithmic": f"F_rhs={F_RHS:.0f}, F_cond={F_COND:.0f} flop (SURVEY §8d) x measured n_rhs, n_cond_eval "
+        "algorithmic": f"F_rhs={F_RHS:.0f}, F_cond={F_COND:.0f} flop (SURVEY §8d) x measured n_rhs, n_cond_eval, n_sampler_cond "
                        "(conditions actually evaluated)",
+        "flop_per_step": {"tracer": flop_trace / args.steps, "sampler": flop_samp / args.steps},
+        "frac_tracer_only": flop_trace / t_job / 1e12 / fp64_peak,
         "per_ray": {"n_acc": agg["n_acc"] / agg["n_rays"], "n_rej": agg["n_rej"] / agg["n_rays"],
                     "n_rhs": agg["n_rhs"] / agg["n_rays"], "n_cond_reference": agg["n_cond"] / agg["n_rays"],
-                    "n_cond_eval": n_cond_eval / agg["n_rays"], "flop": flop_trace / agg["n_rays"]},
-        "frac_if_far_field_points_counted": (agg["n_rhs"] * F_RHS + agg["n_cond"] * F_COND) / t_trace / 1e12 / fp64_peak,
-        "sampler": {"achieved": agg["n_sampler_cond"] * F_SAMPLER_COND / (agg["ms_sampler"] * 1e-3) / 1e12,
-                    "unit": "TFLOP/s", "cond_per_attempt": agg["n_sampler_cond"] / agg["n_attempts"]},
-        "stage_ms_per_step": {k: agg[k] / args.steps for k in ("ms_sampler", "ms_weights", "ms_tracer", "ms_tree", "ms_total")},
-        # hardware view — NOT measured in this run: one `ncu --set full --clock-control none` capture of the same build
-        # and workload (sampler launch; iteration 10 of the wavefront loop), summarised in profiles/r01_final_keys.txt
-        "ncu": NCU_HARDWARE_VIEW,
+                    "n_cond_eval": n_cond_eval / agg["n_rays"], "flop": flop_trace / agg["n_rays"],
+                    "scanned_steps": agg.get("n_scanned_steps", 0) / agg["n_rays"]},
+        "frac_if_every_reference_evaluation_counted": (agg["n_rhs"] * F_RHS + agg["n_cond"] * F_COND + flop_samp) / t_job / 1e12 / fp64_peak,
+        "sampler": {"cond_per_attempt": agg["n_sampler_cond"] / agg["n_attempts"], "ms_kernels_per_step": agg["ms_sampler"] / args.steps},
+        "ms_per_step": {"total": agg["ms_total"] / args.steps, "loop": agg["ms_tracer"] / args.steps},
+        "kernels": kernels,
+        # hardware view — NOT measured in this run: ncu --set full / launch list of this build, profiles/r02_ncu_summary.json
+        "ncu": ncu,
     }
 
     cpu = None
@@ -346,31 +410,36 @@ def main():
         cpu, _, _, _ = cpu_baseline(args.cpu_seconds)
 
     if rank == 0:
+        cfg = {
+            "workload": "BASELINE configs[1]: GR (flat=false), m_a=1e-5 eV, Ax_g=1e-12, B0=1e14 G, rotW=1.0 (the reference's default; "
+                        "P = 1 s is value_p1s), theta_m=0.2, M=1 Msun, R=10 km; 1e6 events per GPU per step (sampler + back-trace "
+                        "+ forward tree)",
+            "events_per_gpu_per_step": E, "seed": SEED, "reltol": p.reltol, "abstol": p.ode_err,
+            "interp_points_ray": p.interp_points_ray, "interp_points_sampler": p.interp_points_sampler,
+            "integrator": ("Vern6 (Verner 9-stage 6(5), the reference's solve(prob, Vern6()) RT.jl:383), lazy 6th-order dense output"
+                           if p.integrator == 0 else "DP5(4) FSAL (round 1's scheme)") + ", OrdinaryDiffEq PI controller",
+            "l2": "working set ~9 KB per event slot x 2^20 slots ~ 9 GB >> 126 MB L2, no flush needed",
+            "events_per_s": agg["n_events"] * world / (ms_dev * 1e-3),
+            "ray_propagations_per_s": agg["n_rays"] * world / (ms_dev * 1e-3),
+            "wall_ms_per_step": wall_dev / args.steps,
+            "submission": f"the {args.steps} steps are one pipelined job (art_run_device_batches): ray slots freed by step s are "
+                          "refilled with events of step s+1, only the last step drains alone",
+            "ms_per_step_single_call": single,
+            "pool_blocks_per_step": agg.get("n_pool_blocks", 0) / args.steps,
+        }
+        cfg.update(extra)
         line = {
             "metric": "rays traced to observer/sec (GR mode)", "value": value, "unit": "rays/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {
-                "workload": "BASELINE configs[1]: GR (flat=false), m_a=1e-5 eV, Ax_g=1e-12, B0=1e14 G, rotW=1.0, theta_m=0.2, "
-                            "M=1 Msun, R=10 km; 1e6 events per GPU per step (sampler + back-trace + forward tree)",
-                "events_per_gpu_per_step": E, "seed": SEED, "reltol": p.reltol, "abstol": p.ode_err,
-                "interp_points_ray": p.interp_points_ray, "interp_points_sampler": p.interp_points_sampler,
-                "integrator": ("Vern6 (Verner 9-stage 6(5), the reference's solve(prob, Vern6()) RT.jl:383), lazy 6th-order dense output"
-                               if p.integrator == 0 else "DP5(4) FSAL (round 1's scheme)") + ", OrdinaryDiffEq PI controller",
-                "l2": "working set ~8 GB per step >> 126 MB L2, no flush needed",
-                "events_per_s": agg["n_events"] * world / (ms_dev * 1e-3),
-                "ray_propagations_per_s": agg["n_rays"] * world / (ms_dev * 1e-3),
-                "wall_ms_per_step": wall_dev / args.steps,
-                "submission": f"{args.steps} steps as one pipelined job (art_run_device_batches): freed ray slots of step s are "
-                              "refilled with events of step s+1",
-                "ms_per_step_single_call": single,
-            },
+            "config": cfg,
             "hist_check": hist_check,
-            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": 208,
+            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": 216,
                     "d2h_bytes_per_step": int(d2h / args.steps),
-                    "note": "art_run through the C ABI: inputs are the 208-byte art_params + seed (the path has no bulk "
-                            "input), outputs = rows (ordered on the device, one DMA copy into a page-locked host buffer) + histogram"},
-            "gpu_launches": int(agg["n_launches"] + args.steps),
+                    "note": "art_run_device_batches + art_fetch_rows + art_comm_allreduce_hist + art_hist_get_global through the C ABI: "
+                            "inputs are the 216-byte art_params + seed (the path has no bulk input), outputs = rows (ordered on the "
+                            "device, one DMA copy into a page-locked host buffer) + histogram; chunks of <= 8 steps"},
+            "gpu_launches": int(agg["n_launches"] + 1),
             "roofline": roofline,
             "cpu_baseline": cpu,
             "clocks": clk,

@@ -137,6 +137,12 @@ typedef struct art_stats {
   int64_t n_launches;     /* kernels launched by the pipeline call                          */
   int64_t n_cond_eval;    /* … of n_cond, evaluations actually performed (the rest were decided by the
                              exact far-field shortcut r > Rcut)                             */
+  int64_t n_scanned_steps; /* accepted steps that went through the crossing scan (= records the compaction pass
+                              k_wf_detect read; the others carried a certified sign)         */
+  int64_t n_pool_blocks;  /* blocks of events injected into the pool by the call             */
+  double ms_k_stages;     /* per-kernel device time, ms — only measured when the environment variable       */
+  double ms_k_scan;       /* ART_TIME_KERNELS is set (CUDA events around every launch of the main stream,   */
+  double ms_k_detect;     /* which costs a few per cent): stage kernel, crossing scan, compaction pass      */
 } art_stats;
 
 typedef struct art_handle art_handle;
