@@ -169,7 +169,8 @@ struct art_handle {
   int bulk_min_go = 16;           // a warp goes on to its next attempt while this many lanes can (ART_BULK_MIN_GO)
   int tail_nstep = 4;             // attempts per stage launch once fewer rays than one resident wave are left (ART_TAIL_NSTEP)
   long long pool_slots = 1 << 20;  // event slots of the pool = events in flight at a time (ART_POOL_SLOTS); 2 rays per slot
-  long long refill_min = 0;        // free slots at which the next block of events is sampled (ART_REFILL_MIN; default pool / 8)
+  long long refill_min = 0;        // free slots at which sampled events are injected (ART_REFILL_MIN; default pool / 16)
+  long long sample_block = 1 << 16; // smallest sampler launch, events (ART_SAMPLE_BLOCK)
 };
 
 namespace {
@@ -216,15 +217,19 @@ int ensure_lanes(art_handle* h, int n) {
 // loop runs, injected into free slots by the side pass.
 struct PoolJob {
   uint64_t seed = 0;
-  long long first_event = 0, n_events = 0, next_e = 0;
-  long long batch_size = 1, batch_stride = 1;  // event (index e) has id first_event + (e / batch_size) batch_stride + e % batch_size
-  long long S = 0;                // event slots
-  unsigned long long head = 0;    // free-slot ring: slots [head, tail) are free; tail lives on the device
-  int state = 0;                  // 0 idle, 1 sampling, 2 sampled: inject in the next side pass
-  int m = 0, e0 = 0;              // block being sampled / injected
+  EventIds ids{0, 1, 1};
+  long long n_events = 0;
+  long long S = 0;                 // event slots
+  unsigned long long head = 0;     // free-slot ring: slots [head, tail) are free; tail lives on the device
+  // sample FIFO (capacity fifo = 2 blocks): events [0, produced) have been handed to the sampler stream, [0, sampled) are
+  // known to be complete, [0, consumed) have been injected into the loop.  The sampler always works on whole blocks —
+  // small launches leave its persistent threads one or two events each and cost three times as much per event.
+  long long block = 0, fifo = 0, produced = 0, sampled = 0, consumed = 0;
+  bool busy = false;               // a sampler launch is in flight
+  int m = 0;                       // events the next side pass injects (0: none)
   unsigned long long* gctr = nullptr;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> samp_ev;  // timing of the sampler launches
-  long long n_blocks = 0;
+  long long n_blocks = 0, n_injections = 0;
 };
 
 int wf_alloc(art_handle* h, Lane& L, long long n_rays, int seg_doubles, WfPool& W) {
@@ -270,49 +275,55 @@ int wf_loop(art_handle* h, Lane& L, WfPool W, long long n_act0, RayOut* out, dou
   cudaStream_t s3 = side ? L.stream3 : st;
   const bool timek = getenv("ART_TIME_KERNELS") != nullptr;  // CUDA events around every launch of the main stream
   std::vector<cudaEvent_t> tk;
-  const long long refill_min = job ? (h->refill_min > 0 ? h->refill_min : std::max<long long>(job->S / 8, 1)) : 0;
+  const long long refill_min = job ? (h->refill_min > 0 ? h->refill_min : std::max<long long>(job->S / 16, 1)) : 0;
   long long iter_cap = 64LL * h->params.maxiters;
   if (job) iter_cap *= (job->n_events / std::max<long long>(job->S, 1) + 2);
   unsigned long long ring_tail = job ? (unsigned long long)job->S : 0ull;  // as of the last counter read (k_ring_init: all slots free)
   for (long long iter = 0;;) {
-    // ---- host check: start sampling the next block of events when enough slots are free ------------------------------
+    // ---- host check: keep the sampler one block ahead; hand freshly sampled events to the next side pass ---------------
     if (job) {
-      const long long n_free = (long long)(ring_tail - job->head);
-      const long long remaining = job->n_events - job->next_e;
-      // a block never straddles two batches of the call (the sampler numbers its events from one first id)
-      const long long batch_left = job->batch_size - job->next_e % job->batch_size;
-      if (job->state == 0 && remaining > 0 && n_free >= std::min(std::min(remaining, batch_left), refill_min)) {
-        job->m = (int)std::min(std::min(remaining, batch_left), n_free);
-        job->e0 = (int)job->next_e;
-        job->next_e += job->m;
+      if (job->busy) {
+        // nothing in flight and nothing to inject: wait for the block; otherwise pick it up as soon as it is there
+        const bool must_wait = n_act == 0 && job->sampled == job->consumed;
+        const cudaError_t q = must_wait ? cudaEventSynchronize(L.ev_samp) : cudaEventQuery(L.ev_samp);
+        if (q == cudaSuccess) {
+          job->sampled = job->produced;
+          job->busy = false;
+        } else if (q != cudaErrorNotReady) {
+          return fail(h, ART_ERR_CUDA, std::string("sampler: ") + cudaGetErrorString(q));
+        }
+      }
+      if (!job->busy && job->produced < job->n_events && job->produced - job->consumed + job->block <= job->fifo) {
+        const long long m = std::min(job->block, job->n_events - job->produced);
         cudaEvent_t ea = evg.make(), eb = evg.make();
         if (!ea || !eb) return fail(h, ART_ERR_CUDA, "cudaEventCreate");
-        if (side) CU(cudaStreamWaitEvent(s3, L.ev_side, 0));  // (the sample buffer of the previous block has been consumed)
+        if (side) CU(cudaStreamWaitEvent(s3, L.ev_side, 0));  // (every injection enqueued so far has read its part of the FIFO)
         CU(cudaMemsetAsync(L.ctr.p, 0, 64, s3));
         CU(cudaEventRecord(ea, s3));
-        const int blocks = (int)std::min<long long>(h->blocks_sample, (job->m + SAMPLE_THREADS - 1) / SAMPLE_THREADS);
-        const long long id0 = job->first_event + (job->e0 / job->batch_size) * job->batch_stride + job->e0 % job->batch_size;
-        k_sample_events<<<blocks, SAMPLE_THREADS, 0, s3>>>(h->dp, job->seed, id0, job->m,
-                                                           L.samples.as<EventSample>(), L.ctr.as<unsigned long long>(), stats, job->gctr);
+        const int blocks = (int)std::min<long long>(h->blocks_sample, (m + SAMPLE_THREADS - 1) / SAMPLE_THREADS);
+        k_sample_events<<<blocks, SAMPLE_THREADS, 0, s3>>>(h->dp, job->seed, job->ids, job->produced, m,
+                                                           L.samples.as<EventSample>() + job->produced % job->fifo,
+                                                           L.ctr.as<unsigned long long>(), stats, job->gctr);
         CU(cudaGetLastError());
         CU(cudaEventRecord(eb, s3));
         CU(cudaEventRecord(L.ev_samp, s3));
         job->samp_ev.emplace_back(ea, eb);
         job->n_blocks++;
         h->launches++;
-        job->state = 1;
+        job->produced += m;
+        job->busy = true;
+        if (n_act == 0 && job->sampled == job->consumed) continue;  // (first block: wait for it at the top of the loop)
       }
-      if (job->state == 1) {
-        // nothing in flight: wait for the block; otherwise pick it up as soon as it is there
-        const cudaError_t q = n_act == 0 ? cudaEventSynchronize(L.ev_samp) : cudaEventQuery(L.ev_samp);
-        if (q == cudaSuccess) job->state = 2;
-        else if (q != cudaErrorNotReady) return fail(h, ART_ERR_CUDA, std::string("sampler: ") + cudaGetErrorString(q));
-      }
-      if (n_act == 0 && job->state == 0 && job->n_events - job->next_e == 0) break;
+      const long long n_free = (long long)(ring_tail - job->head);
+      const long long avail = job->sampled - job->consumed;
+      const long long left = job->n_events - job->consumed;
+      job->m = 0;
+      if (avail > 0 && n_free >= std::min(std::min(left, avail), refill_min)) job->m = (int)std::min(avail, n_free);
+      if (n_act == 0 && job->m == 0 && !job->busy && left == 0) break;
     } else if (n_act == 0) {
       break;
     }
-    const long long n_plan = n_act + (job && job->state == 2 ? 2LL * job->m : 0);  // … with the block about to be injected
+    const long long n_plan = n_act + (job ? 2LL * job->m : 0);  // … with the events about to be injected
     const int burst = n_plan > 500000 ? 8 : (n_plan > 65536 ? 16 : 32);  // steps between host checks (deep queue: host jitter must not idle the GPU)
     const bool tail_mode = n_plan < h->tail_below;                        // thin tail: any lane keeps its warp stepping
     for (int b = 0; b < burst; ++b, ++iter) {
@@ -330,14 +341,16 @@ int wf_loop(art_handle* h, Lane& L, WfPool W, long long n_act0, RayOut* out, dou
       else
         k_wf_collect<<<grid(n_act / 4 + 1, WF_THREADS), WF_THREADS, 0, s2>>>(h->dp, W, k, out, stats);
       h->launches += 2;
-      if (job && job->state == 2) {
-        if (side) CU(cudaStreamWaitEvent(s2, L.ev_samp, 0));
-        k_wf_inject<IG><<<grid(2LL * job->m, WF_THREADS), WF_THREADS, 0, s2>>>(h->dp, W, *tree, k, L.samples.as<EventSample>(), job->m,
-                                                                               job->e0, job->head, rec, rec_cap, stats);
+      if (job && job->m > 0) {
+        k_wf_inject<IG><<<grid(2LL * job->m, WF_THREADS), WF_THREADS, 0, s2>>>(h->dp, W, *tree, k, L.samples.as<EventSample>(),
+                                                                               (int)job->fifo, job->m, (int)job->consumed, job->head, rec,
+                                                                               rec_cap, stats);
         h->launches++;
         job->head += (unsigned long long)job->m;
+        job->consumed += job->m;
+        job->n_injections++;
         n_act += 2LL * job->m;
-        job->state = 0;
+        job->m = 0;
       }
       if (side) CU(cudaEventRecord(L.ev_side, s2));
       const int gs = (int)std::max<long long>(1, std::min<long long>((long long)h->n_sm * h->stage_grid_per_sm, (n_act + STAGE_THREADS - 1) / STAGE_THREADS));
@@ -375,13 +388,13 @@ int wf_loop(art_handle* h, Lane& L, WfPool W, long long n_act0, RayOut* out, dou
       const double now = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
       static thread_local double t_prev = 0.0;
       fprintf(stderr, "[wf] iter %lld in flight %lld (ax %llu ph %llu roots %llu finished %llu) started %lld free %lld +%.2f ms = %.0f us/iteration\n",
-              iter, n_act, na0, na1, c[kl * WC_SET + WC_ROOTS], c[kl * WC_SET + WC_FIN], job ? job->next_e : 0,
+              iter, n_act, na0, na1, c[kl * WC_SET + WC_ROOTS], c[kl * WC_SET + WC_FIN], job ? job->consumed : 0,
               job ? (long long)(c[WC_RING_TAIL] - job->head) : 0, t_prev > 0 ? now - t_prev : 0.0, t_prev > 0 ? (now - t_prev) * 1e3 / burst : 0.0);
       t_prev = now;
     }
     if (iter > iter_cap) return fail(h, ART_ERR_CUDA, "wavefront tracer did not terminate");
   }
-  if (job) L.n_blocks += job->n_blocks;
+  if (job) L.n_blocks += job->n_injections;
   for (size_t i = 0; i + 3 < tk.size(); i += 4)  // (the loop ends with a synchronised stream: every event has completed)
     for (int j = 0; j < 3; ++j) {
       float ms = 0;
@@ -488,6 +501,7 @@ int art_create(const art_params* p, int device_id, art_handle** out) {
   if (const char* t = getenv("ART_TAIL_BELOW")) h->tail_below = std::max(0LL, atoll(t));
   if (const char* t = getenv("ART_POOL_SLOTS")) h->pool_slots = std::max(32LL, atoll(t));
   if (const char* t = getenv("ART_REFILL_MIN")) h->refill_min = std::max(1LL, atoll(t));
+  if (const char* t = getenv("ART_SAMPLE_BLOCK")) h->sample_block = std::max(32LL, atoll(t));
   ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (ce != cudaSuccess) {
     std::string m = cudaGetErrorString(ce);
@@ -545,7 +559,7 @@ int art_sample(art_handle* h, uint64_t seed, int64_t first_event, int64_t n, dou
   CU(L.ctr.ensure(64));
   CU(cudaMemsetAsync(L.ctr.p, 0, 64, h->stream));
   const int blocks = (int)std::min<long long>(h->blocks_sample, (n + SAMPLE_THREADS - 1) / SAMPLE_THREADS);
-  k_sample_events<<<blocks, SAMPLE_THREADS, 0, h->stream>>>(h->dp, seed, first_event, n, L.samples.as<EventSample>(),
+  k_sample_events<<<blocks, SAMPLE_THREADS, 0, h->stream>>>(h->dp, seed, EventIds{first_event, n, n}, 0, n, L.samples.as<EventSample>(),
                                                             L.ctr.as<unsigned long long>(), nullptr, nullptr);
   CU(cudaGetLastError());
   std::vector<EventSample> host((size_t)n);
@@ -730,7 +744,9 @@ static int run_pool(art_handle* h, Lane& L, uint64_t seed, int64_t first_event, 
   const int stack_stride = h->params.max_nodes + 4;
   const long long S = std::max<long long>(32, std::min<long long>(h->pool_slots, n_events));
   cudaStream_t st = L.stream;
-  CU(L.samples.ensure(S * sizeof(EventSample)));
+  // sampler blocks: half a pool, at least 2^16 events (smaller launches are inefficient), never more than the call
+  const long long block = std::min<long long>(n_events, std::max<long long>(S / 2, h->sample_block));
+  CU(L.samples.ensure(2 * block * sizeof(EventSample)));
   CU(L.tstate.ensure(S * sizeof(TreeState)));
   CU(L.stacks.ensure((size_t)S * stack_stride * sizeof(TreeNode)));
   CU(L.rec.ensure((size_t)2 * S * cap * 8 * sizeof(double)));
@@ -748,11 +764,11 @@ static int run_pool(art_handle* h, Lane& L, uint64_t seed, int64_t first_event, 
   T.ev = h->events.as<EventData>(); T.fin_count = h->fin_count.as<int>(); T.fin_info = h->fin_info.as<int>();
   T.ts = L.tstate.as<TreeState>(); T.stacks = L.stacks.as<TreeNode>(); T.slot_event = L.slot_event.as<int>();
   T.slot_parts = L.slot_parts.as<int>(); T.ring = L.ring.as<int>(); T.stack_stride = stack_stride; T.n_slots = (int)S;
-  T.seed = seed; T.first_event = first_event; T.batch_size = batch_size; T.batch_stride = batch_stride; T.sink = sink;
+  T.seed = seed; T.ids = EventIds{first_event, batch_size, batch_stride}; T.sink = sink;
   T.tot_count = gctr + 1;
   PoolJob job;
-  job.seed = seed; job.first_event = first_event; job.n_events = n_events; job.S = S; job.gctr = gctr + 0;
-  job.batch_size = batch_size; job.batch_stride = batch_stride;
+  job.seed = seed; job.ids = T.ids; job.n_events = n_events; job.S = S; job.gctr = gctr + 0;
+  job.block = block; job.fifo = 2 * block;
   cudaEvent_t t0 = evg.make(), t1 = evg.make();
   if (!t0 || !t1) return fail(h, ART_ERR_CUDA, "cudaEventCreate");
   CU(cudaEventRecord(t0, st));

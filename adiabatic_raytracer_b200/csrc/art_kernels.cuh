@@ -65,8 +65,16 @@ struct EventSample {
 #ifndef ART_SAMPLE_MINBLOCKS
 #define ART_SAMPLE_MINBLOCKS 4
 #endif
+// Event ids of a pipeline call: event e (index in the call) has id first + (e / bsize) bstride + e % bsize (batches of a
+// pipelined job, art_run_device_batches); a plain range is bsize = bstride = anything ≥ the number of events.
+struct EventIds {
+  long long first, bsize, bstride;
+  __host__ __device__ long long id(long long e) const { return first + (e / bsize) * bstride + e % bsize; }
+};
+
+// events e0 … e0 + n − 1 of the call; sample of event e0 + i goes to out[i]
 __global__ void __launch_bounds__(SAMPLE_THREADS, ART_SAMPLE_MINBLOCKS)
-k_sample_events(const __grid_constant__ DevParams P, unsigned long long seed, long long first_event, long long n,
+k_sample_events(const __grid_constant__ DevParams P, unsigned long long seed, EventIds ids, long long e0, long long n,
                 EventSample* __restrict__ out, unsigned long long* head, DevStats* stats,
                 unsigned long long* n_failed_total) {
   __shared__ double taus_sm[SAMP_KEEP * SAMPLE_THREADS];
@@ -86,7 +94,7 @@ k_sample_events(const __grid_constant__ DevParams P, unsigned long long seed, lo
         idx = got;
         attempt = 0;
         double U[10];
-        sampler_uniforms(seed, (unsigned long long)(first_event + idx), attempt, U);
+        sampler_uniforms(seed, (unsigned long long)ids.id(e0 + idx), attempt, U);
         u_idx = U[9];
         S.begin(P, U);
         have = true;
@@ -114,7 +122,7 @@ k_sample_events(const __grid_constant__ DevParams P, unsigned long long seed, lo
         } else {  // MainRunner.jl:463-494: try again (f_inx counts the failure)
           attempt++;
           double U[10];
-          sampler_uniforms(seed, (unsigned long long)(first_event + idx), attempt, U);
+          sampler_uniforms(seed, (unsigned long long)ids.id(e0 + idx), attempt, U);
           u_idx = U[9];
           S.begin(P, U);
         }

@@ -101,8 +101,7 @@ struct WfTree {  // per-event tree context of the fused pipeline
   int stack_stride;
   int n_slots;            // S: ray id < S = back-trace of slot id, otherwise forward tree of slot id − S
   unsigned long long seed;
-  long long first_event;  // event id of the call's event 0; event e has id first_event + (e / batch_size) batch_stride + e % batch_size
-  long long batch_size, batch_stride;
+  EventIds ids;           // event ids of the call (art_kernels.cuh)
   RowSink sink;
   unsigned long long* tot_count;
 };
@@ -615,7 +614,7 @@ __device__ __forceinline__ bool wf_tree_step(const DevParams& P, const WfTree& T
   const EventData E = T.ev[e];  // (the back-trace only writes back_weight / prob0 / c_bck, which the forward tree does not read)
   TreeState S = T.ts[slot];
   tree_forward_update(P, E, S, T.stacks + (size_t)slot * T.stack_stride, ro, rc, T.seed,
-                      (unsigned long long)(T.first_event + (e / T.batch_size) * T.batch_stride + e % T.batch_size), (long long)e, T.sink);
+                      (unsigned long long)T.ids.id(e), (long long)e, T.sink);
   bool spawn = false;
   if (S.active) {
     RayIn in;
@@ -677,14 +676,15 @@ k_wf_tree(const __grid_constant__ DevParams P, WfPool W, WfTree T, int k, double
 }
 
 // ---- injection of freshly sampled events into free slots (side pass of iteration k) -------------------
-// Event j of the block (index e0 + j in the call) takes the slot ring[(head + j) % S]: per-sample weights
+// Event j of the block (index e0 + j in the call; its sample sits at position (e0 + j) % fifo of the sample FIFO the
+// sampler stream fills ahead of the loop) takes the slot ring[(head + j) % S]: per-sample weights
 // (MainRunner.jl:498-557), first tree node, and the IC transform / first right-hand side / initial step size /
 // starting sign of its two rays — the back-traced axion in ray slot s (MR.jl:581-589: −k, t = 0, Δω = −1, all
 // crossings) and the forward photon in ray slot S + s (MR.jl:653-657).  Both join iteration k + 1.
 template <int IG>
 __global__ void __launch_bounds__(WF_THREADS)
-k_wf_inject(const __grid_constant__ DevParams P, WfPool W, WfTree T, int k, const EventSample* __restrict__ samples, int m, int e0,
-            unsigned long long head, double* __restrict__ rec, int rec_cap, DevStats* stats) {
+k_wf_inject(const __grid_constant__ DevParams P, WfPool W, WfTree T, int k, const EventSample* __restrict__ samples, int fifo, int m,
+            int e0, unsigned long long head, double* __restrict__ rec, int rec_cap, DevStats* stats) {
   unsigned long long n_start = 0;
   const long long nthreads = (long long)gridDim.x * blockDim.x;
   const long long n2 = 2LL * m;
@@ -702,7 +702,7 @@ k_wf_inject(const __grid_constant__ DevParams P, WfPool W, WfTree T, int k, cons
       const int j = (int)(fwd ? t - m : t);
       const int slot = T.ring[(head + (unsigned long long)j) % (unsigned long long)T.n_slots];
       const int e = e0 + j;
-      const EventSample smp = samples[j];
+      const EventSample smp = samples[(e0 + j) % fifo];
       const SampleWeights Wt = sample_weights(P, smp.x, smp.vloc, smp.vinf);
       RayIn in;
       for (int c = 0; c < 3; ++c) { in.x0[c] = smp.x[c]; in.k0[c] = fwd ? Wt.k_init[c] : -Wt.k_init[c]; }
