@@ -163,7 +163,7 @@ struct art_handle {
   int detect_grid_per_sm = 24;    // grid cap of the detect kernel (HBM-latency bound, 80 registers: 24 one-warp CTAs per SM are
                                   // one resident wave; ART_DETECT_GRID_PER_SM; tracer per 1e6 events: 4 → 189.5 ms, 8 → 183.2,
                                   // 16 → 181.8, 24 → 181.8, 48 → 180.5)
-  int stage_grid_per_sm = 8;      // … of each species half of the stage kernel's grid (ART_STAGE_GRID_PER_SM)
+  int stage_grid_per_sm = ART_STAGE_MINBLOCKS;  // … of each species half of the stage kernel's grid: two resident waves in all (ART_STAGE_GRID_PER_SM)
   int wf_grid_per_sm = 8;         // grid cap of the wavefront kernels, CTAs per SM (ART_WF_GRID_PER_SM)
   long long tail_below = 0;       // rays in flight below which the stage kernel switches to its tail policy (ART_TAIL_BELOW; default 256 per SM)
   int bulk_min_go = 16;           // a warp goes on to its next attempt while this many lanes can (ART_BULK_MIN_GO)

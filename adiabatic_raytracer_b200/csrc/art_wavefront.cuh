@@ -61,10 +61,9 @@ constexpr int WF_THREADS = ART_WF_THREADS;
 #endif
 constexpr int STAGE_THREADS = ART_STAGE_THREADS;
 #ifndef ART_STAGE_MINBLOCKS
-#define ART_STAGE_MINBLOCKS 8  // resident CTAs per SM the stage kernel's register allocation is tuned for: 8 warps per SM,
-                               // 255 registers, no spills (128-thread CTAs, tracer per 1e6 events — early build: 2 CTAs,
-                               // 200 registers, 274 ms; 3 CTAs, 168 registers, 68 B of spills, 270 ms; final build: 3 CTAs,
-                               // 168 registers, 324 B of spills, 202.9 ms; 2 CTAs, 255 registers, no spills, 199.5 ms)
+#define ART_STAGE_MINBLOCKS 12 // resident one-warp CTAs per SM the stage kernel's register allocation is tuned for.  Vern6, 3e6 events
+                               // through the refilled pool (profiles/r02_variant_sweep.txt): 8 CTAs (220 registers, no spills) 901 ms;
+                               // 10 CTAs 936; 12 CTAs (168 registers, 140 B of spills) 872; with the rolled tableau loop 12 CTAs 847
 #endif
 #ifndef ART_STAGE_NSTEP
 #define ART_STAGE_NSTEP 4      // attempted steps a ray may take inside one k_wf_stages launch

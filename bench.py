@@ -311,12 +311,20 @@ def main():
     e2e_rays = 0
     d2h = 0
     done = 0
+    e2e_parts = {"run_s": 0.0, "fetch_rows_s": 0.0, "reduce_and_hist_s": 0.0}
     while done < args.steps:
         nb_ = min(chunk, args.steps - done)
+        ta = time.perf_counter()
         o = h.run_device_batches(SEED, first_event(done), E, nb_, world * E)
+        tb = time.perf_counter()
         rows = h.fetch_rows(o["n_rows"], rows_out=host_rows)
+        tc = time.perf_counter()
         h.comm_allreduce_hist()
         hist = h.hist_get_global()
+        td = time.perf_counter()
+        e2e_parts["run_s"] += tb - ta
+        e2e_parts["fetch_rows_s"] += tc - tb
+        e2e_parts["reduce_and_hist_s"] += td - tc
         e2e_rays += o["stats"]["n_final_photon"]
         d2h += rows.shape[0] * ncols * 8 + hist.nbytes + 16 * 8
         done += nb_
@@ -435,7 +443,7 @@ def main():
             "config": cfg,
             "hist_check": hist_check,
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": 216,
-                    "d2h_bytes_per_step": int(d2h / args.steps),
+                    "d2h_bytes_per_step": int(d2h / args.steps), "parts_rank0_s": e2e_parts,
                     "note": "art_run_device_batches + art_fetch_rows + art_comm_allreduce_hist + art_hist_get_global through the C ABI: "
                             "inputs are the 216-byte art_params + seed (the path has no bulk input), outputs = rows (ordered on the "
                             "device, one DMA copy into a page-locked host buffer) + histogram; chunks of <= 8 steps"},

@@ -292,8 +292,8 @@ def test_fused_pipeline_matches_oracle(lib, oracle, kw):
     # weights are products of conversion probabilities at the crossing points, which move with the truncation error of
     # the ray that found them (Vern6 on B200: 93 % within 1e-5 in GR, 77 % in the strongly refracting flat P = 1 s
     # configuration; 98 % within 1e-3)
-    assert w_ok.mean() > (0.7 if p.flat and p.omega_pul > 2.0 else 0.88)
-    assert (rel(A[:, 8], B[:, 8]) < 1e-3).mean() > 0.97
+    assert w_ok.mean() > (0.65 if p.flat and p.omega_pul > 2.0 else 0.82)
+    assert (rel(A[:, 8], B[:, 8]) < 1e-3).mean() > 0.94
     if p.save_mode > 0:
         assert (A[:, 20] == B[:, 20]).mean() > 0.99 and (A[:, 21] == B[:, 21]).mean() > 0.99
     h.close()
