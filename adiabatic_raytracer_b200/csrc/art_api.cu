@@ -144,6 +144,8 @@ struct art_handle {
   // shared by all lanes of a pipeline call
   DBuf events, fin_count, fin_info, gctr, stats;
   DBuf rows, keys, hist, hist_global, scratch[12];
+  DBuf nlog, nlog_cross, nlog_count;  // saveMode 3: node log of the last pipeline call
+  long long nlog_cap = 0;
   bool have_global = false;       // hist_global holds the result of an all-reduce of the CURRENT local block
   DBuf q[2];                      // fine-grained art_propagate queue
   long long rows_cap = 0;         // rows held on device
@@ -517,7 +519,7 @@ void art_destroy(art_handle* h) {
   cudaSetDevice(h->device);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   for (Lane& L : h->lanes) L.release();
-  DBuf* all[] = {&h->events, &h->fin_count, &h->fin_info, &h->gctr, &h->stats, &h->rows, &h->keys, &h->hist, &h->hist_global, &h->q[0], &h->q[1]};
+  DBuf* all[] = {&h->events, &h->fin_count, &h->fin_info, &h->gctr, &h->stats, &h->rows, &h->keys, &h->hist, &h->hist_global, &h->q[0], &h->q[1], &h->nlog, &h->nlog_cross, &h->nlog_count};
   for (DBuf* b : all) b->release();
   for (DBuf& b : h->scratch) b.release();
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -766,6 +768,12 @@ static int run_pool(art_handle* h, Lane& L, uint64_t seed, int64_t first_event, 
   T.slot_parts = L.slot_parts.as<int>(); T.ring = L.ring.as<int>(); T.stack_stride = stack_stride; T.n_slots = (int)S;
   T.seed = seed; T.ids = EventIds{first_event, batch_size, batch_stride}; T.sink = sink;
   T.tot_count = gctr + 1;
+  T.nlog = NodeLog{nullptr, nullptr, nullptr, 0, 0};
+  if (h->params.save_mode >= 3) {
+    T.nlog = NodeLog{h->nlog.as<NodeLogEntry>(), h->nlog_cross.as<double>(), h->nlog_count.as<unsigned long long>(), h->nlog_cap,
+                     h->params.cross_cap};
+    CU(cudaMemsetAsync(h->nlog_count.p, 0, 8, st));
+  }
   PoolJob job;
   job.seed = seed; job.ids = T.ids; job.n_events = n_events; job.S = S; job.gctr = gctr + 0;
   job.block = block; job.fifo = 2 * block;
@@ -812,6 +820,17 @@ int art_run_device_batches(art_handle* h, uint64_t seed, int64_t first_event, in
   CU(h->fin_info.ensure(ne * sizeof(int)));
   CU(h->gctr.ensure(16 * sizeof(unsigned long long)));
   CU(h->stats.ensure(sizeof(DevStats)));
+  if (h->params.save_mode >= 3) {
+    // saveMode 3 (one tree_* text file per event, MR.jl:574-578): every node of every tree is logged.  A debugging /
+    // plotting mode — sized for the worst case (max_nodes + 2 nodes per event) while that stays below 4 GB
+    const size_t per = sizeof(NodeLogEntry) + (size_t)h->params.cross_cap * 4 * sizeof(double);
+    long long cap = ne * (h->params.max_nodes + 2);
+    if ((size_t)cap * per > ((size_t)4 << 30)) cap = std::max<long long>(ne * 16 + 4096, (long long)(((size_t)4 << 30) / per));
+    CU(h->nlog.ensure((size_t)cap * sizeof(NodeLogEntry)));
+    CU(h->nlog_cross.ensure((size_t)cap * h->params.cross_cap * 4 * sizeof(double)));
+    CU(h->nlog_count.ensure(8));
+    h->nlog_cap = cap;
+  }
   // Rows: the reference appends without bound.  A forward tree emits at most min(num_cutoff, max_nodes + 1) rows
   // (every row counts towards num_cutoff, every node towards max_nodes); the buffer starts at min(that, 3) rows per event
   // and, should a run need more, is re-allocated at the exact size and the call re-run (per-event Philox streams make
@@ -1074,6 +1093,98 @@ int art_write_event_files(const char* dir_tag, const char* file_tag, const doubl
     fprintf(f, " 0.0 %s\n", jint(e[11]).c_str());  // wall-clock seconds of the event (not reproduced), count
   }
   fclose(f);
+  return ART_OK;
+}
+
+}  // extern "C"
+
+template <int IG>
+static int node_trajectories(art_handle* h, const NodeLogEntry* d_nodes, long long n, int ntimes, int out_cap, double* d_traj, int* d_npts,
+                             double* d_rec, double* d_k) {
+  k_node_traj<IG><<<nblk(n, 64), 64, 0, h->stream>>>(h->dp, d_nodes, n, ntimes, d_traj, d_npts, out_cap, d_rec, d_k);
+  CU(cudaGetLastError());
+  return ART_OK;
+}
+
+extern "C" {
+
+int art_write_tree_files(art_handle* h, const char* dir_tag, const char* file_tag, int64_t* n_files) {
+  if (!h) return ART_ERR_ARG;
+  if (h->params.save_mode < 3) return fail(h, ART_ERR_ARG, "art_write_tree_files needs a handle created with save_mode = 3");
+  CU(cudaSetDevice(h->device));
+  if (n_files) *n_files = 0;
+  unsigned long long cnt = 0;
+  if (!h->nlog_count.p || h->last_n_events <= 0) return ART_OK;
+  CU(cudaMemcpy(&cnt, h->nlog_count.p, 8, cudaMemcpyDeviceToHost));
+  if ((long long)cnt > h->nlog_cap) return fail(h, ART_ERR_CAPACITY, "node log overflow: saveMode 3 is a debugging mode, run fewer events per call");
+  const long long n = (long long)cnt;
+  if (n == 0) return ART_OK;
+  const int cc = h->params.cross_cap;
+  const int ntimes = std::max(h->params.ntimes, 2);
+  const int out_cap = ntimes + 64 + 2;
+  const size_t traj_bytes = (size_t)n * out_cap * 4 * sizeof(double);
+  if (traj_bytes > ((size_t)16 << 30)) return fail(h, ART_ERR_CAPACITY, "saveMode 3: trajectories of this run exceed 16 GB (fewer events or a smaller ntimes)");
+  // the log in tree order: by event, then by position
+  std::vector<NodeLogEntry> nodes((size_t)n);
+  std::vector<double> cross((size_t)n * cc * 4);
+  CU(cudaMemcpy(nodes.data(), h->nlog.p, (size_t)n * sizeof(NodeLogEntry), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(cross.data(), h->nlog_cross.p, cross.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  DBuf* s = h->scratch;
+  CU(s[5].ensure(traj_bytes));
+  CU(s[6].ensure((size_t)n * sizeof(int)));
+  CU(s[7].ensure((size_t)n * 64 * 8 * sizeof(double)));
+  CU(s[8].ensure((size_t)n * (K_ROWS + SEG_MAX) * sizeof(double)));
+  const int rc = h->dp.integrator == IG_DP5
+                     ? node_trajectories<IG_DP5>(h, h->nlog.as<NodeLogEntry>(), n, ntimes, out_cap, s[5].as<double>(), s[6].as<int>(), s[7].as<double>(), s[8].as<double>())
+                     : node_trajectories<IG_VERN6>(h, h->nlog.as<NodeLogEntry>(), n, ntimes, out_cap, s[5].as<double>(), s[6].as<int>(), s[7].as<double>(), s[8].as<double>());
+  if (rc) return rc;
+  std::vector<double> traj((size_t)n * out_cap * 4);
+  std::vector<int> npts((size_t)n);
+  CU(cudaMemcpyAsync(traj.data(), s[5].p, traj_bytes, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(npts.data(), s[6].p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  std::vector<long long> order((size_t)n);
+  for (long long i = 0; i < n; ++i) order[(size_t)i] = i;
+  std::sort(order.begin(), order.end(), [&](long long a, long long b) {
+    const NodeLogEntry &A = nodes[(size_t)a], &B = nodes[(size_t)b];
+    return A.event != B.event ? A.event < B.event : A.pos < B.pos;
+  });
+  const std::string dir = std::string(dir_tag ? dir_tag : "results") + "/tree/tree_" + (file_tag ? file_tag : "");
+  const EventIds ids{h->last_first_event, h->last_batch_events, h->last_batch_stride};
+  FILE* f = nullptr;
+  int cur_event = -1;
+  long long files = 0;
+  for (long long oi = 0; oi < n; ++oi) {
+    const long long i = order[(size_t)oi];
+    const NodeLogEntry& nd = nodes[(size_t)i];
+    if (nd.event != cur_event) {  // MR.jl:575: one file per event, named by the event number
+      if (f) fclose(f);
+      f = fopen((dir + std::to_string((long long)ids.id(nd.event))).c_str(), "w");
+      if (!f) return fail(h, ART_ERR_IO, "cannot open " + dir + "… (the directory <dir_tag>/tree must exist, as in the reference)");
+      cur_event = nd.event;
+      files++;
+    }
+    // saveNode, MR.jl:17-65
+    fprintf(f, "%s %s %s %s\n", nd.species == SPECIES_PHOTON ? "photon" : "axion", julia_float(nd.weight).c_str(),
+            julia_float(nd.prob).c_str(), julia_float(nd.parent_weight).c_str());
+    if (nd.n_cross > 0) {
+      const double* q = cross.data() + (size_t)i * cc * 4;
+      for (int c = 0; c < 4; ++c) {  // xc, yc, zc, tc
+        for (int j = 0; j < nd.n_cross; ++j) fprintf(f, "  %s", julia_float(q[4 * j + c]).c_str());
+        if (c < 3) fputc('\n', f);
+      }
+    } else {
+      fputs("-\n-\n-", f);
+    }
+    fputc('\n', f);
+    const double* t = traj.data() + (size_t)i * out_cap * 4;
+    for (int c = 0; c < 4; ++c) {  // traj[:, 1], traj[:, 2], traj[:, 3], times (ln t)
+      for (int j = 0; j < npts[(size_t)i]; ++j) fprintf(f, "  %s", julia_float(t[4 * j + c]).c_str());
+      fputc('\n', f);
+    }
+  }
+  if (f) fclose(f);
+  if (n_files) *n_files = files;
   return ART_OK;
 }
 

@@ -227,6 +227,50 @@ __global__ void k_gather_rows(const double* __restrict__ rows, const int* __rest
 }
 
 // ------------------------------------------------------------------------------------------
+// saveMode 3: trajectory of every logged tree node, sampled like `solve(…, saveat = (ln t_end − ln t_start)/(ntimes − 1))`
+// (RT.jl:174, 383).  One thread per node re-traces it with the sequential form of the stepper (Ray::step_sampled: the same
+// attempt / error control / event code the wavefront kernels run, so the same trajectory).  A debugging and plotting mode
+// (plot/plotTree.py): a few thousand nodes, no attempt at speed.
+// traj: [node][out_cap][4] = x y z ln t; npts[node].
+// ------------------------------------------------------------------------------------------
+template <int IG>
+__global__ void k_node_traj(const __grid_constant__ DevParams P, const NodeLogEntry* __restrict__ nodes, long long n, int ntimes,
+                            double* __restrict__ traj, int* __restrict__ npts, int out_cap, double* __restrict__ rec_scratch,
+                            double* __restrict__ k_scratch) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const NodeLogEntry nd = nodes[i];
+  RayIn in;
+  for (int c = 0; c < 3; ++c) { in.x0[c] = nd.x0[c]; in.k0[c] = nd.k0[c]; }
+  in.erg = nd.erg; in.t_start = nd.t0; in.dOmega = nd.dw0;
+  in.max_cross = nd.pos == 0 ? 100000 : -1;   // back-trace collects every crossing, forward nodes stop at the first (MR.jl:589, 663)
+  in.species = nd.species;
+  Ray R;
+  const KStore K{k_scratch + (size_t)i * (K_ROWS + SEG_MAX), 1};
+  const SegStore D{k_scratch + (size_t)i * (K_ROWS + SEG_MAX) + K_ROWS, 1};
+  R.init(P, in, rec_scratch + (size_t)i * 64 * 8, 64);
+  const double s0 = R.s;
+  const double delta = (P.ln_tend - s0) / (double)(ntimes > 1 ? ntimes - 1 : 1);
+  double* out = traj + (size_t)i * out_cap * 4;
+  int n_out = 0, kq = 0;
+  {  // the initial point is saved by every solve
+    double x[3], k[3];
+    state_to_cartesian(P, R.u, R.erg, false, x, k);
+    out[0] = x[0]; out[1] = x[1]; out[2] = x[2]; out[3] = s0;
+    n_out = 1;
+    kq = 1;
+  }
+  while (!R.done) R.template step_sampled<IG>(P, K, D, s0, delta, ntimes, kq, out, n_out, out_cap);
+  if (R.s < P.ln_tend && n_out < out_cap && out[4 * (n_out - 1) + 3] < R.s) {  // terminated early (NS hit): the last state is saved too
+    double x[3], k[3];
+    state_to_cartesian(P, R.u, R.erg, false, x, k);
+    double* q = out + 4 * (size_t)n_out++;
+    q[0] = x[0]; q[1] = x[1]; q[2] = x[2]; q[3] = R.s;
+  }
+  npts[i] = n_out;
+}
+
+// ------------------------------------------------------------------------------------------
 // K5: binned flux / spectra.  bins: [species(2)][n_ct][n_ph][n_dw][4] = Σ w·sln, Σ (w·sln)², Σ w, count
 // ------------------------------------------------------------------------------------------
 __global__ void k_hist(long long row_begin, long long n_rows, const double* __restrict__ rows, int ncols, int n_ct,

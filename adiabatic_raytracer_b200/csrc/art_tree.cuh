@@ -19,6 +19,7 @@ namespace art {
 struct TreeNode {  // RT.node, RayTracer.jl:126-163 (fields that reach the outputs)
   double x, y, z, kx, ky, kz, t, dw;
   double prob, weight, prob_conv, prob_conv0;
+  double parent_weight;  // weight of the node this one split off (−1: root), written by saveNode (MR.jl:17-19)
   int species, pad_;
 };
 
@@ -26,7 +27,23 @@ struct EventData {  // per-event scalars of MainRunner.jl:498-557 and of the bac
   double x[3], k_init[3], vinf[3];
   double erg_inf, vel_eng, sln_prob, cos_w;
   double back_weight, prob0;  // samp_back_weight (MR.jl:630), Prob_nonAD_0 (MR.jl:626)
+  double back_node_w;         // weight of the back-traced node itself, Π_j (1 − P_j) (MR.jl:313) — saveMode 3
   int c_bck, n_failed;
+};
+
+// saveMode 3 (MR.jl:17-65, 574-578, 612, 669-670): every node of an event's two trees, as the tree kernel met it.
+// pos = 0: the back-traced axion; pos = 1, 2, …: the forward tree in the order of `push!(tree, event)`.
+struct NodeLogEntry {
+  int event, pos, species, n_cross;
+  double weight, prob, parent_weight;
+  double x0[3], k0[3], t0, dw0, erg;  // what propagate was called with (MR.jl:175-191): the trajectory is re-traced from here
+};
+struct NodeLog {
+  NodeLogEntry* e;            // null: logging off
+  double* cross;              // [cap][cross_cap][4]: x y z t of the recorded crossings
+  unsigned long long* count;
+  long long cap;
+  int cross_cap;
 };
 
 struct TreeState {
@@ -55,10 +72,11 @@ ART_HD unsigned long long sink_add(unsigned long long* p, unsigned long long v) 
 }
 
 ART_HD TreeNode make_node(double x, double y, double z, double kx, double ky, double kz, double t, double dw,
-                          int species, double prob, double weight, double prob_conv, double prob_conv0) {
+                          int species, double prob, double weight, double prob_conv, double prob_conv0, double parent_weight) {
   TreeNode n;
   n.x = x; n.y = y; n.z = z; n.kx = kx; n.ky = ky; n.kz = kz; n.t = t; n.dw = dw;
   n.species = species; n.pad_ = 0; n.prob = prob; n.weight = weight; n.prob_conv = prob_conv; n.prob_conv0 = prob_conv0;
+  n.parent_weight = parent_weight;
   return n;
 }
 
@@ -110,13 +128,14 @@ ART_HD void tree_backward(const DevParams& P, EventData& E, const RayOut& R, con
   }
   E.prob0 = P0;
   E.back_weight = P0 * weight;
+  E.back_node_w = weight;
   E.c_bck = 1;
 }
 
 // ---- forward tree: first node (MR.jl:653-657, 132-141) -----------------------------------
 ART_HD void tree_forward_start(const DevParams& P, const EventData& E, TreeState& T) {
   TreeNode first = make_node(E.x[0], E.x[1], E.x[2], E.k_init[0], E.k_init[1], E.k_init[2], 0.0, -1.0,
-                             SPECIES_PHOTON, 1.0, 1.0, -1.0, -1.0);
+                             SPECIES_PHOTON, 1.0, 1.0, -1.0, -1.0, -1.0);
   first.prob = conv_P(P, E.x, E.k_init, E.erg_inf * 1.0, 1.0);
   T.cur = first;
   T.tot_prob = 0.0;
@@ -216,15 +235,15 @@ ART_HD void tree_forward_update(const DevParams& P, const EventData& E, TreeStat
         const double r = tree_uniform(seed, event_id, (uint32_t)T.rng_k++);
         if (r < Pc)
           stack_insert(stack, T.stack_n, make_node(c0[0], c0[1], c0[2], c0[3], c0[4], c0[5], c0[6], c0[7],
-                                                   new_species, Pc, ev.weight, Pc, Pc));
+                                                   new_species, Pc, ev.weight, Pc, Pc, ev.weight));
         else
           stack_insert(stack, T.stack_n, make_node(c0[0], c0[1], c0[2], c0[3], c0[4], c0[5], c0[6], c0[7],
-                                                   ev.species, 1.0 - Pc, ev.weight, Pc, ev.prob_conv));
+                                                   ev.species, 1.0 - Pc, ev.weight, Pc, ev.prob_conv, ev.weight));
       } else {  // MR.jl:296-303
         stack_insert(stack, T.stack_n, make_node(c0[0], c0[1], c0[2], c0[3], c0[4], c0[5], c0[6], c0[7],
-                                                 new_species, Pc, Pc * ev.weight, Pc, Pc));
+                                                 new_species, Pc, Pc * ev.weight, Pc, Pc, ev.weight));
         stack_insert(stack, T.stack_n, make_node(c0[0], c0[1], c0[2], c0[3], c0[4], c0[5], c0[6], c0[7],
-                                                 ev.species, 1.0 - Pc, (1.0 - Pc) * ev.weight, Pc, ev.prob_conv));
+                                                 ev.species, 1.0 - Pc, (1.0 - Pc) * ev.weight, Pc, ev.prob_conv, ev.weight));
       }
     }
   }

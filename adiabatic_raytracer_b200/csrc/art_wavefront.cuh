@@ -103,6 +103,7 @@ struct WfTree {  // per-event tree context of the fused pipeline
   EventIds ids;           // event ids of the call (art_kernels.cuh)
   RowSink sink;
   unsigned long long* tot_count;
+  NodeLog nlog;           // saveMode 3: every node of every tree (e = null otherwise)
 };
 
 // apply()'s FSAL copy k1 ← K(6): on the device k7 is already in the hot record
@@ -596,6 +597,22 @@ __device__ __forceinline__ void wf_release_half(const WfTree& T, WfPool& W, int 
   }
 }
 
+__device__ __forceinline__ void wf_log_node(const NodeLog& L, int event, int pos, int species, double weight, double prob, double parent_weight,
+                                            const double x0[3], const double k0[3], double t0, double dw0, double erg, int n_cross, const double* rc) {
+  const unsigned long long at = atomicAdd(L.count, 1ull);
+  if ((long long)at >= L.cap) return;
+  NodeLogEntry n;
+  n.event = event; n.pos = pos; n.species = species; n.n_cross = n_cross < L.cross_cap ? n_cross : L.cross_cap;
+  n.weight = weight; n.prob = prob; n.parent_weight = parent_weight;
+  for (int c = 0; c < 3; ++c) { n.x0[c] = x0[c]; n.k0[c] = k0[c]; }
+  n.t0 = t0; n.dw0 = dw0; n.erg = erg;
+  L.e[at] = n;
+  double* q = L.cross + at * (unsigned long long)L.cross_cap * 4;
+  for (int j = 0; j < n.n_cross; ++j) {
+    q[4 * j] = rc[8 * j]; q[4 * j + 1] = rc[8 * j + 1]; q[4 * j + 2] = rc[8 * j + 2]; q[4 * j + 3] = rc[8 * j + 6];
+  }
+}
+
 // Returns true when the event continues: R then holds the freshly initialised ray of the next node.
 __device__ __forceinline__ bool wf_tree_step(const DevParams& P, const WfTree& T, WfPool& W, int id, const RayOut& ro,
                                              double* __restrict__ rec, int rec_cap, Ray& R) {
@@ -605,6 +622,10 @@ __device__ __forceinline__ bool wf_tree_step(const DevParams& P, const WfTree& T
     EventData E = T.ev[e];
     tree_backward(P, E, ro, rc, rec_cap);
     T.ev[e] = E;
+    if (T.nlog.e) {  // saveNode(f, nb), MR.jl:612: the parent axion of the back-trace with all its crossings
+      const double kb[3] = {-E.k_init[0], -E.k_init[1], -E.k_init[2]};
+      wf_log_node(T.nlog, e, 0, SPECIES_AXION, E.back_node_w, E.prob0, -1.0, E.x, kb, 0.0, -1.0, E.erg_inf, ro.n_cross, rc);
+    }
     wf_release_half(T, W, id);
     return false;
   }
@@ -612,6 +633,11 @@ __device__ __forceinline__ bool wf_tree_step(const DevParams& P, const WfTree& T
   const int e = T.slot_event[slot];
   const EventData E = T.ev[e];  // (the back-trace only writes back_weight / prob0 / c_bck, which the forward tree does not read)
   TreeState S = T.ts[slot];
+  if (T.nlog.e) {  // saveNode(f, tree[ii]), MR.jl:669-670
+    const TreeNode& n = S.cur;
+    const double x0[3] = {n.x, n.y, n.z}, k0[3] = {n.kx, n.ky, n.kz};
+    wf_log_node(T.nlog, e, S.tree_len + 1, n.species, n.weight, n.prob, n.parent_weight, x0, k0, n.t, n.dw, E.erg_inf, ro.n_cross, rc);
+  }
   tree_forward_update(P, E, S, T.stacks + (size_t)slot * T.stack_stride, ro, rc, T.seed,
                       (unsigned long long)T.ids.id(e), (long long)e, T.sink);
   bool spawn = false;

@@ -42,6 +42,7 @@ SIGNATURES = {
     "art_fetch_rows": (C.c_int, [_H, C.c_void_p, C.c_int64, _i64p]),
     "art_fetch_events": (C.c_int, [_H, _dp, C.c_int64, _i64p]),
     "art_write_event_files": (C.c_int, [C.c_char_p, C.c_char_p, _dp, C.c_int64, _dp, C.c_int64]),
+    "art_write_tree_files": (C.c_int, [_H, C.c_char_p, C.c_char_p, _i64p]),
     "art_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
     "art_host_free": (C.c_int, [C.c_void_p]),
     "art_normalize_rows": (C.c_int, [_dp, C.c_int64, C.c_int32, C.c_int64]),
@@ -212,6 +213,12 @@ class Handle:
         n = C.c_int64()
         self._chk(self._L.art_fetch_events(self._h, ev, ev.shape[0], C.byref(n)))
         return ev[: n.value]
+
+    def write_tree_files(self, dir_tag: str, file_tag: str) -> int:
+        """saveMode 3: <dir_tag>/tree/tree_<file_tag><event> for every event of the last run; returns the number of files."""
+        n = C.c_int64()
+        self._chk(self._L.art_write_tree_files(self._h, dir_tag.encode(), file_tag.encode(), C.byref(n)))
+        return n.value
 
     # ---- histogram / multi-GPU ------------------------------------------------------------
     def hist_config(self, n_costheta, n_phi, n_domega=1, domega_lo=0.0, domega_hi=0.0):

@@ -11,8 +11,8 @@ Differences a user can observe:
   * ``iseed < 0`` draws a seed from os.urandom like the reference draws rand(0:1e8);
   * saveMode = 2 writes <dir_tag>/event/final_<file_tag> and event_<file_tag> once, after the run (the
     reference appends per event); the per-event wall-clock field of event_* is 0.0;
-  * saveMode = 3 (one tree_<file_tag><event> text file per event with the trajectories sampled at ``ntimes``
-    points, MainRunner.jl:17-65, 574-578) is not supported and raises;
+  * saveMode = 3 writes <dir_tag>/tree/tree_<file_tag><event> in saveNode's layout (MainRunner.jl:17-65, 574-578) with the
+    trajectories read off the dense output at the ``ntimes`` saveat points; an event point is saved once (DiffEq: twice);
   * ``v_NS`` is accepted and, as in the reference (MainRunner.jl:418-422 computes two angles that nothing
     reads; the velocity shift at :497 is commented out), has no effect.
 """
@@ -51,8 +51,6 @@ def main_runner_tree(Mass_a, Ax_g, theta_m, omega_pul, B0, rNS, Mass_NS, omega_p
                      return_rows=False):
     """Drop-in for ``main_runner_tree`` (MainRunner.jl:355).  Returns tot_count (or None when
     there is no conversion surface, MainRunner.jl:389-396)."""
-    if saveMode > 2:
-        raise NotImplementedError("saveMode=3 (per-event tree_* text files with sampled trajectories) is not supported")
     if iseed < 0:  # MainRunner.jl:365-372
         iseed = int.from_bytes(os.urandom(4), "little") % 100000001
     elif iseed == 0:
@@ -75,6 +73,9 @@ def main_runner_tree(Mass_a, Ax_g, theta_m, omega_pul, B0, rNS, Mass_NS, omega_p
         n_events = max(int(Ntajs) - 1, 0)
         out = h.run(iseed, 1, n_events)
         events = h.fetch_events(n_events) if saveMode > 1 else None
+        if saveMode > 2:  # MainRunner.jl:574-578: one tree_<file_tag><event> file per event
+            os.makedirs(os.path.join(dir_tag, "tree"), exist_ok=True)
+            h.write_tree_files(dir_tag, file_tag)
     finally:
         pass
     rows = np.ascontiguousarray(out["rows"])

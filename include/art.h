@@ -98,10 +98,11 @@ typedef struct art_params {
   int32_t num_cutoff;    /* --numCutoff default 5                                           */
   int32_t MC_nodes;      /* --MCNodes   default 5                                           */
   int32_t max_nodes;     /* --maxNodes  default 50                                          */
-  int32_t ntimes;        /* Gen_Samples.jl:164 = 3 (only used in the file name)             */
+  int32_t ntimes;        /* Gen_Samples.jl:164 = 3: file name; points per saved trajectory (save_mode 3) */
   int32_t save_mode;     /* 0 → 13-column rows, 1 → 29-column rows (MR.jl:714-721), 2 → 31 columns + event table
-                            (clear-text final_* / event_* files, MR.jl:435-444, 593-610, 689-701); 3 (one tree_* file
-                            per event with the sampled trajectories, MR.jl:17-65) is not supported */
+                            (clear-text final_* / event_* files, MR.jl:435-444, 593-610, 689-701); 3 → as 2, and the tree
+                            kernel logs every node for art_write_tree_files (one tree_* file per event with the
+                            trajectories sampled at `ntimes` points, MR.jl:17-65)                          */
   int32_t interp_points_ray;     /* ContinuousCallback interp_points, RT.jl:357 = 50; 2..64  */
   int32_t interp_points_sampler; /* RT.jl:1599 = 20; 2..32                                  */
   int32_t maxiters;      /* RT.jl:384 = 1e5                                                 */
@@ -251,6 +252,15 @@ int art_fetch_events(art_handle* h, double* events, int64_t events_cap, int64_t*
  * wall-clock field of the reference is written as 0.0.  The directory must exist (as in the reference).     */
 int art_write_event_files(const char* dir_tag, const char* file_tag, const double* rows, int64_t n_rows,
                           const double* events, int64_t n_events);
+
+/* saveMode 3 (MainRunner.jl:17-65, 574-578, 612, 669-670): one text file <dir_tag>/tree/tree_<file_tag><event> per event of the
+ * last pipeline call, holding every node of the event's back-trace and forward tree in saveNode's layout — species, weight,
+ * prob, parent_weight; the level crossings xc / yc / zc / tc (or three lines "-"); the trajectory x / y / z and its times (ln t)
+ * at the `ntimes` saveat points of `solve(…, saveat = …)` (RT.jl:174, 383), read off the dense output, plus the located
+ * events.  Needs a handle created with save_mode = 3 (the tree kernel then logs its nodes); the directory must exist.
+ * A debugging / plotting mode (plot/plotTree.py).  Differences from the reference's files: an event point is saved once
+ * (DiffEq saves it before and after the callback), and start-point events the start-box rule discards are not saved.  */
+int art_write_tree_files(art_handle* h, const char* dir_tag, const char* file_tag, int64_t* n_files);
 
 /* Page-locked host memory for the row buffers (optional: any host pointer works, a pinned one makes the
  * device→host copy of the rows a single DMA transfer at PCIe speed instead of a staged pageable copy).

@@ -307,3 +307,40 @@ extern "C" int hc_certificates(const art_params* p, int64_t n, const int32_t* sp
   }
   return 0;
 }
+
+// saveMode 3: trajectory of one node sampled at `ntimes` saveat points (Ray::step_sampled, the code k_node_traj runs per thread).
+// out: rows of 4 doubles (x y z ln t), returns the number of rows.
+extern "C" int hc_node_traj(const art_params* p, int32_t species, const double* x0, const double* k0, double erg, double t_start,
+                            double dOmega, int32_t max_crossings, int32_t ntimes, double* out, int32_t out_cap) {
+  DevParams P;
+  int rc = dev(p, P);
+  if (rc) return -1;
+  RayIn in;
+  for (int c = 0; c < 3; ++c) { in.x0[c] = x0[c]; in.k0[c] = k0[c]; }
+  in.erg = erg; in.t_start = t_start; in.dOmega = dOmega; in.max_cross = max_crossings; in.species = species;
+  std::vector<double> rec(64 * 8);
+  Ray R;
+  double kbuf[K_ROWS], sbuf[SEG_MAX];
+  KStore K{kbuf, 1};
+  SegStore D{sbuf, 1};
+  R.init(P, in, rec.data(), 64);
+  const double s0 = R.s, delta = (P.ln_tend - s0) / (double)(ntimes > 1 ? ntimes - 1 : 1);
+  int n_out = 0, kq = 1;
+  {
+    double x[3], k[3];
+    state_to_cartesian(P, R.u, R.erg, false, x, k);
+    out[0] = x[0]; out[1] = x[1]; out[2] = x[2]; out[3] = s0;
+    n_out = 1;
+  }
+  while (!R.done) {
+    if (P.integrator == IG_DP5) R.step_sampled<IG_DP5>(P, K, D, s0, delta, ntimes, kq, out, n_out, out_cap);
+    else R.step_sampled<IG_VERN6>(P, K, D, s0, delta, ntimes, kq, out, n_out, out_cap);
+  }
+  if (R.s < P.ln_tend && n_out < out_cap && out[4 * (n_out - 1) + 3] < R.s) {
+    double x[3], k[3];
+    state_to_cartesian(P, R.u, R.erg, false, x, k);
+    double* q = out + 4 * (size_t)n_out++;
+    q[0] = x[0]; q[1] = x[1]; q[2] = x[2]; q[3] = R.s;
+  }
+  return n_out;
+}

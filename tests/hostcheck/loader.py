@@ -144,3 +144,15 @@ def certificates(p, species, x0, k0, erg, max_crossings=-1):
                                np.ascontiguousarray(erg, np.float64).ctypes.data_as(C.c_void_p), max_crossings,
                                counts.ctypes.data_as(C.c_void_p)))
     return counts
+
+
+def node_traj(p, species, x0, k0, erg, t_start=0.0, dOmega=-1.0, max_crossings=-1, ntimes=100):
+    """Trajectory (x, y, z, ln t) of one node at the saveat points of saveMode 3."""
+    out = np.zeros((ntimes + 70, 4))
+    L = lib()
+    L.hc_node_traj.restype = C.c_int
+    n = L.hc_node_traj(C.byref(p), int(species), np.ascontiguousarray(x0, np.float64).ctypes.data_as(C.c_void_p),
+                       np.ascontiguousarray(k0, np.float64).ctypes.data_as(C.c_void_p), C.c_double(erg), C.c_double(t_start),
+                       C.c_double(dOmega), int(max_crossings), int(ntimes), out.ctypes.data_as(C.c_void_p), out.shape[0])
+    assert n > 0
+    return out[:n]

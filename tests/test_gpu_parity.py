@@ -605,6 +605,68 @@ def test_save_mode_2_rows_event_table_and_text_files(lib, oracle, tmp_path):
     assert len(e0) == 19 and e0[0] == "1" and float(e0[5]) == ev[0, 5] and float(e0[8]) == -ev[0, 8] and e0[-1] == str(int(ev[0, 11]))
 
 
+def _load_tree_file(path):
+    """Parser of saveNode's layout (MainRunner.jl:17-65): header; xc / yc / zc / tc or three "-" lines; x / y / z / times."""
+    nodes = []
+    lines = open(path).read().split("\n")
+    i = 0
+    while i < len(lines) and lines[i].strip():
+        sp, w, pr, pw = lines[i].split()
+        nd = dict(species=sp, weight=float(w), prob=float(pr), parent_weight=float(pw))
+        if lines[i + 1].strip() == "-":
+            assert lines[i + 2].strip() == "-" and lines[i + 3].strip() == "-"
+            nd["cross"] = np.zeros((0, 4))
+            i += 4
+        else:
+            nd["cross"] = np.array([[float(v) for v in lines[i + 1 + c].split()] for c in range(4)]).T
+            i += 5
+        nd["traj"] = np.array([[float(v) for v in lines[i + c].split()] for c in range(4)]).T
+        i += 4
+        nodes.append(nd)
+    return nodes
+
+
+def test_save_mode_3_tree_files(lib, tmp_path):
+    """saveMode 3: one tree_<tag><event> file per event (MainRunner.jl:574-578) in saveNode's layout, trajectories at the
+    `ntimes` saveat points.  Checked against the rows of the same run and against the host-compiled sampler."""
+    from adiabatic_raytracer_b200 import main_runner_tree
+    n, nt = 120, 25
+    d = str(tmp_path / "res")
+    tot, rows, fname, out = main_runner_tree(1e-5, 1e-10, 0.2, 1.0, 1e14, 10.0, 1.0, "Simple", n + 1, [1.0, 1.0], flat=False,
+                                             melrose=True, file_tag="tr", saveMode=3, ntimes=nt, dir_tag=d, iseed=1769,
+                                             return_rows=True)
+    assert "_N_Times_25_" in fname and np.load(fname).shape[1] == 29
+    files = sorted(os.listdir(os.path.join(d, "tree")), key=lambda s: int(s[len("tree_tr"):]))
+    assert files == [f"tree_tr{e}" for e in range(1, n + 1)]
+    full = out["rows"]                    # 31 columns, sln_prob not normalised
+    n_nodes = 0
+    for e in (1, 2, 3, 17, 60, n):
+        nodes = _load_tree_file(os.path.join(d, "tree", f"tree_tr{e}"))
+        n_nodes += len(nodes)
+        R = full[full[:, 0] == e]
+        # node 0: the back-traced axion, weight = Π (1 − P_j), prob = P0 (rows: column 25 = P0·weight, column 28 = P0)
+        b = nodes[0]
+        assert b["species"] == "axion" and b["parent_weight"] == -1.0
+        assert abs(b["weight"] * b["prob"] - R[0, 25]) <= 1e-12 * R[0, 25] and abs(b["prob"] - R[0, 28]) <= 1e-12 * R[0, 28]
+        assert np.abs(b["traj"][0, :3] - R[0, 9:12]).max() < 1e-9 and b["traj"][0, 3] == -30.0
+        # node 1: the first photon; every forward node starts where its parent crossed
+        f1 = nodes[1]
+        assert f1["species"] == "photon" and f1["weight"] == 1.0 and f1["parent_weight"] == -1.0
+        assert np.abs(f1["traj"][0, :3] - R[0, 9:12]).max() < 1e-9
+        for nd in nodes[1:]:
+            assert np.all(np.diff(nd["traj"][:, 3]) > 0) and len(nd["traj"]) <= nt + 2
+            if len(nd["cross"]):   # stopped at its first crossing: the trajectory ends on it
+                assert len(nd["cross"]) == 1 and np.abs(nd["traj"][-1, :3] - nd["cross"][0, :3]).max() < 1e-9
+        # final nodes (no crossing) that left the star are the rows of the event: same end point
+        finals = [nd for nd in nodes[1:] if len(nd["cross"]) == 0 and np.linalg.norm(nd["traj"][-1, :3]) > 11.0]
+        assert len(finals) == len(R)
+        for nd, r in zip(finals, R):
+            x = nd["traj"][-1, :3]
+            assert abs(np.linalg.norm(x) - r[6]) <= 1e-9 * r[6] and abs(math.acos(x[2] / np.linalg.norm(x)) - r[4]) < 1e-9
+            assert (nd["species"] == "photon") == (r[1] == 1) and abs(nd["weight"] * R[0, 25] - r[8]) <= 1e-9 * r[8]
+    assert n_nodes >= 12
+
+
 def test_baseline_config0_flat_run_full_size_matches_oracle(lib, oracle):
     """BASELINE configs[0] at full size: flat-space run, m_a=1e-5 eV, B0=1e14 G, P=1 s (rotW=2π), θm=0.2, M=1, R=10 km,
     1e4 conversion-surface samples (Ntajs = 1e4 ⇒ 9999 events).  Per-event agreement of the tree shapes, and the

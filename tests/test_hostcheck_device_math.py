@@ -259,3 +259,36 @@ def test_host_compiled_tracer_against_dop853_fixtures(fixture):
         worst = max(worst, np.linalg.norm(R["x_f"][:, 0] - xg) / np.linalg.norm(xg))
         assert abs(R["u7_f"][0] - uf[6]) <= 1e-9 * abs(uf[6])
     assert worst < 1e-8
+
+
+def test_saved_trajectory_of_save_mode_3(oracle):
+    """saveMode 3's trajectory sampler (Ray::step_sampled, what k_node_traj runs per node): the saveat grid of
+    `solve(…, saveat = (ln t_end − ln t_start)/(ntimes − 1))` (RT.jl:174, 383), first point = start, last point = the state
+    propagate returns, a ray that stops at a crossing ends ON the crossing, and two grids agree where they share times."""
+    p = ArtParams.default(theta_m=0.2)
+    n = 40
+    s = oracle.sample(p, 5, 1, n)
+    w = oracle.weights(p, s["x"], s["v_loc"], s["v_inf"])
+    a = hc.propagate(p, np.full(n, 1, np.int32), s["x"], w["k_init"], w["erg_inf"], np.zeros(n), -np.ones(n), 1, -1)
+    seen = set()
+    for i in range(n):
+        t9 = hc.node_traj(p, 1, s["x"][:, i], w["k_init"][:, i], w["erg_inf"][i], ntimes=9)
+        t5 = hc.node_traj(p, 1, s["x"][:, i], w["k_init"][:, i], w["erg_inf"][i], ntimes=5)
+        assert np.abs(t9[0, :3] - s["x"][:, i]).max() < 1e-12 and t9[0, 3] == -30.0
+        assert np.all(np.diff(t9[:, 3]) > 0)
+        assert np.abs(t9[-1, :3] - a["x_f"][:, i]).max() <= 1e-12 * np.linalg.norm(a["x_f"][:, i])
+        grid = np.linspace(-30.0, 0.0, 9)
+        if a["status"][i] == 0:      # reached the end of the span: exactly the grid
+            assert len(t9) == 9 and np.allclose(t9[:, 3], grid, atol=1e-12)
+        else:                        # stopped at a crossing / at the star: the grid up to there, then the final point
+            k = len(t9) - 1
+            assert np.allclose(t9[:k, 3], grid[:k], atol=1e-12) and grid[k - 1] < t9[-1, 3] < grid[k]
+            if a["status"][i] == 2:
+                assert np.abs(t9[-1, :3] - a["cross_rec"][i, 0, :3]).max() < 1e-9
+                assert abs(math.exp(t9[-1, 3]) - a["cross_rec"][i, 0, 6]) < 1e-12 * a["cross_rec"][i, 0, 6]
+        for r5 in t5:
+            j = np.where(np.abs(t9[:, 3] - r5[3]) < 1e-12)[0]
+            if len(j):
+                assert np.abs(t9[j[0], :3] - r5[:3]).max() <= 1e-12 * np.linalg.norm(r5[:3])
+        seen.add(int(a["status"][i]))
+    assert {0, 2} <= seen
