@@ -266,7 +266,7 @@ template <int IG>
 int wf_loop(art_handle* h, Lane& L, WfPool W, long long n_act0, RayOut* out, double* rec, int rec_cap, DevStats* stats,
             const WfTree* tree, PoolJob* job, EvGuard& evg) {
   cudaStream_t st = L.stream;
-  const size_t ksmem = (size_t)(K_ROWS + K_PARK) * STAGE_THREADS * sizeof(double);
+  const size_t ksmem = (size_t)(K_ROWS + K_PARK + (Scheme<IG>::BL ? K_XROWS : 0)) * STAGE_THREADS * sizeof(double);
   const int gmax = h->n_sm * h->wf_grid_per_sm;
   auto grid = [&](long long work, int threads) { return (int)std::max<long long>(1, std::min<long long>(gmax, (work + threads - 1) / threads)); };
   long long n_act = n_act0;  // upper bound of the rays in flight, refreshed at every host check
@@ -426,8 +426,9 @@ int launch_trace_wf_t(art_handle* h, Lane& L, const QueuedRay* q, long long n, R
 
 int launch_trace_wf(art_handle* h, Lane& L, const QueuedRay* q, long long n, RayOut* out, double* rec, int rec_cap,
                     DevStats* stats) {
-  return h->dp.integrator == IG_DP5 ? launch_trace_wf_t<IG_DP5>(h, L, q, n, out, rec, rec_cap, stats)
-                                    : launch_trace_wf_t<IG_VERN6>(h, L, q, n, out, rec, rec_cap, stats);
+  if (h->dp.integrator == IG_DP5) return launch_trace_wf_t<IG_DP5>(h, L, q, n, out, rec, rec_cap, stats);
+  if (h->dp.bl > 0.0) return launch_trace_wf_t<IG_VERN6_BL>(h, L, q, n, out, rec, rec_cap, stats);
+  return launch_trace_wf_t<IG_VERN6>(h, L, q, n, out, rec, rec_cap, stats);
 }
 
 }  // namespace
@@ -490,6 +491,8 @@ int art_create(const art_params* p, int device_id, art_handle** out) {
   cudaFuncSetAttribute(k_wf_stages<IG_VERN6>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(k_wf_stages<IG_DP5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((K_ROWS + K_PARK) * STAGE_THREADS * sizeof(double)));
   cudaFuncSetAttribute(k_wf_stages<IG_DP5>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(k_wf_stages<IG_VERN6_BL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((K_ROWS + K_PARK + K_XROWS) * STAGE_THREADS * sizeof(double)));
+  cudaFuncSetAttribute(k_wf_stages<IG_VERN6_BL>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sample_events, SAMPLE_THREADS, 0);
   h->blocks_sample = h->n_sm * std::max(occ, 1);
   if (const char* t = getenv("ART_BULK_NSTEP")) h->bulk_nstep = std::max(1, atoi(t));
@@ -871,7 +874,9 @@ int art_run_device_batches(art_handle* h, uint64_t seed, int64_t first_event, in
     if (n_events > 0) {
       const int rc = h->dp.integrator == IG_DP5
                          ? run_pool<IG_DP5>(h, L, seed, first_event, n_events, h->last_batch_events, batch_stride, sink, gctr, dstats, evg)
-                         : run_pool<IG_VERN6>(h, L, seed, first_event, n_events, h->last_batch_events, batch_stride, sink, gctr, dstats, evg);
+                         : (h->dp.bl > 0.0
+                                ? run_pool<IG_VERN6_BL>(h, L, seed, first_event, n_events, h->last_batch_events, batch_stride, sink, gctr, dstats, evg)
+                                : run_pool<IG_VERN6>(h, L, seed, first_event, n_events, h->last_batch_events, batch_stride, sink, gctr, dstats, evg));
       if (rc) return rc;
     }
     CU(cudaMemcpy(hc, gctr, sizeof(hc), cudaMemcpyDeviceToHost));
@@ -1133,10 +1138,12 @@ int art_write_tree_files(art_handle* h, const char* dir_tag, const char* file_ta
   CU(s[5].ensure(traj_bytes));
   CU(s[6].ensure((size_t)n * sizeof(int)));
   CU(s[7].ensure((size_t)n * 64 * 8 * sizeof(double)));
-  CU(s[8].ensure((size_t)n * (K_ROWS + SEG_MAX) * sizeof(double)));
+  CU(s[8].ensure((size_t)n * NODE_SCRATCH * sizeof(double)));
   const int rc = h->dp.integrator == IG_DP5
                      ? node_trajectories<IG_DP5>(h, h->nlog.as<NodeLogEntry>(), n, ntimes, out_cap, s[5].as<double>(), s[6].as<int>(), s[7].as<double>(), s[8].as<double>())
-                     : node_trajectories<IG_VERN6>(h, h->nlog.as<NodeLogEntry>(), n, ntimes, out_cap, s[5].as<double>(), s[6].as<int>(), s[7].as<double>(), s[8].as<double>());
+                     : (h->dp.bl > 0.0
+                            ? node_trajectories<IG_VERN6_BL>(h, h->nlog.as<NodeLogEntry>(), n, ntimes, out_cap, s[5].as<double>(), s[6].as<int>(), s[7].as<double>(), s[8].as<double>())
+                            : node_trajectories<IG_VERN6>(h, h->nlog.as<NodeLogEntry>(), n, ntimes, out_cap, s[5].as<double>(), s[6].as<int>(), s[7].as<double>(), s[8].as<double>()));
   if (rc) return rc;
   std::vector<double> traj((size_t)n * out_cap * 4);
   std::vector<int> npts((size_t)n);

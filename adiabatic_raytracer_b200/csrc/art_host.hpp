@@ -16,8 +16,9 @@ inline int make_dev_params(const art_params& p, DevParams& d, std::string& err) 
     err = "Mass_a, rNS, omega_pul must be positive";
     return ART_ERR_ARG;
   }
-  if (p.bndry_lyr > 0) {
-    err = "bndry_lyr > 0 (boundary-layer plasma term, RayTracer.jl:1156-1162) is not supported by this build";
+  if (p.bndry_lyr > 0 && (!p.melrose || p.integrator != ART_INTEGRATOR_VERN6)) {
+    // (the reference's CLI, the only place that exposes --bndry_lyr, hard-wires melrose = true: Gen_Samples.jl:167)
+    err = "bndry_lyr > 0 (boundary-layer plasma term, RayTracer.jl:1156-1162) is implemented for melrose = true and integrator = Vern6";
     return ART_ERR_ARG;
   }
   if (p.integrator != ART_INTEGRATOR_VERN6 && p.integrator != ART_INTEGRATOR_DP5) {
@@ -86,6 +87,23 @@ inline int make_dev_params(const art_params& p, DevParams& d, std::string& err) 
   d.mh[1] = d.sm * d.spsi0;
   d.mh[2] = d.cm;
   d.T_samp = 2.2 * d.maxR;
+  d.bl = p.bndry_lyr > 0 ? p.bndry_lyr : -1.0;
+  d.wpole = sqrt(2.0 * d.Q / (p.rNS * p.rNS * p.rNS));
+  d.bl_rmax = p.rNS * pow(d.wpole / p.Mass_a, 2.0 / 3.0);
+  d.bl_rmax_def = p.rNS * pow(d.wpole / 1e-5, 2.0 / 3.0);
+  if (d.bl > 0) {
+    // far-field radius with the boundary layer: beyond it max over angles of ωp = √(Q bz_max/r³) + B(r) stays below m_a
+    const double bzmax = 0.5 * (3.0 + fabs(d.cm));
+    auto excess = [&](double r) { return sqrt(d.Q * bzmax / (r * r * r)) + bl_w(d, r, d.bl_rmax) - p.Mass_a; };
+    double lo = d.Rcut, hi = d.Rcut;
+    for (int k = 0; k < 200 && excess(hi) > 0.0; ++k) hi *= 1.05;
+    for (int k = 0; k < 100; ++k) {
+      const double mid = 0.5 * (lo + hi);
+      if (excess(mid) > 0.0) lo = mid;
+      else hi = mid;
+    }
+    d.Rcut = hi * (1.0 + 1e-9);
+  }
   d.inv_r_int = 1.0 / d.r_int;
   if (d.maxR < p.rNS) {
     err = "Too small Max R (no conversion surface outside the star), MainRunner.jl:389-396";

@@ -190,8 +190,9 @@ __global__ void k_rhs_api(const __grid_constant__ DevParams P, long long n, cons
   double o[6];
   const double t = exp(lnt[i]);
   if (species[i] == SPECIES_PHOTON) {
-    rhs_photon(P, v[0], v[1], v[2], v[3] * erg[i], v[4] * erg[i], v[5] * erg[i], -v[6], t, 1.0 / erg[i], o);
-    du[7 * i + 6] = P.Omega * erg[i] / C_KM * o[5];
+    double dd = 0.0;
+    rhs_photon(P, v[0], v[1], v[2], v[3] * erg[i], v[4] * erg[i], v[5] * erg[i], -v[6], t, 1.0 / erg[i], o, P.bl > 0.0 ? &dd : nullptr);
+    du[7 * i + 6] = P.Omega * erg[i] / C_KM * o[5] + dd;
   } else {
     rhs_axion(P, v[0], v[1], v[3] * erg[i], v[4] * erg[i], v[5] * erg[i], t, erg[i], 1.0 / erg[i], o);
     du[7 * i + 6] = 0.0;
@@ -233,6 +234,7 @@ __global__ void k_gather_rows(const double* __restrict__ rows, const int* __rest
 // (plot/plotTree.py): a few thousand nodes, no attempt at speed.
 // traj: [node][out_cap][4] = x y z ln t; npts[node].
 // ------------------------------------------------------------------------------------------
+constexpr int NODE_SCRATCH = K_ROWS + K_PARK + K_XROWS + SEG_MAX;  // doubles of per-node scratch (stage store + segment)
 template <int IG>
 __global__ void k_node_traj(const __grid_constant__ DevParams P, const NodeLogEntry* __restrict__ nodes, long long n, int ntimes,
                             double* __restrict__ traj, int* __restrict__ npts, int out_cap, double* __restrict__ rec_scratch,
@@ -246,8 +248,8 @@ __global__ void k_node_traj(const __grid_constant__ DevParams P, const NodeLogEn
   in.max_cross = nd.pos == 0 ? 100000 : -1;   // back-trace collects every crossing, forward nodes stop at the first (MR.jl:589, 663)
   in.species = nd.species;
   Ray R;
-  const KStore K{k_scratch + (size_t)i * (K_ROWS + SEG_MAX), 1};
-  const SegStore D{k_scratch + (size_t)i * (K_ROWS + SEG_MAX) + K_ROWS, 1};
+  const KStore K{k_scratch + (size_t)i * NODE_SCRATCH, 1};
+  const SegStore D{k_scratch + (size_t)i * NODE_SCRATCH + K_ROWS + K_PARK + K_XROWS, 1};
   R.init(P, in, rec_scratch + (size_t)i * 64 * 8, 64);
   const double s0 = R.s;
   const double delta = (P.ln_tend - s0) / (double)(ntimes > 1 ? ntimes - 1 : 1);

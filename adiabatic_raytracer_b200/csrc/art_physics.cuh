@@ -226,7 +226,26 @@ struct DevParams {
   double cpsi0, spsi0, mh[3];  // cos/sin Ω t0 and the magnetic axis m̂ at the field time t0 (sampler)
   double T_samp;               // length of the sampler's line march, 2.2 maxR (RT.jl:1611)
   double inv_r_int;            // 1 / r_int
+  // boundary-layer term of the plasma frequency (bndry_lyr > 0, RT.jl:1155-1162): for r ≥ rNS
+  //   ωp = √(Q|b_z|/r³) + ωpole (rNS/r)^{3/2} exp(−(r − rmax·bl)/(0.1 rmax)),  ωpole = √(2Q/rNS³), rmax = rNS (ωpole/m_a)^{2/3}
+  double bl;                   // bndry_lyr (≤ 0: off)
+  double wpole;                // plasma frequency at the pole of the surface
+  double bl_rmax;              // rmax with the run's axion mass (sampler, ray condition, du7, g_det, ∇ωp of the conversion probability)
+  double bl_rmax_def;          // rmax with GJ_Model_ωp_vecSPH's DEFAULT Mass_a = 1e-5: get_Prob_nonAD's own ωp call does not pass
+                               // the mass (MR.jl:99) — quirk kept
 };
+
+// boundary-layer term B(r) and its r-derivative (r ≥ rNS; the callers apply the r ≥ rNS / zeroIn rules)
+ART_HD double bl_w(const DevParams& P, double r, double rmax) {
+  const double q = P.rNS / r;
+  return P.wpole * q * sqrt(q) * exp(-(r - rmax * P.bl) / (0.1 * rmax));
+}
+ART_HD double bl_dw(const DevParams& P, double r, double rmax) { return bl_w(P, r, rmax) * (-1.5 / r - 1.0 / (0.1 * rmax)); }
+// ωp² with the boundary layer from the Goldreich–Julian ωp0² (r ≥ rNS)
+ART_HD double bl_wp2(const DevParams& P, double Pp0, double r, double rmax) {
+  const double w = (Pp0 > 0.0 ? sqrt(Pp0) : 0.0) + bl_w(P, r, rmax);
+  return w * w;
+}
 
 struct Met {
   double gtt, grr, dgtt, dgrr;  // g^tt, g^rr and their r-derivatives
@@ -348,10 +367,15 @@ ART_HD MetHot metric_hot(double r, double rinv, double rs, double R) {
 // k = (k_r,k_θ,k_φ) = u[4:6]·erg, om = −u7, t = e^{ln t}, einv = 1/erg.
 // Five reciprocals (r, sinθ, D, ω, via rsqrt: g^rr), no division.
 // ---------------------------------------------------------------------------------------
+// ddelta (bndry_lyr > 0 only, else null): d/d(ln t) of δ = u7 − [u7₀ + (Ω·erg/c_km)(u6 − u6₀)].  The reference differentiates
+// the boundary-layer term in du7 ONLY (hamiltonian is called with bndry_lyr at RT.jl:88, without at RT.jl:84-85), so with
+// ωp_b = ωp0 + B(r):  ∂ψ(ωp_b²) = (ωp_b/ωp0) ∂ψ(ωp0²),  W_b = ωp_b²/(Dω²)  and
+//   dδ = −Ω t g^rr/ω · ½[(ωp_b/ωp0 − 1)·sg·∂ψb_z·X − (W_b − W) g^rr (2N ∂ψN − N² ∂ψD/D)]      (Melrose form).
 ART_HD void rhs_photon(const DevParams& P, double r, double th, double ph, double kr, double kt,
-                       double kp, double om, double t, double einv, double du[6]) {
+                       double kp, double om, double t, double einv, double du[6], double* ddelta = nullptr) {
   if (r <= P.rNS101) {  // RT.jl:86
     for (int i = 0; i < 6; ++i) du[i] = 0.0;
+    if (ddelta) *ddelta = 0.0;
     return;
   }
   const double rinv = frcp(r);
@@ -431,6 +455,18 @@ ART_HD void rhs_photon(const DevParams& P, double r, double th, double ph, doubl
   du[3] = -H_r * face;
   du[4] = -H_t * face;
   du[5] = -H_p * face;
+  if (ddelta) {
+    const double w0 = sqrt(Pp), wb = w0 + bl_w(P, r, P.bl_rmax);  // (r > 1.01 rNS here)
+    const double ratio = wb / w0 - 1.0;                             // ωp_b/ωp0 − 1 (∞ on the null surface, like the reference's √|b_z|)
+    double dW = (wb * wb - Pp) * Dinv * om2inv;                     // W_b − W
+    double Xp = X;
+    if (P.isotropic) {
+      dW = 0.0;
+      Xp = 1.0;
+    }
+    const double dHp = 0.5 * (ratio * sg * f.bz_p * Xp - dW * m.grr * (2.0 * N * N_p - N * N * f.D_p * Dinv));
+    *ddelta = -P.Omega * t * m.grr * ominv * dHp;
+  }
 }
 
 // Axion right-hand side: func_axion!, RT.jl:95-123 (geodesic; interior metric inside the star).
@@ -470,6 +506,7 @@ ART_HD double thick_condition_f(const DevParams& P, double r, const Fld& f, doub
   const Met m = metric(r, rs, P.r_int);
   const double rinv = 1.0 / r, sinv = 1.0 / f.s;
   double Pp = P.Q * rinv * rinv * rinv * fabs(f.bz);
+  if (P.bl > 0.0 && r >= P.rNS) Pp = bl_wp2(P, Pp, r, P.bl_rmax);
   if (zero_in && r <= P.rNS) Pp = 0.0;
   const double wts = wt * rinv, wps = wp * rinv * sinv;
   const double ww = m.grr * wr * wr + wts * wts + wps * wps;
@@ -520,6 +557,10 @@ ART_HD double thick_F(const DevParams& P, double r, double th, double psi, doubl
     gn = grr * nrm;
   }
   double Pq = P.Q * fabs(f.bz);
+  if (P.bl > 0.0 && r >= P.rNS) {  // boundary layer: ωp = √(Q|b_z|/r³) + B(r), Pq = ωp² r³
+    const double r3 = r * r * r;
+    Pq = bl_wp2(P, Pq / r3, r, P.bl_rmax) * r3;
+  }
   if (zero_in && r <= P.rNS) Pq = 0.0;
   const double mr3 = P.ma2 * (r * r * r);
   if (SIGN_ONLY && Pq < mr3) return -1.0;
@@ -670,7 +711,13 @@ ART_HD SampleWeights sample_weights(const DevParams& P, const double x[3], const
     W.jac_gr = 1.0;
   } else {
     const Met mg = metric(r, P.rs_real, P.rNS);
-    const double dr_th = P_x[1] / P_x[0], dr_p = P_x[2] / P_x[0];
+    double dr_th = P_x[1] / P_x[0], dr_p = P_x[2] / P_x[0];
+    if (P.bl > 0.0 && r >= P.rNS) {  // ∂ωp with the boundary layer (RT.jl:743): only ∂r changes
+      const double h2 = 0.5 / sqrt(Pp);
+      const double wr = P_x[0] * h2 + bl_dw(P, r, P.bl_rmax);
+      dr_th = P_x[1] * h2 / wr;
+      dr_p = P_x[2] * h2 / wr;
+    }
     const double s2 = f.s * f.s;
     W.jac_gr = sqrt(s2 * (mg.grr * r * r + dr_th * dr_th) + dr_p * dr_p) /
                sqrt(s2 * (r * r + dr_th * dr_th) + dr_p * dr_p);
@@ -715,15 +762,20 @@ ART_HD double conv_prob_nonAD(const DevParams& P, const double pos[3], const dou
   double stB = sin(acos(ctB));                                                           // MR.jl:81
   const double wE = erg_scaled / sqrt(1.0 - P.rs_real / r);                              // MR.jl:94
   const double q3 = P.Q * rinv * rinv2;
-  double Pp = q3 * fabs(f.bz);
-  if (r <= P.rNS) Pp = 0.0;                                                              // zeroIn=true, MR.jl:99
-  const double wp = sqrt(Pp);
+  double Pp0 = q3 * fabs(f.bz);
+  if (r <= P.rNS) Pp0 = 0.0;                                                             // zeroIn=true, MR.jl:99
+  const double wp0 = sqrt(Pp0);
+  const bool blon = P.bl > 0.0 && r > P.rNS;
+  // boundary layer: the value comes from get_Prob_nonAD's own ωp call, which does not pass Mass_a (default 1e-5, MR.jl:99);
+  // the gradient from conversion_prob's, which does (RT.jl:1427)
+  const double wp = blon ? wp0 + bl_w(P, r, P.bl_rmax_def) : wp0;
+  const double Pp = wp * wp;
   const double vloc = sqrt(wE * wE - P.ma2) / wE;                                        // RT.jl:1410
   const double wE2 = wE * wE, wE4 = wE2 * wE2;
-  // ∂μ ωp = ∂μ(ωp²)/(2ωp)
+  // ∂μ ωp = ∂μ(ωp0²)/(2ωp0) (+ B'(r))
   const double sg = signbit(f.bz) ? -q3 : q3;
-  const double h = 0.5 / wp;
-  const double dwp[3] = {-3.0 * Pp * rinv * h, sg * f.bz_t * h, sg * f.bz_p * h};        // RT.jl:1427
+  const double h = 0.5 / wp0;
+  const double dwp[3] = {-3.0 * Pp0 * rinv * h + (blon ? bl_dw(P, r, P.bl_rmax) : 0.0), sg * f.bz_t * h, sg * f.bz_p * h};  // RT.jl:1427
   // ∂μ |B|·1.95e-2,  |B| = |Bn| √D                                                        RT.jl:1429
   const double sD = sqrt(f.D);
   const double aBn = fabs(Bn) * c195;
@@ -757,7 +809,8 @@ ART_HD double conv_prob_nonAD(const DevParams& P, const double pos[3], const dou
     const double term1 = ks[0] * dBr[j] + ks[1] * dBt[j] + ks[2] * dBp[j];
     const double dct = (term1 + t2[j]) / (kmag * Bmag) - ctB * dB[j] / Bmag;             // RT.jl:1438
     double dE = preF * (wE4 * stB * stB * dwp[j] - wE2 * ctB * wp * (wE2 - wp2) * dct);  // RT.jl:1449
-    if (P.isotropic) dE = wp * dwp[j] / sqrt(kmag * kmag + wp2);
+    // (isotropic: ∇ω of omega_function, which is called WITHOUT bndry_lyr, RT.jl:1420-1422)
+    if (P.isotropic) dE = wp0 * (j == 0 ? -3.0 * Pp0 * rinv * h : dwp[j]) / sqrt(kmag * kmag + Pp0);
     vhat += gk[j] * dE;                                                                  // RT.jl:1460
   }
   const double prefactor = wE4 * stB * stB / (ctB * ctB * wp2 * (wp2 - 2.0 * wE2) + wE4);   // RT.jl:1467

@@ -82,7 +82,8 @@ struct Sampler {
     const double cz = z * rinv;                                          // ẑ·r̂
     const double D = 3.0 * mx * mx + 1.0;
     const double bz = 3.0 * mx * cz - P.cm;
-    const double Pq = P.Q * fabs(bz) * rinv * rinv * rinv;               // ωp²
+    double Pq = P.Q * fabs(bz) * rinv * rinv * rinv;                     // ωp²
+    if (P.bl > 0.0 && r >= P.rNS) Pq = bl_wp2(P, Pq, r, P.bl_rmax);     // boundary layer (GJ_Model_ωp_vec, RT.jl:1092-1098)
     // thick_surface = false (RT.jl:1548-1551): log ωp − log m_a, i.e. the sign and zeros of ωp² − m_a²
     // (GJ_Model_ωp_vec: no zeroIn, the plasma frequency continues inside the star)
     if (!P.thick) return Pq - P.ma2;
@@ -133,7 +134,8 @@ struct Sampler {
     const double r = r2 * rinv;
     const double mx = (P.mh[0] * u[0] + P.mh[1] * u[1] + P.mh[2] * u[2]) * rinv;
     const double bz = 3.0 * mx * (u[2] * rinv) - P.cm;
-    const double wp2 = P.Q * fabs(bz) * rinv * rinv * rinv;
+    double wp2 = P.Q * fabs(bz) * rinv * rinv * rinv;
+    if (P.bl > 0.0 && r >= P.rNS) wp2 = bl_wp2(P, wp2, r, P.bl_rmax);
     double grr = 1.0 - P.rs_real * rinv;
     if (!(r > P.r_int)) grr = metric(r, P.rs_real, P.r_int).grr;
     if (r > P.rNS && E2 > grr * wp2) {
@@ -166,6 +168,7 @@ struct Sampler {
   // b_z = 3(m̂·r̂)(ẑ·r̂) − cosθm.  A direction-aware refinement of the Rcut sphere: only the steps that straddle
   // the conversion surface (and those inside the star) are left to evaluate.
   ART_HD int seg_sign(const DevParams& P, double t0, double L) const {
+    if (P.bl > 0.0) return 0;  // the bounds below assume the pure Goldreich–Julian ωp
     const double hm = 0.5 * L, tm = t0 + hm;
     const double x = xs[0] + tm * va[0], y = xs[1] + tm * va[1], z = xs[2] + tm * va[2];
     const double r2 = x * x + y * y + z * z;

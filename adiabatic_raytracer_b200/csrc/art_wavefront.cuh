@@ -109,7 +109,9 @@ struct WfTree {  // per-event tree context of the fused pipeline
 // apply()'s FSAL copy k1 ← K(6): on the device k7 is already in the hot record
 struct K7View {
   const double* k7;
+  double k7x;
   __device__ __forceinline__ double operator()(int, int i) const { return k7[i]; }
+  __device__ __forceinline__ double kx(int) const { return k7x; }
 };
 
 struct WfStat {
@@ -231,6 +233,11 @@ __device__ __forceinline__ void wf_stages_body(const DevParams& P, const WfPool&
     id_b = t + 2 * nthreads < n ? act[t + 2 * nthreads] : -1;
     Ray R;
     if (valid) static_cast<RayHot&>(R) = W.hot[id];
+    if constexpr (Scheme<IG>::BL) {
+      R.delta = valid ? W.cold[id].delta : 0.0;
+      R.k1x = valid ? W.cold[id].k1x : 0.0;
+      R.dn = R.delta;
+    }
     bool go = valid && !R.done;
     done = valid && R.done;
     // Rounds.  A step round runs the LAST stages of one attempted step for every lane that can go on, at ONE call
@@ -268,7 +275,7 @@ __device__ __forceinline__ void wf_stages_body(const DevParams& P, const WfPool&
           const RayCold& C = W.cold[id];
           const double s0_[3] = {C.s0[0], C.s0[1], C.s0[2]};
           if (R.template step_in_start_box<IG>(K, s0_, C.box_m)) {
-            const double E = R.u7_of(R.un[5]);
+            const double E = R.u7_of(R.un[5]) + (Scheme<IG>::BL ? R.dn : 0.0);
             const double g = thick_F<true>(P, R.un[0], R.un[1], R.un[2] - P.Omega * K.park(TNEW), R.un[3], R.un[4], R.un[5], E,
                                            P.rs_ray, true);
             n_full++;
@@ -285,6 +292,10 @@ __device__ __forceinline__ void wf_stages_body(const DevParams& P, const WfPool&
           for (int i = 0; i < 6; ++i) {
             R.u[i] = R.un[i];
             R.k1[i] = K(LAST, i);
+          }
+          if constexpr (Scheme<IG>::BL) {
+            R.delta = R.dn;
+            R.k1x = K.kx(LAST);
           }
           R.s = R.s_new;
           R.sgn_end = cs;
@@ -312,10 +323,20 @@ __device__ __forceinline__ void wf_stages_body(const DevParams& P, const WfPool&
         R.u[i] = R.un[i];
         R.k1[i] = K(LAST, i);
       }
+      if constexpr (Scheme<IG>::BL) {
+        R.delta = R.dn;
+        R.k1x = K.kx(LAST);
+      }
       R.s = R.s_new;
       R.dt = R.dt_new;
     }
     if (valid) W.hot[id] = static_cast<const RayHot&>(R);
+    if constexpr (Scheme<IG>::BL) {
+      if (valid) {
+        W.cold[id].delta = R.delta;
+        W.cold[id].k1x = R.k1x;
+      }
+    }
     wf_route(W, k, valid, id, done, pending, SP == SPECIES_AXION);
   }
   n_full = warp_sum(n_full);
@@ -456,6 +477,10 @@ __device__ __forceinline__ void wf_load_pending(Ray& R, const SegAoS D) {
     R.un[i] = R.u[i];
     R.u[i] = D(Seg<IG>::U + i);
   }
+  if constexpr (Scheme<IG>::BL) {
+    R.dn = R.delta;
+    R.delta = D(Seg<IG>::DELTA);
+  }
   R.s_new = R.s;
   R.s = D(Seg<IG>::S);
   R.h = D(Seg<IG>::H);
@@ -549,12 +574,16 @@ k_wf_root(const __grid_constant__ DevParams P, WfPool W, int k, DevStats* stats)
       }
       const SegAoS D{segl};
       wf_load_pending<IG>(R, D);
-      const K7View K{R.k1};
+      const K7View K{R.k1, R.k1x};
       const int c0 = R.n_cond;
       const double th = (R.br_b == -2) ? 1.0 : R.template locate<IG>(P, D, R.br_a, R.br_b);
       n_full += (unsigned long long)(R.n_cond - c0);
       R.template apply<IG>(P, K, D, th, R.br_sg);
       W.hot[id] = static_cast<const RayHot&>(R);
+      if constexpr (Scheme<IG>::BL) {
+        W.cold[id].delta = R.delta;
+        W.cold[id].k1x = R.k1x;
+      }
       done = R.done;
       axion = R.axion;
     }
@@ -565,9 +594,10 @@ k_wf_root(const __grid_constant__ DevParams P, WfPool W, int k, DevStats* stats)
 }
 
 // result of a finished ray
-__device__ __forceinline__ RayOut wf_result(const DevParams& P, const RayHot& H, WfStat& st) {
+__device__ __forceinline__ RayOut wf_result(const DevParams& P, const RayHot& H, const RayCold& C, WfStat& st) {
   Ray R;
   static_cast<RayHot&>(R) = H;
+  R.delta = P.bl > 0.0 ? C.delta : 0.0;
   RayOut o;
   R.finish(P, o);
   st.add(o, R.axion);
@@ -582,7 +612,7 @@ k_wf_collect(const __grid_constant__ DevParams P, WfPool W, int k, RayOut* __res
   const int* __restrict__ fin = ((k - 1) & 1) ? W.fin[1] : W.fin[0];
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
     const int id = fin[t];
-    out[id] = wf_result(P, W.hot[id], st);
+    out[id] = wf_result(P, W.hot[id], W.cold[id], st);
   }
   st.flush(stats);
 }
@@ -679,7 +709,7 @@ k_wf_tree(const __grid_constant__ DevParams P, WfPool W, WfTree T, int k, double
     int id = -1;
     if (t < n && (t0 % spread) == 0) {
       id = fin[t];
-      const RayOut o = wf_result(P, W.hot[id], st);
+      const RayOut o = wf_result(P, W.hot[id], W.cold[id], st);
       spawn = wf_tree_step(P, T, W, id, o, rec, rec_cap, R);
       if (spawn) {
         // a re-initialised ray that is already past the end of the span stays `done`: the next

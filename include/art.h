@@ -75,7 +75,8 @@ typedef struct art_params {
   double rNS;       /* stellar radius [km]                 --rNS    default 10             */
   double Mass_NS;   /* stellar mass [M_sun]                --Mass_NS default 1             */
   /* keyword arguments */
-  double bndry_lyr;   /* boundary-layer switch; only <= 0 (off) is supported (SURVEY §8 f) */
+  double bndry_lyr;   /* --bndry_lyr (Gen_Samples.jl:127-130): > 0 adds the boundary-layer term to ωp (RT.jl:1155-1162);
+                         needs melrose = 1 and integrator = Vern6; <= 0 (default −1): off      */
   double ode_err;     /* abstol of the ray integrator      Gen_Samples.jl:163 = 1e-6        */
   double reltol;      /* reltol of the ray integrator      RayTracer.jl:383   = 1e-7        */
   double fix_time;    /* field time used for maxR          Gen_Samples.jl:162 = 0           */

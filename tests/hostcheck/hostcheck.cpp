@@ -21,7 +21,7 @@ static int dev(const art_params* p, DevParams& d) {
 
 static void trace_one(const DevParams& P, const RayIn& in, double* rec, int cap, RayOut& o) {
   Ray R;
-  double kbuf[K_ROWS], sbuf[SEG_MAX];
+  double kbuf[K_ROWS + K_PARK + K_XROWS], sbuf[SEG_MAX];
   KStore K{kbuf, 1};
   SegStore D{sbuf, 1};
   R.init(P, in, rec, cap);
@@ -75,8 +75,9 @@ int hc_rhs(const art_params* p, int64_t n, const int32_t* species, const double*
     double* o = du + 7 * i;
     double t = exp(lnt[i]);
     if (species[i] == SPECIES_PHOTON) {
-      rhs_photon(P, v[0], v[1], v[2], v[3] * erg[i], v[4] * erg[i], v[5] * erg[i], -v[6], t, 1.0 / erg[i], o);
-      o[6] = P.Omega * erg[i] / C_KM * o[5];
+      double dd = 0.0;
+      rhs_photon(P, v[0], v[1], v[2], v[3] * erg[i], v[4] * erg[i], v[5] * erg[i], -v[6], t, 1.0 / erg[i], o, P.bl > 0.0 ? &dd : nullptr);
+      o[6] = P.Omega * erg[i] / C_KM * o[5] + dd;
     } else {
       rhs_axion(P, v[0], v[1], v[3] * erg[i], v[4] * erg[i], v[5] * erg[i], t, erg[i], 1.0 / erg[i], o);
       o[6] = 0.0;
@@ -238,7 +239,7 @@ extern "C" int hc_trace_ray(const art_params* p, int32_t species, const double* 
   std::vector<double> rec((size_t)p->cross_cap * 8);
   int n = 0;
   Ray R;
-  double kbuf[K_ROWS], sbuf[SEG_MAX];
+  double kbuf[K_ROWS + K_PARK + K_XROWS], sbuf[SEG_MAX];
   KStore K{kbuf, 1};
   SegStore D{sbuf, 1};
   R.init(P, in, rec.data(), p->cross_cap);
@@ -259,7 +260,7 @@ extern "C" int hc_trace_ray(const art_params* p, int32_t species, const double* 
 template <int IG>
 static void certify_ray(const DevParams& P, const RayIn& in, double* rec, int cap, long long counts[5]) {
   Ray R;
-  double kbuf[K_ROWS], sbuf[SEG_MAX];
+  double kbuf[K_ROWS + K_PARK + K_XROWS], sbuf[SEG_MAX];
   KStore K{kbuf, 1};
   SegStore D{sbuf, 1};
   R.init(P, in, rec, cap);
@@ -303,6 +304,7 @@ extern "C" int hc_certificates(const art_params* p, int64_t n, const int32_t* sp
     for (int c = 0; c < 3; ++c) { in.x0[c] = x0[c * n + i]; in.k0[c] = k0[c * n + i]; }
     in.erg = erg[i]; in.t_start = 0.0; in.dOmega = -1.0; in.max_cross = max_crossings; in.species = species[i];
     if (P.integrator == IG_DP5) certify_ray<IG_DP5>(P, in, rec.data(), p->cross_cap, counts);
+    else if (P.bl > 0.0) certify_ray<IG_VERN6_BL>(P, in, rec.data(), p->cross_cap, counts);
     else certify_ray<IG_VERN6>(P, in, rec.data(), p->cross_cap, counts);
   }
   return 0;
@@ -320,7 +322,7 @@ extern "C" int hc_node_traj(const art_params* p, int32_t species, const double* 
   in.erg = erg; in.t_start = t_start; in.dOmega = dOmega; in.max_cross = max_crossings; in.species = species;
   std::vector<double> rec(64 * 8);
   Ray R;
-  double kbuf[K_ROWS], sbuf[SEG_MAX];
+  double kbuf[K_ROWS + K_PARK + K_XROWS], sbuf[SEG_MAX];
   KStore K{kbuf, 1};
   SegStore D{sbuf, 1};
   R.init(P, in, rec.data(), 64);
@@ -334,6 +336,7 @@ extern "C" int hc_node_traj(const art_params* p, int32_t species, const double* 
   }
   while (!R.done) {
     if (P.integrator == IG_DP5) R.step_sampled<IG_DP5>(P, K, D, s0, delta, ntimes, kq, out, n_out, out_cap);
+    else if (P.bl > 0.0) R.step_sampled<IG_VERN6_BL>(P, K, D, s0, delta, ntimes, kq, out, n_out, out_cap);
     else R.step_sampled<IG_VERN6>(P, K, D, s0, delta, ntimes, kq, out, n_out, out_cap);
   }
   if (R.s < P.ln_tend && n_out < out_cap && out[4 * (n_out - 1) + 3] < R.s) {

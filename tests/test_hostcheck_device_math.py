@@ -217,7 +217,8 @@ _OTHERS = [dict(theta_m=1.8), dict(theta_m=2.9, omega_pul=3.0), dict(theta_m=0.2
            dict(theta_m=0.5, Mass_a=2e-6), dict(theta_m=0.2, Ax_g=3e-10, MC_nodes=1, max_nodes=8, num_cutoff=2),
            dict(theta_m=0.2, Ax_g=1e-9, prob_cutoff=1e-3), dict(theta_m=0.0), dict(theta_m=0.2, n_maxSample=8),
            dict(theta_m=0.2, n_maxSample=1), dict(theta_m=0.2, save_mode=1, B0=5e13, omega_pul=2 * math.pi),
-           dict(theta_m=0.2, fix_time=0.3, t0_sample=0.3), dict(theta_m=0.2, ode_err=1e-8, reltol=1e-9)]
+           dict(theta_m=0.2, fix_time=0.3, t0_sample=0.3), dict(theta_m=0.2, ode_err=1e-8, reltol=1e-9),
+           dict(theta_m=0.2, bndry_lyr=0.5), dict(theta_m=0.6, bndry_lyr=0.8, omega_pul=3.0), dict(theta_m=0.2, bndry_lyr=0.5, isotropic=1)]
 
 
 @pytest.mark.parametrize("kw", _SWITCHES + _OTHERS, ids=lambda kw: ",".join(f"{k}={v}" for k, v in kw.items() if k != "theta_m" or len(kw) == 1))
@@ -292,3 +293,59 @@ def test_saved_trajectory_of_save_mode_3(oracle):
                 assert np.abs(t9[j[0], :3] - r5[:3]).max() <= 1e-12 * np.linalg.norm(r5[:3])
         seen.add(int(a["status"][i]))
     assert {0, 2} <= seen
+
+
+@pytest.mark.parametrize("kw", [dict(theta_m=0.2, bndry_lyr=0.5), dict(theta_m=0.6, bndry_lyr=0.8, omega_pul=3.0),
+                                dict(theta_m=0.2, bndry_lyr=0.5, isotropic=1), dict(theta_m=0.2, bndry_lyr=0.5, Mass_a=2e-5)])
+def test_boundary_layer_plasma_term_matches_oracle(oracle, kw):
+    """bndry_lyr > 0 (RT.jl:1155-1162; CLI flag Gen_Samples.jl:127-130): the boundary-layer term of ωp in the sampler condition,
+    the ray crossing condition, g_det, the conversion probability (value with the DEFAULT mass 1e-5 of MR.jl:99, gradient with
+    the run's mass, RT.jl:1427) and in du7 ONLY (RT.jl:88 vs 84-85), which makes u7 a genuinely integrated 7th component."""
+    p = ArtParams.default(**kw)
+    rng = np.random.default_rng(3)
+    n = 2048
+    u = np.zeros((n, 7))
+    u[:, 0] = 10.2 + 40 * rng.random(n)
+    u[:, 1] = 0.05 + 3.0 * rng.random(n)
+    u[:, 2] = -3 + 6 * rng.random(n)
+    u[:, 3] = rng.normal(size=n) * 0.5
+    u[:, 4] = rng.normal(size=n) * 0.5 * u[:, 0]
+    u[:, 5] = rng.normal(size=n) * 0.5 * u[:, 0] * np.sin(u[:, 1])
+    erg = np.full(n, 1.0000003 * p.Mass_a)
+    u[:, 6] = -erg * (1 + 1e-6 * rng.normal(size=n))
+    lnt = rng.uniform(-25, -4, n)
+    sp = np.full(n, 1, np.int32)
+    a, b = hc.rhs(p, sp, u, erg, lnt), oracle.rhs(p, sp, u, erg, lnt)
+    scale = np.abs(b[:, :6]).max(axis=1, keepdims=True) + 1e-300
+    assert (np.abs(a[:, :6] - b[:, :6]) / scale).max() < 1e-11
+    assert (np.abs(a[:, 6] - b[:, 6]) / np.abs(b[:, 6])).max() < 1e-9
+    # the term matters: du7 is no longer (Ω·erg/c_km)·du6
+    lin = p.omega_pul * erg / 2.99792e5 * b[:, 5]
+    assert np.median(np.abs(b[:, 6] - lin) / np.abs(b[:, 6])) > 1e-7
+    # sampler (a line that grazes r = rNS, where the term switches on, can keep or drop that root: ≤ 1 %)
+    U = rng.random((3000, 10))
+    sa, sb = hc.sample_from_uniforms(p, U), oracle.sample_from_uniforms(p, U)
+    same = (sa["accepted"] == sb["accepted"]) & (sa["n_cross"] == sb["n_cross"])
+    assert same.mean() > 0.99
+    m = (sb["accepted"] == 1) & same
+    assert np.abs(sa["x"] - sb["x"])[:, m].max() < 1e-9
+    # weights and conversion probability
+    s = oracle.sample(p, 7, 1, 800)
+    wa, wb = hc.weights(p, s["x"], s["v_loc"], s["v_inf"]), oracle.weights(p, s["x"], s["v_loc"], s["v_inf"])
+    for k in wb:
+        assert (np.abs(wa[k] - wb[k]) / np.abs(wb[k])).max() < 1e-11, k
+    w0 = oracle.weights(p.copy(bndry_lyr=-1.0), s["x"], s["v_loc"], s["v_inf"])
+    assert np.median(np.abs(w0["jac_gr"] - wb["jac_gr"]) / wb["jac_gr"]) > 1e-3   # g_det sees the term
+    for bs, kk in ((1, wb["k_init"]), (-1, -wb["k_init"])):
+        Pa, Pb = hc.conv_prob(p, s["x"], kk, wb["erg_inf"], bs), oracle.conv_prob(p, s["x"], kk, wb["erg_inf"], bs)
+        assert (np.abs(Pa - Pb) / Pb).max() < 1e-9
+    # rays: same outcomes; at tight tolerance the integrated u7 agrees
+    q = p.copy(reltol=1e-11, ode_err=1e-13)
+    n = 150
+    s = oracle.sample(q, 5, 1, n)
+    w = oracle.weights(q, s["x"], s["v_loc"], s["v_inf"])
+    args = (np.full(n, 1, np.int32), s["x"], w["k_init"], w["erg_inf"], np.zeros(n), -np.ones(n), 1, -1)
+    a, b = hc.propagate(q, *args), oracle.propagate(q, *args)
+    assert np.array_equal(a["status"], b["status"]) and np.array_equal(a["n_cross"], b["n_cross"])
+    dx = np.linalg.norm(a["x_f"] - b["x_f"], axis=0) / np.linalg.norm(b["x_f"], axis=0)
+    assert dx.max() < 1e-6 and (np.abs(a["u7_f"] - b["u7_f"]) / np.abs(b["u7_f"])).max() < 1e-6
