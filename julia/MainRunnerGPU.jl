@@ -65,15 +65,20 @@ function main_runner_tree(Mass_a, Ax_g, θm, ωPul, B0, rNS, Mass_NS, ωProp, Nt
     h = Ref{Ptr{Cvoid}}(C_NULL)
     art_check(ccall((:art_create, LIBART), Cint, (Ref{ArtParams}, Cint, Ref{Ptr{Cvoid}}), p, device, h))
     n_events = max(Ntajs - 1, 0)      # `while photon_trajs < desired_trajs`, photon_trajs starts at 1
-    saveMode > 2 && error("saveMode=3 (per-event tree_* text files) is not supported by the GPU path")
     ncols = saveMode > 1 ? 31 : (saveMode > 0 ? 29 : 13)
     cap = 3 * n_events + 1024
     rows = Matrix{Float64}(undef, ncols, cap)   # column-major ncols×cap == row-major cap×ncols for C
     n_rows = Ref{Int64}(0); f_inx = Ref{Int64}(0); tot_count = Ref{Int64}(0)
     GC.@preserve rows begin
-        art_check(ccall((:art_run, LIBART), Cint,
-                        (Ptr{Cvoid}, UInt64, Int64, Int64, Ptr{Cdouble}, Int64, Ref{Int64}, Ref{Int64}, Ref{Int64}, Ptr{Cvoid}),
-                        h[], UInt64(iseed), 1, n_events, rows, cap, n_rows, f_inx, tot_count, C_NULL), h[])
+        rc = ccall((:art_run, LIBART), Cint,
+                   (Ptr{Cvoid}, UInt64, Int64, Int64, Ptr{Cdouble}, Int64, Ref{Int64}, Ref{Int64}, Ref{Int64}, Ptr{Cvoid}),
+                   h[], UInt64(iseed), 1, n_events, rows, cap, n_rows, f_inx, tot_count, C_NULL)
+        if rc == -4 && n_rows[] > cap   # ART_ERR_CAPACITY: the reference appends rows without bound — enlarge and fetch again
+            cap = n_rows[]
+            rows = Matrix{Float64}(undef, ncols, cap)
+            rc = ccall((:art_fetch_rows, LIBART), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Int64, Ref{Int64}), h[], rows, cap, n_rows)
+        end
+        art_check(rc, h[])
         art_check(ccall((:art_normalize_rows, LIBART), Cint, (Ptr{Cdouble}, Int64, Cint, Int64),
                         rows, n_rows[], ncols, f_inx[]))           # saveAll[:, 8] ./= f_inx, MainRunner.jl:749
         if saveMode > 1   # clear-text final_* / event_* files, MainRunner.jl:435-444, 593-610, 689-701
@@ -84,6 +89,11 @@ function main_runner_tree(Mass_a, Ax_g, θm, ωPul, B0, rNS, Mass_NS, ωProp, Nt
             art_check(ccall((:art_write_event_files, LIBART), Cint,
                             (Cstring, Cstring, Ptr{Cdouble}, Int64, Ptr{Cdouble}, Int64),
                             dir_tag, file_tag, rows, n_rows[], events, n_ev[]))
+        end
+        if saveMode > 2   # one tree_<file_tag><event> file per event in saveNode's layout, MainRunner.jl:17-65, 574-578
+            n_files = Ref{Int64}(0)
+            art_check(ccall((:art_write_tree_files, LIBART), Cint, (Ptr{Cvoid}, Cstring, Cstring, Ref{Int64}),
+                            h[], dir_tag, file_tag, n_files), h[])
         end
     end
     ccall((:art_destroy, LIBART), Cvoid, (Ptr{Cvoid},), h[])
@@ -100,4 +110,34 @@ function main_runner_tree(Mass_a, Ax_g, θm, ωPul, B0, rNS, Mass_NS, ωProp, Nt
     fileN *= "_"*file_tag*".npy"
     npzwrite(fileN, saveAll)
     return tot_count[]
+end
+
+
+# One job over several GPUs, one Julia process per GPU (replaces runner_GR_tasks.sh:22-28 + Combine_Files.py): the events
+# 1 … Ntajs−1 of ONE seeded job are split in contiguous ranges over the ranks, every rank writes its own
+# tree_…_<file_tag><rank>.npy, and column 8 is normalised by the ALL-REDUCED f_inx (MainRunner.jl:749).  comm_id: the 128
+# bytes of art_comm_unique_id from rank 0, passed on by any means (a file, MPI, sockets).  Python mirror with the same
+# semantics: adiabatic_raytracer_b200/main_runner.py, main_runner_tree_multi (verified on 2 and 8 GPUs).
+function main_runner_tree_multi(p::ArtParams, Ntajs, rank, world, comm_id::Vector{UInt8}; iseed=1769, device=rank, n_costheta=16, n_phi=32)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    art_check(ccall((:art_create, LIBART), Cint, (Ref{ArtParams}, Cint, Ref{Ptr{Cvoid}}), p, device, h))
+    art_check(ccall((:art_hist_config, LIBART), Cint, (Ptr{Cvoid}, Int32, Int32), h[], n_costheta, n_phi), h[])
+    world > 1 && art_check(ccall((:art_comm_init, LIBART), Cint, (Ptr{Cvoid}, Int32, Int32, Ptr{UInt8}), h[], world, rank, comm_id), h[])
+    n_total = max(Ntajs - 1, 0)
+    base, rem = divrem(n_total, world)
+    first = 1 + rank * base + min(rank, rem); count = base + (rank < rem ? 1 : 0)
+    n_rows = Ref{Int64}(0); f_inx = Ref{Int64}(0); tot_count = Ref{Int64}(0)
+    art_check(ccall((:art_run_device, LIBART), Cint, (Ptr{Cvoid}, UInt64, Int64, Int64, Ref{Int64}, Ref{Int64}, Ref{Int64}, Ptr{Cvoid}),
+                    h[], UInt64(iseed), first, count, n_rows, f_inx, tot_count, C_NULL), h[])
+    art_check(ccall((:art_comm_allreduce_hist, LIBART), Cint, (Ptr{Cvoid},), h[]), h[])       # the only collective
+    len = ccall((:art_hist_len, LIBART), Int64, (Ptr{Cvoid},), h[])
+    hist = zeros(len)
+    art_check(ccall((:art_hist_get_global, LIBART), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Int64), h[], hist, len), h[])
+    f_inx_total = Int64(hist[end-7])                                                          # trailing counters: f_inx, n_rows, n_events, …
+    ncols = p.save_mode > 1 ? 31 : (p.save_mode > 0 ? 29 : 13)
+    rows = Matrix{Float64}(undef, ncols, max(n_rows[], 1))
+    art_check(ccall((:art_fetch_rows, LIBART), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Int64, Ref{Int64}), h[], rows, size(rows, 2), n_rows), h[])
+    art_check(ccall((:art_normalize_rows, LIBART), Cint, (Ptr{Cdouble}, Int64, Cint, Int64), rows, n_rows[], ncols, f_inx_total))
+    ccall((:art_destroy, LIBART), Cvoid, (Ptr{Cvoid},), h[])
+    return permutedims(rows[1:min(ncols, 29), 1:n_rows[]]), hist, tot_count[]                 # caller: npzwrite(<name>_<tag><rank>.npy, …)
 end
