@@ -258,7 +258,7 @@ extern "C" int hc_trace_ray(const art_params* p, int32_t species, const double* 
 // whose literal scan holds a point of another sign, [3] steps certified "inside the start box", [4] of those, steps with
 // a scan point outside the box.
 template <int IG>
-static void certify_ray(const DevParams& P, const RayIn& in, double* rec, int cap, long long counts[5]) {
+static void certify_ray(const DevParams& P, const RayIn& in, double* rec, int cap, long long counts[12]) {
   Ray R;
   double kbuf[K_ROWS + K_PARK + K_XROWS], sbuf[SEG_MAX];
   KStore K{kbuf, 1};
@@ -282,7 +282,17 @@ static void certify_ray(const DevParams& P, const RayIn& in, double* rec, int ca
       const unsigned long long other = cs < 0 ? (m.pos | m.zero) : (m.neg | m.zero);
       if (other) counts[2]++;
     }
-    if (R.n_cross == 0 && R.template step_in_start_box<IG>(K, s0, R.box_m)) {
+    const bool inbox = R.n_cross == 0 && R.template step_in_start_box<IG>(K, s0, R.box_m);
+    if (cs == 0 && !inbox) {  // what the scan kernel gets: uniformly negative / positive / mixed, and where
+      const unsigned long long all = m.pos | m.neg | m.zero;
+      if (m.neg == all && all) counts[5]++;
+      else if (m.pos == all && all) counts[6]++;
+      else counts[7]++;
+      if (R.u[0] > P.Rcut) counts[8]++;          // starts beyond the far-field radius
+      if (R.h < 1e-3) counts[9]++;               // tiny steps (kink bursts)
+      if (R.event_last) counts[10]++;
+    }
+    if (inbox) {
       counts[3]++;
       bool all_in = true;
       for (int i = 1; i < M; ++i) all_in = all_in && R.template in_start_box<IG>(P, D, seg_theta(P, i));
@@ -297,7 +307,7 @@ extern "C" int hc_certificates(const art_params* p, int64_t n, const int32_t* sp
   DevParams P;
   int rc = dev(p, P);
   if (rc) return rc;
-  for (int k = 0; k < 5; ++k) counts[k] = 0;
+  for (int k = 0; k < 12; ++k) counts[k] = 0;
   std::vector<double> rec((size_t)p->cross_cap * 8);
   for (int64_t i = 0; i < n; ++i) {
     RayIn in;

@@ -138,7 +138,7 @@ def certificates(p, species, x0, k0, erg, max_crossings=-1):
     """Certified-sign shortcuts vs the literal scan: [accepted steps, certified, contradicted, in-box, in-box contradicted]."""
     x0 = np.ascontiguousarray(x0, np.float64)
     n = x0.shape[1]
-    counts = np.zeros(5, np.int64)
+    counts = np.zeros(12, np.int64)
     _chk(lib().hc_certificates(C.byref(p), n, np.ascontiguousarray(species, np.int32).ctypes.data_as(C.c_void_p),
                                x0.ctypes.data_as(C.c_void_p), np.ascontiguousarray(k0, np.float64).ctypes.data_as(C.c_void_p),
                                np.ascontiguousarray(erg, np.float64).ctypes.data_as(C.c_void_p), max_crossings,
