@@ -288,9 +288,27 @@ static void certify_ray(const DevParams& P, const RayIn& in, double* rec, int ca
       if (m.neg == all && all) counts[5]++;
       else if (m.pos == all && all) counts[6]++;
       else counts[7]++;
-      if (R.u[0] > P.Rcut) counts[8]++;          // starts beyond the far-field radius
-      if (R.h < 1e-3) counts[9]++;               // tiny steps (kink bursts)
       if (R.event_last) counts[10]++;
+      {  // would a momentum-free bound do?  pointwise dark (Q|bz| < m_a² r³) / lit (Q|bz| g^rr > E² r³) at every scan point
+        bool dark = true, lit = true;
+        for (int i = 1; i < M; ++i) {
+          double w[6];
+          const double th = seg_theta(P, i);
+          seg_state<IG>(D, th, w);
+          const double E = D(Seg<IG>::U70) + D(Seg<IG>::FAC7) * (w[5] - D(Seg<IG>::U60));
+          const double t = exp(D(Seg<IG>::S) + th * D(Seg<IG>::H));
+          const double ps = w[2] - P.Omega * t;
+          const double bz = fabs(P.cm * (3.0 * cos(w[1]) * cos(w[1]) - 1.0) + 3.0 * P.sm * sin(w[1]) * cos(w[1]) * cos(ps));
+          const double r3 = w[0] * w[0] * w[0];
+          dark = dark && P.Q * bz < P.ma2 * r3;
+          lit = lit && P.Q * bz * (1.0 - P.rs_ray / w[0]) > E * E * r3;
+        }
+        if (dark || lit) {
+          counts[11]++;
+          if (R.template step_sign<IG>(P, K, exp(R.s_new), 0.0) != 0) counts[8]++;  // slack is what stops it
+          else if (R.u[0] < P.rNS || R.un[0] < P.rNS) counts[9]++;
+        }
+      }
     }
     if (inbox) {
       counts[3]++;
