@@ -115,16 +115,19 @@ struct Lane {
   cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr;
   cudaEvent_t ev_main = nullptr, ev_side = nullptr, ev_samp = nullptr;
   DBuf samples, tstate, stacks, q0, rout, rec, ctr;
+  DBuf carry[2];                          // sampler carry-over lists (k_sample_events)
+  unsigned long long* hctr = nullptr;     // page-locked copy of the sampler's counters, valid once ev_samp has completed
   DBuf slot_event, slot_parts, ring;
   DBuf wf_hot, wf_cold, wf_seg, wf_need, wf_neg, wf_pend, wf_sign, wf_act[4], wf_roots[2], wf_fin[2], wf_ctr;
   float ms_sampler = 0, ms_weights = 0, ms_tracer = 0;
   float ms_k[3] = {0, 0, 0};  // ART_TIME_KERNELS: stage kernel, scan, detect
   long long n_blocks = 0;
   void release() {
-    DBuf* all[] = {&samples, &tstate, &stacks, &q0, &rout, &rec, &ctr, &slot_event, &slot_parts, &ring, &wf_hot, &wf_cold, &wf_seg,
+    DBuf* all[] = {&samples, &tstate, &stacks, &q0, &rout, &rec, &ctr, &carry[0], &carry[1], &slot_event, &slot_parts, &ring, &wf_hot, &wf_cold, &wf_seg,
                    &wf_need, &wf_neg, &wf_pend, &wf_sign, &wf_act[0], &wf_act[1], &wf_act[2], &wf_act[3], &wf_roots[0], &wf_roots[1],
                    &wf_fin[0], &wf_fin[1], &wf_ctr};
     for (DBuf* b : all) b->release();
+    if (hctr) { cudaFreeHost(hctr); hctr = nullptr; }
     for (cudaStream_t* st : {&stream, &stream2, &stream3})
       if (*st) { cudaStreamDestroy(*st); *st = nullptr; }
     for (cudaEvent_t* e : {&ev_main, &ev_side, &ev_samp})
@@ -227,6 +230,12 @@ struct PoolJob {
   // known to be complete, [0, consumed) have been injected into the loop.  The sampler always works on whole blocks —
   // small launches leave its persistent threads one or two events each and cost three times as much per event.
   long long block = 0, fifo = 0, produced = 0, sampled = 0, consumed = 0;
+  // An event needs a geometric number of attempts; a launch does not wait for its unluckiest events: once its work queue is
+  // empty, failed attempts are carried over to the next launch (k_sample_events).  So `produced` counts the fresh events
+  // handed out, `sampled` / `consumed` count completed samples in the ring (in completion order, each with its event index),
+  // and carry_n events wait in carry list carry_cur.  The launch that takes the last fresh events draws everything to the end.
+  long long carry_n = 0;
+  int carry_cur = 0;
   bool busy = false;               // a sampler launch is in flight
   int m = 0;                       // events the next side pass injects (0: none)
   unsigned long long* gctr = nullptr;
@@ -289,25 +298,32 @@ int wf_loop(art_handle* h, Lane& L, WfPool W, long long n_act0, RayOut* out, dou
         const bool must_wait = n_act == 0 && job->sampled == job->consumed;
         const cudaError_t q = must_wait ? cudaEventSynchronize(L.ev_samp) : cudaEventQuery(L.ev_samp);
         if (q == cudaSuccess) {
-          job->sampled = job->produced;
+          job->sampled += (long long)L.hctr[SC_OUT];
+          job->carry_n = (long long)L.hctr[SC_CARRY];
+          job->carry_cur ^= 1;
           job->busy = false;
         } else if (q != cudaErrorNotReady) {
           return fail(h, ART_ERR_CUDA, std::string("sampler: ") + cudaGetErrorString(q));
         }
       }
-      if (!job->busy && job->produced < job->n_events && job->produced - job->consumed + job->block <= job->fifo) {
-        const long long m = std::min(job->block, job->n_events - job->produced);
+      const long long m_next = std::min(job->block, job->n_events - job->produced);
+      if (!job->busy && (m_next > 0 || job->carry_n > 0) && job->sampled - job->consumed + m_next + job->carry_n <= job->fifo) {
+        const long long m = m_next;
+        const int drain = job->produced + m >= job->n_events;
         cudaEvent_t ea = evg.make(), eb = evg.make();
         if (!ea || !eb) return fail(h, ART_ERR_CUDA, "cudaEventCreate");
         if (side) CU(cudaStreamWaitEvent(s3, L.ev_side, 0));  // (every injection enqueued so far has read its part of the FIFO)
         CU(cudaMemsetAsync(L.ctr.p, 0, 64, s3));
         CU(cudaEventRecord(ea, s3));
-        const int blocks = (int)std::min<long long>(h->blocks_sample, (m + SAMPLE_THREADS - 1) / SAMPLE_THREADS);
+        const int blocks = (int)std::min<long long>(h->blocks_sample, (m + job->carry_n + SAMPLE_THREADS - 1) / SAMPLE_THREADS);
         k_sample_events<<<blocks, SAMPLE_THREADS, 0, s3>>>(h->dp, job->seed, job->ids, job->produced, m,
-                                                           L.samples.as<EventSample>() + job->produced % job->fifo,
-                                                           L.ctr.as<unsigned long long>(), stats, job->gctr);
+                                                                 L.carry[job->carry_cur].as<SampleCarry>(), job->carry_n,
+                                                                 L.carry[job->carry_cur ^ 1].as<SampleCarry>(), 1, drain,
+                                                                 L.samples.as<EventSample>(), job->fifo, job->sampled,
+                                                                 L.ctr.as<unsigned long long>(), stats, job->gctr);
         CU(cudaGetLastError());
         CU(cudaEventRecord(eb, s3));
+        CU(cudaMemcpyAsync(L.hctr, L.ctr.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s3));
         CU(cudaEventRecord(L.ev_samp, s3));
         job->samp_ev.emplace_back(ea, eb);
         job->n_blocks++;
@@ -345,7 +361,7 @@ int wf_loop(art_handle* h, Lane& L, WfPool W, long long n_act0, RayOut* out, dou
       h->launches += 2;
       if (job && job->m > 0) {
         k_wf_inject<IG><<<grid(2LL * job->m, WF_THREADS), WF_THREADS, 0, s2>>>(h->dp, W, *tree, k, L.samples.as<EventSample>(),
-                                                                               (int)job->fifo, job->m, (int)job->consumed, job->head, rec,
+                                                                               job->fifo, job->m, job->consumed, job->head, rec,
                                                                                rec_cap, stats);
         h->launches++;
         job->head += (unsigned long long)job->m;
@@ -564,8 +580,9 @@ int art_sample(art_handle* h, uint64_t seed, int64_t first_event, int64_t n, dou
   CU(L.ctr.ensure(64));
   CU(cudaMemsetAsync(L.ctr.p, 0, 64, h->stream));
   const int blocks = (int)std::min<long long>(h->blocks_sample, (n + SAMPLE_THREADS - 1) / SAMPLE_THREADS);
-  k_sample_events<<<blocks, SAMPLE_THREADS, 0, h->stream>>>(h->dp, seed, EventIds{first_event, n, n}, 0, n, L.samples.as<EventSample>(),
-                                                            L.ctr.as<unsigned long long>(), nullptr, nullptr);
+  k_sample_events<<<blocks, SAMPLE_THREADS, 0, h->stream>>>(h->dp, seed, EventIds{first_event, n, n}, 0, n, nullptr, 0, nullptr, 0, 1,
+                                                                   L.samples.as<EventSample>(), n, 0, L.ctr.as<unsigned long long>(),
+                                                                   nullptr, nullptr);
   CU(cudaGetLastError());
   std::vector<EventSample> host((size_t)n);
   CU(cudaMemcpyAsync(host.data(), L.samples.p, n * sizeof(EventSample), cudaMemcpyDeviceToHost, h->stream));
@@ -751,7 +768,10 @@ static int run_pool(art_handle* h, Lane& L, uint64_t seed, int64_t first_event, 
   cudaStream_t st = L.stream;
   // sampler blocks: half a pool, at least 2^16 events (smaller launches are inefficient), never more than the call
   const long long block = std::min<long long>(n_events, std::max<long long>(S / 2, h->sample_block));
-  CU(L.samples.ensure(2 * block * sizeof(EventSample)));
+  const long long n_lanes = (long long)h->blocks_sample * SAMPLE_THREADS;  // (a launch carries at most one event per lane)
+  CU(L.samples.ensure((2 * block + n_lanes) * sizeof(EventSample)));
+  for (int c = 0; c < 2; ++c) CU(L.carry[c].ensure(n_lanes * sizeof(SampleCarry)));
+  if (!L.hctr) CU(cudaHostAlloc((void**)&L.hctr, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
   CU(L.tstate.ensure(S * sizeof(TreeState)));
   CU(L.stacks.ensure((size_t)S * stack_stride * sizeof(TreeNode)));
   CU(L.rec.ensure((size_t)2 * S * cap * 8 * sizeof(double)));
@@ -779,7 +799,7 @@ static int run_pool(art_handle* h, Lane& L, uint64_t seed, int64_t first_event, 
   }
   PoolJob job;
   job.seed = seed; job.ids = T.ids; job.n_events = n_events; job.S = S; job.gctr = gctr + 0;
-  job.block = block; job.fifo = 2 * block;
+  job.block = block; job.fifo = 2 * block + n_lanes;
   cudaEvent_t t0 = evg.make(), t1 = evg.make();
   if (!t0 || !t1) return fail(h, ART_ERR_CUDA, "cudaEventCreate");
   CU(cudaEventRecord(t0, st));

@@ -60,6 +60,13 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 struct EventSample {
   double x[3], vloc[3], vinf[3];
   int n_cross, n_failed;
+  long long e;  // index of the event in the call (compact output: events complete out of order)
+};
+
+// An event whose attempt failed when the launch had no fresh work left: the next launch goes on with attempt `attempt`.
+struct SampleCarry {
+  long long idx;
+  unsigned attempt, pad_;
 };
 
 #ifndef ART_SAMPLE_MINBLOCKS
@@ -72,62 +79,94 @@ struct EventIds {
   __host__ __device__ long long id(long long e) const { return first + (e / bsize) * bstride + e % bsize; }
 };
 
-// events e0 … e0 + n − 1 of the call; sample of event e0 + i goes to out[i]
+// Work counters of one sampler launch (zeroed before it)
+enum { SC_HEAD = 0, SC_OUT = 1, SC_CARRY = 2 };
+
+// One launch works through n_carry carried events (carry_in) and then the fresh events e0 … e0 + n − 1 of the call.
+//   compact = 0 (art_sample): the sample of event e0 + i goes to out[i]; every event is drawn until it is accepted.
+//   compact = 1 (fused pipeline): accepted samples are APPENDED to the ring `out` (ring entries, first free position
+//   out_base) in completion order, each carrying its event index.  An event needs a geometric number of attempts (≈ 4.6 on
+//   average, 50 for the unluckiest of 10⁵), one after the other: a launch that drew every event to the end spent most of its
+//   warp time on a long tail of warps with one or two live lanes (12.9 of 32 lanes per instruction, profiles/r02_*).  So
+//   once the work queue is empty, an event whose attempt fails is handed to carry_out instead and the launch ends within
+//   one attempt; the next launch starts with the carried events.  `drain` (last launch of a job) switches that off.
+// Attempt j of event e draws from the Philox stream (seed, id(e), j) wherever and whenever it runs: same samples.
+// ONE instantiation and ONE call site of Sampler::begin serve both modes and every attempt, carried or not: the bits of a
+// sample do not depend on where its attempt ran.
 __global__ void __launch_bounds__(SAMPLE_THREADS, ART_SAMPLE_MINBLOCKS)
 k_sample_events(const __grid_constant__ DevParams P, unsigned long long seed, EventIds ids, long long e0, long long n,
-                EventSample* __restrict__ out, unsigned long long* head, DevStats* stats,
-                unsigned long long* n_failed_total) {
+                const SampleCarry* __restrict__ carry_in, long long n_carry, SampleCarry* __restrict__ carry_out, int compact,
+                int drain, EventSample* __restrict__ out, long long ring, long long out_base, unsigned long long* ctr,
+                DevStats* stats, unsigned long long* n_failed_total) {
   __shared__ double taus_sm[SAMP_KEEP * SAMPLE_THREADS];
   Sampler S;
   S.taus = taus_sm + threadIdx.x;
   S.taus_stride = SAMPLE_THREADS;
   S.done = true;
-  bool have = false, exhausted = false;
+  bool have = false, exhausted = false, fresh = false;  // fresh: (idx, attempt) name an attempt that has not begun yet
   long long idx = -1;
   unsigned attempt = 0;
   double u_idx = 0.0;
   unsigned long long c_att = 0, c_cond = 0, c_fail = 0;
+  const long long n_total = n_carry + n;
+  const bool may_carry = compact && !drain;
   for (;;) {
-    const long long got = warp_pop(head, !have && !exhausted);
+    const long long got = warp_pop(ctr + SC_HEAD, !have && !exhausted);
     if (!have && !exhausted) {
-      if (got >= 0 && got < n) {
-        idx = got;
-        attempt = 0;
-        double U[10];
-        sampler_uniforms(seed, (unsigned long long)ids.id(e0 + idx), attempt, U);
-        u_idx = U[9];
-        S.begin(P, U);
+      if (got >= 0 && got < n_total) {
+        if (got < n_carry) {
+          idx = carry_in[got].idx;
+          attempt = carry_in[got].attempt;
+        } else {
+          idx = e0 + (got - n_carry);
+          attempt = 0;
+        }
         have = true;
+        fresh = true;
       } else {
         exhausted = true;
       }
     }
+    if (fresh) {
+      double U[10];
+      sampler_uniforms(seed, (unsigned long long)ids.id(idx), attempt, U);
+      u_idx = U[9];
+      S.begin(P, U);
+      fresh = false;
+    }
+    const bool queue_empty = __any_sync(FULL, exhausted);
     if (__ballot_sync(FULL, have) == 0) break;
     // one trip = M−1 condition evaluations for every lane (art_sampler.cuh)
     S.trip(P, have);
-    if (have) {
-      if (S.done) {
-        SampleResult R;
-        S.finish(P, u_idx, R);
-        c_att++;
-        c_cond += R.n_cond;
-        if (R.accepted) {
-          EventSample e;
-          for (int c = 0; c < 3; ++c) { e.x[c] = R.x[c]; e.vloc[c] = R.vloc[c]; e.vinf[c] = R.vinf[c]; }
-          e.n_cross = R.n_cross;
-          e.n_failed = (int)attempt;
-          c_fail += attempt;
-          out[idx] = e;
-          have = false;
-        } else {  // MainRunner.jl:463-494: try again (f_inx counts the failure)
-          attempt++;
-          double U[10];
-          sampler_uniforms(seed, (unsigned long long)ids.id(e0 + idx), attempt, U);
-          u_idx = U[9];
-          S.begin(P, U);
-        }
+    bool emit = false, carry = false;
+    EventSample es;
+    if (have && S.done) {
+      SampleResult R;
+      S.finish(P, u_idx, R);
+      c_att++;
+      c_cond += R.n_cond;
+      if (R.accepted) {
+        for (int c = 0; c < 3; ++c) { es.x[c] = R.x[c]; es.vloc[c] = R.vloc[c]; es.vinf[c] = R.vinf[c]; }
+        es.n_cross = R.n_cross;
+        es.n_failed = (int)attempt;
+        es.e = idx;
+        c_fail += attempt;
+        emit = true;
+      } else {  // MainRunner.jl:463-494: try again (f_inx counts the failure)
+        attempt++;
+        if (may_carry && queue_empty) carry = true;
+        else fresh = true;
       }
     }
+    if (compact) {
+      const long long po = warp_pop(ctr + SC_OUT, emit);
+      if (emit) out[(out_base + po) % ring] = es;
+      const long long pc = warp_pop(ctr + SC_CARRY, carry);
+      if (carry) carry_out[pc] = SampleCarry{idx, attempt, 0u};
+    } else if (emit) {
+      out[idx - e0] = es;
+    }
+    if (emit || carry) have = false;
   }
   c_att = warp_sum(c_att);
   c_cond = warp_sum(c_cond);

@@ -731,15 +731,15 @@ k_wf_tree(const __grid_constant__ DevParams P, WfPool W, WfTree T, int k, double
 }
 
 // ---- injection of freshly sampled events into free slots (side pass of iteration k) -------------------
-// Event j of the block (index e0 + j in the call; its sample sits at position (e0 + j) % fifo of the sample FIFO the
-// sampler stream fills ahead of the loop) takes the slot ring[(head + j) % S]: per-sample weights
+// Sample j of the injection (position (c0 + j) % fifo of the sample ring the sampler stream fills ahead of the loop, in
+// completion order; the record names its event) takes the slot ring[(head + j) % S]: per-sample weights
 // (MainRunner.jl:498-557), first tree node, and the IC transform / first right-hand side / initial step size /
 // starting sign of its two rays — the back-traced axion in ray slot s (MR.jl:581-589: −k, t = 0, Δω = −1, all
 // crossings) and the forward photon in ray slot S + s (MR.jl:653-657).  Both join iteration k + 1.
 template <int IG>
 __global__ void __launch_bounds__(WF_THREADS)
-k_wf_inject(const __grid_constant__ DevParams P, WfPool W, WfTree T, int k, const EventSample* __restrict__ samples, int fifo, int m,
-            int e0, unsigned long long head, double* __restrict__ rec, int rec_cap, DevStats* stats) {
+k_wf_inject(const __grid_constant__ DevParams P, WfPool W, WfTree T, int k, const EventSample* __restrict__ samples, long long fifo, int m,
+            long long c0, unsigned long long head, double* __restrict__ rec, int rec_cap, DevStats* stats) {
   unsigned long long n_start = 0;
   const long long nthreads = (long long)gridDim.x * blockDim.x;
   const long long n2 = 2LL * m;
@@ -756,8 +756,8 @@ k_wf_inject(const __grid_constant__ DevParams P, WfPool W, WfTree T, int k, cons
       const bool fwd = t >= m;
       const int j = (int)(fwd ? t - m : t);
       const int slot = T.ring[(head + (unsigned long long)j) % (unsigned long long)T.n_slots];
-      const int e = e0 + j;
-      const EventSample smp = samples[(e0 + j) % fifo];
+      const EventSample smp = samples[(c0 + j) % fifo];
+      const int e = (int)smp.e;
       const SampleWeights Wt = sample_weights(P, smp.x, smp.vloc, smp.vinf);
       RayIn in;
       for (int c = 0; c < 3; ++c) { in.x0[c] = smp.x[c]; in.k0[c] = fwd ? Wt.k_init[c] : -Wt.k_init[c]; }

@@ -279,8 +279,12 @@ static void certify_ray(const DevParams& P, const RayIn& in, double* rec, int ca
     const int cs = R.template step_all_far<IG>(P, K) ? -1 : R.template step_sign<IG>(P, K, exp(R.s_new));
     if (cs != 0) {
       counts[1]++;
-      const unsigned long long other = cs < 0 ? (m.pos | m.zero) : (m.neg | m.zero);
-      if (other) counts[2]++;
+      // every scanned point must carry the certified sign: no other sign, no zero, no NaN (a NaN end point would leave the
+      // literal path with reference sign 0 instead of cs)
+      unsigned long long want = 0ull;
+      for (int i = R.event_last ? 0 : 1; i < M; ++i) want |= 1ull << i;
+      const unsigned long long got = cs < 0 ? m.neg : m.pos;
+      if (got != want) counts[2]++;
     }
     const bool inbox = R.n_cross == 0 && R.template step_in_start_box<IG>(K, s0, R.box_m);
     if (cs == 0 && !inbox) {  // what the scan kernel gets: uniformly negative / positive / mixed, and where

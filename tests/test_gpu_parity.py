@@ -189,7 +189,8 @@ def test_propagate_matches_oracle(lib, oracle, kw, integrator):
         else:
             steps = same  # Vern6: see the module doc
             # the device skips the three dense-output stages of steps with a certified sign: fewer RHS than the literal oracle
-            assert 0.8 * b["counters"][:, 2].mean() < a["counters"][:, 2].mean() < b["counters"][:, 2].mean()
+            # (at least the 8 new stages of every attempt against the oracle's 8 + 3 per accepted step: ratio > 8/11)
+            assert 0.73 * b["counters"][:, 2].mean() < a["counters"][:, 2].mean() < b["counters"][:, 2].mean()
         dx = np.linalg.norm(a["x_f"] - b["x_f"], axis=0) / np.linalg.norm(b["x_f"], axis=0)
         dk = np.linalg.norm(a["k_f"] - b["k_f"], axis=0) / np.linalg.norm(b["k_f"], axis=0)
         if sp == 1:
@@ -533,7 +534,7 @@ def test_pinned_row_buffer_and_evaluation_counters(lib):
         assert np.array_equal(a["rows"], b["rows"])
     st = a["stats"]
     assert 0 < st["n_cond_eval"] < st["n_cond"]
-    assert st["n_cond_eval"] > 0.2 * st["n_cond"]
+    assert st["n_cond_eval"] > 0.1 * st["n_cond"]  # (18 % with the dark / lit / in-star / far-field certificates)
     h.close()
 
 
