@@ -35,6 +35,12 @@ inline int make_dev_params(const art_params& p, DevParams& d, std::string& err) 
     err = "numerics parameter out of range";
     return ART_ERR_ARG;
   }
+  if (p.metric_interior_radius != 10.0) {
+    // g_schwartz's kwarg rNS = 10.0 (RT.jl:455) is never overridden on this path (only g_det passes the real rNS, which the
+    // library does by itself): the field records the quirk, another value has no reference behaviour and no oracle
+    err = "metric_interior_radius must be 10.0 (the reference's fixed g_schwartz switch radius)";
+    return ART_ERR_ARG;
+  }
   d.cm = cos(p.theta_m);
   d.sm = sin(p.theta_m);
   d.Omega = p.omega_pul;

@@ -162,7 +162,7 @@ struct Sampler {
   // Certified sign of the condition on the WHOLE segment [t0, t0 + L] of the line, when the momentum is not
   // needed to know it (cond(): F = base·(ωp² − m_a²) − ωp²·g^rr NrmSq·ww N², 0 ≤ N² ≤ ww D):
   //   ωp² < m_a² everywhere on the segment          ⇒ F < 0  ("dark"), return −1
-  //   ωp² (1 − rs/r) > E² everywhere, outside the star ⇒ F > 0  ("lit"),  return +1
+  //   ωp² (1 − rs/r) > E² everywhere, outside the star ⇒ F > 0  ("lit"),  return +1  (inside the star: see below)
   // Rigorous interval bound: on the segment |x − x_mid| ≤ L/2, so r ∈ [r_mid − L/2, r_mid + L/2] and, for a
   // unit vector n, n·x ∈ [n·x_mid ± (L/2)|n·â|]; hence intervals for m̂·r̂ and ẑ·r̂, for their product, and for
   // b_z = 3(m̂·r̂)(ẑ·r̂) − cosθm.  A direction-aware refinement of the Rcut sphere: only the steps that straddle
@@ -187,15 +187,27 @@ struct Sampler {
     if (P.Q * bzmax * ilo * ilo * ilo < P.ma2 * (1.0 - 1e-9)) return -1;
     const double bzmin = (b0 > 0.0) ? b0 : ((b1 < 0.0) ? -b1 : 0.0);
     if (!P.thick) return (P.Q * bzmin * ihi * ihi * ihi > P.ma2 * (1.0 + 1e-9)) ? 1 : 0;  // ωp > m_a on the whole segment
-    if (!P.isotropic && rlo > P.rNS && rlo > P.r_int &&
-        P.Q * bzmin * ihi * ihi * ihi * (1.0 - P.rs_real * ilo) > E2 * (1.0 + 1e-9))
-      return 1;
+    if (P.isotropic) return 0;
+    if (rlo > P.rNS && rlo > P.r_int) return (P.Q * bzmin * ihi * ihi * ihi * (1.0 - P.rs_real * ilo) > E2 * (1.0 + 1e-9)) ? 1 : 0;
+    // wholly inside the star (a line through it spends up to 40 steps there): the plasma frequency continues inwards
+    // (no zeroIn in the sampler) and dwarfs m_a except near b_z = 0.  cond(): N² ≤ ww D (Cauchy–Schwarz on the covariant
+    // components, any metric branch), so F ≥ ww D [ωp² (E² − g^rr NrmSq·ww) − m_a² E²]; in the interior metric −g^tt grows
+    // and g^rr falls with r, hence g^rr NrmSq·ww ≤ g^rr(r_lo) (−E² g^tt(r_hi) − m_a²), and NrmSq > 0 because −g^tt ≥ 1.
+    const double rhi = rm + hm;
+    if (rhi < P.rNS && rhi < P.r_int) {
+      const double gn_max = metric(rlo, P.rs_real, P.r_int).grr * (-E2 * metric(rhi, P.rs_real, P.r_int).gtt - P.ma2);
+      const double room = E2 - gn_max;
+      return (room > 0.0 && P.Q * bzmin * ihi * ihi * ihi * room > P.ma2 * E2 * (1.0 + 1e-9)) ? 1 : 0;
+    }
     return 0;
   }
 
   // Steps whose sign is certified and agrees with the reference sign hold no event: all their grid points
-  // have that sign.  They are passed over in blocks (16, 4, 1 steps; at most 42 per call), with the
-  // reference's own accumulation of tau.  Called where a step ends without an event.
+  // have that sign.  They are passed over in blocks of 16, 4 or 1 steps — greedily, until a single step cannot be
+  // certified: the block shrinks on failure and grows back after four successes in a row — with the reference's own
+  // accumulation of tau.  Called where a step ends without an event.  (Round 2, first form: six fixed passes
+  // 16-16-4-4-1-1, at most 42 steps per call; where long blocks could not be certified every third or eleventh step of a
+  // dark stretch was scanned although its own certificate held — a third of all scan trips, measured on host attempts.)
   ART_HD void skip_certified_steps(const DevParams& P) {
 #if defined(ART_NO_DARK_SKIP)
     return;
@@ -203,19 +215,27 @@ struct Sampler {
     if (done || mode != SCAN) return;
     const double lim = fmin(P.T_samp, tau_out);
     bool any = false;
+    int blk = 16, streak = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-    for (int pass = 0; pass < 6; ++pass) {
-      const int blk = pass < 2 ? 16 : (pass < 4 ? 4 : 1);
+    for (int pass = 0; pass < 96; ++pass) {
       const double L = (double)blk * P.samp_dt;
-      if (tau + L < lim) {
-        const int sg = seg_sign(P, tau, L);
-        if (sg != 0 && sgn_prev * sg >= 0) {
-          for (int q = 0; q < blk; ++q) tau += P.samp_dt;
-          sgn_prev = sg;
-          any = true;
+      int sg = 0;
+      if (tau + L < lim) sg = seg_sign(P, tau, L);
+      if (sg != 0 && sgn_prev * sg >= 0) {
+        for (int q = 0; q < blk; ++q) tau += P.samp_dt;
+        sgn_prev = sg;
+        any = true;
+        if (++streak >= 4 && blk < 16) {
+          blk <<= 2;
+          streak = 0;
         }
+      } else if (blk > 1) {
+        blk >>= 2;
+        streak = 0;
+      } else {
+        break;
       }
     }
     if (any) next_step(P);

@@ -88,7 +88,8 @@ typedef struct art_params {
                          the reference hard-wires 0 (RT.jl:1480, MR.jl:74); phase-resolved
                          runs (BASELINE config 4) set 2π j/(64 ωPul)                       */
   double metric_interior_radius; /* g_schwartz kwarg rNS=10.0 that no caller overrides
-                                    (RT.jl:455) — quirk kept, see SURVEY §8 a5             */
+                                    (RT.jl:455) — quirk kept; must be 10.0
+                                    (any other value is refused with ART_ERR_ARG)          */
   double sampler_dt;  /* Euler march step of the surface sampler [km], RT.jl:1613 = 0.5     */
   double dtmin;       /* RT.jl:384 = 1e-13 (forced)                                         */
   int32_t flat;          /* Gen_Samples.jl:165 = false ("mixed" flat mode)       */

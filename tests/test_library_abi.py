@@ -83,7 +83,7 @@ def test_unsupported_switches_fail_loudly(L):
     switches this build does not implement are refused with ART_ERR_ARG, the implemented ones are accepted."""
     from adiabatic_raytracer_b200 import lib
     for kw in (dict(bndry_lyr=0.5, melrose=0), dict(bndry_lyr=0.5, integrator=1), dict(n_maxSample=9), dict(integrator=7),
-               dict(interp_points_ray=65), dict(cross_cap=0)):
+               dict(interp_points_ray=65), dict(cross_cap=0), dict(metric_interior_radius=12.0)):
         rc, _ = lib.max_radius(ArtParams.default(theta_m=0.2, **kw))
         assert rc == -1, kw
     for kw in (dict(melrose=0), dict(thick_surface=0), dict(isotropic=1), dict(flat=1), dict(integrator=1), dict(integrator=0),
