@@ -49,8 +49,11 @@ struct Sampler {
   // mode: what the attempt evaluates next — SCAN: the M−1 grid points of one Euler step (a whole trip());
   // ROOT: one root-finder iterate; NUDGE: the reference sign 1 % into the step after an event; INIT: the sign at
   // the first point of the march
-  enum { SCAN = 0, ROOT = 1, NUDGE = 2, INIT = 3 };
+  // SKIP: the attempt is passing over certified steps and has not come to one it must scan yet (skip_certified_steps
+  // does a bounded number of tests per trip; the lane idles through the evaluation slots of the trip)
+  enum { SCAN = 0, ROOT = 1, NUDGE = 2, INIT = 3, SKIP = 4 };
   int sgn_prev, side, it, mode, rinit;
+  int sblk;  // skip_certified_steps: current block size (16, 4 or 1 steps) and, in bits 8.., successes in a row
   int n_cross, n_cond;
   bool event_last, done, pure;
 
@@ -191,11 +194,12 @@ struct Sampler {
     if (rlo > P.rNS && rlo > P.r_int) return (P.Q * bzmin * ihi * ihi * ihi * (1.0 - P.rs_real * ilo) > E2 * (1.0 + 1e-9)) ? 1 : 0;
     // wholly inside the star (a line through it spends up to 40 steps there): the plasma frequency continues inwards
     // (no zeroIn in the sampler) and dwarfs m_a except near b_z = 0.  cond(): N² ≤ ww D (Cauchy–Schwarz on the covariant
-    // components, any metric branch), so F ≥ ww D [ωp² (E² − g^rr NrmSq·ww) − m_a² E²]; in the interior metric −g^tt grows
-    // and g^rr falls with r, hence g^rr NrmSq·ww ≤ g^rr(r_lo) (−E² g^tt(r_hi) − m_a²), and NrmSq > 0 because −g^tt ≥ 1.
+    // components, any metric branch), so F ≥ ww D [ωp² (E² − g^rr NrmSq·ww) − m_a² E²]; in the interior metric g^rr ≤ 1 and
+    // −g^tt grows with r up to 1/(1 − rs/r_int) at the switch radius (metric(): den falls with r), hence
+    // g^rr NrmSq·ww ≤ E²/(1 − rs/r_int) − m_a², and NrmSq > 0 because −g^tt ≥ 1.
     const double rhi = rm + hm;
     if (rhi < P.rNS && rhi < P.r_int) {
-      const double gn_max = metric(rlo, P.rs_real, P.r_int).grr * (-E2 * metric(rhi, P.rs_real, P.r_int).gtt - P.ma2);
+      const double gn_max = E2 * frcp(1.0 - P.rs_real * P.inv_r_int) - P.ma2;
       const double room = E2 - gn_max;
       return (room > 0.0 && P.Q * bzmin * ihi * ihi * ihi * room > P.ma2 * E2 * (1.0 + 1e-9)) ? 1 : 0;
     }
@@ -203,30 +207,41 @@ struct Sampler {
   }
 
   // Steps whose sign is certified and agrees with the reference sign hold no event: all their grid points
-  // have that sign.  They are passed over in blocks of 16, 4 or 1 steps — greedily, until a single step cannot be
-  // certified: the block shrinks on failure and grows back after four successes in a row — with the reference's own
-  // accumulation of tau.  Called where a step ends without an event.  (Round 2, first form: six fixed passes
-  // 16-16-4-4-1-1, at most 42 steps per call; where long blocks could not be certified every third or eleventh step of a
-  // dark stretch was scanned although its own certificate held — a third of all scan trips, measured on host attempts.)
+  // have that sign.  They are passed over in blocks of 16, 4 or 1 steps, with the reference's own accumulation of tau:
+  // the block shrinks on failure and grows back after four successes in a row; a failed single step ends the skipping
+  // (that step is scanned).  At most SKIP_PASSES tests per call — the lanes of a warp run this together at the end of a
+  // trip, and a lane in a long dark stretch must not keep the others waiting: it stays in mode SKIP, sits out the next
+  // trip's evaluation slots and goes on skipping at its end.  Called where a step ends without an event.
+  // (Tuning history, profiles/r02_*: six fixed passes 16-16-4-4-1-1 scanned every third or eleventh step of a stretch
+  // whose long blocks could not be certified — a third of all scan trips; an unbounded greedy loop evaluated 44 % fewer
+  // conditions but ran slower, its tail of one or two lanes holding up the warp.)
+#ifndef ART_SKIP_PASSES
+#define ART_SKIP_PASSES 8
+#endif
+  static constexpr int SKIP_PASSES = ART_SKIP_PASSES;
   ART_HD void skip_certified_steps(const DevParams& P) {
 #if defined(ART_NO_DARK_SKIP)
     return;
 #endif
-    if (done || mode != SCAN) return;
+    if (done || (mode != SCAN && mode != SKIP)) return;
     const double lim = fmin(P.T_samp, tau_out);
-    bool any = false;
-    int blk = 16, streak = 0;
+    int blk = sblk & 0xff, streak = sblk >> 8;
+    bool stopped = false;  // a single step could not be certified
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-    for (int pass = 0; pass < 96; ++pass) {
+    for (int pass = 0; pass < SKIP_PASSES; ++pass) {
       const double L = (double)blk * P.samp_dt;
       int sg = 0;
       if (tau + L < lim) sg = seg_sign(P, tau, L);
       if (sg != 0 && sgn_prev * sg >= 0) {
-        for (int q = 0; q < blk; ++q) tau += P.samp_dt;
+        // (the reference's own accumulation: after an event tau is not a multiple of the step, and blk additions need not
+        // round like one multiplication; unrolled and predicated — as a loop of blk trips it ran for two lanes at a time)
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int q = 0; q < 16; ++q) tau = (q < blk) ? tau + P.samp_dt : tau;
         sgn_prev = sg;
-        any = true;
         if (++streak >= 4 && blk < 16) {
           blk <<= 2;
           streak = 0;
@@ -235,10 +250,17 @@ struct Sampler {
         blk >>= 2;
         streak = 0;
       } else {
+        stopped = true;
         break;
       }
     }
-    if (any) next_step(P);
+    next_step(P);  // (event_last is false here: mode = SCAN unless the march is over)
+    if (stopped) {
+      sblk = 4;  // the next skipping phase starts with a modest block
+    } else {
+      sblk = blk | (streak << 8);
+      if (!done) mode = SKIP;
+    }
   }
 
   // set up one attempt from its 10 uniforms (RT.jl:1486-1542)
@@ -278,6 +300,7 @@ struct Sampler {
     pure = false;
     mode = INIT;
     sgn_prev = 0; side = 0; it = 0; rinit = 0;
+    sblk = 16;
     tau_new = h = a = fa = b = fb = f0 = w1 = w2 = 0.0;
     // chord of the line inside the sphere r = Rcut
     const double bq = xs[0] * va[0] + xs[1] * va[1] + xs[2] * va[2];
@@ -323,7 +346,8 @@ struct Sampler {
                         // a tenth of the kernel's instructions, profiles/r01_final_lines.txt)
     // what this lane evaluates in the current slot: SCAN for the whole trip, or ROOT / NUDGE / INIT until the
     // attempt is ready to scan (then −1: idle until the next trip); re-derived only where the mode changes
-    int md = scanning ? SCAN : ((active && !done && mode != SCAN) ? mode : -1);
+    int md = scanning ? SCAN : ((active && !done && mode != SCAN && mode != SKIP) ? mode : -1);
+    if (active && !done && mode == SKIP) skip = true;
     for (int k = 1; k <= M - 1; ++k) {
       double tq = tau, th = 0.0;
       bool ev = (md >= 0);
@@ -392,7 +416,7 @@ struct Sampler {
         next_step(P);
         skip = true;  // (the lane idles for the rest of the trip: mode is SCAN now)
       }
-      if (md > SCAN) md = (done || mode == SCAN) ? -1 : mode;
+      if (md > SCAN) md = (done || mode == SCAN || mode == SKIP) ? -1 : mode;
     }
     if (scanning) {
       // first point whose sign is opposite to the reference sign; the left end of the bracket is the last

@@ -121,23 +121,24 @@ int hc_sample_from_uniforms(const art_params* p, int64_t n, const double* u, dou
   return 0;
 }
 
-// How the sampler's trips are spent (tuning aid): counts[mode at the start of the trip] += 1 for SCAN / ROOT / NUDGE / INIT,
-// counts[4] += condition evaluations, counts[5] += attempts that never enter the loop (the line misses the Rcut sphere).
+// How the sampler's trips are spent (tuning aid): counts[mode at the start of the trip] += 1 for SCAN / ROOT / NUDGE / INIT / SKIP,
+// counts[5] += condition evaluations, counts[6] += attempts that never enter the loop (the line misses the Rcut sphere),
+// counts[7] / counts[8]: scanned steps that are pointwise dark / lit (a sharper momentum-free bound could pass them over).
 int hc_sampler_trips(const art_params* p, int64_t n, const double* u, long long* counts) {
   DevParams P;
   int rc = dev(p, P);
   if (rc) return rc;
-  for (int k = 0; k < 8; ++k) counts[k] = 0;
+  for (int k = 0; k < 12; ++k) counts[k] = 0;
   for (int64_t i = 0; i < n; ++i) {
     Sampler S;
     double taus[SAMP_KEEP];
     S.taus = taus;
     S.taus_stride = 1;
     S.begin(P, u + 10 * i);
-    if (S.done) counts[5]++;
+    if (S.done) counts[6]++;
     while (!S.done) {
       counts[S.mode]++;
-      if (S.mode == Sampler::SCAN) {  // is the step pointwise dark (ωp² < m_a²) or lit (ωp² g^rr > E², outside the star) at all grid points?
+      if (S.mode == Sampler::SCAN) {
         bool dark = true, lit = true;
         for (int k = 0; k <= P.M_samp - 1; ++k) {
           const double t = S.tau + (double)k / (P.M_samp - 1) * S.h;
@@ -150,21 +151,12 @@ int hc_sampler_trips(const art_params* p, int64_t n, const double* u, long long*
           dark = dark && Pq < P.ma2;
           lit = lit && r > P.rNS && Pq * (1.0 - P.rs_real / r) > S.E2;
         }
-        if (dark) counts[6]++;
-        if (dark && getenv("HC_SAMPLER_DEBUG") && counts[6] % 5000 == 1) {
-          double x[3];
-          S.point(S.tau + 0.5 * S.h, x);
-          const double r = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
-          const double mx = (P.mh[0] * x[0] + P.mh[1] * x[1] + P.mh[2] * x[2]) / r;
-          const double bz = 3.0 * mx * x[2] / r - P.cm;
-          fprintf(stderr, "dark step not certified: r %.3f h %.3f Pq/ma2 %.4f bz %.4f sgn_prev %d seg_sign %d event_last %d tau %.3f lim %.3f\n", r, S.h,
-                  P.Q * fabs(bz) / (r * r * r) / P.ma2, bz, S.sgn_prev, S.seg_sign(P, S.tau, S.h), (int)S.event_last, S.tau, fmin(P.T_samp, S.tau_out));
-        }
-        if (lit) counts[7]++;
+        if (dark) counts[7]++;
+        if (lit) counts[8]++;
       }
       S.trip(P, true);
     }
-    counts[4] += S.n_cond;
+    counts[5] += S.n_cond;
   }
   return 0;
 }
