@@ -719,6 +719,30 @@ def test_refilled_pool_runs_equal_the_single_block_run(lib, monkeypatch):
             assert b["stats"]["n_launches"] > a["stats"]["n_launches"]  # it was refilled
 
 
+def test_carried_events_draw_the_same_samples_as_art_sample(lib, monkeypatch):
+    """The sampler does not wait for its unluckiest events: once a launch's queue is empty, an event whose attempt fails is
+    carried to the next launch and samples are appended in completion order (k_sample_events).  Attempt j of event e draws
+    from the Philox stream (seed, id(e), j) wherever it runs: the conversion point a pipeline row carries (columns 9..11)
+    and the failure count f_inx sums must be those of art_sample, bit for bit, also with blocks so small that almost every
+    event is carried at least once."""
+    p = ArtParams.default(theta_m=0.2)
+    n = 20000
+    for env in (dict(), dict(ART_SAMPLE_BLOCK="300", ART_POOL_SLOTS="2048"), dict(ART_SAMPLE_BLOCK="5000", ART_POOL_SLOTS="4096")):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        h = lib.Handle(p, 0)
+        a = h.run(23, 1, n)
+        smp = h.sample(23, 1, n)
+        h.close()
+        for k in env:
+            monkeypatch.delenv(k)
+        ev = a["rows"][:, 0].astype(np.int64)
+        assert np.array_equal(a["rows"][:, 9:12], smp["x"][:, ev - 1].T), env
+        # (f_inx = failed attempts + photons that reached the observer, MainRunner.jl:463-494, 725)
+        assert a["f_inx"] == int(smp["n_failed"].sum()) + a["stats"]["n_final_photon"], env
+        assert a["stats"]["n_attempts"] == n + int(smp["n_failed"].sum())
+
+
 def test_batches_as_one_pipelined_job_equal_separate_calls(lib):
     """art_run_device_batches: contiguous and strided batches (the multi-GPU bench gives rank r the event ids
     1 + (step·world + r)·E + [0, E)) against one art_run per batch."""
