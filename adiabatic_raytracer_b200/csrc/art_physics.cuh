@@ -122,17 +122,28 @@ ART_HD void fsincos(double x, double* sn, double* cs) {
   r = fma(-k, FM_PIO2[2], r);
   r = fma(-k, FM_PIO2[3], r);
   const double z = r * r;
+#if !defined(ART_ESTRIN)
   double ps = fma(z, FM_SIN[5], FM_SIN[4]);
   ps = fma(z, ps, FM_SIN[3]);
   ps = fma(z, ps, FM_SIN[2]);
   ps = fma(z, ps, FM_SIN[1]);
   ps = fma(z, ps, FM_SIN[0]);
-  const double S = fma(r * z, ps, r);
   double pc = fma(z, FM_COS[5], FM_COS[4]);
   pc = fma(z, pc, FM_COS[3]);
   pc = fma(z, pc, FM_COS[2]);
   pc = fma(z, pc, FM_COS[1]);
   pc = fma(z, pc, FM_COS[0]);
+#else
+  // Estrin (tuning variant, -DART_ESTRIN): pairs in z, combined in z² — three dependent FMAs per polynomial instead of
+  // five.  Measured 2 % SLOWER on the whole step than Horner (580 vs 567 ms per 3e6 events): the extra multiplies and live
+  // values cost more than the shorter chains save
+  const double z2 = z * z;
+  const double s01 = fma(z, FM_SIN[1], FM_SIN[0]), s23 = fma(z, FM_SIN[3], FM_SIN[2]), s45 = fma(z, FM_SIN[5], FM_SIN[4]);
+  const double c01 = fma(z, FM_COS[1], FM_COS[0]), c23 = fma(z, FM_COS[3], FM_COS[2]), c45 = fma(z, FM_COS[5], FM_COS[4]);
+  const double ps = fma(z2, fma(z2, s45, s23), s01);
+  const double pc = fma(z2, fma(z2, c45, c23), c01);
+#endif
+  const double S = fma(r * z, ps, r);
   const double C = fma(z * z, pc, fma(-0.5, z, 1.0));
   const int n = (int)k;
   const double a = (n & 1) ? C : S, b = (n & 1) ? S : C;
@@ -146,6 +157,7 @@ ART_HD double fexp(double x) {
   const double k = rint(x * FM_LN2[0]);
   double r = fma(-k, FM_LN2[1], x);
   r = fma(-k, FM_LN2[2], r);
+#if !defined(ART_ESTRIN)
   double p = fma(r, FM_EXP[11], FM_EXP[10]);
   p = fma(r, p, FM_EXP[9]);
   p = fma(r, p, FM_EXP[8]);
@@ -157,6 +169,14 @@ ART_HD double fexp(double x) {
   p = fma(r, p, FM_EXP[2]);
   p = fma(r, p, FM_EXP[1]);
   p = fma(r, p, FM_EXP[0]);
+#else
+  // Estrin: six pairs in r, three quadruples in r², combined in r⁴ — five dependent operations instead of eleven
+  const double r2 = r * r, r4 = r2 * r2;
+  const double e01 = fma(r, FM_EXP[1], FM_EXP[0]), e23 = fma(r, FM_EXP[3], FM_EXP[2]), e45 = fma(r, FM_EXP[5], FM_EXP[4]);
+  const double e67 = fma(r, FM_EXP[7], FM_EXP[6]), e89 = fma(r, FM_EXP[9], FM_EXP[8]), eab = fma(r, FM_EXP[11], FM_EXP[10]);
+  const double q0 = fma(r2, e23, e01), q1 = fma(r2, e67, e45), q2 = fma(r2, eab, e89);
+  double p = fma(r4, fma(r4, q2, q1), q0);
+#endif
   p = fma(r * r, p, r) + 1.0;
 #if defined(__CUDA_ARCH__)
   return __hiloint2double(__double2hiint(p) + ((int)k << 20), __double2loint(p));
