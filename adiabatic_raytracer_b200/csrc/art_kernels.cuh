@@ -93,6 +93,16 @@ enum { SC_HEAD = 0, SC_OUT = 1, SC_CARRY = 2 };
 // Attempt j of event e draws from the Philox stream (seed, id(e), j) wherever and whenever it runs: same samples.
 // ONE instantiation and ONE call site of Sampler::begin serve both modes and every attempt, carried or not: the bits of a
 // sample do not depend on where its attempt ran.
+//
+// Scheduling inside a warp.  The lanes of a warp are at different places of their attempts (art_sampler.cuh: SCAN trips,
+// ROOT / NUDGE / INIT point evaluations, SKIP tests) or between attempts (result to process, next work item to pop, begin()).
+// Every round the warp runs ONE kind of work — the one most of its lanes are waiting for — for exactly those lanes; the
+// others sit the round out (no instruction slots, only latency, and nothing waits for a single event here).  Run as one loop
+// in which every lane did whatever it needed, each kind ran at 2–9 lanes and the kernel averaged 10 of 32 lanes per
+// instruction.
+#ifndef ART_SAMP_FIN_BIAS
+#define ART_SAMP_FIN_BIAS 0
+#endif
 __global__ void __launch_bounds__(SAMPLE_THREADS, ART_SAMPLE_MINBLOCKS)
 k_sample_events(const __grid_constant__ DevParams P, unsigned long long seed, EventIds ids, long long e0, long long n,
                 const SampleCarry* __restrict__ carry_in, long long n_carry, SampleCarry* __restrict__ carry_out, int compact,
@@ -103,70 +113,91 @@ k_sample_events(const __grid_constant__ DevParams P, unsigned long long seed, Ev
   S.taus = taus_sm + threadIdx.x;
   S.taus_stride = SAMPLE_THREADS;
   S.done = true;
-  bool have = false, exhausted = false, fresh = false;  // fresh: (idx, attempt) name an attempt that has not begun yet
+  S.mode = Sampler::SCAN;
+  bool have = false, exhausted = false;
   long long idx = -1;
   unsigned attempt = 0;
   double u_idx = 0.0;
   unsigned long long c_att = 0, c_cond = 0, c_fail = 0;
   const long long n_total = n_carry + n;
   const bool may_carry = compact && !drain;
+  const int M = P.M_samp;
   for (;;) {
-    const long long got = warp_pop(ctr + SC_HEAD, !have && !exhausted);
-    if (!have && !exhausted) {
-      if (got >= 0 && got < n_total) {
-        if (got < n_carry) {
-          idx = carry_in[got].idx;
-          attempt = carry_in[got].attempt;
-        } else {
-          idx = e0 + (got - n_carry);
-          attempt = 0;
+    const bool running = have && !S.done;
+    const int n_between = __popc(__ballot_sync(FULL, (have && S.done) || (!have && !exhausted)));
+    const int n_scan = __popc(__ballot_sync(FULL, running && S.mode == Sampler::SCAN));
+    const int n_point = __popc(__ballot_sync(FULL, running && S.in_point_mode()));
+    const int n_skip = __popc(__ballot_sync(FULL, running && S.mode == Sampler::SKIP));
+    if (n_between + n_scan + n_point + n_skip == 0) break;
+    const int top = max(max(n_between + ART_SAMP_FIN_BIAS * (n_between > 0), n_scan), max(n_point, n_skip));
+    if (n_between > 0 && n_between + ART_SAMP_FIN_BIAS >= top) {
+      // ---- between attempts: result of the finished one, next work item, begin() ----
+      const bool queue_empty = __any_sync(FULL, exhausted);
+      bool emit = false, carry = false, fresh = false;
+      EventSample es;
+      if (have && S.done) {
+        SampleResult R;
+        S.finish(P, u_idx, R);
+        c_att++;
+        c_cond += R.n_cond;
+        if (R.accepted) {
+          for (int c = 0; c < 3; ++c) { es.x[c] = R.x[c]; es.vloc[c] = R.vloc[c]; es.vinf[c] = R.vinf[c]; }
+          es.n_cross = R.n_cross;
+          es.n_failed = (int)attempt;
+          es.e = idx;
+          c_fail += attempt;
+          emit = true;
+        } else {  // MainRunner.jl:463-494: try again (f_inx counts the failure)
+          attempt++;
+          if (may_carry && queue_empty) carry = true;
+          else fresh = true;
         }
-        have = true;
-        fresh = true;
-      } else {
-        exhausted = true;
+      }
+      if (compact) {
+        const long long po = warp_pop(ctr + SC_OUT, emit);
+        if (emit) out[(out_base + po) % ring] = es;
+        const long long pc = warp_pop(ctr + SC_CARRY, carry);
+        if (carry) carry_out[pc] = SampleCarry{idx, attempt, 0u};
+      } else if (emit) {
+        out[idx - e0] = es;
+      }
+      if (emit || carry) have = false;
+      const long long got = warp_pop(ctr + SC_HEAD, !have && !exhausted);
+      if (!have && !exhausted) {
+        if (got >= 0 && got < n_total) {
+          if (got < n_carry) {
+            idx = carry_in[got].idx;
+            attempt = carry_in[got].attempt;
+          } else {
+            idx = e0 + (got - n_carry);
+            attempt = 0;
+          }
+          have = true;
+          fresh = true;
+        } else {
+          exhausted = true;
+        }
+      }
+      if (fresh) {
+        double U[10];
+        sampler_uniforms(seed, (unsigned long long)ids.id(idx), attempt, U);
+        u_idx = U[9];
+        S.begin(P, U);
+      }
+    } else if (n_scan == top) {
+      if (running && S.mode == Sampler::SCAN) S.scan_trip(P);
+    } else if (n_skip == top) {
+      if (running && S.mode == Sampler::SKIP) S.skip_certified_steps(P);
+    } else {
+      // ---- point evaluations: until every lane that was in a point mode has left it (a root takes ≈ 12) ----
+      bool mine = running && S.in_point_mode();
+#pragma unroll 1
+      for (int k = 1; k <= M - 1; ++k) {
+        const bool w = mine && !S.done && S.in_point_mode();
+        if (!__any_sync(FULL, w)) break;
+        if (w) S.point_slot(P);
       }
     }
-    if (fresh) {
-      double U[10];
-      sampler_uniforms(seed, (unsigned long long)ids.id(idx), attempt, U);
-      u_idx = U[9];
-      S.begin(P, U);
-      fresh = false;
-    }
-    const bool queue_empty = __any_sync(FULL, exhausted);
-    if (__ballot_sync(FULL, have) == 0) break;
-    // one trip = M−1 condition evaluations for every lane (art_sampler.cuh)
-    S.trip(P, have);
-    bool emit = false, carry = false;
-    EventSample es;
-    if (have && S.done) {
-      SampleResult R;
-      S.finish(P, u_idx, R);
-      c_att++;
-      c_cond += R.n_cond;
-      if (R.accepted) {
-        for (int c = 0; c < 3; ++c) { es.x[c] = R.x[c]; es.vloc[c] = R.vloc[c]; es.vinf[c] = R.vinf[c]; }
-        es.n_cross = R.n_cross;
-        es.n_failed = (int)attempt;
-        es.e = idx;
-        c_fail += attempt;
-        emit = true;
-      } else {  // MainRunner.jl:463-494: try again (f_inx counts the failure)
-        attempt++;
-        if (may_carry && queue_empty) carry = true;
-        else fresh = true;
-      }
-    }
-    if (compact) {
-      const long long po = warp_pop(ctr + SC_OUT, emit);
-      if (emit) out[(out_base + po) % ring] = es;
-      const long long pc = warp_pop(ctr + SC_CARRY, carry);
-      if (carry) carry_out[pc] = SampleCarry{idx, attempt, 0u};
-    } else if (emit) {
-      out[idx - e0] = es;
-    }
-    if (emit || carry) have = false;
   }
   c_att = warp_sum(c_att);
   c_cond = warp_sum(c_cond);

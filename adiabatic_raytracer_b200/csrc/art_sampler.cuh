@@ -223,7 +223,7 @@ struct Sampler {
 #if defined(ART_NO_DARK_SKIP)
     return;
 #endif
-    if (done || (mode != SCAN && mode != SKIP)) return;
+    if (done || mode != SKIP) return;
     const double lim = fmin(P.T_samp, tau_out);
     int blk = sblk & 0xff, streak = sblk >> 8;
     bool stopped = false;  // a single step could not be certified
@@ -333,136 +333,150 @@ struct Sampler {
     next_step(P);
   }
 
-  // One trip = M−1 condition evaluations, at ONE call site, for every lane of a warp together.
-  //   * An attempt in SCAN mode spends the trip on the M−1 grid points of its Euler step and keeps nothing
-  //     but the signs (two bit masks); after the trip the first sign change — with the reference's rule for
-  //     the left end of the bracket: the last point that still had the old sign — starts the root finder,
-  //     otherwise the step is done.  Per evaluation that is the condition plus ≈ 10 instructions.
-  //   * The other modes do one evaluation per slot of the trip: the root finder's iterates (its two bracket
-  //     values are re-evaluated first — same numbers as the scan saw), the nudge point after an event, the
-  //     first point of the march; when they are through they wait for the next trip to scan.
-  // The earlier form — one evaluation per call with the whole state machine around it, predicated — executed
-  // ≈ 440 instructions per evaluation, two thirds of them bookkeeping (profiles/r01_sampler_v2_v3_hotlines.txt).
-  ART_HD void trip(const DevParams& P, bool active) {
+  // ---- the attempt as three kinds of work -------------------------------------------------------------------------------
+  // An attempt alternates between
+  //   SCAN   the M−1 grid points of one Euler step (scan_trip): nothing is kept but the signs (three bit masks); the first
+  //          sign change — with the reference's rule for the left end of the bracket: the last point that still had the old
+  //          sign — starts the root finder, otherwise the step is done and the attempt goes on to SKIP;
+  //   ROOT / NUDGE / INIT   one condition evaluation at a time (point_slot): the root finder's iterates (its two bracket
+  //          values are re-evaluated first — same numbers as the scan saw), the reference sign 1 % into the step after an
+  //          event, the sign at the first point of the march;
+  //   SKIP   certified steps are passed over without evaluating anything (skip_certified_steps).
+  // The sampler kernel runs each kind for the lanes of a warp that are in it TOGETHER and only when enough of them are
+  // (k_sample_events): as one loop over "slots" in which every lane did whatever its mode asked for, the root finder's
+  // iterate ran for 2–3 lanes, the interior-metric branch for 6, the skip tests for 4–9, and the kernel averaged 10 of 32
+  // lanes per instruction (profiles/r02_ncu_summary.txt).  The host check calls them one after the other (trip()).
+  ART_HD bool in_point_mode() const { return mode == ROOT || mode == NUDGE || mode == INIT; }
+
+  // the step has ended without an event: reference sign for the next one, then on to the certified-step tests
+  ART_HD void step_done(const DevParams& P, int sg_end) {
+    sgn_prev = sg_end;
+    tau = tau_new;
+    event_last = false;
+    next_step(P);
+    if (!done) mode = SKIP;
+  }
+
+  ART_HD void scan_trip(const DevParams& P) {
     const int M = P.M_samp;
-    const bool scanning = active && !done && mode == SCAN;
     unsigned mpos = 0u, mneg = 0u, mzero = 0u;
-    bool skip = false;  // the next step starts without an event: pass over certified steps (ONE call site, at the end
-                        // of the trip — inlined at the INIT slot as well it ran for one lane at a time and made up
-                        // a tenth of the kernel's instructions, profiles/r01_final_lines.txt)
-    // what this lane evaluates in the current slot: SCAN for the whole trip, or ROOT / NUDGE / INIT until the
-    // attempt is ready to scan (then −1: idle until the next trip); re-derived only where the mode changes
-    int md = scanning ? SCAN : ((active && !done && mode != SCAN && mode != SKIP) ? mode : -1);
-    if (active && !done && mode == SKIP) skip = true;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
     for (int k = 1; k <= M - 1; ++k) {
-      double tq = tau, th = 0.0;
-      bool ev = (md >= 0);
-      if (md == SCAN) {
-        tq = (k == M - 1) ? tau_new : tau + ((double)k * P.inv_Msm1) * h;
-      } else if (md == ROOT) {
-        if (rinit > 0) {  // bracket values first: fa, then fb
-          th = (rinit == 2) ? a : b;
-        } else {
-          const double tol = ROOT_RTOL * fmax(fmax(fabs(a), fabs(b)), 0.01);
-          const double width = fabs(b - a);
-          if (width <= tol || it >= 200) {
-            event(P, fmin(a, b));
-            ev = false;
-          } else {
-            if (it == 3 && fmin(fabs(fa), fabs(fb)) > 0.25 * f0) pure = true;
-            double c = (a * fb - b * fa) * frcp(fb - fa);
-            const double lo = fmin(a, b), hi = fmax(a, b);
-            if (pure || (it >= 3 && width > 0.5 * w2) || !(c > lo && c < hi) || width <= 2.0 * tol) c = 0.5 * (a + b);
-            else if (fabs(c - b) < tol) c = b + copysign(tol, a - b);
-            w2 = w1;
-            w1 = width;
-            th = c;
-          }
-        }
-        tq = tau + th * h;
-      } else if (md == NUDGE) {  // DiffEqBase repeat_nudge = 1/100
-        tq = tau + 0.01 * h;
-      }
-      double g = 0.0;
-      if (ev) g = cond(P, tq);
-      if (md == SCAN) {
-        const unsigned bit = 1u << k;
-        mpos |= (g > 0.0) ? bit : 0u;
-        mneg |= (g < 0.0) ? bit : 0u;
-        mzero |= (g == 0.0) ? bit : 0u;
-      } else if (md == ROOT) {
-        if (ev) {
-          if (rinit == 2) {
-            fa = g;
-            rinit = 1;
-          } else if (rinit == 1) {
-            fb = g;
-            rinit = 0;
-            f0 = fmin(fabs(fa), fabs(fb));
-          } else {
-            it++;
-            if (g == 0.0) {
-              event(P, th);
-            } else {
-              if ((g < 0.0) != (fb < 0.0)) {
-                a = b; fa = fb; side = 0;
-              } else {
-                if (side == 1) fa *= 0.5;
-                side = 1;
-              }
-              b = th; fb = g;
-            }
-          }
-        }
-      } else if (md == NUDGE) {
-        sgn_prev = (g > 0.0) - (g < 0.0);
-        mode = SCAN;
-      } else if (md == INIT) {
-        sgn_prev = (g > 0.0) - (g < 0.0);
-        next_step(P);
-        skip = true;  // (the lane idles for the rest of the trip: mode is SCAN now)
-      }
-      if (md > SCAN) md = (done || mode == SCAN || mode == SKIP) ? -1 : mode;
+      const double tq = (k == M - 1) ? tau_new : tau + ((double)k * P.inv_Msm1) * h;
+      const double g = cond(P, tq);
+      const unsigned bit = 1u << k;
+      mpos |= (g > 0.0) ? bit : 0u;
+      mneg |= (g < 0.0) ? bit : 0u;
+      mzero |= (g == 0.0) ? bit : 0u;
     }
-    if (scanning) {
-      // first point whose sign is opposite to the reference sign; the left end of the bracket is the last
-      // point before it that still had the reference sign (exact zeros and NaNs neither trigger nor move it)
-      const unsigned opp = sgn_prev > 0 ? mneg : (sgn_prev < 0 ? mpos : 0u);
-      if (opp) {
+    // first point whose sign is opposite to the reference sign; the left end of the bracket is the last
+    // point before it that still had the reference sign (exact zeros and NaNs neither trigger nor move it)
+    const unsigned opp = sgn_prev > 0 ? mneg : (sgn_prev < 0 ? mpos : 0u);
+    if (opp) {
 #if defined(__CUDA_ARCH__)
-        const int ib = __ffs((int)opp) - 1;
+      const int ib = __ffs((int)opp) - 1;
 #else
-        const int ib = __builtin_ffs((int)opp) - 1;
+      const int ib = __builtin_ffs((int)opp) - 1;
 #endif
-        const unsigned same = (sgn_prev > 0 ? mpos : mneg) & ((1u << ib) - 1u);
-        int ia = 0;
-        if (same) {
+      const unsigned same = (sgn_prev > 0 ? mpos : mneg) & ((1u << ib) - 1u);
+      int ia = 0;
+      if (same) {
 #if defined(__CUDA_ARCH__)
-          ia = 31 - __clz((int)same);
+        ia = 31 - __clz((int)same);
 #else
-          ia = 31 - __builtin_clz(same);
+        ia = 31 - __builtin_clz(same);
 #endif
-        }
-        a = (ia == 0) ? (event_last ? 0.01 : 0.0) : (double)ia * P.inv_Msm1;
-        b = (ib == M - 1) ? 1.0 : (double)ib * P.inv_Msm1;
-        w1 = w2 = 2.0;
-        pure = false;
-        side = 0;
-        it = 0;
-        rinit = 2;
-        mode = ROOT;
-      } else if (sgn_prev != 0 && ((mzero >> (M - 1)) & 1u)) {
-        event(P, 1.0);  // the end point lies exactly on the surface
+      }
+      a = (ia == 0) ? (event_last ? 0.01 : 0.0) : (double)ia * P.inv_Msm1;
+      b = (ib == M - 1) ? 1.0 : (double)ib * P.inv_Msm1;
+      w1 = w2 = 2.0;
+      pure = false;
+      side = 0;
+      it = 0;
+      rinit = 2;
+      mode = ROOT;
+    } else if (sgn_prev != 0 && ((mzero >> (M - 1)) & 1u)) {
+      event(P, 1.0);  // the end point lies exactly on the surface
+    } else {
+      const unsigned endbit = 1u << (M - 1);
+      step_done(P, (mpos & endbit) ? 1 : ((mneg & endbit) ? -1 : 0));
+    }
+  }
+
+  // one evaluation of an attempt in ROOT, NUDGE or INIT mode
+  ART_HD void point_slot(const DevParams& P) {
+    double tq = tau, th = 0.0;
+    bool ev = true;
+    if (mode == ROOT) {
+      if (rinit > 0) {  // bracket values first: fa, then fb
+        th = (rinit == 2) ? a : b;
       } else {
-        const unsigned endbit = 1u << (M - 1);
-        sgn_prev = (mpos & endbit) ? 1 : ((mneg & endbit) ? -1 : 0);
-        tau = tau_new;
-        event_last = false;
-        next_step(P);
-        skip = true;
+        const double tol = ROOT_RTOL * fmax(fmax(fabs(a), fabs(b)), 0.01);
+        const double width = fabs(b - a);
+        if (width <= tol || it >= 200) {
+          event(P, fmin(a, b));
+          ev = false;
+        } else {
+          if (it == 3 && fmin(fabs(fa), fabs(fb)) > 0.25 * f0) pure = true;
+          double c = (a * fb - b * fa) * frcp(fb - fa);
+          const double lo = fmin(a, b), hi = fmax(a, b);
+          if (pure || (it >= 3 && width > 0.5 * w2) || !(c > lo && c < hi) || width <= 2.0 * tol) c = 0.5 * (a + b);
+          else if (fabs(c - b) < tol) c = b + copysign(tol, a - b);
+          w2 = w1;
+          w1 = width;
+          th = c;
+        }
       }
+      tq = tau + th * h;
+      if (!ev) return;  // (the root was accepted: event() has moved the attempt on)
+    } else if (mode == NUDGE) {  // DiffEqBase repeat_nudge = 1/100
+      tq = tau + 0.01 * h;
     }
-    if (skip) skip_certified_steps(P);
+    const double g = cond(P, tq);
+    if (mode == ROOT) {
+      if (rinit == 2) {
+        fa = g;
+        rinit = 1;
+      } else if (rinit == 1) {
+        fb = g;
+        rinit = 0;
+        f0 = fmin(fabs(fa), fabs(fb));
+      } else {
+        it++;
+        if (g == 0.0) {
+          event(P, th);
+        } else {
+          if ((g < 0.0) != (fb < 0.0)) {
+            a = b; fa = fb; side = 0;
+          } else {
+            if (side == 1) fa *= 0.5;
+            side = 1;
+          }
+          b = th; fb = g;
+        }
+      }
+    } else if (mode == NUDGE) {
+      sgn_prev = (g > 0.0) - (g < 0.0);
+      mode = SCAN;
+    } else {  // INIT
+      sgn_prev = (g > 0.0) - (g < 0.0);
+      next_step(P);
+      if (!done) mode = SKIP;
+    }
+  }
+
+  // sequential form (host check, fine-grained API): one call = one piece of work of whatever kind the attempt is in
+  ART_HD void trip(const DevParams& P, bool active) {
+    if (!active || done) return;
+    if (mode == SCAN) {
+      scan_trip(P);
+    } else if (mode == SKIP) {
+      skip_certified_steps(P);
+    } else {
+      for (int k = 1; k <= P.M_samp - 1 && !done && in_point_mode(); ++k) point_slot(P);
+    }
   }
 
   // selection of one crossing, RT.jl:1618-1640
