@@ -70,7 +70,7 @@ struct SampleCarry {
 };
 
 #ifndef ART_SAMPLE_MINBLOCKS
-#define ART_SAMPLE_MINBLOCKS 4
+#define ART_SAMPLE_MINBLOCKS 5
 #endif
 // Event ids of a pipeline call: event e (index in the call) has id first + (e / bsize) bstride + e % bsize (batches of a
 // pipelined job, art_run_device_batches); a plain range is bsize = bstride = anything ≥ the number of events.
@@ -100,8 +100,10 @@ enum { SC_HEAD = 0, SC_OUT = 1, SC_CARRY = 2 };
 // others sit the round out (no instruction slots, only latency, and nothing waits for a single event here).  Run as one loop
 // in which every lane did whatever it needed, each kind ran at 2–9 lanes and the kernel averaged 10 of 32 lanes per
 // instruction.
+// (ART_SAMP_FIN_BIAS: head start of the between-attempts work in that vote — it is cheap and feeds the other kinds; measured per
+// 3e6 events: bias 0 548 ms, 4 544, 12 554; five resident CTAs per SM (102 registers) instead of four 544 vs 548, three 556)
 #ifndef ART_SAMP_FIN_BIAS
-#define ART_SAMP_FIN_BIAS 0
+#define ART_SAMP_FIN_BIAS 4
 #endif
 __global__ void __launch_bounds__(SAMPLE_THREADS, ART_SAMPLE_MINBLOCKS)
 k_sample_events(const __grid_constant__ DevParams P, unsigned long long seed, EventIds ids, long long e0, long long n,
