@@ -151,9 +151,10 @@ ART_HD void fsincos(double x, double* sn, double* cs) {
   *cs = ((n + 1) & 2) ? -b : b;
 }
 
-// e^x for |x| < 700: x = k ln2 + r, |r| ≤ ln2/2, Taylor to r¹³ (truncation 4e-18), scaled through the
+// e^x for x < 700 (arguments below −700 are clamped there): x = k ln2 + r, |r| ≤ ln2/2, Taylor to r¹³ (truncation 4e-18), scaled through the
 // exponent field.  Branch-free; ≤ 1 ulp.
 ART_HD double fexp(double x) {
+  x = fmax(x, -700.0);  // (the exponent-field scaling below has no underflow path: e^-700 = 1e-304 stands in for 0)
   const double k = rint(x * FM_LN2[0]);
   double r = fma(-k, FM_LN2[1], x);
   r = fma(-k, FM_LN2[2], r);
@@ -256,14 +257,16 @@ struct DevParams {
 };
 
 // boundary-layer term B(r) and its r-derivative (r ≥ rNS; the callers apply the r ≥ rNS / zeroIn rules)
+// (the branch-free helpers: with the library's sqrt / exp / division the boundary-layer kernels spent a third of their
+// instructions in slow paths)
 ART_HD double bl_w(const DevParams& P, double r, double rmax) {
-  const double q = P.rNS / r;
-  return P.wpole * q * sqrt(q) * exp(-(r - rmax * P.bl) / (0.1 * rmax));
+  const double q = P.rNS * frcp(r);
+  return P.wpole * q * fsqrt(q) * fexp(-(r - rmax * P.bl) * frcp(0.1 * rmax));
 }
-ART_HD double bl_dw(const DevParams& P, double r, double rmax) { return bl_w(P, r, rmax) * (-1.5 / r - 1.0 / (0.1 * rmax)); }
+ART_HD double bl_dw(const DevParams& P, double r, double rmax) { return bl_w(P, r, rmax) * (-1.5 * frcp(r) - frcp(0.1 * rmax)); }
 // ωp² with the boundary layer from the Goldreich–Julian ωp0² (r ≥ rNS)
 ART_HD double bl_wp2(const DevParams& P, double Pp0, double r, double rmax) {
-  const double w = (Pp0 > 0.0 ? sqrt(Pp0) : 0.0) + bl_w(P, r, rmax);
+  const double w = (Pp0 > 0.0 ? fsqrt(Pp0) : 0.0) + bl_w(P, r, rmax);
   return w * w;
 }
 
@@ -476,8 +479,15 @@ ART_HD void rhs_photon(const DevParams& P, double r, double th, double ph, doubl
   du[4] = -H_t * face;
   du[5] = -H_p * face;
   if (ddelta) {
+#if defined(__CUDA_ARCH__)
+    const double w0i = Pp > 0.0 ? frsqrt(Pp) : INFINITY, w0 = Pp > 0.0 ? Pp * w0i : 0.0;  // (on the null surface: √0 and 1/0, as below)
+    const double wb = w0 + bl_w(P, r, P.bl_rmax);                   // (r > 1.01 rNS here)
+    const double ratio = wb * w0i - 1.0;
+#else
     const double w0 = sqrt(Pp), wb = w0 + bl_w(P, r, P.bl_rmax);  // (r > 1.01 rNS here)
-    const double ratio = wb / w0 - 1.0;                             // ωp_b/ωp0 − 1 (∞ on the null surface, like the reference's √|b_z|)
+    const double ratio = wb / w0 - 1.0;
+#endif
+    // (ratio = ωp_b/ωp0 − 1: ∞ on the null surface, like the reference's √|b_z|)
     double dW = (wb * wb - Pp) * Dinv * om2inv;                     // W_b − W
     double Xp = X;
     if (P.isotropic) {

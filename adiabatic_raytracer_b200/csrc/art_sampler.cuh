@@ -171,7 +171,6 @@ struct Sampler {
   // b_z = 3(m̂·r̂)(ẑ·r̂) − cosθm.  A direction-aware refinement of the Rcut sphere: only the steps that straddle
   // the conversion surface (and those inside the star) are left to evaluate.
   ART_HD int seg_sign(const DevParams& P, double t0, double L) const {
-    if (P.bl > 0.0) return 0;  // the bounds below assume the pure Goldreich–Julian ωp
     const double hm = 0.5 * L, tm = t0 + hm;
     const double x = xs[0] + tm * va[0], y = xs[1] + tm * va[1], z = xs[2] + tm * va[2];
     const double r2 = x * x + y * y + z * z;
@@ -187,7 +186,15 @@ struct Sampler {
     const double plo = fmin(fmin(p1, p2), fmin(p3, p4)), phi = fmax(fmax(p1, p2), fmax(p3, p4));
     const double b0 = 3.0 * plo - P.cm, b1 = 3.0 * phi - P.cm;  // b_z ∈ [b0, b1]
     const double bzmax = fmax(fabs(b0), fabs(b1));
-    if (P.Q * bzmax * ilo * ilo * ilo < P.ma2 * (1.0 - 1e-9)) return -1;
+    if (P.bl > 0.0) {
+      // boundary layer (cond(): for r ≥ rNS ωp = √(Q|b_z|/r³) + B(r), B ≥ 0 falling with r): ωp ≤ √(Q b_z,max/r_lo³) + B(r_lo)
+      // on the whole segment (points inside the star carry no B: smaller still); the lit bounds below stay sufficient as
+      // they are — the term only raises ωp, and F grows with ωp²
+      const double wmax = sqrt(P.Q * bzmax * ilo * ilo * ilo) + bl_w(P, rlo, P.bl_rmax);
+      if (wmax * wmax < P.ma2 * (1.0 - 1e-9)) return -1;
+    } else if (P.Q * bzmax * ilo * ilo * ilo < P.ma2 * (1.0 - 1e-9)) {
+      return -1;
+    }
     const double bzmin = (b0 > 0.0) ? b0 : ((b1 < 0.0) ? -b1 : 0.0);
     if (!P.thick) return (P.Q * bzmin * ihi * ihi * ihi > P.ma2 * (1.0 + 1e-9)) ? 1 : 0;  // ωp > m_a on the whole segment
     if (P.isotropic) return 0;

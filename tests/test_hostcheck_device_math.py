@@ -134,6 +134,19 @@ def test_certified_step_signs_never_contradict_the_literal_scan(oracle, kw, inte
         assert c[2] == 0 and c[4] == 0
 
 
+def test_certified_step_signs_with_the_boundary_layer_term(oracle):
+    """bndry_lyr > 0: ωp = √(Q|b_z|/r³) + B(r) with B ≥ 0 falling with r; the dark bound uses ωp ≤ √(Q b_z,max/r_lo³) + B(r_lo), the
+    lit bound stays as it is (the term only raises ωp), the energy carries the extra channel δ.  Same check as above."""
+    p = ArtParams.default(theta_m=0.2, bndry_lyr=0.5)
+    n = 250
+    s = oracle.sample(p, 5, 1, n)
+    w = oracle.weights(p, s["x"], s["v_loc"], s["v_inf"])
+    for sp, mc, bs in ((1, -1, 1), (0, 100000, -1)):
+        c = hc.certificates(p, np.full(n, sp, np.int32), s["x"], w["k_init"] * bs, w["erg_inf"], mc)
+        assert c[0] > 30 * n and c[1] > 0.4 * c[0]
+        assert c[2] == 0 and c[4] == 0
+
+
 def test_host_compiled_sampler_matches_oracle(oracle):
     for kw in (dict(theta_m=0.2), dict(theta_m=0.2, rNS=12.0), dict(theta_m=0.2, rNS=8.0), dict(theta_m=0.2, thick_surface=0),
                dict(theta_m=1.1, Mass_a=2e-5, B0=2e14, omega_pul=3.0, thick_surface=0)):
