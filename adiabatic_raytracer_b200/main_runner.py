@@ -42,6 +42,15 @@ def params_from_call(Mass_a, Ax_g, theta_m, omega_pul, B0, rNS, Mass_NS, *, flat
         ntimes=int(ntimes), rho_DM=rho_DM, vmean_ax=vmean_ax, save_mode=int(saveMode), n_maxSample=int(n_maxSample),
         num_cutoff=int(num_cutoff), MC_nodes=int(MC_nodes), max_nodes=int(max_nodes), prob_cutoff=prob_cutoff, **extra)
 
+def _check_crossing_capacity(stats, cross_cap):
+    """The reference keeps every crossing of a ray (an unbounded list); the library keeps cross_cap records per ray and reports
+    rays that had more as ART_RAY_CROSS_OVERFLOW.  A back-trace weight built from a truncated list would silently differ from
+    the reference's, so the runner refuses the result instead (rerun with a larger cross_cap, at most 64)."""
+    n_over = int(stats["n_status"][4])
+    if n_over:
+        raise RuntimeError(f"{n_over} rays crossed the conversion surface more than cross_cap = {cross_cap} times: their records "
+                           "were truncated (ART_RAY_CROSS_OVERFLOW); rerun with a larger cross_cap")
+
 
 def main_runner_tree(Mass_a, Ax_g, theta_m, omega_pul, B0, rNS, Mass_NS, omega_prop, Ntajs, gammaF, *,
                      flat=True, isotropic=False, melrose=False, thick_surface=True, bndry_lyr=-1, ode_err=1e-6,
@@ -72,6 +81,7 @@ def main_runner_tree(Mass_a, Ax_g, theta_m, omega_pul, B0, rNS, Mass_NS, omega_p
         # numbered 1 … Ntajs−1 (MainRunner.jl:399,450)
         n_events = max(int(Ntajs) - 1, 0)
         out = h.run(iseed, 1, n_events)
+        _check_crossing_capacity(out["stats"], p.cross_cap)
         events = h.fetch_events(n_events) if saveMode > 1 else None
         if saveMode > 2:  # MainRunner.jl:574-578: one tree_<file_tag><event> file per event
             os.makedirs(os.path.join(dir_tag, "tree"), exist_ok=True)
@@ -158,6 +168,7 @@ def main_runner_tree_multi(Mass_a, Ax_g, theta_m, omega_pul, B0, rNS, Mass_NS, o
         h.comm_init(world, rank, comm_id)
     t0 = time.perf_counter()
     out = h.run_device(iseed, first, count)
+    _check_crossing_capacity(out["stats"], p.cross_cap)
     h.comm_allreduce_hist()            # the only collective: [bins | f_inx, n_rows, n_events, …]
     G = h.hist_get_global()
     wall = time.perf_counter() - t0
