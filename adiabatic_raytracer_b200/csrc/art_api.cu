@@ -162,6 +162,7 @@ struct art_handle {
   void* comm = nullptr;
   int nranks = 1, rank = 0;
   std::atomic<long long> launches{0};  // kernels launched since the current pipeline call began
+  int bulk_burst = 8;              // iterations between host checks while the pool is full (ART_BULK_BURST)
   int bulk_nstep = ART_STAGE_NSTEP;  // attempts per stage launch in the bulk (ART_BULK_NSTEP)
   int scan_grid_per_sm = ART_SCAN_MINBLOCKS;  // grid of the scan kernel = one resident wave (ART_SCAN_GRID_PER_SM; tracer per 1e6
                                   // events: 3 CTAs per SM 182.6 ms, 6 183.4, 8 185.3, 12 185.7, 24 189.0)
@@ -342,7 +343,7 @@ int wf_loop(art_handle* h, Lane& L, WfPool W, long long n_act0, RayOut* out, dou
       break;
     }
     const long long n_plan = n_act + (job ? 2LL * job->m : 0);  // … with the events about to be injected
-    const int burst = n_plan > 500000 ? 8 : (n_plan > 65536 ? 16 : 32);  // steps between host checks (deep queue: host jitter must not idle the GPU)
+    const int burst = n_plan > 500000 ? h->bulk_burst : (n_plan > 65536 ? 16 : 32);  // steps between host checks (deep queue: host jitter must not idle the GPU)
     const bool tail_mode = n_plan < h->tail_below;                        // thin tail: any lane keeps its warp stepping
     for (int b = 0; b < burst; ++b, ++iter) {
       const int k = (int)(iter & 0x3fffffff);
@@ -512,6 +513,7 @@ int art_create(const art_params* p, int device_id, art_handle** out) {
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sample_events, SAMPLE_THREADS, 0);
   h->blocks_sample = h->n_sm * std::max(occ, 1);
   if (const char* t = getenv("ART_BULK_NSTEP")) h->bulk_nstep = std::max(1, atoi(t));
+  if (const char* t = getenv("ART_BULK_BURST")) h->bulk_burst = std::max(1, std::min(64, atoi(t)));
   if (const char* t = getenv("ART_TAIL_NSTEP")) h->tail_nstep = std::max(1, atoi(t));
   if (const char* t = getenv("ART_BULK_MIN_GO")) h->bulk_min_go = std::max(1, std::min(32, atoi(t)));
   if (const char* t = getenv("ART_WF_GRID_PER_SM")) h->wf_grid_per_sm = std::max(1, atoi(t));

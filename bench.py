@@ -37,6 +37,12 @@ F_SAMPLER_COND = 150.0
 NS = dict(Mass_a=1e-5, Ax_g=1e-12, theta_m=0.2, omega_pul=1.0, B0=1e14, rNS=10.0, Mass_NS=1.0, flat=0, integrator=0)
 SEED = 1769
 
+# the same string in both arms (the reference arm runs a bounded sample of it)
+WORKLOAD = ("BASELINE configs[1]: GR (flat=false), m_a=1e-5 eV, Ax_g=1e-12, B0=1e14 G, rotW=1.0 (the reference's default; "
+            "P = 1 s is value_p1s), theta_m=0.2, M=1 Msun, R=10 km; 1e6 events per GPU per step (sampler + back-trace "
+            "+ forward tree)")
+
+
 
 # hardware view of the kernels (ncu --set full / launch list of THIS build, written by tools/ncu_summary.py): loaded, never
 # hard-coded; absent file ⇒ the keys are null
@@ -169,8 +175,9 @@ def run_reference(args):
         "impl": "reference", "metric": "rays traced to observer/sec (GR mode)", "value": v, "unit": "rays/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1]: GR, m_a=1e-5 eV, B0=1e14 G, rotW=1, theta_m=0.2, M=1, R=10 km; "
-                               f"bounded sample of {n} events per step on the host CPU"},
+        "config": {"workload": WORKLOAD, "events_per_step": n, "seed": SEED,
+                   "sample": f"bounded sample of the workload: {n} events per step on the host CPU",
+                   "integrator": "Vern6 (the oracle's restatement of the reference's solve(prob, Vern6()), RT.jl:383)"},
         "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
                          "sample": f"{n} events/step x {args.steps} steps, oracle/ OpenMP on {cores} threads (Vern6; a faster-than-"
                                    "reference port: no per-call allocation, no GC per event)"},
@@ -421,9 +428,7 @@ def main():
 
     if rank == 0:
         cfg = {
-            "workload": "BASELINE configs[1]: GR (flat=false), m_a=1e-5 eV, Ax_g=1e-12, B0=1e14 G, rotW=1.0 (the reference's default; "
-                        "P = 1 s is value_p1s), theta_m=0.2, M=1 Msun, R=10 km; 1e6 events per GPU per step (sampler + back-trace "
-                        "+ forward tree)",
+            "workload": WORKLOAD,
             "events_per_gpu_per_step": E, "seed": SEED, "reltol": p.reltol, "abstol": p.ode_err,
             "interp_points_ray": p.interp_points_ray, "interp_points_sampler": p.interp_points_sampler,
             "integrator": ("Vern6 (Verner 9-stage 6(5), the reference's solve(prob, Vern6()) RT.jl:383), lazy 6th-order dense output"
