@@ -156,3 +156,15 @@ def node_traj(p, species, x0, k0, erg, t_start=0.0, dOmega=-1.0, max_crossings=-
                        C.c_double(dOmega), int(max_crossings), int(ntimes), out.ctypes.data_as(C.c_void_p), out.shape[0])
     assert n > 0
     return out[:n]
+
+
+def sampler_trips(p, u):
+    """How the sampler's attempts are spent: dict of pieces of work per kind, condition evaluations, and how many scanned
+    steps a sharper momentum-free bound could still pass over (hc_sampler_trips)."""
+    u = np.ascontiguousarray(u, np.float64)
+    counts = np.zeros(12, np.int64)
+    L = lib()
+    L.hc_sampler_trips.restype = C.c_int
+    _chk(L.hc_sampler_trips(C.byref(p), C.c_int64(u.shape[0]), u.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p)))
+    return dict(scan=int(counts[0]), root=int(counts[1]), nudge=int(counts[2]), init=int(counts[3]), skip=int(counts[4]),
+                n_cond=int(counts[5]), missed=int(counts[6]), scanned_dark=int(counts[7]), scanned_lit=int(counts[8]))

@@ -160,6 +160,19 @@ def test_host_compiled_sampler_matches_oracle(oracle):
         assert np.abs(a["x"] - b["x"])[:, m].max() < 1e-10
 
 
+def test_sampler_passes_over_certified_steps():
+    """The sampler's march evaluates the condition only where its sign is not certified (Sampler::seg_sign /
+    skip_certified_steps: dark, lit outside and inside the star, blocks of 16 / 4 / 1 steps).  The literal march evaluates
+    19 points on every one of the ≈ 90 Euler steps inside the far-field sphere (≈ 1700 per attempt); measured here: 238.
+    That the passed-over steps hold no crossing is what test_host_compiled_sampler_matches_oracle checks."""
+    p = ArtParams.default(theta_m=0.2)
+    n = 20000
+    t = hc.sampler_trips(p, np.random.default_rng(1).random((n, 10)))
+    assert 150 * n < t["n_cond"] < 300 * n
+    assert t["skip"] > 5 * n and t["scan"] < 15 * n
+    assert t["scanned_dark"] + t["scanned_lit"] < 0.45 * t["scan"]  # what is scanned is mostly the shell itself
+
+
 def _same_shape_rows(ra, rb, n):
     """Rows of the events whose trees have the same sequence of final species on both sides."""
     def sig(rows):
